@@ -1,0 +1,396 @@
+// attention.cu — fused joint (text+image) flash attention for sm_100a, head_dim 128, no mask.
+//
+//   O = softmax(Q K^T / sqrt(128)) V          (reference: MLXFast.scaledDotProductAttention call sites
+//                                              Flux2Attention.swift:168-174, Flux2ParallelAttention.swift:104-110;
+//                                              KV-cached variant Flux2Attention.swift:393-398)
+//
+// One CTA owns 256 query rows of one head: two 128-row Q tiles, each served by its own softmax warpgroup, share
+// every K/V tile (ping-pong, so the tensor pipe works on one tile while the other is in softmax).
+//   warps 0-3 / 4-7 : softmax warpgroup 0 / 1 (thread == query row == TMEM lane)
+//   warp 8          : TMA producer (Q once, K/V ring)
+//   warp 9          : tcgen05.mma issuer + TMEM allocator
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); fp32 accumulators never touch registers
+// except for the online-softmax correction of O (done only when a row maximum actually moved).
+// K is consumed K-major (d contiguous), V MN-major (d contiguous, keys along the MMA K dimension) straight from the
+// row-major [tokens, heads*128] activation matrices — the [txt|img] concatenation, the per-head split and the
+// "extra cached reference K/V" of the klein-9b-kv path are all expressed as TMA coordinates / key segments, no copies.
+// Two variants of the P operand: kPTmem=false stages P (bf16) through swizzled shared memory with 64-key tiles,
+// kPTmem=true writes P back into the S columns of TMEM and issues the PV MMA with A from TMEM (128-key tiles).
+#include "attention.cuh"
+#include "ptx.cuh"
+
+#include <string>
+
+namespace f2b {
+
+extern bool gemm_init();
+bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
+__device__ __forceinline__ uint32_t apk2(float a, float b, int f16) {
+  if (f16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(a, b);
+}
+static constexpr int HD = 128;  // head dim
+static constexpr int QT = 128;  // query rows per softmax warpgroup
+
+struct AttnKParams {
+  CUtensorMap tmQ;
+  CUtensorMap tmK[3];
+  CUtensorMap tmV[3];
+  int sq, num_heads;
+  float scale_log2;
+  int q_row0;
+  long long q_bs;
+  uint16_t* o;
+  long long ldo;
+  int o_row0;
+  long long o_bs;
+  int f16;
+  int nseg;
+  int seg_row0[3];
+  int seg_len[3];
+  long long seg_bs[3];
+};
+
+template <int BN, bool kPTmem>
+struct ACfg {
+  static constexpr int STAGES = kPTmem ? 2 : 3;
+  static constexpr int Q_BYTES = QT * HD * 2;        // 32 KB per Q tile (2 panels of 128 rows x 128 B)
+  static constexpr int KV_BYTES = BN * HD * 2;       // per K or V tile (2 panels of BN rows x 128 B)
+  static constexpr int KV_PANEL = BN * 128;          // bytes between the d[0,64) and d[64,128) panels
+  static constexpr int P_BYTES = kPTmem ? 0 : QT * BN * 2;
+  static constexpr int OFF_K = 2 * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+};
+
+template <int BN, bool kPTmem>
+__global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
+  using C = ACfg<BN, kPTmem>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;                      // [2]
+  uint64_t* k_full = bars + 2;                  // [STAGES]
+  uint64_t* v_full = k_full + C::STAGES;        // [STAGES]
+  uint64_t* kv_empty = v_full + C::STAGES;      // [STAGES]
+  uint64_t* s_ready = kv_empty + C::STAGES;     // [2]
+  uint64_t* p_ready = s_ready + 2;              // [2]
+  uint64_t* o_done = p_ready + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int q_blk0 = blockIdx.x * 2 * QT;  // first query row (within the batch item) of this CTA
+
+  // total number of key tiles over all segments
+  int n_tiles = 0;
+  for (int s = 0; s < p.nseg; ++s) n_tiles += (p.seg_len[s] + BN - 1) / BN;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    for (int s = 0; s < p.nseg; ++s) { tma_prefetch_desc(&p.tmK[s]); tma_prefetch_desc(&p.tmV[s]); }
+  }
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      const int qrow = p.q_row0 + (int)(b * p.q_bs) + q_blk0;
+      for (int w = 0; w < 2; ++w) {
+        mbar_expect_tx(&q_full[w], C::Q_BYTES);
+        uint8_t* dst = smem + w * C::Q_BYTES;
+        tma_load_2d(dst, &p.tmQ, &q_full[w], head * HD, qrow + w * QT);
+        tma_load_2d(dst + QT * 128, &p.tmQ, &q_full[w], head * HD + 64, qrow + w * QT);
+      }
+      int j = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int tiles = (p.seg_len[s] + BN - 1) / BN;
+        const int row_base = p.seg_row0[s] + (int)(b * p.seg_bs[s]);
+        for (int t = 0; t < tiles; ++t, ++j) {
+          const int st = j % C::STAGES;
+          const uint32_t ph = (j / C::STAGES) & 1;
+          mbar_wait(&kv_empty[st], ph ^ 1, 10);
+          uint8_t* kd = smem + C::OFF_K + st * C::KV_BYTES;
+          uint8_t* vd = smem + C::OFF_V + st * C::KV_BYTES;
+          const int row = row_base + t * BN;
+          mbar_expect_tx(&k_full[st], C::KV_BYTES);
+          tma_load_2d(kd, &p.tmK[s], &k_full[st], head * HD, row);
+          tma_load_2d(kd + C::KV_PANEL, &p.tmK[s], &k_full[st], head * HD + 64, row);
+          mbar_expect_tx(&v_full[st], C::KV_BYTES);
+          tma_load_2d(vd, &p.tmV[s], &v_full[st], head * HD, row);
+          tma_load_2d(vd + C::KV_PANEL, &p.tmV[s], &v_full[st], head * HD + 64, row);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(QT, BN, p.f16 == 0, false, false);  // S = Q K^T   (both K-major)
+      const uint32_t idesc_o = make_idesc_f16(QT, HD, p.f16 == 0, false, true);   // O += P V    (V MN-major)
+      auto issue_s = [&](int w, int st) {
+        const uint32_t qa = smem_u32(smem + w * C::Q_BYTES);
+        const uint32_t ka = smem_u32(smem + C::OFF_K + st * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint64_t ad = make_smem_desc(qa + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024, SWZ_128B);
+          const uint64_t bd = make_smem_desc(ka + (k / 4) * C::KV_PANEL + (k % 4) * 32, 16, 1024, SWZ_128B);
+          umma_f16_ss<1>(tmem_base + w * 128, ad, bd, idesc_s, k ? 1u : 0u);
+        }
+        umma_commit(&s_ready[w]);
+      };
+      auto issue_pv = [&](int w, int st, bool accumulate) {
+        const uint32_t va = smem_u32(smem + C::OFF_V + st * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          // B = V tile, MN-major: 64-wide d panels KV_PANEL bytes apart (LBO), 8-key groups 1024 B apart (SBO);
+          // 16 keys per MMA = 2048 B along the key (MMA-K) direction.
+          const uint64_t bd = make_smem_desc(va + k * 2048, C::KV_PANEL, 1024, SWZ_128B);
+          const uint32_t acc = (accumulate || k) ? 1u : 0u;
+          if constexpr (kPTmem) {
+            umma_f16_ts(tmem_base + 256 + w * 128, tmem_base + w * 128 + k * 8, bd, idesc_o, acc);
+          } else {
+            const uint32_t pa = smem_u32(smem + C::OFF_P + w * C::P_BYTES);
+            const uint64_t ad = make_smem_desc(pa + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024, SWZ_128B);
+            umma_f16_ss<1>(tmem_base + 256 + w * 128, ad, bd, idesc_o, acc);
+          }
+        }
+        umma_commit(&o_done[w]);
+      };
+      mbar_wait(&q_full[0], 0, 20);
+      mbar_wait(&k_full[0], 0, 21);
+      tc_fence_after();
+      issue_s(0, 0);
+      mbar_wait(&q_full[1], 0, 22);
+      tc_fence_after();
+      issue_s(1, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % C::STAGES;
+        const uint32_t ph = (j / C::STAGES) & 1;
+        const int stn = (j + 1) % C::STAGES;
+        const uint32_t phn = ((j + 1) / C::STAGES) & 1;
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(&p_ready[w], j & 1, 23);
+          if (w == 0) mbar_wait(&v_full[st], ph, 24);
+          tc_fence_after();
+          issue_pv(w, st, j > 0);
+          if (w == 1) umma_commit(&kv_empty[st]);
+          if (j + 1 < n_tiles) {
+            if (w == 0) mbar_wait(&k_full[stn], phn, 25);
+            tc_fence_after();
+            issue_s(w, stn);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================================================ softmax warpgroups
+    const int w = warp >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // row inside the Q tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + w * 128;
+    const uint32_t t_o = tmem_base + lane_off + 256 + w * 128;
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint32_t v[32];
+    int j = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      const int tiles = (p.seg_len[s] + BN - 1) / BN;
+      for (int t = 0; t < tiles; ++t, ++j) {
+        const int nvalid = min(BN, p.seg_len[s] - t * BN);
+        mbar_wait(&s_ready[w], j & 1, 30);
+        tc_fence_after();
+        // ---- pass 1: row maximum
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          tmem_ld_32x32(t_s + c * 32, v);
+          tmem_ld_wait();
+          if (nvalid >= (c + 1) * 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+        }
+        const float m_new = fmaxf(m_run, mx * sl2);
+        const float alpha = fast_exp2(m_run - m_new);  // first tile: exp2(-inf) = 0
+        if (j > 0) {
+          // O of the previous tile must have landed before it is corrected / before P storage is reused
+          mbar_wait(&o_done[w], (j - 1) & 1, 31);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+            for (int c = 0; c < HD / 32; ++c) {
+              tmem_ld_32x32(t_o + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_32x32(t_o + c * 32, v);
+            }
+            tmem_st_wait();
+          }
+        }
+        // ---- pass 2: P = exp2(S*scale - m), row sum, hand P to the tensor core
+        float rs = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          tmem_ld_32x32(t_s + c * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sl2, -m_new));
+            float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_new));
+            if (c * 32 + 2 * i >= nvalid) p0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= nvalid) p1 = 0.f;
+            rs += p0 + p1;
+            pk[i] = apk2(p0, p1, p.f16);
+          }
+          if constexpr (kPTmem) {
+            tmem_st_32x16(t_s + c * 16, pk);
+          } else {
+            // K-major 128B-swizzled A tile: row r at r*128 B inside a 64-key panel, 16 B chunk index ^= (r & 7)
+            uint8_t* pbase = smem + C::OFF_P + w * C::P_BYTES + ((c * 32) / 64) * (QT * 128) + row * 128;
+            const int ch0 = ((c * 32) % 64) / 8;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int ch = (ch0 + q4) ^ (row & 7);
+              *reinterpret_cast<uint4*>(pbase + ch * 16) =
+                  make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+            }
+          }
+        }
+        l_run = l_run * alpha + rs;
+        m_run = m_new;
+        if constexpr (kPTmem) {
+          tmem_st_wait();
+        } else {
+          fence_proxy_async_smem();
+        }
+        tc_fence_before();
+        mbar_arrive(&p_ready[w]);
+      }
+    }
+    // ---- finalize: O / l
+    mbar_wait(&o_done[w], (n_tiles - 1) & 1, 32);
+    tc_fence_after();
+    const int qrow = q_blk0 + w * QT + row;
+    const bool ok = qrow < p.sq;
+    const float inv_l = 1.0f / l_run;
+    uint16_t* orow = p.o + ((long long)p.o_row0 + b * p.o_bs + qrow) * p.ldo + head * HD;
+#pragma unroll 1
+    for (int c = 0; c < HD / 32; ++c) {
+      tmem_ld_32x32(t_o + c * 32, v);
+      tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 u;
+          u.x = apk2(__uint_as_float(v[8 * q4 + 0]) * inv_l, __uint_as_float(v[8 * q4 + 1]) * inv_l, p.f16);
+          u.y = apk2(__uint_as_float(v[8 * q4 + 2]) * inv_l, __uint_as_float(v[8 * q4 + 3]) * inv_l, p.f16);
+          u.z = apk2(__uint_as_float(v[8 * q4 + 4]) * inv_l, __uint_as_float(v[8 * q4 + 5]) * inv_l, p.f16);
+          u.w = apk2(__uint_as_float(v[8 * q4 + 6]) * inv_l, __uint_as_float(v[8 * q4 + 7]) * inv_l, p.f16);
+          *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
+}
+
+template <int BN, bool kPTmem>
+static cudaError_t launch_attn(const AttnProblem& a, cudaStream_t stream) {
+  using C = ACfg<BN, kPTmem>;
+  AttnKParams p{};
+  {
+    uint64_t d[2] = {(uint64_t)a.ldq, (uint64_t)a.q_rows_total};
+    uint64_t s[1] = {(uint64_t)a.ldq * 2};
+    uint32_t bx[2] = {64, QT};
+    if (!make_tmap_bf16(&p.tmQ, a.q, 2, d, s, bx)) return cudaErrorInvalidValue;
+  }
+  for (int i = 0; i < a.num_segments; ++i) {
+    const KVSegment& g = a.seg[i];
+    uint64_t dk[2] = {(uint64_t)g.ldk, (uint64_t)g.rows_total};
+    uint64_t sk[1] = {(uint64_t)g.ldk * 2};
+    uint64_t dv[2] = {(uint64_t)g.ldv, (uint64_t)g.rows_total};
+    uint64_t sv[1] = {(uint64_t)g.ldv * 2};
+    uint32_t bx[2] = {64, (uint32_t)BN};
+    if (!make_tmap_bf16(&p.tmK[i], g.k, 2, dk, sk, bx)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16(&p.tmV[i], g.v, 2, dv, sv, bx)) return cudaErrorInvalidValue;
+    p.seg_row0[i] = g.row0;
+    p.seg_len[i] = g.len;
+    p.seg_bs[i] = g.batch_stride;
+  }
+  p.nseg = a.num_segments;
+  p.sq = a.sq;
+  p.num_heads = a.num_heads;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.q_row0 = a.q_row0;
+  p.q_bs = a.q_batch_stride;
+  p.o = reinterpret_cast<uint16_t*>(a.o);
+  p.f16 = a.f16;
+  p.ldo = a.ldo;
+  p.o_row0 = a.o_row0;
+  p.o_bs = a.o_batch_stride;
+
+  auto kern = attn_kernel<BN, kPTmem>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((a.sq + 2 * QT - 1) / (2 * QT), a.num_heads, a.batch);
+  kern<<<grid, 320, C::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t attention_launch(const AttnProblem& a, cudaStream_t stream) {
+  if (!gemm_init()) return cudaErrorInitializationError;
+  if (a.sq <= 0 || a.num_heads <= 0 || a.batch <= 0) return cudaSuccess;
+  int total = 0;
+  for (int i = 0; i < a.num_segments; ++i) total += a.seg[i].len;
+  if (total <= 0 || a.num_segments < 1 || a.num_segments > 3) return cudaErrorInvalidValue;
+  for (int i = 0; i < a.num_segments; ++i)
+    if (a.seg[i].len <= 0) return cudaErrorInvalidValue;
+  const int variant = a.variant ? a.variant : 1;
+  if (variant == 2) return launch_attn<128, true>(a, stream);
+  return launch_attn<64, false>(a, stream);
+}
+
+}  // namespace f2b

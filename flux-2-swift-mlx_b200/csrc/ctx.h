@@ -1,0 +1,211 @@
+// ctx.h — the context object behind the C ABI: owns the device, stream, weights, workspaces and profiler.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/flux2b.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "quant.cuh"
+
+namespace f2b {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define F2B_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return f2b::fail(FLUX2B_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) +      \
+                                            (f2b::gemm_last_error()[0] ? std::string(" / ") + f2b::gemm_last_error() : std::string()));    \
+  } while (0)
+#define F2B_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != 0) return _r;    \
+  } while (0)
+
+inline size_t dtype_size(int dt) {
+  switch (dt) {
+    case FLUX2B_F32: case FLUX2B_U32: case FLUX2B_I32: return 4;
+    case FLUX2B_F16: case FLUX2B_BF16_T: return 2;
+    default: return 1;
+  }
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  cudaError_t alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n; else p = nullptr;
+    return e;
+  }
+  cudaError_t ensure(size_t n) { return (n <= bytes && p) ? cudaSuccess : alloc(n); }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Tensor {
+  DevBuf buf;
+  int dtype = FLUX2B_F32;
+  std::vector<int64_t> shape;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+// dense 16-bit working copy of a (possibly fused / re-tiled) Linear weight [N, K]
+struct Lin {
+  DevBuf w;
+  int N = 0, K = 0;
+};
+struct DoubleBlockW {
+  Lin qkv_img, qkv_txt, out_img, out_txt, ff_in_img, ff_out_img, ff_in_txt, ff_out_txt;
+  DevBuf nq_img, nk_img, nq_txt, nk_txt;  // fp32 [128]
+  bool ff_tiled = false;
+};
+struct SingleBlockW {
+  Lin qkv, mlp, out;
+  DevBuf nq, nk;
+  bool mlp_tiled = false;
+};
+struct ConvW {
+  DevBuf w;     // 16-bit OHWI [Cout, taps, Cin]
+  DevBuf bias;  // fp32 [Cout]
+  int cin = 0, cout = 0, taps = 0;
+};
+struct NormW { DevBuf gamma, beta; int C = 0; };
+struct ResnetW { NormW n1, n2; ConvW c1, c2, sc; bool has_sc = false; int cin = 0, cout = 0; };
+struct VaeW {
+  bool ready = false;
+  ConvW post_quant, conv_in, conv_out;
+  ResnetW mid1, mid2;
+  NormW attn_norm;
+  Lin attn_qkv, attn_out;        // qkv fused [3C, C]
+  DevBuf attn_qkv_bias, attn_out_bias;
+  std::vector<std::vector<ResnetW>> up;
+  std::vector<ConvW> upconv;
+  std::vector<bool> has_upconv;
+  NormW norm_out;
+  DevBuf bn_mean, bn_var;  // fp32 [128]
+  bool has_bn = false;
+};
+
+struct ProfKind {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t used = 0;
+  double flops = 0, bytes = 0;
+  int64_t launches = 0;
+};
+
+}  // namespace f2b
+
+struct flux2b_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool has_dit = false, has_vae = false;
+  flux2b_dit_config dit{};
+  flux2b_vae_config vae{};
+  int quant = 0;
+  std::map<std::string, int> opt;
+  std::unordered_map<std::string, f2b::Tensor> tensors;
+  bool finalized = false;
+
+  // ---- DiT working weights
+  int D = 0, H = 0, Hm = 0;
+  f2b::Lin x_embed, ctx_embed, t_lin1, t_lin2, g_lin1, g_lin2, mod_img, mod_txt, mod_single, norm_out, proj_out;
+  std::vector<f2b::DoubleBlockW> dbl;
+  std::vector<f2b::SingleBlockW> sgl;
+  f2b::VaeW vw;
+
+  // ---- workspaces (grown on demand)
+  f2b::DevBuf ws_x, ws_xn, ws_qkv, ws_cat, ws_cos, ws_sin, ws_ids, ws_small, ws_hid16, ws_enc16, ws_out;
+  f2b::DevBuf ws_rec;  // recorded block outputs
+  int rec_S = 0, rec_count = 0;
+  std::vector<f2b::DevBuf> vae_ws;
+  f2b::DevBuf gn_stats;
+  // KV cache (klein-9b-kv): per layer K and V of the reference tokens, 16-bit [S_ref, D]
+  std::vector<f2b::DevBuf> kv_k, kv_v;
+  int kv_S_ref = 0;
+
+  // ---- staging for host <-> device marshalling (freed at the end of every API call)
+  std::vector<f2b::DevBuf> staging;
+
+  // ---- profiler
+  bool prof_on = false;
+  f2b::ProfKind prof[FLUX2B_PROF_KINDS];
+  int64_t launches = 0;
+
+  int option(const char* k, int dflt) const { auto it = opt.find(k); return it == opt.end() ? dflt : it->second; }
+  bool f16() const { return option("compute_f16", 0) != 0; }
+};
+
+namespace f2b {
+
+// RAII profiler bracket: records events around one kernel launch when profiling is on.
+struct ProfScope {
+  flux2b_ctx* c; int kind; bool on;
+  cudaEvent_t stop = nullptr;
+  ProfScope(flux2b_ctx* ctx, int k, double flops, double bytes) : c(ctx), kind(k), on(ctx->prof_on) {
+    c->launches++;
+    ProfKind& pk = c->prof[kind];
+    pk.launches++; pk.flops += flops; pk.bytes += bytes;
+    if (!on) return;
+    if (pk.used == pk.ev.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      pk.ev.emplace_back(a, b);
+    }
+    cudaEventRecord(pk.ev[pk.used].first, c->stream);
+    stop = pk.ev[pk.used].second;
+    pk.used++;
+  }
+  ~ProfScope() { if (on) cudaEventRecord(stop, c->stream); }
+};
+
+// marshalling helpers (api.cu)
+int dev_in(flux2b_ctx* c, const void* src, size_t bytes, const void** out);     // host -> staged device copy, device -> as is
+int dev_out(flux2b_ctx* c, void* dst, size_t bytes, void** dev, bool* is_host);  // device scratch for a host destination
+int finish_out(flux2b_ctx* c, void* dst, const void* dev, size_t bytes, bool is_host);
+int end_call(flux2b_ctx* c, bool sync);
+bool is_device_ptr(const void* p);
+
+// weights (weights.cu)
+int dense16_from_key(flux2b_ctx* c, const std::string& base, DevBuf* out, int* N, int* K);
+int finalize_dit(flux2b_ctx* c);
+int finalize_vae(flux2b_ctx* c);
+
+// forward passes
+struct DitIO {
+  int B, S_img, S_txt;
+  const float* hidden; const void* enc; int enc_dtype;
+  const float* timestep; const float* guidance;
+  const int32_t* img_ids; const int32_t* txt_ids;
+  float* out;
+  // kv variants
+  int kv_mode = 0;  // 0 none, 1 extract, 2 cached
+  int S_ref = 0; const float* ref_hidden = nullptr; const int32_t* ref_ids = nullptr;
+};
+int dit_forward_device(flux2b_ctx* c, const DitIO& io);  // all pointers already on device
+int vae_decode_device(flux2b_ctx* c, int B, int h8, int w8, const void* latents_nhwc16, void** out_nhwc16, int* out_ld);
+
+}  // namespace f2b

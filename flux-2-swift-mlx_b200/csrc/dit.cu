@@ -1,0 +1,302 @@
+// dit.cu — one Flux.2 DiT forward on the device (reference: Transformer/Flux2Transformer.swift:123-327).
+//
+// Data layout in HBM for one batch item with S = S_txt + S_img tokens (txt rows first — the reference's concat
+// order, Flux2Attention.swift:161-163, Flux2Transformer.swift:252):
+//   X    fp32  [S, D]      residual stream; double blocks update the txt / img row ranges in place, single blocks
+//                          the whole matrix, so the [txt|img] concatenation of :252 is free
+//   XN   16bit [S, D]      LayerNorm+modulate output (A operand of the next GEMM)
+//   QKV  16bit [S, 3D]     q|k|v, already RMS-normed and rotated by the QKV GEMM epilogue
+//   CAT  16bit [S, D+Hm]   attention output in columns [0,D), SwiGLU output in [D, D+Hm): the single-stream
+//                          concat([attn, mlp]) of Flux2ParallelAttention.swift:119 is again free
+// Kernel sequence per double block: 2x ln_modulate, 2x GEMM(QKV+norm+RoPE), attention, 2x GEMM(out, gate+residual),
+// 2x ln_modulate, 2x GEMM(FF-in, SwiGLU), 2x GEMM(FF-out, gate+residual); per single block: ln_modulate,
+// GEMM(QKV+norm+RoPE), GEMM(MLP-in, SwiGLU), attention, GEMM(out, gate+residual).
+#include "ctx.h"
+
+namespace f2b {
+
+static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int M, int N_override, const void* Bptr,
+                    Epilogue epi, int kind = FLUX2B_PROF_GEMM) {
+  GemmProblem g;
+  g.A = A; g.lda = lda;
+  g.B = Bptr ? Bptr : W.w.p; g.ldb = W.K;
+  g.M = M; g.N = N_override ? N_override : W.N; g.K = W.K;
+  epi.f16 = c->f16() ? 1 : 0;
+  g.epi = epi;
+  g.force_cta_group = c->option("gemm_cta_group", 0);
+  const double flops = 2.0 * M * (double)g.N * g.K;
+  const double bytes = 2.0 * ((double)M * g.K + (double)g.N * g.K + (double)M * g.N);
+  ProfScope ps(c, kind, flops, bytes);
+  F2B_CUDA(gemm_launch(g, c->stream));
+  return 0;
+}
+
+static int ensure_ws(flux2b_ctx* c, int S, int S_img, int S_txt) {
+  const int D = c->D, Hm = c->Hm;
+  F2B_CUDA(c->ws_x.ensure((size_t)S * D * 4));
+  F2B_CUDA(c->ws_xn.ensure((size_t)S * D * 2));
+  F2B_CUDA(c->ws_qkv.ensure((size_t)S * 3 * D * 2));
+  F2B_CUDA(c->ws_cat.ensure((size_t)S * (D + 3 * Hm) * 2));  // CAT [S, D+Hm] + room for the unfused [gate|value] fallback
+  F2B_CUDA(c->ws_cos.ensure((size_t)S * 128 * 4));
+  F2B_CUDA(c->ws_sin.ensure((size_t)S * 128 * 4));
+  F2B_CUDA(c->ws_ids.ensure((size_t)S * 4 * 4));
+  F2B_CUDA(c->ws_small.ensure((size_t)(32 * D + 1024) * 4));
+  F2B_CUDA(c->ws_hid16.ensure((size_t)S_img * c->dit.in_channels * 2));
+  F2B_CUDA(c->ws_enc16.ensure((size_t)S_txt * c->dit.joint_attention_dim * 2));
+  return 0;
+}
+
+static int attention(flux2b_ctx* c, int S_q, int q_row0, const KVSegment* segs, int nseg, void* out, int64_t ldo,
+                     int o_row0, int64_t rows_total) {
+  AttnProblem a;
+  a.q = c->ws_qkv.p; a.ldq = 3 * c->D; a.q_rows_total = rows_total; a.q_row0 = q_row0; a.sq = S_q;
+  a.o = out; a.ldo = ldo; a.o_row0 = o_row0;
+  a.num_heads = c->H; a.batch = 1;
+  a.scale = 1.0f / sqrtf(128.0f);
+  a.num_segments = nseg;
+  double keys = 0;
+  for (int i = 0; i < nseg; ++i) { a.seg[i] = segs[i]; keys += segs[i].len; }
+  a.f16 = c->f16() ? 1 : 0;
+  a.variant = c->option("attn_variant", 0);
+  ProfScope ps(c, FLUX2B_PROF_ATTN, 4.0 * S_q * keys * c->D, 2.0 * (2.0 * S_q * c->D + 2.0 * keys * c->D));
+  F2B_CUDA(attention_launch(a, c->stream));
+  return 0;
+}
+
+static int record_block(flux2b_ctx* c, int idx, int S) {
+  if (!c->option("record_blocks", 0)) return 0;
+  const int total = c->dit.num_layers + c->dit.num_single_layers;
+  F2B_CUDA(c->ws_rec.ensure((size_t)total * S * c->D * 4));
+  c->rec_S = S; c->rec_count = total;
+  F2B_CUDA(cudaMemcpyAsync(c->ws_rec.as<float>() + (size_t)idx * S * c->D, c->ws_x.p, (size_t)S * c->D * 4,
+                           cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+// One batch item. hidden [S_img, in_ch] f32, enc [S_txt, joint] (dtype), t/g scalars on device, ids on device.
+static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden, const void* enc, int enc_dtype,
+                       const float* t, const float* g, const int32_t* img_ids, const int32_t* txt_ids, float* out,
+                       int kv_mode, int S_ref, const float* ref_hidden, const int32_t* ref_ids) {
+  const flux2b_dit_config& cfg = c->dit;
+  const int D = c->D, Hm = c->Hm;
+  const bool f16 = c->f16();
+  cudaStream_t st = c->stream;
+  // token layout of this pass: [txt | (ref) | img]
+  const int S_mid = (kv_mode == 1) ? S_ref : 0;
+  const int S_im_all = S_mid + S_img;   // rows of the "image" stream
+  const int S = S_txt + S_im_all;
+  F2B_TRY(ensure_ws(c, S, S_im_all, S_txt));
+  float* X = c->ws_x.as<float>();
+  float* Ximg = X + (size_t)S_txt * D;
+  uint16_t* XN = c->ws_xn.as<uint16_t>();
+  uint16_t* QKV = c->ws_qkv.as<uint16_t>();
+  uint16_t* CAT = c->ws_cat.as<uint16_t>();
+  float* cosT = c->ws_cos.as<float>();
+  float* sinT = c->ws_sin.as<float>();
+  float* sm = c->ws_small.as<float>();
+  float* sinus = sm;                 // [256] (+256 guidance)
+  float* h1 = sm + 512;              // [D]
+  float* temb = h1 + D;              // [D]
+  float* h2 = temb + D;              // [D] guidance hidden
+  float* mod_img = h2 + D;           // [6D]
+  float* mod_txt = mod_img + 6 * D;  // [6D]
+  float* mod_sgl = mod_txt + 6 * D;  // [3D]
+  float* mod_out = mod_sgl + 3 * D;  // [2D]
+
+  // ---- timestep (+guidance) embedding: Flux2Transformer.swift:145-149, Flux2Embeddings.swift:124-141
+  {
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 0);
+    F2B_CUDA(timestep_sinusoid(t, sinus, 1, 1000.0f, st));
+  }
+  auto gemv_p = [&](const float* x, const Lin& W, float* y, bool silu_in, bool accumulate) -> int {
+    ProfScope ps(c, FLUX2B_PROF_GEMV, 2.0 * W.N * W.K, 2.0 * W.N * W.K);
+    F2B_CUDA(gemv(x, W.K, W.w.p, W.K, y, W.N, 1, W.N, W.K, silu_in, accumulate, f16, st));
+    return 0;
+  };
+  F2B_TRY(gemv_p(sinus, c->t_lin1, h1, false, false));
+  F2B_TRY(gemv_p(h1, c->t_lin2, temb, true, false));
+  if (cfg.guidance_embeds && g) {
+    {
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 0);
+      F2B_CUDA(timestep_sinusoid(g, sinus + 256, 1, 1000.0f, st));
+    }
+    F2B_TRY(gemv_p(sinus + 256, c->g_lin1, h2, false, false));
+    F2B_TRY(gemv_p(h2, c->g_lin2, temb, true, true));  // temb += guidance embedding (Flux2Embeddings.swift:134-138)
+  }
+  // ---- modulation, once per forward (Flux2Transformer.swift:160-161,256; Flux2Modulation.swift:49-75)
+  F2B_TRY(gemv_p(temb, c->mod_img, mod_img, true, false));
+  F2B_TRY(gemv_p(temb, c->mod_txt, mod_txt, true, false));
+  F2B_TRY(gemv_p(temb, c->mod_single, mod_sgl, true, false));
+  F2B_TRY(gemv_p(temb, c->norm_out, mod_out, true, false));
+
+  // ---- RoPE table over [txt | (ref) | img] ids (Flux2Transformer.swift:153-154)
+  {
+    int32_t* ids = c->ws_ids.as<int32_t>();
+    F2B_CUDA(cudaMemcpyAsync(ids, txt_ids, (size_t)S_txt * 16, cudaMemcpyDeviceToDevice, st));
+    if (S_mid) F2B_CUDA(cudaMemcpyAsync(ids + (size_t)S_txt * 4, ref_ids, (size_t)S_mid * 16, cudaMemcpyDeviceToDevice, st));
+    F2B_CUDA(cudaMemcpyAsync(ids + (size_t)(S_txt + S_mid) * 4, img_ids, (size_t)S_img * 16, cudaMemcpyDeviceToDevice, st));
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)S * 128 * 8);
+    F2B_CUDA(rope_table(ids, S, cfg.axes_dims_rope, cfg.rope_theta, cosT, sinT, st));
+  }
+
+  // ---- input embedders (Flux2Transformer.swift:137-138)
+  {
+    uint16_t* hid16 = c->ws_hid16.as<uint16_t>();
+    {
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)S_im_all * cfg.in_channels * 6);
+      if (S_mid) F2B_CUDA(f32_to_16(ref_hidden, cfg.in_channels, hid16, cfg.in_channels, S_mid, cfg.in_channels, f16, st));
+      F2B_CUDA(f32_to_16(hidden, cfg.in_channels, hid16 + (size_t)S_mid * cfg.in_channels, cfg.in_channels, S_img,
+                         cfg.in_channels, f16, st));
+    }
+    Epilogue e; e.mode = EPI_F32; e.out = Ximg; e.ldo = D;
+    F2B_TRY(run_gemm(c, hid16, cfg.in_channels, c->x_embed, S_im_all, 0, nullptr, e));
+    uint16_t* enc16 = c->ws_enc16.as<uint16_t>();
+    {
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)S_txt * cfg.joint_attention_dim * 6);
+      const int64_t n = (int64_t)S_txt * cfg.joint_attention_dim;
+      if (enc_dtype == FLUX2B_F32) F2B_CUDA(f32_to_16((const float*)enc, cfg.joint_attention_dim, enc16, cfg.joint_attention_dim, S_txt, cfg.joint_attention_dim, f16, st));
+      else F2B_CUDA(any16_to_16(enc, enc_dtype == FLUX2B_F16, enc16, f16, n, st));
+    }
+    Epilogue e2; e2.mode = EPI_F32; e2.out = X; e2.ldo = D;
+    F2B_TRY(run_gemm(c, enc16, cfg.joint_attention_dim, c->ctx_embed, S_txt, 0, nullptr, e2));
+  }
+
+  const bool fuse_qk = c->option("fuse_qk_rope", 1) != 0;
+  auto ln_mod = [&](const float* x, int rows, const float* shift, const float* scale, uint16_t* o) -> int {
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * D * 6);
+    F2B_CUDA(ln_modulate(x, D, o, D, rows, D, shift, scale, 0, rows, 1e-6f, f16, st));
+    return 0;
+  };
+  auto qkv_gemm = [&](const uint16_t* a, const Lin& W, int rows, int row0, const DevBuf& nq, const DevBuf& nk) -> int {
+    Epilogue e;
+    e.out = QKV + (size_t)row0 * 3 * D; e.ldo = 3 * D;
+    if (fuse_qk) {
+      e.mode = EPI_QKV_ROPE; e.cos = cosT + (size_t)row0 * 128; e.sin = sinT + (size_t)row0 * 128;
+      e.norm_q = nq.as<float>(); e.norm_k = nk.as<float>(); e.dmodel = D; e.eps = 1e-6f;
+      F2B_TRY(run_gemm(c, a, D, W, rows, 0, nullptr, e));
+    } else {
+      e.mode = EPI_BF16;
+      F2B_TRY(run_gemm(c, a, D, W, rows, 0, nullptr, e));
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * D * 8);
+      F2B_CUDA(qk_norm_rope(QKV + (size_t)row0 * 3 * D, 3 * D, rows, D, nq.as<float>(), nk.as<float>(),
+                            cosT + (size_t)row0 * 128, sinT + (size_t)row0 * 128, 1e-6f, f16, st));
+    }
+    return 0;
+  };
+  auto gate_res_gemm = [&](const uint16_t* a, int64_t lda, const Lin& W, int rows, float* x, const float* gate) -> int {
+    Epilogue e; e.mode = EPI_GATE_RES; e.out = x; e.ldo = D; e.res = x; e.ldr = D; e.gate = gate;
+    return run_gemm(c, a, lda, W, rows, 0, nullptr, e);
+  };
+  // SwiGLU producer: out[rows, Hm] (leading dim ldo) = silu(gate) * value
+  auto swiglu_gemm = [&](const uint16_t* a, const Lin& W, bool tiled, int rows, uint16_t* o, int64_t ldo, uint16_t* scratch) -> int {
+    if (tiled) {
+      Epilogue e; e.mode = EPI_SWIGLU; e.out = o; e.ldo = (int)ldo;
+      return run_gemm(c, a, D, W, rows, 0, nullptr, e);
+    }
+    Epilogue e; e.mode = EPI_BF16; e.out = scratch; e.ldo = 2 * Hm;
+    F2B_TRY(run_gemm(c, a, D, W, rows, 0, nullptr, e));
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * Hm * 6);
+    F2B_CUDA(swiglu(scratch, 2 * Hm, o, ldo, rows, Hm, f16, st));
+    return 0;
+  };
+
+  // attention key segments for this pass
+  auto full_attention = [&](int layer, void* o, int64_t ldo) -> int {
+    const int64_t rows_total = S;
+    uint16_t* Kp = QKV + D;
+    uint16_t* Vp = QKV + 2 * D;
+    if (kv_mode == 0) {
+      KVSegment sg; sg.k = Kp; sg.v = Vp; sg.ldk = sg.ldv = 3 * D; sg.rows_total = rows_total; sg.row0 = 0; sg.len = S;
+      return attention(c, S, 0, &sg, 1, o, ldo, 0, rows_total);
+    }
+    if (kv_mode == 1) {
+      // extraction pass [txt | ref | img] (Flux2Attention.swift:245-330): the additive mask of :422-437 blocks
+      // reference queries from the output keys; text and output queries see everything. The mask is block-aligned, so
+      // it is expressed as query ranges x key segments instead of an S x S float matrix.
+      // (a) txt + img queries over all keys
+      KVSegment all; all.k = Kp; all.v = Vp; all.ldk = all.ldv = 3 * D; all.rows_total = rows_total; all.row0 = 0; all.len = S;
+      F2B_TRY(attention(c, S_txt, 0, &all, 1, o, ldo, 0, rows_total));
+      F2B_TRY(attention(c, S_img, S_txt + S_ref, &all, 1, o, ldo, S_txt + S_ref, rows_total));
+      // (b) ref queries over [txt | ref] keys
+      KVSegment rf = all; rf.row0 = 0; rf.len = S_txt + S_ref;
+      F2B_TRY(attention(c, S_ref, S_txt, &rf, 1, o, ldo, S_txt, rows_total));
+      // cache post-norm, post-RoPE reference K / V of this layer (TransformerKVCache.swift:13-79)
+      F2B_CUDA(c->kv_k[layer].ensure((size_t)S_ref * D * 2));
+      F2B_CUDA(c->kv_v[layer].ensure((size_t)S_ref * D * 2));
+      F2B_CUDA(cudaMemcpy2DAsync(c->kv_k[layer].p, (size_t)D * 2, Kp + (size_t)S_txt * 3 * D, (size_t)3 * D * 2,
+                                 (size_t)D * 2, S_ref, cudaMemcpyDeviceToDevice, st));
+      F2B_CUDA(cudaMemcpy2DAsync(c->kv_v[layer].p, (size_t)D * 2, Vp + (size_t)S_txt * 3 * D, (size_t)3 * D * 2,
+                                 (size_t)D * 2, S_ref, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
+    // cached pass: queries [txt | img], keys [txt | cachedRef | img] (Flux2Attention.swift:393-395)
+    KVSegment sg[3];
+    sg[0].k = Kp; sg[0].v = Vp; sg[0].ldk = sg[0].ldv = 3 * D; sg[0].rows_total = rows_total; sg[0].row0 = 0; sg[0].len = S_txt;
+    sg[1].k = c->kv_k[layer].p; sg[1].v = c->kv_v[layer].p; sg[1].ldk = sg[1].ldv = D; sg[1].rows_total = c->kv_S_ref;
+    sg[1].row0 = 0; sg[1].len = c->kv_S_ref;
+    sg[2] = sg[0]; sg[2].row0 = S_txt; sg[2].len = S_img;
+    return attention(c, S, 0, sg, 3, o, ldo, 0, rows_total);
+  };
+
+  // ---- double-stream blocks (Flux2TransformerBlock.swift:80-168)
+  for (int i = 0; i < cfg.num_layers; ++i) {
+    DoubleBlockW& b = c->dbl[i];
+    F2B_TRY(ln_mod(Ximg, S_im_all, mod_img + 0, mod_img + D, XN + (size_t)S_txt * D));
+    F2B_TRY(ln_mod(X, S_txt, mod_txt + 0, mod_txt + D, XN));
+    F2B_TRY(qkv_gemm(XN + (size_t)S_txt * D, b.qkv_img, S_im_all, S_txt, b.nq_img, b.nk_img));
+    F2B_TRY(qkv_gemm(XN, b.qkv_txt, S_txt, 0, b.nq_txt, b.nk_txt));
+    F2B_TRY(full_attention(i, CAT, D));
+    F2B_TRY(gate_res_gemm(CAT + (size_t)S_txt * D, D, b.out_img, S_im_all, Ximg, mod_img + 2 * D));
+    F2B_TRY(gate_res_gemm(CAT, D, b.out_txt, S_txt, X, mod_txt + 2 * D));
+    F2B_TRY(ln_mod(Ximg, S_im_all, mod_img + 3 * D, mod_img + 4 * D, XN + (size_t)S_txt * D));
+    F2B_TRY(ln_mod(X, S_txt, mod_txt + 3 * D, mod_txt + 4 * D, XN));
+    uint16_t* Hbuf = CAT;                       // [S, Hm]
+    uint16_t* scratch = CAT + (size_t)S * Hm;   // [S, 2Hm] unfused fallback
+    F2B_TRY(swiglu_gemm(XN + (size_t)S_txt * D, b.ff_in_img, b.ff_tiled, S_im_all, Hbuf + (size_t)S_txt * Hm, Hm, scratch));
+    F2B_TRY(gate_res_gemm(Hbuf + (size_t)S_txt * Hm, Hm, b.ff_out_img, S_im_all, Ximg, mod_img + 5 * D));
+    F2B_TRY(swiglu_gemm(XN, b.ff_in_txt, b.ff_tiled, S_txt, Hbuf, Hm, scratch));
+    F2B_TRY(gate_res_gemm(Hbuf, Hm, b.ff_out_txt, S_txt, X, mod_txt + 5 * D));
+    F2B_TRY(record_block(c, i, S));
+  }
+  // ---- single-stream blocks (Flux2SingleBlock.swift:59-98, Flux2ParallelAttention.swift:72-123)
+  const int ldc = D + Hm;
+  for (int i = 0; i < cfg.num_single_layers; ++i) {
+    SingleBlockW& b = c->sgl[i];
+    F2B_TRY(ln_mod(X, S, mod_sgl + 0, mod_sgl + D, XN));
+    F2B_TRY(qkv_gemm(XN, b.qkv, S, 0, b.nq, b.nk));
+    uint16_t* scratch = CAT + (size_t)S * ldc;  // [S, 2Hm] unfused fallback lives behind CAT (see ensure_ws)
+    F2B_TRY(swiglu_gemm(XN, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
+    F2B_TRY(full_attention(cfg.num_layers + i, CAT, ldc));
+    F2B_TRY(gate_res_gemm(CAT, ldc, b.out, S, X, mod_sgl + 2 * D));
+    F2B_TRY(record_block(c, cfg.num_layers + i, S));
+  }
+  // ---- output: AdaLayerNormContinuous (scale first, Flux2Modulation.swift:146-148) + projOut (:321-324)
+  float* Xout = X + (size_t)(S_txt + S_mid) * D;
+  F2B_TRY(ln_mod(Xout, S_img, mod_out + D, mod_out + 0, XN));
+  Epilogue e; e.mode = EPI_F32; e.out = out; e.ldo = cfg.out_channels;
+  F2B_TRY(run_gemm(c, XN, D, c->proj_out, S_img, 0, nullptr, e));
+  return 0;
+}
+
+int dit_forward_device(flux2b_ctx* c, const DitIO& io) {
+  if (!c->has_dit || !c->finalized) return fail(FLUX2B_ERR_MODEL_NOT_LOADED, "transformer weights not finalized");
+  const flux2b_dit_config& cfg = c->dit;
+  if (io.B < 1 || io.S_img < 1 || io.S_txt < 1) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "empty batch / sequence");
+  if (io.kv_mode) {
+    const int layers = cfg.num_layers + cfg.num_single_layers;
+    if ((int)c->kv_k.size() != layers) { c->kv_k.clear(); c->kv_v.clear(); c->kv_k.resize(layers); c->kv_v.resize(layers); }
+    if (io.kv_mode == 1) c->kv_S_ref = io.S_ref;
+    if (io.kv_mode == 2 && c->kv_S_ref <= 0) return fail(FLUX2B_ERR_GENERATION_FAILED, "kv cache is empty: run kv_extract first");
+    if (io.B != 1) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "kv-cached forward supports batch 1 (as the reference pipeline)");
+  }
+  for (int b = 0; b < io.B; ++b) {
+    const size_t enc_elems = (size_t)io.S_txt * cfg.joint_attention_dim;
+    const void* enc_b = reinterpret_cast<const uint8_t*>(io.enc) + (size_t)b * enc_elems * dtype_size(io.enc_dtype);
+    F2B_TRY(forward_one(c, io.S_img, io.S_txt, io.hidden + (size_t)b * io.S_img * cfg.in_channels, enc_b, io.enc_dtype,
+                        io.timestep + b, io.guidance ? io.guidance + b : nullptr, io.img_ids, io.txt_ids,
+                        io.out + (size_t)b * io.S_img * cfg.out_channels, io.kv_mode, io.S_ref, io.ref_hidden, io.ref_ids));
+  }
+  return 0;
+}
+
+}  // namespace f2b

@@ -1,0 +1,681 @@
+// elementwise.cu — the bandwidth-bound kernels of the denoising path (no tensor cores: these are HBM-bound,
+// so the work is coalescing, 16 B vector access, keeping a row in registers between its reductions, and grids that
+// oversubscribe the 148 SMs).
+#include "elementwise.cuh"
+#include "ptx.cuh"
+#include <algorithm>
+
+namespace f2b {
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool f16) {
+  if (f16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(a, b);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, bool f16) {
+  if (f16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ float load16(const void* p, int64_t i, bool f16) {
+  return f16 ? __half2float(reinterpret_cast<const __half*>(p)[i])
+             : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void store16(void* p, int64_t i, float v, bool f16) {
+  if (f16) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  float r = (l < NT / 32) ? sm[l] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+// ------------------------------------------------------------------ LayerNorm + modulate
+// one CTA (256 threads) per row; the row stays in registers across the mean / variance reductions.
+template <int MAXV>  // float4 vectors per thread
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, int64_t ldx, void* __restrict__ out,
+                                                          int64_t ldo, int D, const float* __restrict__ shift,
+                                                          const float* __restrict__ scale, int64_t mod_bs,
+                                                          int rows_per_batch, float eps, bool f16) {
+  __shared__ float sm[8];
+  const int row = blockIdx.x;
+  const int b = row / rows_per_batch;
+  const float* xr = x + (int64_t)row * ldx;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 256 + threadIdx.x) * 4;
+    if (c < D) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = block_sum<256>(s, sm) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 256 + threadIdx.x) * 4;
+    if (c < D) {
+      float a = v[i].x - mean, bq = v[i].y - mean, cq = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + bq * bq) + (cq * cq + d * d);
+    }
+  }
+  const float rstd = rsqrtf(block_sum<256>(q, sm) / (float)D + eps);
+  const float* sh = shift + b * mod_bs;
+  const float* sc = scale + b * mod_bs;
+  uint16_t* orow = reinterpret_cast<uint16_t*>(out) + (int64_t)row * ldo;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 256 + threadIdx.x) * 4;
+    if (c < D) {
+      const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + c));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + c));
+      const float o0 = (v[i].x - mean) * rstd * (1.f + c4.x) + h4.x;
+      const float o1 = (v[i].y - mean) * rstd * (1.f + c4.y) + h4.y;
+      const float o2 = (v[i].z - mean) * rstd * (1.f + c4.z) + h4.z;
+      const float o3 = (v[i].w - mean) * rstd * (1.f + c4.w) + h4.w;
+      *reinterpret_cast<uint2*>(orow + c) = make_uint2(pack2(o0, o1, f16), pack2(o2, o3, f16));
+    }
+  }
+}
+
+cudaError_t ln_modulate(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int D, const float* shift,
+                        const float* scale, int64_t mod_bs, int rows_per_batch, float eps, bool f16, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  if (D % 4 || D > 8192 || ldx % 4 || ldo % 4) return cudaErrorInvalidValue;
+  if (D <= 1024) ln_modulate_kernel<1><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
+  else if (D <= 3072) ln_modulate_kernel<3><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
+  else if (D <= 4096) ln_modulate_kernel<4><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
+  else if (D <= 6144) ln_modulate_kernel<6><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
+  else ln_modulate_kernel<8><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ GEMV (M = batch <= 8): weight-bandwidth bound
+template <int MAXB>
+__global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, int64_t ldx, const void* __restrict__ W,
+                                                   int64_t ldw, float* __restrict__ y, int64_t ldy, int B, int N, int K,
+                                                   bool silu_in, bool accumulate, bool f16) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const uint16_t* wr = reinterpret_cast<const uint16_t*>(W) + (int64_t)warp * ldw;
+  float acc[MAXB];
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+  for (int k = lane * 8; k < K; k += 256) {
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wr + k));
+    float wf[8];
+    {
+      float2 t;
+      t = unpack2(wv.x, f16); wf[0] = t.x; wf[1] = t.y;
+      t = unpack2(wv.y, f16); wf[2] = t.x; wf[3] = t.y;
+      t = unpack2(wv.z, f16); wf[4] = t.x; wf[5] = t.y;
+      t = unpack2(wv.w, f16); wf[6] = t.x; wf[7] = t.y;
+    }
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+      if (b < B) {
+        const float4 x0 = *reinterpret_cast<const float4*>(x + b * ldx + k);
+        const float4 x1 = *reinterpret_cast<const float4*>(x + b * ldx + k + 4);
+        float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xi = silu_in ? silu_f(xv[i]) : xv[i];
+          acc[b] = fmaf(xi, wf[i], acc[b]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) {
+    if (b < B) {
+      const float r = warp_sum(acc[b]);
+      if (lane == 0) y[b * ldy + warp] = accumulate ? y[b * ldy + warp] + r : r;
+    }
+  }
+}
+cudaError_t gemv(const float* x, int64_t ldx, const void* W16, int64_t ldw, float* y, int64_t ldy, int B, int N, int K,
+                 bool silu_in, bool accumulate, bool f16, cudaStream_t s) {
+  if (B > 8 || K % 8 || ldw % 8 || ldx % 4) return cudaErrorInvalidValue;
+  const int blocks = (N * 32 + 255) / 256;
+  if (B <= 1) gemv_kernel<1><<<blocks, 256, 0, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
+  else if (B <= 2) gemv_kernel<2><<<blocks, 256, 0, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
+  else gemv_kernel<8><<<blocks, 256, 0, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ sinusoid / rope table
+__global__ void sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int B, float pre_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 128) return;
+  const int b = i / 128, j = i % 128;
+  const float exponent = (-logf(10000.0f) * (float)j) / 128.0f;
+  const float f = expf(exponent);
+  const float a = (t[b] * pre_scale) * f;
+  out[b * 256 + j] = cosf(a);
+  out[b * 256 + 128 + j] = sinf(a);
+}
+cudaError_t timestep_sinusoid(const float* t, float* out, int B, float pre_scale, cudaStream_t s) {
+  sinusoid_kernel<<<(B * 128 + 127) / 128, 128, 0, s>>>(t, out, B, pre_scale);
+  return cudaGetLastError();
+}
+
+struct RopeAxes { int dims[4]; int off[4]; };
+__global__ void rope_table_kernel(const int32_t* __restrict__ ids, int S, RopeAxes ax, float theta,
+                                  float* __restrict__ cos_out, float* __restrict__ sin_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, pair)
+  const int total_pairs = (ax.off[3] + ax.dims[3]) / 2;
+  if (i >= S * total_pairs) return;
+  const int row = i / total_pairs, pr = i % total_pairs;
+  const int col = pr * 2;
+  int a = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k)
+    if (col >= ax.off[k]) a = k;
+  const int j2 = col - ax.off[a];  // = 2j
+  const float inv_freq = 1.0f / powf(theta, (float)j2 / (float)ax.dims[a]);
+  const float ang = (float)ids[row * 4 + a] * inv_freq;
+  const float c = cosf(ang), sn = sinf(ang);
+  const int W = ax.off[3] + ax.dims[3];
+  cos_out[(int64_t)row * W + col] = c;
+  cos_out[(int64_t)row * W + col + 1] = c;
+  sin_out[(int64_t)row * W + col] = sn;
+  sin_out[(int64_t)row * W + col + 1] = sn;
+}
+cudaError_t rope_table(const int32_t* ids, int S, const int* axes_dims, float theta, float* cos_out, float* sin_out,
+                       cudaStream_t s) {
+  RopeAxes ax;
+  int off = 0;
+  for (int i = 0; i < 4; ++i) { ax.dims[i] = axes_dims[i]; ax.off[i] = off; off += axes_dims[i]; }
+  const int n = S * (off / 2);
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, s>>>(ids, S, ax, theta, cos_out, sin_out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ QK RMSNorm + RoPE (unfused path)
+// one warp per (row, head, q|k): 128 elements = 4 per lane (two interleaved pairs)
+__global__ void __launch_bounds__(256) qk_norm_rope_kernel(void* __restrict__ qkv, int64_t ld, int rows, int D,
+                                                           const float* __restrict__ nq, const float* __restrict__ nk,
+                                                           const float* __restrict__ cs, const float* __restrict__ sn,
+                                                           float eps, bool f16) {
+  const int H = D / 128;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (int64_t)rows * H * 2) return;
+  const int which = (int)(wid % 2);
+  const int h = (int)((wid / 2) % H);
+  const int64_t row = wid / (2 * H);
+  uint16_t* p = reinterpret_cast<uint16_t*>(qkv) + row * ld + which * D + h * 128 + lane * 4;
+  const uint2 raw = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack2(raw.x, f16), b = unpack2(raw.y, f16);
+  float ss = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss * (1.f / 128.f) + eps);
+  const float4 w = __ldg(reinterpret_cast<const float4*>((which ? nk : nq) + lane * 4));
+  const float4 c = __ldg(reinterpret_cast<const float4*>(cs + row * 128 + lane * 4));
+  const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn + row * 128 + lane * 4));
+  const float x0 = a.x * rstd * w.x, x1 = a.y * rstd * w.y, x2 = b.x * rstd * w.z, x3 = b.y * rstd * w.w;
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack2(x0 * c.x - x1 * s4.x, x1 * c.y + x0 * s4.y, f16),
+                                            pack2(x2 * c.z - x3 * s4.z, x3 * c.w + x2 * s4.w, f16));
+}
+cudaError_t qk_norm_rope(void* qkv16, int64_t ld, int rows, int D, const float* norm_q, const float* norm_k,
+                         const float* cos_t, const float* sin_t, float eps, bool f16, cudaStream_t s) {
+  const int64_t warps = (int64_t)rows * (D / 128) * 2;
+  const int64_t blocks = (warps * 32 + 255) / 256;
+  qk_norm_rope_kernel<<<(unsigned)blocks, 256, 0, s>>>(qkv16, ld, rows, D, norm_q, norm_k, cos_t, sin_t, eps, f16);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ SwiGLU / gate+residual (unfused fallbacks)
+__global__ void swiglu_kernel(const void* __restrict__ in, int64_t ldi, void* __restrict__ out, int64_t ldo, int rows,
+                              int H, bool f16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 8 outputs per thread
+  const int per_row = H / 8;
+  if (i >= (int64_t)rows * per_row) return;
+  const int64_t r = i / per_row;
+  const int c = (int)(i % per_row) * 8;
+  const uint16_t* ip = reinterpret_cast<const uint16_t*>(in) + r * ldi + c;
+  const uint4 g = *reinterpret_cast<const uint4*>(ip);
+  const uint4 u = *reinterpret_cast<const uint4*>(ip + H);
+  const uint32_t gg[4] = {g.x, g.y, g.z, g.w}, uu[4] = {u.x, u.y, u.z, u.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 a = unpack2(gg[k], f16), b = unpack2(uu[k], f16);
+    o[k] = pack2(silu_f(a.x) * b.x, silu_f(a.y) * b.y, f16);
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + r * ldo + c) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+cudaError_t swiglu(const void* in16, int64_t ldi, void* out16, int64_t ldo, int rows, int H, bool f16, cudaStream_t s) {
+  if (H % 8 || ldi % 8 || ldo % 8) return cudaErrorInvalidValue;
+  const int64_t n = (int64_t)rows * (H / 8);
+  swiglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in16, ldi, out16, ldo, rows, H, f16);
+  return cudaGetLastError();
+}
+__global__ void gate_residual_kernel(const void* __restrict__ y, int64_t ldy, const float* __restrict__ gate,
+                                     int64_t gbs, int rpb, float* __restrict__ x, int64_t ldx, int rows, int D,
+                                     bool f16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 4 per thread
+  const int per_row = D / 4;
+  if (i >= (int64_t)rows * per_row) return;
+  const int64_t r = i / per_row;
+  const int c = (int)(i % per_row) * 4;
+  const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(y) + r * ldy + c);
+  const float2 a = unpack2(raw.x, f16), b = unpack2(raw.y, f16);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (r / rpb) * gbs + c));
+  float4 xv = *reinterpret_cast<float4*>(x + r * ldx + c);
+  xv.x = fmaf(g.x, a.x, xv.x); xv.y = fmaf(g.y, a.y, xv.y); xv.z = fmaf(g.z, b.x, xv.z); xv.w = fmaf(g.w, b.y, xv.w);
+  *reinterpret_cast<float4*>(x + r * ldx + c) = xv;
+}
+cudaError_t gate_residual(const void* y16, int64_t ldy, const float* gate, int64_t gbs, int rpb, float* x, int64_t ldx,
+                          int rows, int D, bool f16, cudaStream_t s) {
+  if (D % 4) return cudaErrorInvalidValue;
+  const int64_t n = (int64_t)rows * (D / 4);
+  gate_residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y16, ldy, gate, gbs, rpb, x, ldx, rows, D, f16);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ conversions
+__global__ void f32_to_16_kernel(const float* __restrict__ in, int64_t ldi, void* __restrict__ out, int64_t ldo, int rows,
+                                 int cols, bool f16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = (cols + 3) / 4;
+  if (i >= (int64_t)rows * per_row) return;
+  const int64_t r = i / per_row;
+  const int c = (int)(i % per_row) * 4;
+  if (c + 4 <= cols && (ldi % 4 == 0) && (ldo % 4 == 0)) {
+    const float4 v = *reinterpret_cast<const float4*>(in + r * ldi + c);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + r * ldo + c) = make_uint2(pack2(v.x, v.y, f16), pack2(v.z, v.w, f16));
+  } else {
+    for (int k = c; k < cols && k < c + 4; ++k) store16(out, r * ldo + k, in[r * ldi + k], f16);
+  }
+}
+cudaError_t f32_to_16(const float* in, int64_t ldi, void* out16, int64_t ldo, int rows, int cols, bool f16,
+                      cudaStream_t s) {
+  const int64_t n = (int64_t)rows * ((cols + 3) / 4);
+  if (n <= 0) return cudaSuccess;
+  f32_to_16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, ldi, out16, ldo, rows, cols, f16);
+  return cudaGetLastError();
+}
+__global__ void any16_to_16_kernel(const void* __restrict__ in, int in_f16, void* __restrict__ out, bool f16, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  store16(out, i, load16(in, i, in_f16 != 0), f16);
+}
+cudaError_t any16_to_16(const void* in, int in_is_f16, void* out16, bool f16, int64_t n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  any16_to_16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, in_is_f16, out16, f16, n);
+  return cudaGetLastError();
+}
+__global__ void cvt16_to_f32_kernel(const void* __restrict__ in, float* __restrict__ out, int64_t n, bool f16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = load16(in, i, f16);
+}
+cudaError_t cvt16_to_f32(const void* in16, float* out, int64_t n, bool f16, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  cvt16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in16, out, n, f16);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ scheduler math on latents
+__global__ void euler_kernel(float* __restrict__ x, const float* __restrict__ pred, const float* __restrict__ un,
+                             float cfg, float dt, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = pred[i];
+  if (un) { const float u = un[i]; v = u + cfg * (v - u); }
+  x[i] = x[i] + dt * v;
+}
+cudaError_t euler_step(float* x, const float* pred, const float* pred_uncond, float cfg, float dt, int64_t n,
+                       cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  euler_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, pred, pred_uncond, cfg, dt, n);
+  return cudaGetLastError();
+}
+__global__ void scale_noise_kernel(const float* __restrict__ a, const float* __restrict__ nz, float sigma,
+                                   float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (1.f - sigma) * a[i] + sigma * nz[i];
+}
+cudaError_t scale_noise(const float* sample, const float* noise, float sigma, float* out, int64_t n, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  scale_noise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sample, noise, sigma, out, n);
+  return cudaGetLastError();
+}
+__global__ void repaint_kernel(float* __restrict__ x, const float* __restrict__ x0, const float* __restrict__ e,
+                               const float* __restrict__ m, float sn, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float known = (1.f - sn) * x0[i] + sn * e[i];
+  x[i] = (1.f - m[i]) * known + m[i] * x[i];
+}
+cudaError_t repaint_blend(float* x, const float* x0, const float* eps, const float* mask, float sigma_next, int64_t n,
+                          cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  repaint_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, x0, eps, mask, sigma_next, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ latent plumbing
+struct PermuteArgs { int ndim; int shape[6]; int64_t istride[6]; };
+__global__ void permute_kernel(const float* __restrict__ in, float* __restrict__ out, PermuteArgs a, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t rem = i, off = 0;
+#pragma unroll
+  for (int d = 5; d >= 0; --d) {
+    if (d < a.ndim) {
+      const int64_t idx = rem % a.shape[d];
+      rem /= a.shape[d];
+      off += idx * a.istride[d];
+    }
+  }
+  out[i] = in[off];
+}
+cudaError_t permute_f32(const float* in, float* out, int ndim, const int* out_shape, const int64_t* in_strides,
+                        cudaStream_t s) {
+  if (ndim < 1 || ndim > 6) return cudaErrorInvalidValue;
+  PermuteArgs a{};
+  a.ndim = ndim;
+  int64_t n = 1;
+  for (int d = 0; d < ndim; ++d) { a.shape[d] = out_shape[d]; a.istride[d] = in_strides[d]; n *= out_shape[d]; }
+  if (n <= 0) return cudaSuccess;
+  permute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, a, n);
+  return cudaGetLastError();
+}
+__global__ void bn_affine_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ mean,
+                                 const float* __restrict__ var, float eps, int C, int64_t hw, bool denorm, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)((i / hw) % C);
+  const float sd = sqrtf(var[c] + eps);
+  y[i] = denorm ? x[i] * sd + mean[c] : (x[i] - mean[c]) / sd;
+}
+cudaError_t bn_affine_nchw(const float* x, float* y, const float* mean, const float* var, float eps, int B, int C,
+                           int64_t hw, bool denorm, cudaStream_t s) {
+  const int64_t n = (int64_t)B * C * hw;
+  if (n <= 0) return cudaSuccess;
+  bn_affine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, y, mean, var, eps, C, hw, denorm, n);
+  return cudaGetLastError();
+}
+// seq[b, y*w + x, c*4 + ph*2 + pw] -> out[b, 2y+ph, 2x+pw, c]; one thread per (token, 8 channels of one sub-pixel)
+__global__ void seq_to_vae_kernel(const float* __restrict__ seq, const float* __restrict__ mean,
+                                  const float* __restrict__ var, float eps, void* __restrict__ out, int B, int h, int w,
+                                  bool f16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = (int64_t)B * h * w * 128;
+  if (i >= n) return;
+  const int ch = (int)(i % 128);
+  const int64_t tok = i / 128;
+  const int x = (int)(tok % w), y = (int)((tok / w) % h), b = (int)(tok / ((int64_t)w * h));
+  const int c = ch / 4, ph = (ch / 2) % 2, pw = ch % 2;
+  const float v = seq[i] * sqrtf(var[ch] + eps) + mean[ch];
+  const int64_t o = (((int64_t)b * (2 * h) + 2 * y + ph) * (2 * w) + 2 * x + pw) * 32 + c;
+  store16(out, o, v, f16);
+}
+cudaError_t seq_to_vae_input(const float* seq, const float* mean, const float* var, float eps, void* out16, int B, int h,
+                             int w, bool f16, cudaStream_t s) {
+  const int64_t n = (int64_t)B * h * w * 128;
+  if (n <= 0) return cudaSuccess;
+  seq_to_vae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(seq, mean, var, eps, out16, B, h, w, f16);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ GroupNorm (+SiLU), NHWC
+// pass 1: grid (chunks, B). Each thread owns 8 consecutive channels (one 16 B vector) of a strided set of pixels,
+// accumulates sum / sum-of-squares in fp32, folds lanes that share a group, then one double atomic per (CTA, group).
+__global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ x, double* __restrict__ stats, int64_t HW,
+                                                       int C, int G, bool f16) {
+  extern __shared__ float gsm[];  // [2*G]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) gsm[i] = 0.f;
+  __syncthreads();
+  const int vec_per_pix = C / 8;
+  const int cg = C / G;  // channels per group
+  const uint16_t* xb = reinterpret_cast<const uint16_t*>(x) + (int64_t)b * HW * C;
+  const int64_t nvec = HW * vec_per_pix;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // a thread keeps the same channel slot when stride % vec_per_pix == 0; otherwise flush per element
+  const bool fixed = (stride % vec_per_pix) == 0;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (fixed) {
+    // per-channel register accumulators (8 channels of this thread's slot), folded into groups once at the end
+    float s[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
+    for (int64_t i = i0; i < nvec; i += stride) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack2(u[k], f16);
+        s[2 * k] += f.x; q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
+        s[2 * k + 1] += f.y; q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
+      }
+    }
+    if (i0 < nvec) {
+      const int c0 = (int)(i0 % vec_per_pix) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int g = (c0 + k) / cg;
+        atomicAdd(&gsm[2 * g], s[k]);
+        atomicAdd(&gsm[2 * g + 1], q[k]);
+      }
+    }
+  } else {
+    for (int64_t i = i0; i < nvec; i += stride) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+      const int c0 = (int)(i % vec_per_pix) * 8;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack2(u[k], f16);
+        const int g0 = (c0 + 2 * k) / cg, g1 = (c0 + 2 * k + 1) / cg;
+        atomicAdd(&gsm[2 * g0], f.x); atomicAdd(&gsm[2 * g0 + 1], f.x * f.x);
+        atomicAdd(&gsm[2 * g1], f.y); atomicAdd(&gsm[2 * g1 + 1], f.y * f.y);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(int64_t)b * 2 * G + i], (double)gsm[i]);
+}
+__global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x, void* __restrict__ y,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const double* __restrict__ stats, int64_t HW, int C, int G,
+                                                       float eps, bool silu, bool f16) {
+  const int b = blockIdx.y;
+  const int vec_per_pix = C / 8;
+  const int cg = C / G;
+  const int64_t nvec = HW * vec_per_pix;
+  const uint16_t* xb = reinterpret_cast<const uint16_t*>(x) + (int64_t)b * HW * C;
+  uint16_t* yb = reinterpret_cast<uint16_t*>(y) + (int64_t)b * HW * C;
+  const double cnt = (double)HW * cg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % vec_per_pix) * 8;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack2(u[k], f16);
+      float r[2] = {f.x, f.y};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = c0 + 2 * k + t;
+        const int g = c / cg;
+        const double m = stats[(int64_t)b * 2 * G + 2 * g] / cnt;
+        const double var = stats[(int64_t)b * 2 * G + 2 * g + 1] / cnt - m * m;
+        const float rstd = rsqrtf(fmaxf((float)var, 0.f) + eps);
+        float z = (r[t] - (float)m) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        if (silu) z = silu_f(z);
+        r[t] = z;
+      }
+      o[k] = pack2(r[0], r[1], f16);
+    }
+    *reinterpret_cast<uint4*>(yb + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+cudaError_t groupnorm_silu(const void* x16, void* y16, const float* gamma, const float* beta, double* stats_ws, int B,
+                           int64_t HW, int C, int G, float eps, bool silu, bool f16, cudaStream_t s) {
+  if (C % 8 || C % G) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * G * B, s);
+  if (e != cudaSuccess) return e;
+  const int64_t nvec = HW * (C / 8);
+  int chunks = (int)std::min<int64_t>((nvec + 255) / 256, 148 * 8);
+  // keep gridDim.x * 256 a multiple of C/8 so each thread sees one channel slot
+  const int vpp = C / 8;
+  while (chunks > 1 && ((int64_t)chunks * 256) % vpp) --chunks;
+  gn_stats_kernel<<<dim3(chunks, B), 256, 2 * G * sizeof(float), s>>>(x16, stats_ws, HW, C, G, f16);
+  int chunks2 = (int)std::min<int64_t>((nvec + 255) / 256, 148 * 16);
+  gn_apply_kernel<<<dim3(chunks2, B), 256, 0, s>>>(x16, y16, gamma, beta, stats_ws, HW, C, G, eps, silu, f16);
+  return cudaGetLastError();
+}
+
+__global__ void upsample2x_kernel(const void* __restrict__ x, void* __restrict__ y, int B, int H, int W, int C) {
+  const int vpp = C / 8;
+  const int64_t n = (int64_t)B * (2 * H) * (2 * W) * vpp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpp);
+    const int64_t pix = i / vpp;
+    const int ox = (int)(pix % (2 * W)), oy = (int)((pix / (2 * W)) % (2 * H)), b = (int)(pix / ((int64_t)4 * W * H));
+    const int64_t src = (((int64_t)b * H + oy / 2) * W + ox / 2) * vpp + v;
+    reinterpret_cast<uint4*>(y)[i] = __ldg(reinterpret_cast<const uint4*>(x) + src);
+  }
+}
+cudaError_t upsample_nearest2x(const void* x16, void* y16, int B, int H, int W, int C, cudaStream_t s) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const int64_t n = (int64_t)B * 4 * H * W * (C / 8);
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 32);
+  upsample2x_kernel<<<blocks, 256, 0, s>>>(x16, y16, B, H, W, C);
+  return cudaGetLastError();
+}
+
+// one CTA per row: max, sum(exp), write probabilities
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, int64_t ldx, void* __restrict__ y,
+                                                           int64_t ldy, int cols, float scale, bool f16) {
+  __shared__ float sm[8];
+  const float* xr = x + (int64_t)blockIdx.x * ldx;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, xr[c]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = sm[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, sm[i]);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) s += __expf((xr[c] - mx) * scale);
+  const float tot = block_sum<256>(s, sm);
+  const float inv = 1.f / tot;
+  for (int c = threadIdx.x; c < cols; c += 256)
+    store16(y, (int64_t)blockIdx.x * ldy + c, __expf((xr[c] - mx) * scale) * inv, f16);
+}
+cudaError_t softmax_rows(const float* x, int64_t ldx, void* y16, int64_t ldy, int rows, int cols, float scale, bool f16,
+                         cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  softmax_rows_kernel<<<rows, 256, 0, s>>>(x, ldx, y16, ldy, cols, scale, f16);
+  return cudaGetLastError();
+}
+
+__global__ void transpose16_kernel(const uint16_t* __restrict__ in, int64_t ldi, uint16_t* __restrict__ out, int64_t ldo,
+                                   int rows, int cols) {
+  __shared__ uint16_t tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = by + j, c = bx + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = in[(int64_t)r * ldi + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = bx + j, r = by + threadIdx.x;
+    if (r < rows && c < cols) out[(int64_t)c * ldo + r] = tile[threadIdx.x][j];
+  }
+}
+cudaError_t transpose16(const void* in16, int64_t ldi, void* out16, int64_t ldo, int rows, int cols, cudaStream_t s) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose16_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const uint16_t*>(in16), ldi,
+                                            reinterpret_cast<uint16_t*>(out16), ldo, rows, cols);
+  return cudaGetLastError();
+}
+__global__ void add16_kernel(const void* __restrict__ a, const void* __restrict__ b, void* __restrict__ o, int64_t n,
+                             bool f16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  store16(o, i, load16(a, i, f16) + load16(b, i, f16), f16);
+}
+cudaError_t add16(const void* a16, const void* b16, void* out16, int64_t n, bool f16, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  add16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a16, b16, out16, n, f16);
+  return cudaGetLastError();
+}
+
+__global__ void postprocess_u8_kernel(const void* __restrict__ x, int64_t ldc, uint8_t* __restrict__ out, int64_t npix,
+                                      bool f16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * 3) return;
+  const int64_t p = i / 3;
+  const int c = (int)(i % 3);
+  float v = (load16(x, p * ldc + c, f16) + 1.0f) * 127.5f;
+  v = fminf(fmaxf(v, 0.f), 255.f);
+  out[i] = (uint8_t)v;  // truncation, as MLX asType(.uint8)
+}
+cudaError_t postprocess_u8(const void* x16, int64_t ldc, uint8_t* out, int64_t npix, bool f16, cudaStream_t s) {
+  const int64_t n = npix * 3;
+  if (n <= 0) return cudaSuccess;
+  postprocess_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x16, ldc, out, npix, f16);
+  return cudaGetLastError();
+}
+__global__ void nhwc16_to_nchw_kernel(const void* __restrict__ x, int64_t ldc, float* __restrict__ out, int64_t HW, int C,
+                                      bool f16, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = i % HW;
+  const int c = (int)((i / HW) % C);
+  const int64_t b = i / (HW * C);
+  out[i] = load16(x, (b * HW + p) * ldc + c, f16);
+}
+cudaError_t nhwc16_to_nchw_f32(const void* x16, int64_t ldc, float* out, int B, int64_t HW, int C, bool f16,
+                               cudaStream_t s) {
+  const int64_t n = (int64_t)B * HW * C;
+  if (n <= 0) return cudaSuccess;
+  nhwc16_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x16, ldc, out, HW, C, f16, n);
+  return cudaGetLastError();
+}
+__global__ void nchw_to_nhwc16_kernel(const float* __restrict__ in, void* __restrict__ out, int64_t HW, int C, bool f16,
+                                      int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // output index
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  const int64_t p = (i / C) % HW;
+  const int64_t b = i / (HW * C);
+  store16(out, i, in[(b * C + c) * HW + p], f16);
+}
+cudaError_t nchw_f32_to_nhwc16(const float* in, void* out16, int B, int64_t HW, int C, bool f16, cudaStream_t s) {
+  const int64_t n = (int64_t)B * HW * C;
+  if (n <= 0) return cudaSuccess;
+  nchw_to_nhwc16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out16, HW, C, f16, n);
+  return cudaGetLastError();
+}
+
+}  // namespace f2b

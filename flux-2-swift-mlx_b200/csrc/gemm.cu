@@ -1,0 +1,548 @@
+// gemm.cu — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] · B[N,K]^T   (bf16 operands, fp32 accumulate in TMEM)
+//
+// This one kernel serves every dense contraction on the Flux.2 denoising path:
+//   * the DiT linears (reference: Flux2Attention.swift:115-123,185-189; Flux2ParallelAttention.swift:80-87,122;
+//     Flux2FeedForward.swift:59-67,102-108; Flux2Transformer.swift:137-138,324),
+//   * the VAE decoder 3x3 / 1x1 convolutions as implicit GEMM over NHWC (reference: VAEDecoder.swift:91-121,
+//     ResnetBlock.swift:168-186,229-253) — the A operand is fetched by a 4-D TMA box whose out-of-bounds fill
+//     implements the zero padding,
+// with the elementwise work that follows each of them fused into the TMEM->register epilogue
+// (gate·y + residual, SwiGLU, QK-RMSNorm + RoPE, bias, resnet shortcut add).
+//
+// Structure per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread) + TMEM allocator,
+// warps 2..5 = epilogue (one TMEM lane quarter each). smem ring of kStages {A 128x64, B BNx64} tiles in the
+// 128B-swizzled K-major layout; two accumulator stages in TMEM so the epilogue of tile i overlaps the MMAs of
+// tile i+1. With kCtaGroup == 2 a CTA pair (cluster of 2) computes a 256xBN tile with cta_group::2 MMAs: each CTA
+// loads its 128 rows of A and half of B, the leader CTA issues, commits are multicast to both CTAs.
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+
+namespace f2b {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int CONV_TW = 16;  // spatial patch of one M tile in conv mode: 8 rows x 16 cols = 128 pixels
+static constexpr int CONV_TH = 8;
+
+struct KParams {
+  int M, N, K;
+  int num_m_units, num_n_blks, num_kb;
+  // conv
+  int taps, H, W, Cin, batch, tiles_x, tiles_y, kb_per_tap;
+  Epilogue epi;
+};
+
+template <int BN, int CG>
+struct Cfg {
+  static constexpr int B_ROWS = BN / CG;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+};
+
+// ------------------------------------------------------------------------------------------------ epilogue
+__device__ __forceinline__ uint32_t pk2(float a, float b, int f16) {
+  if (f16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(a, b);
+}
+__device__ __forceinline__ float2 upk2(uint32_t u, int f16) {
+  if (f16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int quarter, int lane, bool row_ok,
+                                              int64_t grow, int n0) {
+  const Epilogue& e = p.epi;
+  const uint32_t tq = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+  uint32_t v[32];
+
+  if (e.mode == EPI_SWIGLU) {
+    // tile columns: [0, BN/2) gate, [BN/2, BN) value  ->  BN/2 outputs at column (n0/2 + j)
+    constexpr int HALF = BN / 2;
+    uint32_t u[32];
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out);
+#pragma unroll 1
+    for (int c = 0; c < HALF / 32; ++c) {
+      tmem_ld_32x32(tq + c * 32, v);
+      tmem_ld_32x32(tq + HALF + c * 32, u);
+      tmem_ld_wait();
+      const int oc = n0 / 2 + c * 32;
+      if (row_ok && oc < p.N / 2) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
+          float u0 = __uint_as_float(u[2 * j]), u1 = __uint_as_float(u[2 * j + 1]);
+          pk[j] = pk2(silu_f(g0) * u0, silu_f(g1) * u1, e.f16);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + grow * e.ldo + oc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+    }
+    return;
+  }
+
+  if (e.mode == EPI_QKV_ROPE) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out);
+#pragma unroll 1
+    for (int h = 0; h < BN / 128; ++h) {
+      const int hc = n0 + h * 128;  // first column of this 128-wide head slab
+      if (hc >= p.N) break;
+      const bool is_v = hc >= 2 * e.dmodel;
+      float rstd = 1.0f;
+      if (!is_v) {
+        float ss = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_32x32(tq + h * 128 + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]);
+            ss = fmaf(x, x, ss);
+          }
+        }
+        rstd = rsqrtf(ss * (1.0f / 128.0f) + e.eps);
+      }
+      const float* nw = (hc < e.dmodel) ? e.norm_q : e.norm_k;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_32x32(tq + h * 128 + c * 32, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        uint32_t pk[16];
+        if (is_v) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pk2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), e.f16);
+        } else {
+          const float4* cs = reinterpret_cast<const float4*>(e.cos + grow * 128 + c * 32);
+          const float4* sn = reinterpret_cast<const float4*>(e.sin + grow * 128 + c * 32);
+          const float4* w4 = reinterpret_cast<const float4*>(nw + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 cc = __ldg(cs + j), s4 = __ldg(sn + j), ww = __ldg(w4 + j);
+            float x0 = __uint_as_float(v[4 * j + 0]) * rstd * ww.x;
+            float x1 = __uint_as_float(v[4 * j + 1]) * rstd * ww.y;
+            float x2 = __uint_as_float(v[4 * j + 2]) * rstd * ww.z;
+            float x3 = __uint_as_float(v[4 * j + 3]) * rstd * ww.w;
+            // interleaved pairs (Flux2Attention.swift:225-226,452-460): (x0,x1) -> (x0 c - x1 s, x1 c + x0 s)
+            pk[2 * j] = pk2(x0 * cc.x - x1 * s4.x, x1 * cc.y + x0 * s4.y, e.f16);
+            pk[2 * j + 1] = pk2(x2 * cc.z - x3 * s4.z, x3 * cc.w + x2 * s4.w, e.f16);
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + grow * e.ldo + hc + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+    }
+    return;
+  }
+
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col = n0 + c * 32;
+    tmem_ld_32x32(tq + c * 32, v);
+    tmem_ld_wait();
+    if (!row_ok || col >= p.N) continue;
+    const bool full = (col + 32 <= p.N);
+    float a[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+    if (e.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (full || col + j < p.N) a[j] += __ldg(e.bias + col + j);
+    }
+    if (e.mode == EPI_GATE_RES) {
+      float* out = reinterpret_cast<float*>(e.out) + grow * e.ldo + col;
+      const float* res = e.res + grow * e.ldr + col;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 r = *reinterpret_cast<const float4*>(res + 4 * j);
+          float4 g = __ldg(reinterpret_cast<const float4*>(e.gate + col + 4 * j));
+          float4 o;
+          o.x = fmaf(g.x, a[4 * j + 0], r.x);
+          o.y = fmaf(g.y, a[4 * j + 1], r.y);
+          o.z = fmaf(g.z, a[4 * j + 2], r.z);
+          o.w = fmaf(g.w, a[4 * j + 3], r.w);
+          *reinterpret_cast<float4*>(out + 4 * j) = o;
+        }
+      } else {
+        for (int j = 0; j < 32 && col + j < p.N; ++j) out[j] = fmaf(__ldg(e.gate + col + j), a[j], res[j]);
+      }
+    } else if (e.mode == EPI_F32) {
+      float* out = reinterpret_cast<float*>(e.out) + grow * e.ldo + col;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(out + 4 * j) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+      } else {
+        for (int j = 0; j < 32 && col + j < p.N; ++j) out[j] = a[j];
+      }
+    } else {  // EPI_BF16
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out) + grow * e.ldo + col;
+      if (e.res16) {
+        const uint16_t* r16 = reinterpret_cast<const uint16_t*>(e.res16) + grow * e.ldr + col;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 q = *reinterpret_cast<const uint4*>(r16 + 8 * j);
+            const uint32_t h2[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float2 f = upk2(h2[k], e.f16);
+              a[8 * j + 2 * k] += f.x;
+              a[8 * j + 2 * k + 1] += f.y;
+            }
+          }
+        } else {
+          for (int j = 0; j < 32 && col + j < p.N; ++j) a[j] += upk2((uint32_t)r16[j], e.f16).x;
+        }
+      }
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 q = make_uint4(pk2(a[8 * j], a[8 * j + 1], e.f16), pk2(a[8 * j + 2], a[8 * j + 3], e.f16),
+                               pk2(a[8 * j + 4], a[8 * j + 5], e.f16), pk2(a[8 * j + 6], a[8 * j + 7], e.f16));
+          *reinterpret_cast<uint4*>(out + 8 * j) = q;
+        }
+      } else {
+        for (int j = 0; j < 32 && col + j < p.N; ++j) reinterpret_cast<uint16_t*>(out)[j] = (uint16_t)(pk2(a[j], 0.f, e.f16) & 0xffff);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int BN, int CG, bool CONV>
+__global__ void __launch_bounds__(192, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+  using C = Cfg<BN, CG>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + C::STAGES;       // [STAGES]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * C::STAGES;   // [2]       MMA -> epilogue
+  uint64_t* tempty = tfull + 2;             // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  const int unit_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int num_units = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
+  const int total_tiles = p.num_m_units * p.num_n_blks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], CG);  // one arrive.expect_tx per CTA of the pair
+      mbar_init(&empty[s], 1);  // one tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);        // one tcgen05.commit
+      mbar_init(&tempty[s], 4 * CG);  // one arrive per epilogue warp (of both CTAs)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = unit_id; t < total_tiles; t += num_units) {
+        const int m_unit = t % p.num_m_units;
+        const int n_blk = t / p.num_m_units;
+        const int m_blk = m_unit * CG + (int)cta_rank;
+        const int nrow0 = n_blk * BN + (int)cta_rank * C::B_ROWS;
+        int img = 0, y0 = 0, x0 = 0;
+        if (CONV) {
+          const int per_img = p.tiles_x * p.tiles_y;
+          img = m_blk / per_img;
+          const int r = m_blk % per_img;
+          y0 = (r / p.tiles_x) * CONV_TH;
+          x0 = (r % p.tiles_x) * CONV_TW;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 1);
+          void* a_dst = smA + stage * C::A_BYTES;
+          void* b_dst = smB + stage * C::B_BYTES;
+          if (CG == 1) {
+            mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            if (CONV) {
+              const int tap = kb / p.kb_per_tap;
+              const int c0 = (kb % p.kb_per_tap) * BK;
+              const int ky = (p.taps == 9) ? tap / 3 - 1 : 0;
+              const int kx = (p.taps == 9) ? tap % 3 - 1 : 0;
+              tma_load_4d(a_dst, &tmA, &full[stage], c0, x0 + kx, y0 + ky, img);
+              tma_load_3d(b_dst, &tmB, &full[stage], c0, tap, nrow0);
+            } else {
+              tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_blk * BM);
+              tma_load_2d(b_dst, &tmB, &full[stage], kb * BK, nrow0);
+            }
+          } else {
+            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+            mbar_expect_tx_cluster(lbar, C::STAGE_BYTES);
+            if (CONV) {
+              const int tap = kb / p.kb_per_tap;
+              const int c0 = (kb % p.kb_per_tap) * BK;
+              const int ky = (p.taps == 9) ? tap / 3 - 1 : 0;
+              const int kx = (p.taps == 9) ? tap % 3 - 1 : 0;
+              tma_load_4d_cg2(a_dst, &tmA, lbar, c0, x0 + kx, y0 + ky, img);
+              // 3-D weight box through the cta_group::2 path is expressed as 4-D with a unit outer dim
+              tma_load_4d_cg2(b_dst, &tmB, lbar, c0, tap, nrow0, 0);
+            } else {
+              tma_load_2d_cg2(a_dst, &tmA, lbar, kb * BK, m_blk * BM);
+              tma_load_2d_cg2(b_dst, &tmB, lbar, kb * BK, nrow0);
+            }
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_f16(BM * CG, BN, p.epi.f16 == 0, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = unit_id; t < total_tiles; t += num_units) {
+        mbar_wait<CG == 2>(&tempty[acc], acc_phase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait<CG == 2>(&full[stage], phase, 3);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(smA + stage * C::A_BYTES), 16, 1024, SWZ_128B);
+          const uint64_t bdesc = make_smem_desc(smem_u32(smB + stage * C::B_BYTES), 16, 1024, SWZ_128B);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the 16 B-unit address field
+            umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          if (CG == 1) umma_commit(&empty[stage]); else umma_commit_cg2_mc(&empty[stage], 0x3);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (CG == 1) umma_commit(&tfull[acc]); else umma_commit_cg2_mc(&tfull[acc], 0x3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== epilogue warps (2..5): TMEM lane quarter = warp % 4
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = unit_id; t < total_tiles; t += num_units) {
+      const int m_unit = t % p.num_m_units;
+      const int n_blk = t / p.num_m_units;
+      const int m_blk = m_unit * CG + (int)cta_rank;
+      const int r = quarter * 32 + lane;
+      bool row_ok;
+      int64_t grow;
+      if (CONV) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int img = m_blk / per_img;
+        const int rr = m_blk % per_img;
+        const int y = (rr / p.tiles_x) * CONV_TH + r / CONV_TW;
+        const int x = (rr % p.tiles_x) * CONV_TW + r % CONV_TW;
+        row_ok = (img < p.batch) && (y < p.H) && (x < p.W);
+        grow = ((int64_t)img * p.H + y) * p.W + x;
+      } else {
+        grow = (int64_t)m_blk * BM + r;
+        row_ok = grow < p.M;
+      }
+      mbar_wait<CG == 2>(&tfull[acc], acc_phase, 4);
+      tc_fence_after();
+      epilogue_tile<BN>(p, tmem_base + acc * BN, quarter, lane, row_ok, grow, n_blk * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(&tempty[acc]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static int g_num_sms = 0;
+static thread_local std::string g_err;
+const char* gemm_last_error() { return g_err.c_str(); }
+
+bool gemm_init() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  });
+  return g_encode != nullptr && g_num_sms > 0;
+}
+
+bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_err = "cuTensorMapEncodeTiled failed, CUresult=" + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
+template <int BN, int CG, bool CONV>
+static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
+  using C = Cfg<BN, CG>;
+  KParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.epi = g.epi;
+  CUtensorMap tmA, tmB;
+  int num_m_blks;
+  if (CONV) {
+    p.taps = g.conv_taps; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.batch = g.batch;
+    p.tiles_x = (g.W + CONV_TW - 1) / CONV_TW;
+    p.tiles_y = (g.H + CONV_TH - 1) / CONV_TH;
+    p.kb_per_tap = (g.Cin + BK - 1) / BK;
+    p.num_kb = g.conv_taps * p.kb_per_tap;
+    num_m_blks = g.batch * p.tiles_x * p.tiles_y;
+    // activations NHWC: dims (C, W, H, N)
+    uint64_t ad[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.batch};
+    uint64_t as[3] = {(uint64_t)g.lda * 2, (uint64_t)g.lda * 2 * g.W, (uint64_t)g.lda * 2 * g.W * g.H};
+    uint32_t ab[4] = {BK, CONV_TW, CONV_TH, 1};
+    if (!make_tmap_bf16(&tmA, g.A, 4, ad, as, ab)) return cudaErrorInvalidValue;
+    // weights OHWI: dims (Cin, taps, Cout[, 1])
+    uint64_t bd[4] = {(uint64_t)g.Cin, (uint64_t)g.conv_taps, (uint64_t)g.N, 1};
+    uint64_t bs[3] = {(uint64_t)g.Cin * 2, (uint64_t)g.Cin * 2 * g.conv_taps, (uint64_t)g.Cin * 2 * g.conv_taps * g.N};
+    uint32_t bb[4] = {BK, 1, (uint32_t)C::B_ROWS, 1};
+    if (!make_tmap_bf16(&tmB, g.B, CG == 2 ? 4 : 3, bd, bs, bb)) return cudaErrorInvalidValue;
+  } else {
+    p.num_kb = (g.K + BK - 1) / BK;
+    num_m_blks = (g.M + BM - 1) / BM;
+    uint64_t ad[2] = {(uint64_t)g.K, (uint64_t)g.M};
+    uint64_t as[1] = {(uint64_t)g.lda * 2};
+    uint32_t ab[2] = {BK, BM};
+    if (!make_tmap_bf16(&tmA, g.A, 2, ad, as, ab)) return cudaErrorInvalidValue;
+    uint64_t bd[2] = {(uint64_t)g.K, (uint64_t)g.N};
+    uint64_t bs[1] = {(uint64_t)g.ldb * 2};
+    uint32_t bb[2] = {BK, (uint32_t)C::B_ROWS};
+    if (!make_tmap_bf16(&tmB, g.B, 2, bd, bs, bb)) return cudaErrorInvalidValue;
+  }
+  p.num_m_units = (num_m_blks + CG - 1) / CG;
+  p.num_n_blks = (g.N + BN - 1) / BN;
+  const int total = p.num_m_units * p.num_n_blks;
+  const int max_units = g_num_sms / CG;
+  const int units = std::min(total, max_units);
+
+  auto kern = gemm_kernel<BN, CG, CONV>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CG;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+}
+
+template <bool CONV>
+static cudaError_t dispatch(const GemmProblem& g, cudaStream_t s, int bn, int cg) {
+#define F2B_CASE(BN_)                                                     \
+  if (bn == BN_) {                                                        \
+    if (cg == 2) return launch_cfg<BN_, 2, CONV>(g, s);                   \
+    return launch_cfg<BN_, 1, CONV>(g, s);                                \
+  }
+  F2B_CASE(256)
+  F2B_CASE(128)
+  F2B_CASE(64)
+  F2B_CASE(32)
+#undef F2B_CASE
+  g_err = "unsupported BN";
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
+  if (!gemm_init()) {
+    g_err = "gemm_init failed (driver entry point or device query)";
+    return cudaErrorInitializationError;
+  }
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaSuccess;
+  const bool conv = g.conv_taps != 0;
+  if (!conv && (g.lda % 8 || g.ldb % 8)) { g_err = "lda/ldb must be multiples of 8 elements (TMA 16 B stride)"; return cudaErrorInvalidValue; }
+  if (conv && (g.Cin % 8 || g.lda % 8)) { g_err = "conv Cin / pixel stride must be multiples of 8"; return cudaErrorInvalidValue; }
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) { g_err = "A/B must be 16 B aligned"; return cudaErrorInvalidValue; }
+  int bn = g.force_bn;
+  if (!bn) bn = g.N > 128 ? 256 : g.N > 64 ? 128 : g.N > 32 ? 64 : 32;
+  if (g.epi.mode == EPI_SWIGLU) bn = 256;
+  if (g.epi.mode == EPI_QKV_ROPE && bn < 128) bn = 128;
+  int cg = g.force_cta_group;
+  if (!cg) cg = 1;
+  const int m_blks = conv ? g.batch * ((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + CONV_TH - 1) / CONV_TH) : (g.M + BM - 1) / BM;
+  if (cg == 2 && (m_blks < 2 || bn < 32)) cg = 1;
+  return conv ? dispatch<true>(g, stream, bn, cg) : dispatch<false>(g, stream, bn, cg);
+}
+
+}  // namespace f2b

@@ -1,0 +1,57 @@
+// gemm.cuh — host-side interface of the tcgen05 GEMM / implicit-GEMM convolution kernel (gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace f2b {
+
+enum EpiMode : int {
+  EPI_BF16 = 0,      // out_bf16[m, n] = acc (+ bias[n]) (+ res16[m, n])
+  EPI_F32 = 1,       // out_f32 [m, n] = acc (+ bias[n])
+  EPI_GATE_RES = 2,  // out_f32 [m, n] = res_f32[m, n] + gate[n] * acc          (Flux2Modulation.applyGate + residual)
+  EPI_SWIGLU = 3,    // out_bf16[m, nb*BN/2 + j] = silu(acc[j]) * acc[BN/2 + j]  (weight rows pre-interleaved per tile)
+  EPI_QKV_ROPE = 4,  // out_bf16 = RoPE(RMSNorm_128(acc) * w) for q/k column ranges, plain for v (BN multiple of 128)
+};
+
+struct Epilogue {
+  int mode = EPI_BF16;
+  int f16 = 0;                  // 16-bit operand / output type: 0 = bf16, 1 = f16
+  void* out = nullptr;
+  int ldo = 0;                  // elements
+  const float* bias = nullptr;  // [N]
+  const float* gate = nullptr;  // [N]            (EPI_GATE_RES)
+  const float* res = nullptr;   // [M, ldr] fp32   (EPI_GATE_RES)
+  const void* res16 = nullptr;  // [M, ldr] 16-bit (EPI_BF16 residual add, VAE resnet shortcut)
+  int ldr = 0;
+  // EPI_QKV_ROPE: columns [0, qk_cols) get per-128 RMSNorm (weights normw[(col / D_model) ...]) and RoPE
+  const float* cos = nullptr;  // [M, 128]
+  const float* sin = nullptr;  // [M, 128]
+  const float* norm_q = nullptr;  // [128]
+  const float* norm_k = nullptr;  // [128]
+  int dmodel = 0;                 // D: columns [0,D) = q, [D,2D) = k, [2D,3D) = v
+  float eps = 1e-6f;
+};
+
+struct GemmProblem {
+  // C[M,N] = A[M,K] * B[N,K]^T ; A, B bf16 row-major with K contiguous
+  const void* A = nullptr;
+  int64_t lda = 0;
+  const void* B = nullptr;
+  int64_t ldb = 0;
+  int M = 0, N = 0, K = 0;
+  // implicit-GEMM 3x3 / 1x1 convolution (NHWC activations, OHWI weights): M = batch*H*W, K = taps*Cin
+  int conv_taps = 0;  // 0 = plain GEMM, 1 = 1x1, 9 = 3x3 (pad 1)
+  int batch = 1, H = 0, W = 0, Cin = 0;
+  Epilogue epi;
+  int force_cta_group = 0;  // 0 = auto, 1, 2
+  int force_bn = 0;         // 0 = auto
+};
+
+// Returns cudaSuccess or the launch error. Never synchronises.
+cudaError_t gemm_launch(const GemmProblem& p, cudaStream_t stream);
+// One-time driver entry point lookup; returns false if cuTensorMapEncodeTiled cannot be resolved.
+bool gemm_init();
+const char* gemm_last_error();
+
+}  // namespace f2b

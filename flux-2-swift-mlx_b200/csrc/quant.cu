@@ -1,0 +1,268 @@
+// quant.cu — bit-exact weight quantizers / dequantizers for the five reference modes.
+//
+// Reference call sites: quantize(model:groupSize:bits:mode:) Flux2Pipeline.swift:567-578,
+// quantized()/dequantized() WeightLoader.swift:795-815, level table QuantizationConfig.swift:51-60. The arithmetic
+// itself lives in mlx-swift 0.31.6 (not in the tree); the rules restated here are the published MLX semantics:
+//   groups run along the input dim of W[out,in]; element j of a uint32 word sits at bits [j*bits, (j+1)*bits).
+//   affine (qint8 8/64, int4 4/64): scale/bias from the group min/max with the "edge" rule, scales/biases f16.
+//   mxfp8 (8/32): E4M3 elements, E8M0 scale = 2^round(log2(amax/448)); mxfp4 (4/32): E2M1 elements, amax/6;
+//   nvfp4 (4/16): E2M1 elements, scale amax/6 stored as E4M3 (no global scale). RNE, saturating.
+// All fp32 steps use explicit _rn intrinsics so that no FMA contraction can make the device disagree with the
+// C oracle (oracle/quant_oracle.c) by an ulp.
+#include "quant.cuh"
+#include "ptx.cuh"
+
+namespace f2b {
+
+struct QSpec { int bits, group, mode; };  // mode: 0 affine, 1 mx (E8M0 scale), 2 nv (E4M3 scale)
+__host__ __device__ inline QSpec qspec(int quant) {
+  switch (quant) {
+    case 1: return {8, 64, 0};
+    case 2: return {4, 64, 0};
+    case 3: return {8, 32, 1};
+    case 4: return {4, 32, 1};
+    case 5: return {4, 16, 2};
+    default: return {16, 0, -1};
+  }
+}
+bool quant_params(int quant, int* bits, int* group, int* has_biases, int* scale_dtype) {
+  QSpec q = qspec(quant);
+  if (q.mode < 0) return false;
+  if (bits) *bits = q.bits;
+  if (group) *group = q.group;
+  if (has_biases) *has_biases = q.mode == 0;
+  if (scale_dtype) *scale_dtype = q.mode == 0 ? 1 /*F16*/ : 4 /*U8*/;
+  return true;
+}
+
+__device__ __forceinline__ float load_w(const void* w, int dtype, int64_t i) {
+  if (dtype == 0) return reinterpret_cast<const float*>(w)[i];
+  if (dtype == 1) return __half2float(reinterpret_cast<const __half*>(w)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(w)[i]);
+}
+__device__ __forceinline__ void store_o(void* o, int dtype, int64_t i, float v) {
+  if (dtype == 0) reinterpret_cast<float*>(o)[i] = v;
+  else if (dtype == 1) reinterpret_cast<__half*>(o)[i] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(o)[i] = __float2bfloat16(v);
+}
+
+// ---- scalar format conversions (integer / compare logic only: deterministic everywhere)
+// round(log2(x)) for x > 0 without libm: exponent + (mantissa >= sqrt(2))
+__device__ __forceinline__ int round_log2_pos(float x) {
+  uint32_t u = __float_as_uint(x);
+  int e = (int)((u >> 23) & 0xff);
+  uint32_t m = u & 0x7fffff;
+  if (e == 0) {  // subnormal: below 2^-126, clamps to -127 anyway
+    return -127;
+  }
+  return (e - 127) + (m >= 0x3504F4u ? 1 : 0);
+}
+__device__ __forceinline__ uint8_t to_e8m0(float x) {
+  if (!(x > 0.f)) return 0;  // zero / negative / NaN -> smallest scale (NaN cannot occur for finite weights)
+  if (isinf(x)) return 0xFF;
+  int n = round_log2_pos(x);
+  n = n < -127 ? -127 : n;
+  n = n > 127 ? 127 : n;
+  return (uint8_t)(n + 127);
+}
+__device__ __forceinline__ float from_e8m0(uint8_t b) {
+  // 2^(b-127); b = 0 -> 2^-127 (subnormal), b = 255 treated as 2^128 -> inf
+  if (b == 0) return __uint_as_float(0x00400000u);
+  if (b == 255) return __uint_as_float(0x7f800000u);
+  return __uint_as_float((uint32_t)b << 23);
+}
+// fp32 -> E4M3 (fn: no inf, max 448), round-to-nearest-even, saturating; sign kept
+__device__ __forceinline__ uint8_t to_e4m3(float x) {
+  uint32_t u = __float_as_uint(x);
+  uint8_t sign = (u >> 31) ? 0x80 : 0;
+  float a = fabsf(x);
+  if (a != a) return sign | 0x7F;
+  if (a >= 448.f) return sign | 0x7E;  // saturate (covers inf)
+  if (a < 0.015625f) {
+    // subnormal range: multiples of 2^-9, RNE
+    float q = rintf(__fmul_rn(a, 512.f));  // exact scaling by a power of two
+    return sign | (uint8_t)q;              // q in [0,8]; 8 == smallest normal 0x08
+  }
+  uint32_t au = __float_as_uint(a);
+  int e = (int)(au >> 23) - 127;   // [-6, 8]
+  uint32_t m = au & 0x7fffff;
+  uint32_t keep = m >> 20;         // 3 mantissa bits
+  uint32_t rem = m & 0xfffff;
+  uint32_t half = 0x80000;
+  if (rem > half || (rem == half && (keep & 1))) ++keep;
+  if (keep == 8) { keep = 0; ++e; }
+  uint32_t code = ((uint32_t)(e + 7) << 3) | keep;
+  if (code > 0x7E) code = 0x7E;
+  return sign | (uint8_t)code;
+}
+__device__ __forceinline__ float from_e4m3(uint8_t b) {
+  const float sgn = (b & 0x80) ? -1.f : 1.f;
+  const int e = (b >> 3) & 0xF;
+  const int m = b & 7;
+  if (e == 0) return sgn * (float)m * 0.001953125f;  // m * 2^-9
+  if (e == 15 && m == 7) return __uint_as_float(0x7fc00000u);
+  return sgn * __uint_as_float((uint32_t)(e - 7 + 127) << 23) * (1.f + (float)m * 0.125f);
+}
+__device__ __forceinline__ uint8_t to_e2m1(float x) {
+  const uint8_t sign = (__float_as_uint(x) >> 31) ? 0x8 : 0x0;
+  const float a = fabsf(x);
+  uint8_t b;
+  if (a != a) b = 0x7;
+  else if (a > 5.0f) b = 0x7;
+  else if (a >= 3.5f) b = 0x6;
+  else if (a > 2.5f) b = 0x5;
+  else if (a >= 1.75f) b = 0x4;
+  else if (a > 1.25f) b = 0x3;
+  else if (a >= 0.75f) b = 0x2;
+  else if (a > 0.25f) b = 0x1;
+  else b = 0x0;
+  return b | sign;
+}
+__device__ __forceinline__ float from_e2m1(uint8_t b) {
+  const float tab[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
+  const float v = tab[b & 7];
+  return (b & 8) ? -v : v;
+}
+
+// ---- one thread per group
+__global__ void quantize_kernel(int quant, const void* __restrict__ w, int w_dtype, int64_t rows, int64_t cols,
+                                uint32_t* __restrict__ packed, void* __restrict__ scales, void* __restrict__ biases) {
+  const QSpec q = qspec(quant);
+  const int64_t groups_per_row = cols / q.group;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * groups_per_row) return;
+  const int64_t row = gid / groups_per_row, gi = gid % groups_per_row;
+  const int64_t base = row * cols + gi * q.group;
+  const int per_word = 32 / q.bits;
+  uint32_t* out = packed + (row * cols + gi * q.group) / per_word;
+
+  if (q.mode == 0) {
+    float wmax = -INFINITY, wmin = INFINITY;
+    for (int i = 0; i < q.group; ++i) {
+      const float v = load_w(w, w_dtype, base + i);
+      wmax = fmaxf(wmax, v);
+      wmin = fminf(wmin, v);
+    }
+    const float n_bins = (float)((1 << q.bits) - 1);
+    float scale = fmaxf(__fdiv_rn(__fsub_rn(wmax, wmin), n_bins), 1e-7f);
+    const bool side = fabsf(wmin) > fabsf(wmax);
+    scale = side ? scale : -scale;
+    const float edge = side ? wmin : wmax;
+    const float q0 = roundf(__fdiv_rn(edge, scale));
+    const bool at_zero = (q0 == 0.0f);
+    scale = at_zero ? scale : __fdiv_rn(edge, q0);
+    const float bias = at_zero ? 0.f : edge;
+    reinterpret_cast<__half*>(scales)[gid] = __float2half_rn(scale);
+    reinterpret_cast<__half*>(biases)[gid] = __float2half_rn(bias);
+    for (int wd = 0; wd < q.group / per_word; ++wd) {
+      uint32_t word = 0;
+      for (int j = 0; j < per_word; ++j) {
+        const float v = load_w(w, w_dtype, base + wd * per_word + j);
+        float r = roundf(__fdiv_rn(__fsub_rn(v, bias), scale));
+        r = fminf(r, n_bins);
+        r = fmaxf(r, 0.f);
+        word |= ((uint32_t)r) << (j * q.bits);
+      }
+      out[wd] = word;
+    }
+    return;
+  }
+  float amax = 0.f;
+  for (int i = 0; i < q.group; ++i) amax = fmaxf(amax, fabsf(load_w(w, w_dtype, base + i)));
+  float scale = __fdiv_rn(amax, q.bits == 4 ? 6.0f : 448.0f);
+  uint8_t sb;
+  if (q.mode == 1) { sb = to_e8m0(scale); scale = from_e8m0(sb); }
+  else { sb = to_e4m3(scale); scale = from_e4m3(sb); }
+  reinterpret_cast<uint8_t*>(scales)[gid] = sb;
+  for (int wd = 0; wd < q.group / per_word; ++wd) {
+    uint32_t word = 0;
+    for (int j = 0; j < per_word; ++j) {
+      const float v = load_w(w, w_dtype, base + wd * per_word + j);
+      const float x = (scale == 0.f) ? 0.f : __fdiv_rn(v, scale);
+      const uint32_t code = (q.bits == 4) ? to_e2m1(x) : to_e4m3(x);
+      word |= code << (j * q.bits);
+    }
+    out[wd] = word;
+  }
+}
+
+__global__ void dequantize_kernel(int quant, const uint32_t* __restrict__ packed, const void* __restrict__ scales,
+                                  const void* __restrict__ biases, int64_t rows, int64_t cols, void* __restrict__ out,
+                                  int out_dtype) {
+  const QSpec q = qspec(quant);
+  const int per_word = 32 / q.bits;
+  const int64_t wid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per packed word
+  const int64_t nwords = rows * cols / per_word;
+  if (wid >= nwords) return;
+  const int64_t e0 = wid * per_word;
+  const int64_t row = e0 / cols, col = e0 % cols;
+  const int64_t gid = row * (cols / q.group) + col / q.group;
+  const uint32_t word = packed[wid];
+  const uint32_t mask = (1u << q.bits) - 1u;
+  if (q.mode == 0) {
+    const float s = __half2float(reinterpret_cast<const __half*>(scales)[gid]);
+    const float b = __half2float(reinterpret_cast<const __half*>(biases)[gid]);
+    for (int j = 0; j < per_word; ++j) {
+      const float qv = (float)((word >> (j * q.bits)) & mask);
+      store_o(out, out_dtype, e0 + j, __fadd_rn(__fmul_rn(qv, s), b));
+    }
+  } else {
+    const uint8_t sb = reinterpret_cast<const uint8_t*>(scales)[gid];
+    const float s = (q.mode == 1) ? from_e8m0(sb) : from_e4m3(sb);
+    for (int j = 0; j < per_word; ++j) {
+      const uint8_t code = (uint8_t)((word >> (j * q.bits)) & mask);
+      const float ev = (q.bits == 4) ? from_e2m1(code) : from_e4m3(code);
+      store_o(out, out_dtype, e0 + j, __fmul_rn(ev, s));
+    }
+  }
+}
+
+cudaError_t quantize_matrix(int quant, const void* w, int w_dtype, int64_t rows, int64_t cols, uint32_t* packed,
+                            void* scales, void* biases, cudaStream_t s) {
+  const QSpec q = qspec(quant);
+  if (q.mode < 0 || cols % q.group) return cudaErrorInvalidValue;
+  const int64_t n = rows * (cols / q.group);
+  if (n <= 0) return cudaSuccess;
+  quantize_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(quant, w, w_dtype, rows, cols, packed, scales, biases);
+  return cudaGetLastError();
+}
+cudaError_t dequantize_matrix(int quant, const uint32_t* packed, const void* scales, const void* biases, int64_t rows,
+                              int64_t cols, void* out, int out_dtype, cudaStream_t s) {
+  const QSpec q = qspec(quant);
+  if (q.mode < 0 || cols % q.group) return cudaErrorInvalidValue;
+  const int64_t n = rows * cols / (32 / q.bits);
+  if (n <= 0) return cudaSuccess;
+  dequantize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(quant, packed, scales, biases, rows, cols, out, out_dtype);
+  return cudaGetLastError();
+}
+
+// W[out,in] (16-bit or f32) += scale * B[out,r] · A[r,in], computed in fp32 and rounded once to the weight dtype
+// (WeightLoader.swift:825-838). Load-time only: a plain CUDA-core kernel (rank is ~16).
+__global__ void lora_add_kernel(void* __restrict__ W, int w_dtype, const float* __restrict__ A, const float* __restrict__ B,
+                                int64_t out_dim, int64_t in_dim, int rank, float scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_dim * in_dim) return;
+  const int64_t o = i / in_dim, c = i % in_dim;
+  float acc = 0.f;
+  for (int r = 0; r < rank; ++r) acc = __fadd_rn(acc, __fmul_rn(B[o * rank + r], A[(int64_t)r * in_dim + c]));
+  // reference (WeightLoader.swift:806-810,832-836): A, B cast to the weight dtype; matmul, scale* and + each produce
+  // an array of that dtype, i.e. every step rounds to it (A, B arrive here already rounded).
+  auto rw = [&](float v) {
+    if (w_dtype == 1) return __half2float(__float2half_rn(v));
+    if (w_dtype == 2) return __bfloat162float(__float2bfloat16(v));
+    return v;
+  };
+  const float ba = rw(acc);
+  const float delta = rw(__fmul_rn(rw(scale), ba));
+  const float wv = load_w(W, w_dtype, i);
+  store_o(W, w_dtype, i, __fadd_rn(wv, delta));
+}
+cudaError_t lora_add(void* W, int w_dtype, const float* A, const float* B, int64_t out_dim, int64_t in_dim, int rank,
+                     float scale, cudaStream_t s) {
+  const int64_t n = out_dim * in_dim;
+  if (n <= 0) return cudaSuccess;
+  lora_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(W, w_dtype, A, B, out_dim, in_dim, rank, scale);
+  return cudaGetLastError();
+}
+
+}  // namespace f2b

@@ -1,0 +1,367 @@
+// weights.cu — turns the tensors handed over under the reference's flattened Swift keys
+// (Loading/WeightLoader.swift:99-204,567-612; PrequantizedCheckpoint.swift:41-59) into the fused / re-tiled 16-bit
+// working copies the kernels consume. The external layout is never changed: get_tensor returns what MLX would hold.
+//   * double blocks: toQ|toK|toV (and addQ|addK|addV) are stacked into one [3D, D] operand,
+//   * SwiGLU producers (ff.activation.proj, the gate|up slab of toQkvMlp) get their rows interleaved per 256-row
+//     tile as [128 gate | 128 value] so the GEMM epilogue can apply silu(gate)*value in registers,
+//   * quantized layers are quantized exactly like quantize(model:) (Flux2Pipeline.swift:567-578) and kept in MLX's
+//     packed form; the dense working copy is their dequantization (W-only path: x · dequant(W)^T).
+#include "ctx.h"
+#include "ptx.cuh"
+
+namespace f2b {
+
+__global__ void copy_rows16_kernel(const uint16_t* __restrict__ src, int64_t src_ld, int64_t src_row0,
+                                   uint16_t* __restrict__ dst, int64_t dst_ld, int64_t dst_row0, int64_t nrows,
+                                   int64_t ncols, int tiled, int64_t Hm) {
+  const int64_t vec_per_row = ncols / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows * vec_per_row) return;
+  const int64_t r = i / vec_per_row, v = i % vec_per_row;
+  int64_t sr = r;
+  if (tiled) {
+    const int64_t tile = r / 256, j = r % 256;
+    sr = (j < 128) ? tile * 128 + j : Hm + tile * 128 + (j - 128);
+  }
+  const uint4 val = *reinterpret_cast<const uint4*>(src + (src_row0 + sr) * src_ld + v * 8);
+  *reinterpret_cast<uint4*>(dst + (dst_row0 + r) * dst_ld + v * 8) = val;
+}
+static int copy_rows16(flux2b_ctx* c, const void* src, int64_t src_ld, int64_t src_row0, void* dst, int64_t dst_ld,
+                       int64_t dst_row0, int64_t nrows, int64_t ncols, bool tiled, int64_t Hm) {
+  if (ncols % 8) return fail(FLUX2B_ERR_WEIGHT_LOADING, "weight inner dimension must be a multiple of 8");
+  const int64_t n = nrows * (ncols / 8);
+  copy_rows16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+      reinterpret_cast<const uint16_t*>(src), src_ld, src_row0, reinterpret_cast<uint16_t*>(dst), dst_ld, dst_row0, nrows,
+      ncols, tiled ? 1 : 0, Hm);
+  F2B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void to16_kernel(const void* __restrict__ src, int src_dtype, void* __restrict__ dst, int f16, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v;
+  if (src_dtype == FLUX2B_F32) v = reinterpret_cast<const float*>(src)[i];
+  else if (src_dtype == FLUX2B_F16) v = __half2float(reinterpret_cast<const __half*>(src)[i]);
+  else v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+  if (f16) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16(v);
+}
+__global__ void to_f32_kernel(const void* __restrict__ src, int src_dtype, float* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v;
+  if (src_dtype == FLUX2B_F32) v = reinterpret_cast<const float*>(src)[i];
+  else if (src_dtype == FLUX2B_F16) v = __half2float(reinterpret_cast<const __half*>(src)[i]);
+  else v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+  dst[i] = v;
+}
+
+static Tensor* find(flux2b_ctx* c, const std::string& key) {
+  auto it = c->tensors.find(key);
+  return it == c->tensors.end() ? nullptr : &it->second;
+}
+static bool is_float_dtype(int dt) { return dt == FLUX2B_F32 || dt == FLUX2B_F16 || dt == FLUX2B_BF16_T; }
+
+int vector_f32_from_key(flux2b_ctx* c, const std::string& key, DevBuf* out, int64_t expect, bool required, float fill) {
+  Tensor* t = find(c, key);
+  if (!t) {
+    if (required) return fail(FLUX2B_ERR_WEIGHT_LOADING, "missing tensor: " + key);
+    std::vector<float> h((size_t)expect, fill);
+    F2B_CUDA(out->alloc(sizeof(float) * expect));
+    F2B_CUDA(cudaMemcpyAsync(out->p, h.data(), sizeof(float) * expect, cudaMemcpyHostToDevice, c->stream));
+    F2B_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  if (!is_float_dtype(t->dtype) || t->numel() != expect)
+    return fail(FLUX2B_ERR_WEIGHT_LOADING, "bad dtype / size for " + key);
+  F2B_CUDA(out->alloc(sizeof(float) * expect));
+  to_f32_kernel<<<(unsigned)((expect + 255) / 256), 256, 0, c->stream>>>(t->buf.p, t->dtype, out->as<float>(), expect);
+  F2B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Dense [N, K] working copy (compute dtype) of Linear `base` — quantizing on the fly / dequantizing as configured.
+// quantize_ok=false keeps the layer dense (VAE linears / convs are never quantized by the reference).
+int dense16_from_key_ex(flux2b_ctx* c, const std::string& base, DevBuf* out, int* N, int* K, bool quantize_ok) {
+  Tensor* w = find(c, base + ".weight");
+  if (!w) return fail(FLUX2B_ERR_WEIGHT_LOADING, "missing tensor: " + base + ".weight");
+  const bool f16 = c->f16();
+  if (w->dtype == FLUX2B_U32) {
+    int bits, group, has_b, sdt;
+    if (!quant_params(c->quant, &bits, &group, &has_b, &sdt))
+      return fail(FLUX2B_ERR_WEIGHT_LOADING, "packed weight for " + base + " but context quantization is bf16");
+    if (w->shape.size() != 2) return fail(FLUX2B_ERR_WEIGHT_LOADING, "packed weight must be 2-D: " + base);
+    const int64_t rows = w->shape[0], cols = w->shape[1] * 32 / bits;
+    Tensor* s = find(c, base + ".scales");
+    Tensor* b = find(c, base + ".biases");
+    if (!s || (has_b && !b)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "missing scales / biases for " + base);
+    if (!has_b && b) return fail(FLUX2B_ERR_WEIGHT_LOADING, "unexpected biases for non-affine mode: " + base);
+    if (s->numel() != rows * (cols / group)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "scales shape mismatch: " + base);
+    F2B_CUDA(out->alloc((size_t)rows * cols * 2));
+    F2B_CUDA(dequantize_matrix(c->quant, w->buf.as<uint32_t>(), s->buf.p, has_b ? b->buf.p : nullptr, rows, cols, out->p,
+                               f16 ? FLUX2B_F16 : FLUX2B_BF16_T, c->stream));
+    *N = (int)rows; *K = (int)cols;
+    return 0;
+  }
+  if (!is_float_dtype(w->dtype)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "unsupported weight dtype for " + base);
+  int64_t rows = w->shape.empty() ? 0 : w->shape[0];
+  int64_t cols = rows ? w->numel() / rows : 0;
+  if (quantize_ok && c->quant != FLUX2B_BF16) {
+    int bits, group, has_b, sdt;
+    quant_params(c->quant, &bits, &group, &has_b, &sdt);
+    if (cols % group) return fail(FLUX2B_ERR_WEIGHT_LOADING, "input dim not divisible by group size: " + base);
+    Tensor packed, scales, biases;
+    packed.dtype = FLUX2B_U32; packed.shape = {rows, cols * bits / 32};
+    scales.dtype = sdt; scales.shape = {rows, cols / group};
+    biases.dtype = FLUX2B_F16; biases.shape = {rows, cols / group};
+    F2B_CUDA(packed.buf.alloc((size_t)packed.numel() * 4));
+    F2B_CUDA(scales.buf.alloc((size_t)scales.numel() * dtype_size(sdt)));
+    if (has_b) F2B_CUDA(biases.buf.alloc((size_t)biases.numel() * 2));
+    F2B_CUDA(quantize_matrix(c->quant, w->buf.p, w->dtype, rows, cols, packed.buf.as<uint32_t>(), scales.buf.p,
+                             has_b ? biases.buf.p : nullptr, c->stream));
+    F2B_CUDA(out->alloc((size_t)rows * cols * 2));
+    F2B_CUDA(dequantize_matrix(c->quant, packed.buf.as<uint32_t>(), scales.buf.p, has_b ? biases.buf.p : nullptr, rows,
+                               cols, out->p, f16 ? FLUX2B_F16 : FLUX2B_BF16_T, c->stream));
+    F2B_CUDA(cudaStreamSynchronize(c->stream));  // the float weight is released below
+    c->tensors[base + ".weight"] = std::move(packed);
+    c->tensors[base + ".scales"] = std::move(scales);
+    if (has_b) c->tensors[base + ".biases"] = std::move(biases);
+    *N = (int)rows; *K = (int)cols;
+    return 0;
+  }
+  F2B_CUDA(out->alloc((size_t)rows * cols * 2));
+  const int64_t n = rows * cols;
+  to16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(w->buf.p, w->dtype, out->p, f16 ? 1 : 0, n);
+  F2B_CUDA(cudaGetLastError());
+  *N = (int)rows; *K = (int)cols;
+  return 0;
+}
+int dense16_from_key(flux2b_ctx* c, const std::string& base, DevBuf* out, int* N, int* K) {
+  return dense16_from_key_ex(c, base, out, N, K, true);
+}
+
+static int expect_shape(const std::string& base, int N, int K, int eN, int eK) {
+  if (N != eN || K != eK)
+    return fail(FLUX2B_ERR_WEIGHT_LOADING, "shape mismatch for " + base + ": got [" + std::to_string(N) + "," +
+                                               std::to_string(K) + "] expected [" + std::to_string(eN) + "," +
+                                               std::to_string(eK) + "]");
+  return 0;
+}
+
+static int build_lin(flux2b_ctx* c, const std::string& base, Lin* L, int eN, int eK) {
+  int N, K;
+  F2B_TRY(dense16_from_key(c, base, &L->w, &N, &K));
+  F2B_TRY(expect_shape(base, N, K, eN, eK));
+  L->N = N; L->K = K;
+  return 0;
+}
+// stack several Linears row-wise into one operand
+static int build_stacked(flux2b_ctx* c, const std::vector<std::string>& bases, Lin* L, int eN_each, int eK) {
+  F2B_CUDA(L->w.alloc((size_t)bases.size() * eN_each * eK * 2));
+  for (size_t i = 0; i < bases.size(); ++i) {
+    DevBuf tmp; int N, K;
+    F2B_TRY(dense16_from_key(c, bases[i], &tmp, &N, &K));
+    F2B_TRY(expect_shape(bases[i], N, K, eN_each, eK));
+    F2B_TRY(copy_rows16(c, tmp.p, K, 0, L->w.p, K, (int64_t)i * eN_each, N, K, false, 0));
+    F2B_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  L->N = (int)bases.size() * eN_each; L->K = eK;
+  return 0;
+}
+// SwiGLU producer [2*Hm, K] = [gate | value] rows -> per-tile interleave (when Hm % 128 == 0 and fusion is on)
+static int build_swiglu(flux2b_ctx* c, const void* dense, int64_t ld, int64_t row0, Lin* L, int Hm, int K, bool* tiled) {
+  *tiled = (Hm % 128 == 0) && c->option("fuse_swiglu", 1);
+  F2B_CUDA(L->w.alloc((size_t)2 * Hm * K * 2));
+  F2B_TRY(copy_rows16(c, dense, ld, row0, L->w.p, K, 0, 2 * (int64_t)Hm, K, *tiled, Hm));
+  L->N = 2 * Hm; L->K = K;
+  return 0;
+}
+
+int finalize_dit(flux2b_ctx* c) {
+  const flux2b_dit_config& g = c->dit;
+  const int D = g.num_attention_heads * g.attention_head_dim;
+  const int Hm = (int)((float)D * g.mlp_ratio);  // Int(Float(dim) * mlpRatio), Flux2TransformerBlock.swift:53
+  c->D = D; c->H = g.num_attention_heads; c->Hm = Hm;
+  if (g.attention_head_dim != 128) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "attention_head_dim must be 128");
+  if (g.axes_dims_rope[0] + g.axes_dims_rope[1] + g.axes_dims_rope[2] + g.axes_dims_rope[3] != 128)
+    return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "axes_dims_rope must sum to 128");
+  if (g.in_channels % 8 || g.joint_attention_dim % 8)
+    return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "in_channels / joint_attention_dim must be multiples of 8");
+
+  F2B_TRY(build_lin(c, "xEmbedder", &c->x_embed, D, g.in_channels));
+  F2B_TRY(build_lin(c, "contextEmbedder", &c->ctx_embed, D, g.joint_attention_dim));
+  F2B_TRY(build_lin(c, "timeGuidanceEmbed.timestepEmbedder.linear1", &c->t_lin1, D, 256));
+  F2B_TRY(build_lin(c, "timeGuidanceEmbed.timestepEmbedder.linear2", &c->t_lin2, D, D));
+  if (g.guidance_embeds) {
+    F2B_TRY(build_lin(c, "timeGuidanceEmbed.guidanceEmbedder.linear1", &c->g_lin1, D, 256));
+    F2B_TRY(build_lin(c, "timeGuidanceEmbed.guidanceEmbedder.linear2", &c->g_lin2, D, D));
+  }
+  F2B_TRY(build_lin(c, "doubleStreamModulationImg.linear", &c->mod_img, 6 * D, D));
+  F2B_TRY(build_lin(c, "doubleStreamModulationTxt.linear", &c->mod_txt, 6 * D, D));
+  F2B_TRY(build_lin(c, "singleStreamModulation.linear", &c->mod_single, 3 * D, D));
+  F2B_TRY(build_lin(c, "normOut.linear", &c->norm_out, 2 * D, D));
+  F2B_TRY(build_lin(c, "projOut", &c->proj_out, g.out_channels, D));
+
+  c->dbl.clear(); c->dbl.resize(g.num_layers);
+  for (int i = 0; i < g.num_layers; ++i) {
+    const std::string p = "transformerBlocks." + std::to_string(i) + ".";
+    DoubleBlockW& b = c->dbl[i];
+    F2B_TRY(build_stacked(c, {p + "attn.toQ", p + "attn.toK", p + "attn.toV"}, &b.qkv_img, D, D));
+    F2B_TRY(build_stacked(c, {p + "attn.addQProj", p + "attn.addKProj", p + "attn.addVProj"}, &b.qkv_txt, D, D));
+    F2B_TRY(build_lin(c, p + "attn.toOut", &b.out_img, D, D));
+    F2B_TRY(build_lin(c, p + "attn.toAddOut", &b.out_txt, D, D));
+    {
+      DevBuf tmp; int N, K;
+      F2B_TRY(dense16_from_key(c, p + "ff.activation.proj", &tmp, &N, &K));
+      F2B_TRY(expect_shape(p + "ff.activation.proj", N, K, 2 * Hm, D));
+      F2B_TRY(build_swiglu(c, tmp.p, K, 0, &b.ff_in_img, Hm, D, &b.ff_tiled));
+      F2B_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    {
+      DevBuf tmp; int N, K;
+      F2B_TRY(dense16_from_key(c, p + "ffContext.activation.proj", &tmp, &N, &K));
+      F2B_TRY(expect_shape(p + "ffContext.activation.proj", N, K, 2 * Hm, D));
+      F2B_TRY(build_swiglu(c, tmp.p, K, 0, &b.ff_in_txt, Hm, D, &b.ff_tiled));
+      F2B_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    F2B_TRY(build_lin(c, p + "ff.linearOut", &b.ff_out_img, D, Hm));
+    F2B_TRY(build_lin(c, p + "ffContext.linearOut", &b.ff_out_txt, D, Hm));
+    F2B_TRY(vector_f32_from_key(c, p + "attn.normQ.weight", &b.nq_img, 128, false, 1.f));
+    F2B_TRY(vector_f32_from_key(c, p + "attn.normK.weight", &b.nk_img, 128, false, 1.f));
+    F2B_TRY(vector_f32_from_key(c, p + "attn.normAddedQ.weight", &b.nq_txt, 128, false, 1.f));
+    F2B_TRY(vector_f32_from_key(c, p + "attn.normAddedK.weight", &b.nk_txt, 128, false, 1.f));
+  }
+  c->sgl.clear(); c->sgl.resize(g.num_single_layers);
+  for (int i = 0; i < g.num_single_layers; ++i) {
+    const std::string p = "singleTransformerBlocks." + std::to_string(i) + ".";
+    SingleBlockW& b = c->sgl[i];
+    DevBuf tmp; int N, K;
+    // fused projection column order q | k | v | gate | up, widths D,D,D,Hm,Hm (Flux2ParallelAttention.swift:56,83-87)
+    F2B_TRY(dense16_from_key(c, p + "attn.toQkvMlp", &tmp, &N, &K));
+    F2B_TRY(expect_shape(p + "attn.toQkvMlp", N, K, 3 * D + 2 * Hm, D));
+    F2B_CUDA(b.qkv.w.alloc((size_t)3 * D * D * 2));
+    F2B_TRY(copy_rows16(c, tmp.p, K, 0, b.qkv.w.p, K, 0, 3 * (int64_t)D, K, false, 0));
+    b.qkv.N = 3 * D; b.qkv.K = D;
+    F2B_TRY(build_swiglu(c, tmp.p, K, 3 * (int64_t)D, &b.mlp, Hm, D, &b.mlp_tiled));
+    F2B_CUDA(cudaStreamSynchronize(c->stream));
+    F2B_TRY(build_lin(c, p + "attn.toOut", &b.out, D, D + Hm));
+    F2B_TRY(vector_f32_from_key(c, p + "attn.normQ.weight", &b.nq, 128, false, 1.f));
+    F2B_TRY(vector_f32_from_key(c, p + "attn.normK.weight", &b.nk, 128, false, 1.f));
+  }
+  F2B_CUDA(cudaStreamSynchronize(c->stream));
+  if (!c->option("keep_raw_weights", 1)) {
+    for (auto it = c->tensors.begin(); it != c->tensors.end();) {
+      const bool dit_key = it->first.rfind("decoder.", 0) != 0 && it->first.rfind("encoder.", 0) != 0 &&
+                           it->first.rfind("postQuantConv", 0) != 0 && it->first.rfind("quantConv", 0) != 0 &&
+                           it->first.rfind("latentBatchNorm", 0) != 0;
+      if (dit_key && is_float_dtype(it->second.dtype) && it->second.shape.size() == 2) it = c->tensors.erase(it);
+      else ++it;
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ VAE
+static int build_conv(flux2b_ctx* c, const std::string& base, ConvW* w, int cout, int cin, int k) {
+  Tensor* t = find(c, base + ".weight");
+  if (!t) return fail(FLUX2B_ERR_WEIGHT_LOADING, "missing tensor: " + base + ".weight");
+  // OHWI (WeightLoader.swift:496-498)
+  if (t->shape.size() != 4 || t->shape[0] != cout || t->shape[1] != k || t->shape[2] != k || t->shape[3] != cin)
+    return fail(FLUX2B_ERR_WEIGHT_LOADING, "conv weight must be OHWI [" + std::to_string(cout) + "," + std::to_string(k) +
+                                               "," + std::to_string(k) + "," + std::to_string(cin) + "]: " + base);
+  int N, K;
+  F2B_TRY(dense16_from_key_ex(c, base, &w->w, &N, &K, false));
+  w->cin = cin; w->cout = cout; w->taps = k * k;
+  F2B_TRY(vector_f32_from_key(c, base + ".bias", &w->bias, cout, false, 0.f));
+  return 0;
+}
+static int build_norm(flux2b_ctx* c, const std::string& base, NormW* n, int C) {
+  n->C = C;
+  F2B_TRY(vector_f32_from_key(c, base + ".weight", &n->gamma, C, false, 1.f));
+  F2B_TRY(vector_f32_from_key(c, base + ".bias", &n->beta, C, false, 0.f));
+  return 0;
+}
+static int build_resnet(flux2b_ctx* c, const std::string& base, ResnetW* r, int cin, int cout) {
+  r->cin = cin; r->cout = cout;
+  F2B_TRY(build_norm(c, base + ".norm1", &r->n1, cin));
+  F2B_TRY(build_conv(c, base + ".conv1", &r->c1, cout, cin, 3));
+  F2B_TRY(build_norm(c, base + ".norm2", &r->n2, cout));
+  F2B_TRY(build_conv(c, base + ".conv2", &r->c2, cout, cout, 3));
+  r->has_sc = cin != cout;
+  if (r->has_sc) F2B_TRY(build_conv(c, base + ".convShortcut", &r->sc, cout, cin, 1));
+  return 0;
+}
+
+int finalize_vae(flux2b_ctx* c) {
+  const flux2b_vae_config& g = c->vae;
+  VaeW& v = c->vw;
+  const bool saved_f16 = c->f16();
+  // the VAE runs in f16 by default (bounded activations, 3 more mantissa bits than bf16); weights follow
+  const int vae_f16 = c->option("vae_f16", 1);
+  c->opt["compute_f16"] = vae_f16;
+  auto restore = [&]() { c->opt["compute_f16"] = saved_f16 ? 1 : 0; };
+  int rc = 0;
+  do {
+    const int C3 = g.decoder_channels[3];
+    if ((rc = build_conv(c, "postQuantConv", &v.post_quant, g.latent_channels, g.latent_channels, 1))) break;
+    if ((rc = build_conv(c, "decoder.convIn", &v.conv_in, C3, g.latent_channels, 3))) break;
+    if ((rc = build_resnet(c, "decoder.midBlock.0", &v.mid1, C3, C3))) break;
+    if ((rc = build_norm(c, "decoder.midBlock.1.groupNorm", &v.attn_norm, C3))) break;
+    {
+      // single-head attention: fuse toQ|toK|toV into one [3C, C] operand (ResnetBlock.swift:258-313)
+      v.attn_qkv.N = 3 * C3; v.attn_qkv.K = C3;
+      if (cudaSuccess != v.attn_qkv.w.alloc((size_t)3 * C3 * C3 * 2)) { rc = fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "vae attn"); break; }
+      if (cudaSuccess != v.attn_qkv_bias.alloc(sizeof(float) * 3 * C3)) { rc = fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "vae attn"); break; }
+      const char* names[3] = {"toQ", "toK", "toV"};
+      for (int i = 0; i < 3 && !rc; ++i) {
+        DevBuf tmp, b; int N, K;
+        const std::string base = std::string("decoder.midBlock.1.") + names[i];
+        if ((rc = dense16_from_key_ex(c, base, &tmp, &N, &K, false))) break;
+        if ((rc = expect_shape(base, N, K, C3, C3))) break;
+        if ((rc = copy_rows16(c, tmp.p, K, 0, v.attn_qkv.w.p, K, (int64_t)i * C3, C3, C3, false, 0))) break;
+        if ((rc = vector_f32_from_key(c, base + ".bias", &b, C3, false, 0.f))) break;
+        cudaMemcpyAsync(v.attn_qkv_bias.as<float>() + (size_t)i * C3, b.p, sizeof(float) * C3, cudaMemcpyDeviceToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);
+      }
+      if (rc) break;
+      int N, K;
+      if ((rc = dense16_from_key_ex(c, "decoder.midBlock.1.toOut", &v.attn_out.w, &N, &K, false))) break;
+      if ((rc = expect_shape("decoder.midBlock.1.toOut", N, K, C3, C3))) break;
+      v.attn_out.N = C3; v.attn_out.K = C3;
+      if ((rc = vector_f32_from_key(c, "decoder.midBlock.1.toOut.bias", &v.attn_out_bias, C3, false, 0.f))) break;
+    }
+    if ((rc = build_resnet(c, "decoder.midBlock.2", &v.mid2, C3, C3))) break;
+    v.up.clear(); v.upconv.clear(); v.has_upconv.clear();
+    v.up.resize(4); v.upconv.resize(4); v.has_upconv.assign(4, false);
+    int prev = C3;
+    for (int i = 0; i < 4 && !rc; ++i) {
+      const int co = g.decoder_channels[3 - i];
+      const int nres = g.layers_per_block + 1;  // VAEDecoder.swift:57
+      v.up[i].resize(nres);
+      for (int j = 0; j < nres && !rc; ++j)
+        rc = build_resnet(c, "decoder.upBlocks." + std::to_string(i) + ".0." + std::to_string(j), &v.up[i][j],
+                          j == 0 ? prev : co, co);
+      prev = co;
+      if (!rc && i < 3) {
+        rc = build_conv(c, "decoder.upBlocks." + std::to_string(i) + ".1.conv", &v.upconv[i], co, co, 3);
+        v.has_upconv[i] = true;
+      }
+    }
+    if (rc) break;
+    if ((rc = build_norm(c, "decoder.convNormOut", &v.norm_out, g.decoder_channels[0]))) break;
+    if ((rc = build_conv(c, "decoder.convOut", &v.conv_out, g.out_channels, g.decoder_channels[0], 3))) break;
+    v.has_bn = find(c, "latentBatchNorm.runningMean") && find(c, "latentBatchNorm.runningVar");
+    if (v.has_bn) {
+      const int64_t n = find(c, "latentBatchNorm.runningMean")->numel();
+      if ((rc = vector_f32_from_key(c, "latentBatchNorm.runningMean", &v.bn_mean, n, true, 0.f))) break;
+      if ((rc = vector_f32_from_key(c, "latentBatchNorm.runningVar", &v.bn_var, n, true, 1.f))) break;
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(FLUX2B_ERR_CUDA, "sync after VAE weights"); break; }
+    v.ready = true;
+  } while (0);
+  restore();
+  return rc;
+}
+
+}  // namespace f2b
