@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Flux2Core denoising hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] — Klein 4B text-to-image 1024x1024 (4096 image + 512 text
+tokens), 4 Euler steps bf16 + small-decoder VAE decode, random-init weights, synthetic inputs. One bench "step" = one
+image = 4 DiT forwards + 4 Euler updates + unpack/BN-denorm/unpatchify + VAE decode + uint8 post-process.
+N > 1 (torchrun): image-parallel — every rank generates its own images with replicated weights, no data-path
+collective (SURVEY.md §8e mode 1), weak scaling; time = max over ranks.
+
+`value`  : DiT steps/s, whole job, inputs resident in HBM (device pointers through the C ABI).
+`e2e`    : the same through the C ABI with pinned HOST buffers (H2D of latents + text embeddings and D2H of the uint8
+           image + final latents inside the timed region).
+`roofline`: the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event time on the launch stream.
+`cpu_baseline` / --impl reference: the restated reference CPU path (oracle, PyTorch-CPU fp32) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "flux-2-swift-mlx_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+HEIGHT = WIDTH = 1024
+S_TXT = 512
+NUM_STEPS = 4
+METRIC = "dit_steps_per_sec"
+UNIT = "steps/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0)), "hbm": d.get("hbm_gbs", 6650.0),
+                "src": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"}
+    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md sustained figure)"}
+
+
+def dit_flops(cfg, S_img, S_txt=512):
+    """Algorithmic FLOPs of one DiT forward (BASELINE.md §3 accounting)."""
+    D, Hm = cfg.inner_dim, cfg.mlp_hidden
+    S = S_img + S_txt
+    g = lambda M, N, K: 2 * M * N * K
+    gemm = g(S_img, D, cfg.in_channels) + g(S_txt, D, cfg.joint_attention_dim) + g(S_img, cfg.out_channels, D)
+    for s in (S_img, S_txt):
+        gemm += cfg.num_layers * (4 * g(s, D, D) + g(s, 2 * Hm, D) + g(s, D, Hm))
+    gemm += cfg.num_single_layers * (g(S, 3 * D + 2 * Hm, D) + g(S, D, D + Hm))
+    attn = (cfg.num_layers + cfg.num_single_layers) * 4 * S * S * D
+    return gemm, attn
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = os.path.join(ROOT, "gpurun_out", f"clocks_rank{gpu_index}.csv")
+
+    def start(self):
+        os.makedirs(os.path.dirname(self.path), exist_ok=True)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            hot = sorted(sm)[len(sm) // 2:]  # samples under load dominate the upper half
+            out = {"sm_mhz": statistics.median(hot), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(threads: int):
+    """Bounded sample of the reference CPU path: 1 double-stream + 2 single-stream Klein-4B blocks at S = 4608
+    (the 1024^2 token count), PyTorch-CPU fp32 (fp32 activations as in the reference); scaled to a full DiT step by
+    block counts (5 double + 20 single). Embedders / final layer (<0.5 % of FLOPs) are not in the sample."""
+    import torch
+    from oracle import flux2_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.klein_4b()
+    small = O.DiTConfig(num_layers=1, num_single_layers=2, num_attention_heads=cfg.num_attention_heads,
+                        joint_attention_dim=cfg.joint_attention_dim, guidance_embeds=False)
+    D, Hm = cfg.inner_dim, cfg.mlp_hidden
+    W = {}
+    for k, (o, i) in O.dit_weight_shapes(small).items():
+        if k.startswith(("transformerBlocks", "singleTransformerBlocks", "doubleStream", "singleStream")):
+            W[k] = torch.empty(o, i).uniform_(-1.0 / math.sqrt(i), 1.0 / math.sqrt(i))
+    S_img = (HEIGHT // 16) * (WIDTH // 16)
+    img, txt = torch.randn(1, S_img, D), torch.randn(1, S_TXT, D)
+    temb = torch.randn(1, D)
+    cos, sin = O.rope_embeddings(torch.cat([O.text_position_ids(S_TXT), O.image_position_ids(HEIGHT, WIDTH)]))
+    im, tm = O.modulation(W, "doubleStreamModulationImg", temb, 2, D), O.modulation(W, "doubleStreamModulationTxt", temb, 2, D)
+    sm = O.modulation(W, "singleStreamModulation", temb, 1, D)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        txt2, img2, _ = O.double_block(W, 0, small, img, txt, im, tm, cos, sin)
+        t_double = time.perf_counter() - t0
+        x = torch.cat([txt2, img2], dim=1)
+        t0 = time.perf_counter()
+        for i in range(2):
+            x, _ = O.single_block(W, i, small, x, sm, cos, sin)
+        t_single = (time.perf_counter() - t0) / 2
+    step_s = cfg.num_layers * t_double + cfg.num_single_layers * t_single
+    gemm, attn = dit_flops(cfg, S_img)
+    return {"step_s": step_s, "t_double": t_double, "t_single": t_single, "tflops": (gemm + attn) / step_s / 1e12,
+            "sample": "1 double-stream + 2 single-stream Klein-4B blocks at S=4608 (1024x1024), PyTorch-CPU fp32 restatement "
+                      "of the reference path (oracle); scaled to one DiT step by block counts (5 double + 20 single)"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(threads)
+    vals = [cpu_sample(threads) for _ in range(max(1, min(args.steps, 3)))]
+    best = min(vals, key=lambda v: v["step_s"])
+    v = 1.0 / best["step_s"]
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": best["step_s"] * 1e3 * NUM_STEPS, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Klein 4B t2i 1024x1024 (4096 img + 512 txt tokens), DiT step; CPU arm = restated reference path "
+                               "(MLX CPU backend not runnable here: no swift / mlx)", "l2": "n/a (host)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": best["sample"],
+                         "cpu_tflops": best["tflops"]},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def make_weights_on_gpu(ctx, cfg, vcfg, device):
+    import torch
+    from oracle import flux2_oracle as O  # shapes / synthetic VAE weights only (input generation, not compute)
+    g = torch.Generator(device=device).manual_seed(0)
+    for k, (o, i) in O.dit_weight_shapes(cfg).items():
+        b = 1.0 / math.sqrt(i)
+        w = torch.empty(o, i, device=device, dtype=torch.float32).uniform_(-b, b, generator=g).to(torch.bfloat16)
+        ctx.set_tensor(k, w)
+        del w
+    ctx.load_weights(O.random_vae_weights(vcfg, seed=1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="flux2b")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="klein4b")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import flux2b
+    from oracle import flux2_oracle as O  # configs + FLOP accounting inputs + cpu_baseline checker leg
+
+    if flux2b.device_count() < 1:
+        raise SystemExit("bench.py needs an sm_100 GPU: flux2b has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    cfg = {"klein4b": O.klein_4b, "klein9b": O.klein_9b, "dev": O.flux2_dev}[args.model]()
+    vcfg = O.vae_small_decoder()
+    ctx = flux2b.Context(dit=cfg, vae=vcfg, device=local_rank, options={"keep_raw_weights": 0})
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    make_weights_on_gpu(ctx, cfg, vcfg, device)
+    ctx.finalize()
+    torch.cuda.empty_cache()
+
+    S_img = (HEIGHT // 16) * (WIDTH // 16)
+    sched = flux2b.FlowMatchEulerScheduler()
+    sched.set_timesteps(NUM_STEPS, S_img)
+    gen = torch.Generator().manual_seed(42 + rank)
+    lat_host = torch.randn(1, S_img, 128, generator=gen).pin_memory()
+    enc_host = torch.randn(1, S_TXT, cfg.joint_attention_dim, generator=torch.Generator().manual_seed(43)).to(torch.bfloat16).pin_memory()
+    guidance = 4.0 if cfg.guidance_embeds else None
+    lat_dev0 = lat_host.to(device)
+    enc_dev = enc_host.to(device)
+    rgb_dev = torch.empty(HEIGHT, WIDTH, 3, dtype=torch.uint8, device=device)
+    rgb_host = torch.empty(HEIGHT, WIDTH, 3, dtype=torch.uint8).pin_memory()
+
+    def one_image_device():
+        x = lat_dev0.clone()
+        ctx.generate(x, enc_dev, sched.sigmas, HEIGHT, WIDTH, rgb_out=rgb_dev, guidance=guidance)
+
+    def one_image_host():
+        x = lat_host.clone().pin_memory()
+        ctx.generate(x, enc_host, sched.sigmas, HEIGHT, WIDTH, rgb_out=rgb_host, guidance=guidance)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        one_image_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.prof_enable(True)
+    ctx.prof_reset()
+    ms = timed(one_image_device, args.steps)
+    prof = {k: ctx.prof_get(i) for k, i in (("gemm", flux2b.PROF_GEMM), ("attn", flux2b.PROF_ATTN), ("elem", flux2b.PROF_ELEMWISE),
+                                            ("conv", flux2b.PROF_CONV), ("gemv", flux2b.PROF_GEMV))}
+    launches = ctx.launch_count()
+    ctx.prof_enable(False)
+    ctx.prof_reset()
+    # DiT-only timing (explains `value`): 4 forwards + Euler on device
+    def dit_only():
+        x = lat_dev0.clone()
+        ctx.denoise(x, enc_dev, sched.sigmas, HEIGHT, WIDTH, guidance=guidance)
+    dit_only()
+    ms_dit = timed(dit_only, args.steps)
+    for _ in range(2):
+        one_image_host()
+    ms_e2e = timed(one_image_host, args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    n_img = args.steps * world
+    ms_per_image = ms / args.steps
+    value = n_img * NUM_STEPS / (ms * 1e-3)
+    e2e_value = n_img * NUM_STEPS / (ms_e2e * 1e-3)
+    pk = peaks()
+    g = prof["gemm"]
+    achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    gemm_f, attn_f = dit_flops(cfg, S_img)
+    total_kernel_ms = sum(p["ms"] for p in prof.values())
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_image, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.model} t2i {HEIGHT}x{WIDTH} ({S_img} img + {S_TXT} txt tokens), {NUM_STEPS} Euler steps bf16 + small-decoder "
+                               "VAE decode (f16) per image; random-init weights; one image per bench step; image-parallel over ranks",
+                   "l2": "inputs larger than L2 (7.8 GB of weights stream through the 126 MB L2 every forward)",
+                   "images_per_rank": args.steps},
+        "images_per_sec": n_img / (ms * 1e-3),
+        "dit_only_steps_per_sec": n_img * NUM_STEPS / (ms_dit * 1e-3),
+        "dit_tflops_per_gpu": (gemm_f + attn_f) * NUM_STEPS * args.steps / (ms_dit * 1e-3) / 1e12,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(lat_host.numel() * 4 + enc_host.numel() * 2),
+                "d2h_bytes_per_step": int(HEIGHT * WIDTH * 3 + lat_host.numel() * 4)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 GEMM, all DiT linears)", "achieved": achieved,
+                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"] if pk["tflops"] else None,
+                     "traffic": None, "peak_source": pk["src"], "launches": g["launches"],
+                     "share_of_kernel_time": g["ms"] / total_kernel_ms if total_kernel_ms else None},
+        "kernel_classes": {k: {"ms_per_image": p["ms"] / args.steps, "launches_per_image": p["launches"] / args.steps,
+                               "tflops": (p["flops"] / (p["ms"] * 1e-3) / 1e12) if p["ms"] > 0 and p["flops"] else None,
+                               "gbs": (p["bytes"] / (p["ms"] * 1e-3) / 1e9) if p["ms"] > 0 and p["bytes"] else None}
+                           for k, p in prof.items()},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        c = cpu_sample(os.cpu_count() or 1)
+        out["cpu_baseline"] = {"value": 1.0 / c["step_s"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": c["sample"], "cpu_tflops": c["tflops"]}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
