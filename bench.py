@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--impl", default="flux2b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="klein4b")
+    ap.add_argument("--profile-one", action="store_true",
+                    help="bracket ONE image with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`); prints no bench line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -259,6 +261,14 @@ def main():
         barrier()
         return ms
 
+    if args.profile_one:
+        one_image_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        one_image_device()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     for _ in range(max(args.warmup, 3)):
         one_image_device()
     sampler = ClockSampler(local_rank)

@@ -29,3 +29,10 @@ def rel_l2(a, b):
     a = torch.as_tensor(a).double().flatten()
     b = torch.as_tensor(b).double().flatten()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """tests/golden/golden.npz — oracle outputs committed by tools/make_golden.py."""
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "golden.npz")))

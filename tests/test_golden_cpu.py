@@ -1,0 +1,49 @@
+"""CPU: the oracle still reproduces the committed fixtures (tests/golden/golden.npz, made by tools/make_golden.py).
+Integer / packed results must match bit for bit; fp32 results within accumulation-order noise of the BLAS in use."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+from oracle import flux2_oracle as O
+from oracle import quant_oracle as Q
+import make_golden as MG
+
+
+def test_quantizer_fixtures_bit_exact(golden):
+    w = golden["quant_w_f16"]
+    for name, q in Q.QUANT.items():
+        if q == 0:
+            continue
+        p, s, b = Q.quantize(q, w)
+        assert np.array_equal(p, golden[f"quant_{name}_packed"])
+        assert np.array_equal(s.view(np.uint8), golden[f"quant_{name}_scales"].view(np.uint8))
+        if b is not None:
+            assert np.array_equal(b.view(np.uint16), golden[f"quant_{name}_biases"].view(np.uint16))
+        d = Q.dequantize(q, p, s, b, 256)
+        assert np.array_equal(d.view(np.uint32), golden[f"quant_{name}_dequant"].view(np.uint32))
+
+
+def test_scheduler_fixtures(golden):
+    for steps, seq, strength in ((4, 4096, 1.0), (4, 256, 1.0), (28, 16384, 1.0), (50, 4096, 0.5)):
+        s = O.FlowMatchEulerScheduler()
+        s.set_timesteps(steps, seq, strength)
+        np.testing.assert_allclose(np.array(s.sigmas, np.float32), golden[f"sigmas_{steps}_{seq}_{int(strength * 100)}"], rtol=1e-6)
+
+
+def test_dit_and_vae_fixtures(golden):
+    cfg, W, hidden, enc = MG.tiny_inputs()
+    assert np.array_equal(hidden.numpy(), golden["dit_hidden"]) and np.array_equal(enc.numpy(), golden["dit_enc"])
+    rec = []
+    y = O.dit_forward(W, cfg, hidden, enc, torch.tensor([0.7]), torch.tensor([4.0]), O.image_position_ids(MG.HW, MG.HW),
+                      O.text_position_ids(MG.S_TXT), record=rec)
+    np.testing.assert_allclose(y.numpy(), golden["dit_out"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(torch.stack(rec).numpy(), golden["dit_blocks"], rtol=1e-4, atol=1e-4)
+    vcfg = O.vae_small_decoder()
+    VW = O.random_vae_weights(vcfg, seed=1)
+    img = O.vae_decode(VW, vcfg, torch.from_numpy(golden["vae_z"]))
+    np.testing.assert_allclose(img.numpy(), golden["vae_out"], rtol=1e-4, atol=1e-4)

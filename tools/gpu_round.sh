@@ -1,0 +1,34 @@
+#!/bin/bash
+# One gpurun call: GPU test-suite, bench (both arms), ncu launch list of one image. Outputs land in gpurun_out/.
+# usage: gpurun --timeout 2400 -- 'bash tools/gpu_round.sh [tests|bench|ncu|full ...]'
+set -u
+mkdir -p gpurun_out
+WHAT="${*:-tests bench ncu}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/smi.txt 2>&1
+for w in $WHAT; do
+  case $w in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -q -rA --durations=15 > gpurun_out/pytest_gpu.log 2>&1
+      echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+      tail -n 60 gpurun_out/pytest_gpu.log ;;
+    smoke)
+      timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 5 gpurun_out/smoke.log ;;
+    bench)
+      timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+      echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err ;;
+    benchref)
+      timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+      echo "bench ref rc=$?"; cat gpurun_out/bench_ref.json ;;
+    ncu)
+      timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 2000 --csv \
+        --log-file gpurun_out/launches.csv python bench.py --profile-one > gpurun_out/ncu_launches.log 2>&1
+      echo "ncu launches rc=$?"; wc -l gpurun_out/launches.csv ;;
+    full)
+      # top kernels, full sections (few launches each)
+      timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \
+        -k regex:'gemm_kernel|attn_kernel' -s 40 -c 8 -o gpurun_out/prof_full -f python bench.py --profile-one > gpurun_out/ncu_full.log 2>&1
+      echo "ncu full rc=$?"; ls -la gpurun_out/*.ncu-rep ;;
+    probe)
+      timeout 1500 python tools/gpu_probe.py gemm_big gemm_ffin gemm_out attn_v1_big attn_v2_big conv3_big > gpurun_out/probe.log 2>&1; tail -n 20 gpurun_out/probe.log ;;
+  esac
+done
