@@ -236,9 +236,11 @@ def main():
         x = lat_dev0.clone()
         ctx.generate(x, enc_dev, sched.sigmas, HEIGHT, WIDTH, rgb_out=rgb_dev, guidance=guidance)
 
+    x_host = torch.empty_like(lat_host).pin_memory()
+
     def one_image_host():
-        x = lat_host.clone().pin_memory()
-        ctx.generate(x, enc_host, sched.sigmas, HEIGHT, WIDTH, rgb_out=rgb_host, guidance=guidance)
+        x_host.copy_(lat_host)
+        ctx.generate(x_host, enc_host, sched.sigmas, HEIGHT, WIDTH, rgb_out=rgb_host, guidance=guidance)
 
     def barrier():
         if dist is not None:

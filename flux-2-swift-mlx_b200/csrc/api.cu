@@ -21,19 +21,17 @@ bool is_device_ptr(const void* p) {
 int dev_in(flux2b_ctx* c, const void* src, size_t bytes, const void** out) {
   if (!src) { *out = nullptr; return 0; }
   if (is_device_ptr(src)) { *out = src; return 0; }
-  c->staging.emplace_back();
-  DevBuf& b = c->staging.back();
-  F2B_CUDA(b.alloc(bytes));
-  F2B_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
-  *out = b.p;
+  DevBuf* b = c->stage(bytes);
+  if (!b) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "staging buffer allocation failed"); }
+  F2B_CUDA(cudaMemcpyAsync(b->p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  *out = b->p;
   return 0;
 }
 int dev_out(flux2b_ctx* c, void* dst, size_t bytes, void** dev, bool* is_host) {
   if (is_device_ptr(dst)) { *dev = dst; *is_host = false; return 0; }
-  c->staging.emplace_back();
-  DevBuf& b = c->staging.back();
-  F2B_CUDA(b.alloc(bytes));
-  *dev = b.p; *is_host = true;
+  DevBuf* b = c->stage(bytes);
+  if (!b) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "staging buffer allocation failed"); }
+  *dev = b->p; *is_host = true;
   return 0;
 }
 int finish_out(flux2b_ctx* c, void* dst, const void* dev, size_t bytes, bool is_host) {
@@ -41,9 +39,10 @@ int finish_out(flux2b_ctx* c, void* dst, const void* dev, size_t bytes, bool is_
   return 0;
 }
 int end_call(flux2b_ctx* c, bool sync) {
-  if (sync || !c->staging.empty()) {
+  // host buffers were staged: the copies must land (and the staging slots must be idle) before the call returns
+  if (sync || c->staging_used) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    c->staging.clear();
+    c->staging_used = 0;
     if (e != cudaSuccess) return fail(FLUX2B_ERR_CUDA, std::string("stream sync: ") + cudaGetErrorString(e));
   }
   return 0;
@@ -55,11 +54,10 @@ struct InOut {
 static int dev_inout(flux2b_ctx* c, void* p, size_t bytes, InOut* io) {
   io->user = p; io->bytes = bytes;
   if (is_device_ptr(p)) { io->dev = p; io->host = false; return 0; }
-  c->staging.emplace_back();
-  DevBuf& b = c->staging.back();
-  F2B_CUDA(b.alloc(bytes));
-  F2B_CUDA(cudaMemcpyAsync(b.p, p, bytes, cudaMemcpyHostToDevice, c->stream));
-  io->dev = b.p; io->host = true;
+  DevBuf* b = c->stage(bytes);
+  if (!b) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "staging buffer allocation failed"); }
+  F2B_CUDA(cudaMemcpyAsync(b->p, p, bytes, cudaMemcpyHostToDevice, c->stream));
+  io->dev = b->p; io->host = true;
   return 0;
 }
 
@@ -495,7 +493,7 @@ int flux2b_op_groupnorm_silu(flux2b_ctx* c, const void* x16, void* y16, const fl
   F2B_TRY(dev_in(c, beta, (size_t)C * 4, &db));
   void* dout; bool ho;
   F2B_TRY(dev_out(c, y16, bytes, &dout, &ho));
-  F2B_CUDA(c->gn_stats.ensure(sizeof(double) * 2 * G * B));
+  F2B_CUDA(c->gn_stats.ensure(groupnorm_ws_bytes(B, G)));
   {
     ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)bytes * 3);
     F2B_CUDA(groupnorm_silu(dx, dout, (const float*)dg, (const float*)db, c->gn_stats.as<double>(), B, HW, C, G, eps, silu != 0, c->f16(), c->stream));

@@ -65,6 +65,12 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// non-owning view of a context-owned scratch buffer
+struct Buf {
+  void* p = nullptr;
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct Tensor {
   DevBuf buf;
   int dtype = FLUX2B_F32;
@@ -147,8 +153,23 @@ struct flux2b_ctx {
   std::vector<f2b::DevBuf> kv_k, kv_v;
   int kv_S_ref = 0;
 
-  // ---- staging for host <-> device marshalling (freed at the end of every API call)
+  // ---- staging for host <-> device marshalling: a pool that is recycled (not freed) at the end of every API call,
+  // so that a steady-state call performs no cudaMalloc / cudaFree (both synchronise the device)
   std::vector<f2b::DevBuf> staging;
+  size_t staging_used = 0;
+  f2b::DevBuf* stage(size_t bytes) {
+    if (staging_used == staging.size()) staging.emplace_back();
+    f2b::DevBuf& b = staging[staging_used];
+    if (b.ensure(bytes) != cudaSuccess) return nullptr;
+    ++staging_used;
+    return &b;
+  }
+  // ---- named, persistent scratch buffers (denoise-loop state, VAE mid-attention scores, ...)
+  std::map<std::string, f2b::DevBuf> scratch;
+  void* scratch_buf(const char* name, size_t bytes) {
+    f2b::DevBuf& b = scratch[name];
+    return b.ensure(bytes) == cudaSuccess ? b.p : nullptr;
+  }
 
   // ---- profiler
   bool prof_on = false;

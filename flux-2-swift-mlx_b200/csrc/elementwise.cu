@@ -341,9 +341,10 @@ __global__ void euler_kernel(float* __restrict__ x, const float* __restrict__ pr
                              float cfg, float dt, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // separate multiply and add roundings, like the reference's array ops (no FMA contraction): bit-exact with the oracle
   float v = pred[i];
-  if (un) { const float u = un[i]; v = u + cfg * (v - u); }
-  x[i] = x[i] + dt * v;
+  if (un) { const float u = un[i]; v = __fadd_rn(u, __fmul_rn(cfg, __fsub_rn(v, u))); }
+  x[i] = __fadd_rn(x[i], __fmul_rn(dt, v));
 }
 cudaError_t euler_step(float* x, const float* pred, const float* pred_uncond, float cfg, float dt, int64_t n,
                        cudaStream_t s) {
@@ -355,7 +356,7 @@ __global__ void scale_noise_kernel(const float* __restrict__ a, const float* __r
                                    float* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = (1.f - sigma) * a[i] + sigma * nz[i];
+  out[i] = __fadd_rn(__fmul_rn(__fsub_rn(1.f, sigma), a[i]), __fmul_rn(sigma, nz[i]));
 }
 cudaError_t scale_noise(const float* sample, const float* noise, float sigma, float* out, int64_t n, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
@@ -366,8 +367,8 @@ __global__ void repaint_kernel(float* __restrict__ x, const float* __restrict__ 
                                const float* __restrict__ m, float sn, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float known = (1.f - sn) * x0[i] + sn * e[i];
-  x[i] = (1.f - m[i]) * known + m[i] * x[i];
+  const float known = __fadd_rn(__fmul_rn(__fsub_rn(1.f, sn), x0[i]), __fmul_rn(sn, e[i]));
+  x[i] = __fadd_rn(__fmul_rn(__fsub_rn(1.f, m[i]), known), __fmul_rn(m[i], x[i]));
 }
 cudaError_t repaint_blend(float* x, const float* x0, const float* eps, const float* mask, float sigma_next, int64_t n,
                           cudaStream_t s) {
@@ -408,8 +409,8 @@ __global__ void bn_affine_kernel(const float* __restrict__ x, float* __restrict_
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int c = (int)((i / hw) % C);
-  const float sd = sqrtf(var[c] + eps);
-  y[i] = denorm ? x[i] * sd + mean[c] : (x[i] - mean[c]) / sd;
+  const float sd = __fsqrt_rn(__fadd_rn(var[c], eps));
+  y[i] = denorm ? __fadd_rn(__fmul_rn(x[i], sd), mean[c]) : __fdiv_rn(__fsub_rn(x[i], mean[c]), sd);
 }
 cudaError_t bn_affine_nchw(const float* x, float* y, const float* mean, const float* var, float eps, int B, int C,
                            int64_t hw, bool denorm, cudaStream_t s) {
@@ -442,112 +443,147 @@ cudaError_t seq_to_vae_input(const float* seq, const float* mean, const float* v
 }
 
 // ------------------------------------------------------------------ GroupNorm (+SiLU), NHWC
-// pass 1: grid (chunks, B). Each thread owns 8 consecutive channels (one 16 B vector) of a strided set of pixels,
-// accumulates sum / sum-of-squares in fp32, folds lanes that share a group, then one double atomic per (CTA, group).
-__global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ x, double* __restrict__ stats, int64_t HW,
+// Two passes over the activation (HBM-bound: 2 reads + 1 write of the tensor), statistics in fp32 / fp64, and a FIXED
+// reduction order everywhere (no atomics), so that a decode is bit-reproducible run to run and independent of batch size.
+//  pass 1 (gn_stats_kernel): grid (chunks, B), blockDim = a multiple of C/8. Thread t owns channel slot t % (C/8)
+//    (8 consecutive channels = one 16 B vector) for a strided set of pixels and keeps 8 (sum, sumsq) pairs in registers;
+//    the CTA folds threads of equal slot, then channels of equal group, in index order and writes one partial per group.
+//  pass 1b (gn_finalize_kernel): sums the per-CTA partials in index order (fp64) -> mean / rstd per (batch, group).
+//  pass 2 (gn_apply_kernel): normalise, affine, optional SiLU.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ x, float* __restrict__ partial, int64_t HW,
                                                        int C, int G, bool f16) {
-  extern __shared__ float gsm[];  // [2*G]
+  extern __shared__ float gsm[];  // [blockDim][16] thread accumulators, then [2*C] channel sums
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) gsm[i] = 0.f;
-  __syncthreads();
-  const int vec_per_pix = C / 8;
-  const int cg = C / G;  // channels per group
+  const int vpp = C / 8;
+  const int cg = C / G;
   const uint16_t* xb = reinterpret_cast<const uint16_t*>(x) + (int64_t)b * HW * C;
-  const int64_t nvec = HW * vec_per_pix;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  // a thread keeps the same channel slot when stride % vec_per_pix == 0; otherwise flush per element
-  const bool fixed = (stride % vec_per_pix) == 0;
-  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (fixed) {
-    // per-channel register accumulators (8 channels of this thread's slot), folded into groups once at the end
-    float s[8], q[8];
+  const int64_t nvec = HW * vpp;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // multiple of vpp: a thread never changes channel slot
+  float s[8], q[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
-    for (int64_t i = i0; i < nvec; i += stride) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack2(u[k], f16);
-        s[2 * k] += f.x; q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
-        s[2 * k + 1] += f.y; q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
-      }
-    }
-    if (i0 < nvec) {
-      const int c0 = (int)(i0 % vec_per_pix) * 8;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int g = (c0 + k) / cg;
-        atomicAdd(&gsm[2 * g], s[k]);
-        atomicAdd(&gsm[2 * g + 1], q[k]);
-      }
-    }
-  } else {
-    for (int64_t i = i0; i < nvec; i += stride) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-      const int c0 = (int)(i % vec_per_pix) * 8;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = unpack2(u[k], f16);
-        const int g0 = (c0 + 2 * k) / cg, g1 = (c0 + 2 * k + 1) / cg;
-        atomicAdd(&gsm[2 * g0], f.x); atomicAdd(&gsm[2 * g0 + 1], f.x * f.x);
-        atomicAdd(&gsm[2 * g1], f.y); atomicAdd(&gsm[2 * g1 + 1], f.y * f.y);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack2(u[k], f16);
+      s[2 * k] += f.x; q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
+      s[2 * k + 1] += f.y; q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
     }
   }
+  float* acc = gsm;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { acc[threadIdx.x * 16 + k] = s[k]; acc[threadIdx.x * 16 + 8 + k] = q[k]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(int64_t)b * 2 * G + i], (double)gsm[i]);
+  // channel sums: channel c = slot*8 + k is held by threads slot, slot + vpp, slot + 2 vpp, ...
+  float cs = 0.f, cq = 0.f;
+  const int reps = blockDim.x / vpp;
+  // each thread folds at most ceil(C / blockDim) channels; C <= 2 * blockDim is enforced by the launcher
+  float ch_s[2] = {0.f, 0.f}, ch_q[2] = {0.f, 0.f};
+  int n_mine = 0;
+  for (int cidx = threadIdx.x; cidx < C; cidx += blockDim.x, ++n_mine) {
+    const int slot = cidx >> 3, k = cidx & 7;
+    cs = 0.f; cq = 0.f;
+    for (int m = 0; m < reps; ++m) {
+      const int t = slot + m * vpp;
+      cs += acc[t * 16 + k];
+      cq += acc[t * 16 + 8 + k];
+    }
+    ch_s[n_mine] = cs; ch_q[n_mine] = cq;
+  }
+  __syncthreads();
+  n_mine = 0;
+  for (int cidx = threadIdx.x; cidx < C; cidx += blockDim.x, ++n_mine) { gsm[cidx] = ch_s[n_mine]; gsm[C + cidx] = ch_q[n_mine]; }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float gs = 0.f, gq = 0.f;
+    for (int j = 0; j < cg; ++j) { gs += gsm[threadIdx.x * cg + j]; gq += gsm[C + threadIdx.x * cg + j]; }
+    float* dst = partial + ((int64_t)b * gridDim.x + blockIdx.x) * 2 * G;
+    dst[threadIdx.x] = gs;
+    dst[G + threadIdx.x] = gq;
+  }
+}
+// grid (B), block 256 = `lanes` sub-lanes per statistic (2G statistics, G <= 128): sub-lane l sums partials l, l + lanes,
+// ... in index order, then thread g folds the sub-lanes of (sum_g, sumsq_g) in index order
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial, double* __restrict__ stats,
+                                                          int chunks, int G, double count, float eps) {
+  __shared__ double sm[256];
+  const int b = blockIdx.x;
+  const int lanes = 256 / (2 * G);
+  const int j = threadIdx.x / lanes, l = threadIdx.x % lanes;  // statistic j in [0, 2G), sub-lane l
+  double a = 0.0;
+  if (j < 2 * G)
+    for (int c = l; c < chunks; c += lanes) a += (double)partial[((int64_t)b * chunks + c) * 2 * G + j];
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < lanes; ++k) { s += sm[threadIdx.x * lanes + k]; q += sm[(G + threadIdx.x) * lanes + k]; }
+    const double m = s / count;
+    const double var = q / count - m * m;
+    stats[((int64_t)b * G + threadIdx.x) * 2] = m;
+    stats[((int64_t)b * G + threadIdx.x) * 2 + 1] = (double)rsqrtf(fmaxf((float)var, 0.f) + eps);
+  }
 }
 __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x, void* __restrict__ y,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const double* __restrict__ stats, int64_t HW, int C, int G,
-                                                       float eps, bool silu, bool f16) {
+                                                       bool silu, bool f16) {
   const int b = blockIdx.y;
-  const int vec_per_pix = C / 8;
+  const int vpp = C / 8;
   const int cg = C / G;
-  const int64_t nvec = HW * vec_per_pix;
+  const int64_t nvec = HW * vpp;
   const uint16_t* xb = reinterpret_cast<const uint16_t*>(x) + (int64_t)b * HW * C;
   uint16_t* yb = reinterpret_cast<uint16_t*>(y) + (int64_t)b * HW * C;
-  const double cnt = (double)HW * cg;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % vec_per_pix) * 8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;  // multiple of vpp: per-thread scale / shift are loop invariant
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= nvec) return;
+  const int c0 = (int)(i0 % vpp) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + k;
+    const int g = c / cg;
+    const float m = (float)stats[((int64_t)b * G + g) * 2];
+    const float rstd = (float)stats[((int64_t)b * G + g) * 2 + 1];
+    const float ga = __ldg(gamma + c);
+    sc[k] = rstd * ga;
+    sh[k] = __ldg(beta + c) - m * rstd * ga;
+  }
+  for (int64_t i = i0; i < nvec; i += stride) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 f = unpack2(u[k], f16);
-      float r[2] = {f.x, f.y};
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int c = c0 + 2 * k + t;
-        const int g = c / cg;
-        const double m = stats[(int64_t)b * 2 * G + 2 * g] / cnt;
-        const double var = stats[(int64_t)b * 2 * G + 2 * g + 1] / cnt - m * m;
-        const float rstd = rsqrtf(fmaxf((float)var, 0.f) + eps);
-        float z = (r[t] - (float)m) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        if (silu) z = silu_f(z);
-        r[t] = z;
-      }
-      o[k] = pack2(r[0], r[1], f16);
+      float z0 = fmaf(f.x, sc[2 * k], sh[2 * k]);
+      float z1 = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
+      if (silu) { z0 = silu_f(z0); z1 = silu_f(z1); }
+      o[k] = pack2(z0, z1, f16);
     }
     *reinterpret_cast<uint4*>(yb + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
+size_t groupnorm_ws_bytes(int B, int G) {
+  // [B, G] x (mean, rstd) doubles followed by the per-CTA partials [B, <= 592 chunks, 2G] floats
+  return sizeof(double) * 2 * G * B + sizeof(float) * 2 * G * B * (148 * 4);
+}
 cudaError_t groupnorm_silu(const void* x16, void* y16, const float* gamma, const float* beta, double* stats_ws, int B,
                            int64_t HW, int C, int G, float eps, bool silu, bool f16, cudaStream_t s) {
-  if (C % 8 || C % G) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * G * B, s);
-  if (e != cudaSuccess) return e;
-  const int64_t nvec = HW * (C / 8);
-  int chunks = (int)std::min<int64_t>((nvec + 255) / 256, 148 * 8);
-  // keep gridDim.x * 256 a multiple of C/8 so each thread sees one channel slot
   const int vpp = C / 8;
-  while (chunks > 1 && ((int64_t)chunks * 256) % vpp) --chunks;
-  gn_stats_kernel<<<dim3(chunks, B), 256, 2 * G * sizeof(float), s>>>(x16, stats_ws, HW, C, G, f16);
-  int chunks2 = (int)std::min<int64_t>((nvec + 255) / 256, 148 * 16);
-  gn_apply_kernel<<<dim3(chunks2, B), 256, 0, s>>>(x16, y16, gamma, beta, stats_ws, HW, C, G, eps, silu, f16);
+  if (C % 8 || C % G || vpp > 256 || G < 1 || G > 128) return cudaErrorInvalidValue;
+  const int threads = (256 / vpp) * vpp;  // largest multiple of the channel-slot count <= 256
+  if (C > 2 * threads) return cudaErrorInvalidValue;  // the CTA fold gives every thread at most two channels
+  const int64_t nvec = HW * vpp;
+  float* partial = reinterpret_cast<float*>(stats_ws + (size_t)2 * G * B);
+  const int chunks = (int)std::min<int64_t>((nvec + threads - 1) / threads, 148 * 4);
+  const size_t smem = std::max((size_t)threads * 16, (size_t)2 * C) * sizeof(float);
+  gn_stats_kernel<<<dim3(chunks, B), threads, smem, s>>>(x16, partial, HW, C, G, f16);
+  gn_finalize_kernel<<<B, 256, 0, s>>>(partial, stats_ws, chunks, G, (double)HW * (C / G), eps);
+  const int chunks2 = (int)std::min<int64_t>((nvec + threads - 1) / threads, 148 * 8);
+  gn_apply_kernel<<<dim3(chunks2, B), threads, 0, s>>>(x16, y16, gamma, beta, stats_ws, HW, C, G, silu, f16);
   return cudaGetLastError();
 }
 

@@ -62,7 +62,9 @@ cudaError_t bn_affine_nchw(const float* x, float* y, const float* mean, const fl
 cudaError_t seq_to_vae_input(const float* seq, const float* mean, const float* var, float eps, void* out16, int B, int h,
                              int w, bool f16, cudaStream_t s);
 
-// GroupNorm (+ optional SiLU) over NHWC 16-bit, fp32 statistics (ResnetBlock.swift:24-54)
+// GroupNorm (+ optional SiLU) over NHWC 16-bit, fp32 statistics (ResnetBlock.swift:24-54); deterministic (no atomics).
+// stats_ws must hold groupnorm_ws_bytes(B, G) bytes.
+size_t groupnorm_ws_bytes(int B, int G);
 cudaError_t groupnorm_silu(const void* x16, void* y16, const float* gamma, const float* beta, double* stats_ws, int B,
                            int64_t HW, int C, int G, float eps, bool silu, bool f16, cudaStream_t s);
 cudaError_t upsample_nearest2x(const void* x16, void* y16, int B, int H, int W, int C, cudaStream_t s);

@@ -243,7 +243,7 @@ int flux2b_merge_lora(flux2b_ctx* c, const char* layer_path, const void* A, cons
     F2B_CUDA(lora_add(w.buf.p, w.dtype, A32.as<float>(), B32.as<float>(), out_dim, in_dim, rank, scale, c->stream));
     F2B_CUDA(cudaStreamSynchronize(c->stream));
   }
-  c->staging.clear();
+  c->staging_used = 0;
   // working copies are rebuilt from the updated tensors
   if (c->finalized && c->has_dit) { c->finalized = false; F2B_TRY(finalize_dit(c)); c->finalized = true; }
   return 0;
@@ -259,14 +259,16 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
   const int S_img = h * w, S_ref = p->ref_latents ? p->S_ref : 0, S_all = S_img + S_ref;
   const size_t n_lat = (size_t)S_img * g.in_channels;
   // device-resident state for the whole loop
-  DevBuf x, hid, pred, pred_u, ids_img, ids_txt, tbuf;
-  F2B_CUDA(x.alloc(n_lat * 4));
-  F2B_CUDA(hid.alloc((size_t)S_all * g.in_channels * 4));
-  F2B_CUDA(pred.alloc((size_t)S_all * g.out_channels * 4));
-  if (p->enc_uncond) F2B_CUDA(pred_u.alloc((size_t)S_all * g.out_channels * 4));
-  F2B_CUDA(ids_img.alloc((size_t)S_all * 16));
-  F2B_CUDA(ids_txt.alloc((size_t)p->S_txt * 16));
-  F2B_CUDA(tbuf.alloc(16));
+  // persistent (context-owned) buffers: a steady-state call allocates nothing
+  Buf x{c->scratch_buf("dn.x", n_lat * 4)}, hid{c->scratch_buf("dn.hid", (size_t)S_all * g.in_channels * 4)},
+      pred{c->scratch_buf("dn.pred", (size_t)S_all * g.out_channels * 4)},
+      pred_u{p->enc_uncond ? c->scratch_buf("dn.pred_u", (size_t)S_all * g.out_channels * 4) : nullptr},
+      ids_img{c->scratch_buf("dn.ids_img", (size_t)S_all * 16)}, ids_txt{c->scratch_buf("dn.ids_txt", (size_t)p->S_txt * 16)},
+      tbuf{c->scratch_buf("dn.sigmas", (size_t)p->num_sigmas * 4)};
+  if (!x.p || !hid.p || !pred.p || (p->enc_uncond && !pred_u.p) || !ids_img.p || !ids_txt.p || !tbuf.p) {
+    cudaGetLastError();
+    return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "denoise state allocation failed");
+  }
   const bool lat_host = !is_device_ptr(latents);
   F2B_CUDA(cudaMemcpyAsync(x.p, latents, n_lat * 4, lat_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
   {
@@ -283,7 +285,8 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
       F2B_CUDA(cudaMemcpyAsync(hid.as<float>() + n_lat, p->ref_latents, (size_t)S_ref * g.in_channels * 4,
                                is_device_ptr(p->ref_latents) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     }
-    F2B_CUDA(cudaStreamSynchronize(c->stream));
+    F2B_CUDA(cudaMemcpyAsync(tbuf.p, p->sigmas, (size_t)p->num_sigmas * 4, cudaMemcpyHostToDevice, c->stream));
+    F2B_CUDA(cudaStreamSynchronize(c->stream));  // ii / ti are locals
   }
   const void *enc_d, *encu_d, *guid_d;
   const size_t enc_bytes = (size_t)p->S_txt * g.joint_attention_dim * dtype_size(p->enc_dtype);
@@ -294,11 +297,10 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
   const int steps = p->num_sigmas - 1;
   for (int i = 0; i < steps; ++i) {
     const float sigma = p->sigmas[i], sigma_next = p->sigmas[i + 1];
-    F2B_CUDA(cudaMemcpyAsync(tbuf.p, &p->sigmas[i], 4, cudaMemcpyHostToDevice, c->stream));
     F2B_CUDA(cudaMemcpyAsync(hid.p, x.p, n_lat * 4, cudaMemcpyDeviceToDevice, c->stream));
     DitIO io{};
     io.B = 1; io.S_img = S_all; io.S_txt = p->S_txt; io.hidden = hid.as<float>(); io.enc = enc_d; io.enc_dtype = p->enc_dtype;
-    io.timestep = tbuf.as<float>(); io.guidance = (const float*)guid_d;
+    io.timestep = tbuf.as<float>() + i; io.guidance = (const float*)guid_d;
     io.img_ids = ids_img.as<int32_t>(); io.txt_ids = ids_txt.as<int32_t>(); io.out = pred.as<float>();
     F2B_TRY(dit_forward_device(c, io));
     if (p->enc_uncond) {
@@ -317,7 +319,7 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
       F2B_CUDA(cudaStreamSynchronize(c->stream));
       flux2b_step_context sc{i, steps, sigma, sigma_next, p->height, p->width, S_ref > 0 ? 1 : 0};
       if (p->hook(&sc, host_lat.data(), n_lat, p->hook_user) != 0) {
-        c->staging.clear();
+        c->staging_used = 0;
         return fail(FLUX2B_ERR_CANCELLED, "generation cancelled by step hook");
       }
       F2B_CUDA(cudaMemcpyAsync(x.p, host_lat.data(), n_lat * 4, cudaMemcpyHostToDevice, c->stream));
@@ -336,16 +338,14 @@ int flux2b_generate(flux2b_ctx* c, const flux2b_denoise_params* p, float* latent
   const int h = p->height / 16, w = p->width / 16;
   const size_t n_lat = (size_t)h * w * 128;
   // keep latents on the device between the loop and the decoder
-  DevBuf xdev;
-  F2B_CUDA(xdev.alloc(n_lat * 4));
+  Buf xdev{c->scratch_buf("gen.x", n_lat * 4)}, z{c->scratch_buf("gen.z", (size_t)4 * h * w * 32 * 2)};
+  if (!xdev.p || !z.p) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "generate state allocation failed"); }
   const bool lat_host = !is_device_ptr(latents);
   F2B_CUDA(cudaMemcpyAsync(xdev.p, latents, n_lat * 4, lat_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
   F2B_TRY(flux2b_denoise(c, p, xdev.as<float>()));
   F2B_CUDA(cudaMemcpyAsync(latents, xdev.p, n_lat * 4, lat_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
   // unpack -> BN denorm (eps 1e-4) -> unpatchify -> NHWC 16-bit, one fused gather (Flux2Pipeline.swift:2059-2079)
   const bool vf16 = c->option("vae_f16", 1) != 0;
-  DevBuf z;
-  F2B_CUDA(z.alloc((size_t)4 * h * w * 32 * 2));
   {
     ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 6.0 * n_lat);
     F2B_CUDA(seq_to_vae_input(xdev.as<float>(), c->vw.bn_mean.as<float>(), c->vw.bn_var.as<float>(), 1e-4f, z.p, 1, h, w, vf16, c->stream));
@@ -371,14 +371,14 @@ static int vae_decode_common(flux2b_ctx* c, int B, int h8, int w8, const float* 
   const bool vf16 = c->option("vae_f16", 1) != 0;
   const void* dl;
   F2B_TRY(dev_in(c, lat, (size_t)B * L * h8 * w8 * 4, &dl));
-  DevBuf z;
-  F2B_CUDA(z.alloc((size_t)B * h8 * w8 * L * 2));
+  void* zp = c->scratch_buf("vae.z", (size_t)B * h8 * w8 * L * 2);
+  if (!zp) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "VAE input allocation failed"); }
   {
     ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 6.0 * B * L * h8 * w8);
-    F2B_CUDA(nchw_f32_to_nhwc16((const float*)dl, z.p, B, (int64_t)h8 * w8, L, vf16, c->stream));
+    F2B_CUDA(nchw_f32_to_nhwc16((const float*)dl, zp, B, (int64_t)h8 * w8, L, vf16, c->stream));
   }
   void* img16; int ld;
-  F2B_TRY(vae_decode_device(c, B, h8, w8, z.p, &img16, &ld));
+  F2B_TRY(vae_decode_device(c, B, h8, w8, zp, &img16, &ld));
   const int64_t npix = (int64_t)B * 64 * h8 * w8;
   const int Co = c->vae.out_channels;
   if (img_f32) {

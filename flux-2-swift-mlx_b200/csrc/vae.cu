@@ -34,7 +34,7 @@ static int conv(flux2b_ctx* c, bool f16, const ConvW& w, const void* x, void* y,
 }
 static int gn(flux2b_ctx* c, bool f16, const NormW& n, const void* x, void* y, int B, int64_t HW, bool silu) {
   const int G = c->vae.norm_num_groups;
-  F2B_CUDA(c->gn_stats.ensure(sizeof(double) * 2 * G * B));
+  F2B_CUDA(c->gn_stats.ensure(groupnorm_ws_bytes(B, G)));
   ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)B * HW * n.C * 6);
   F2B_CUDA(groupnorm_silu(x, y, n.gamma.as<float>(), n.beta.as<float>(), c->gn_stats.as<double>(), B, HW, n.C, G,
                           c->vae.norm_eps, silu, f16, c->stream));
@@ -70,12 +70,12 @@ static int mid_attention(VaeRun& r, void*& x, int H, int W) {
   void* y = r.pick(x, hn);
   // scratch sized for one batch item
   const int chunk = std::max(128, std::min(N, (int)(((size_t)1 << 28) / (size_t)N) / 128 * 128));  // <= 1 GiB of fp32 scores
-  DevBuf qkv, vt, scores, probs, o;
-  F2B_CUDA(qkv.alloc((size_t)N * 3 * C * 2));
-  F2B_CUDA(vt.alloc((size_t)C * N * 2));
-  F2B_CUDA(scores.alloc((size_t)chunk * N * 4));
-  F2B_CUDA(probs.alloc((size_t)chunk * N * 2));
-  F2B_CUDA(o.alloc((size_t)N * C * 2));
+  const int ldn = (N + 7) & ~7;  // TMA needs 16 B row strides; columns [N, ldn) are never read (tensor-map extent is N)
+  // context-owned scratch: allocated once per resolution, so a steady-state decode performs no cudaMalloc / cudaFree
+  Buf qkv{c->scratch_buf("vae.attn.qkv", (size_t)N * 3 * C * 2)}, vt{c->scratch_buf("vae.attn.vt", (size_t)C * ldn * 2)},
+      scores{c->scratch_buf("vae.attn.scores", (size_t)chunk * ldn * 4)}, probs{c->scratch_buf("vae.attn.probs", (size_t)chunk * ldn * 2)},
+      o{c->scratch_buf("vae.attn.o", (size_t)N * C * 2)};
+  if (!qkv.p || !vt.p || !scores.p || !probs.p || !o.p) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "VAE attention scratch"); }
   const float scale = 1.0f / sqrtf((float)C);
   for (int b = 0; b < r.B; ++b) {
     const uint16_t* hb = reinterpret_cast<const uint16_t*>(hn) + (size_t)b * N * C;
@@ -84,18 +84,18 @@ static int mid_attention(VaeRun& r, void*& x, int H, int W) {
     g.epi.mode = EPI_BF16; g.epi.f16 = f16; g.epi.out = qkv.p; g.epi.ldo = 3 * C; g.epi.bias = v.attn_qkv_bias.as<float>();
     { ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * N * 3.0 * C * C, 2.0 * (N * 4.0 * C + 3.0 * C * C)); F2B_CUDA(gemm_launch(g, c->stream)); }
     { ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 4.0 * N * C);
-      F2B_CUDA(transpose16(qkv.as<uint16_t>() + 2 * C, 3 * C, vt.p, N, N, C, c->stream)); }
+      F2B_CUDA(transpose16(qkv.as<uint16_t>() + 2 * C, 3 * C, vt.p, ldn, N, C, c->stream)); }
     for (int q0 = 0; q0 < N; q0 += chunk) {
       const int rows = std::min(chunk, N - q0);
       GemmProblem s;
       s.A = qkv.as<uint16_t>() + (size_t)q0 * 3 * C; s.lda = 3 * C; s.B = qkv.as<uint16_t>() + C; s.ldb = 3 * C;
       s.M = rows; s.N = N; s.K = C;
-      s.epi.mode = EPI_F32; s.epi.f16 = f16; s.epi.out = scores.p; s.epi.ldo = N;
+      s.epi.mode = EPI_F32; s.epi.f16 = f16; s.epi.out = scores.p; s.epi.ldo = ldn;
       { ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * rows * (double)N * C, 4.0 * rows * (double)N); F2B_CUDA(gemm_launch(s, c->stream)); }
       { ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 6.0 * rows * (double)N);
-        F2B_CUDA(softmax_rows(scores.as<float>(), N, probs.p, N, rows, N, scale, f16, c->stream)); }
+        F2B_CUDA(softmax_rows(scores.as<float>(), ldn, probs.p, ldn, rows, N, scale, f16, c->stream)); }
       GemmProblem pv;
-      pv.A = probs.p; pv.lda = N; pv.B = vt.p; pv.ldb = N; pv.M = rows; pv.N = C; pv.K = N;
+      pv.A = probs.p; pv.lda = ldn; pv.B = vt.p; pv.ldb = ldn; pv.M = rows; pv.N = C; pv.K = N;
       pv.epi.mode = EPI_BF16; pv.epi.f16 = f16; pv.epi.out = o.as<uint16_t>() + (size_t)q0 * C; pv.epi.ldo = C;
       { ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * rows * (double)N * C, 2.0 * rows * (double)N); F2B_CUDA(gemm_launch(pv, c->stream)); }
     }
@@ -106,7 +106,6 @@ static int mid_attention(VaeRun& r, void*& x, int H, int W) {
     og.epi.res16 = reinterpret_cast<const uint16_t*>(x) + (size_t)b * N * C; og.epi.ldr = C;
     { ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * N * (double)C * C, 6.0 * N * C); F2B_CUDA(gemm_launch(og, c->stream)); }
   }
-  F2B_CUDA(cudaStreamSynchronize(c->stream));  // scratch buffers are released on return
   x = y;
   return 0;
 }

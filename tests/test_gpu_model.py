@@ -253,7 +253,8 @@ def test_lora_merge_dense_bit_exact(flux2b):
         hidden, enc, t, _, img_ids, txt_ids = dit_inputs(O, cfg, 64, 64)
         out = ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), None, img_ids.numpy(), txt_ids.numpy())
         W2 = dict(W); W2[key + ".weight"] = want.float()
-        assert rel_l2(out, O.dit_forward(W2, cfg, hidden, enc, t, None, img_ids, txt_ids)) < (TOL_OUT if dt == torch.bfloat16 else 6e-4)
+        # (activations are bf16 in both cases: only the stored weight dtype differs)
+        assert rel_l2(out, O.dit_forward(W2, cfg, hidden, enc, t, None, img_ids, txt_ids)) < TOL_OUT
         ctx.close()
 
 
