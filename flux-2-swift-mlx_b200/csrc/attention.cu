@@ -333,15 +333,279 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ At
   if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
-template <int BN, bool kPTmem>
-static cudaError_t launch_attn(const AttnProblem& a, cudaStream_t stream) {
-  using C = ACfg<BN, kPTmem>;
-  AttnKParams p{};
+// ------------------------------------------------------------------------------------------------ variant 3
+// Same ping-pong structure as variant 2 (128-key tiles, P written back into the S columns of TMEM, PV with A from TMEM)
+// with the softmax warpgroup reorganised around the two limits measured on the first kernels (ncu: tensor pipe 24 %,
+// issue slots 41 %, MUFU 25 % busy):
+//   * S is read from TMEM ONCE per tile (four 32-column loads in flight, one wait), row max / exp2 / pack run on
+//     registers with independent accumulators;
+//   * lazy rescaling: the running maximum only moves when it grows by more than 2^8 (P stays < 256, exact in fp32 /
+//     bf16 range), so the O read-modify-write in TMEM happens a handful of times per row instead of every tile;
+//   * no per-tile wait on the PV barrier: s_ready(j) already orders after PV(j-1) (tcgen05.commit tracks every MMA the
+//     issuing thread issued before it), only the last tile signals o_done;
+//   * separate K (3-deep) and V (2-deep) rings: K(j+1) is needed one softmax earlier than V(j+1).
+struct A3 {
+  static constexpr int BN = 128;
+  static constexpr int KS = 3, VS = 2;
+  static constexpr int Q_BYTES = QT * HD * 2;
+  static constexpr int KV_BYTES = BN * HD * 2;
+  static constexpr int KV_PANEL = BN * 128;
+  static constexpr int OFF_K = 2 * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KS * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_V + VS * KV_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__ AttnKParams p) {
+  using C = A3;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;               // [2]
+  uint64_t* k_full = q_full + 2;         // [KS]
+  uint64_t* k_empty = k_full + C::KS;    // [KS]
+  uint64_t* v_full = k_empty + C::KS;    // [VS]
+  uint64_t* v_empty = v_full + C::VS;    // [VS]
+  uint64_t* s_ready = v_empty + C::VS;   // [2]
+  uint64_t* p_ready = s_ready + 2;       // [2]
+  uint64_t* o_done = p_ready + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int q_blk0 = blockIdx.x * 2 * QT;
+
+  int n_tiles = 0;
+  for (int s = 0; s < p.nseg; ++s) n_tiles += (p.seg_len[s] + BN - 1) / BN;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    for (int s = 0; s < p.nseg; ++s) { tma_prefetch_desc(&p.tmK[s]); tma_prefetch_desc(&p.tmV[s]); }
+  }
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    for (int i = 0; i < C::KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < C::VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      const int qrow = p.q_row0 + (int)(b * p.q_bs) + q_blk0;
+      for (int w = 0; w < 2; ++w) {
+        mbar_expect_tx(&q_full[w], C::Q_BYTES);
+        uint8_t* dst = smem + w * C::Q_BYTES;
+        tma_load_2d(dst, &p.tmQ, &q_full[w], head * HD, qrow + w * QT);
+        tma_load_2d(dst + QT * 128, &p.tmQ, &q_full[w], head * HD + 64, qrow + w * QT);
+      }
+      int j = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int tiles = (p.seg_len[s] + BN - 1) / BN;
+        const int row_base = p.seg_row0[s] + (int)(b * p.seg_bs[s]);
+        for (int t = 0; t < tiles; ++t, ++j) {
+          const int row = row_base + t * BN;
+          const int ks = j % C::KS, vs = j % C::VS;
+          mbar_wait(&k_empty[ks], ((j / C::KS) & 1) ^ 1, 10);
+          uint8_t* kd = smem + C::OFF_K + ks * C::KV_BYTES;
+          mbar_expect_tx(&k_full[ks], C::KV_BYTES);
+          tma_load_2d(kd, &p.tmK[s], &k_full[ks], head * HD, row);
+          tma_load_2d(kd + C::KV_PANEL, &p.tmK[s], &k_full[ks], head * HD + 64, row);
+          mbar_wait(&v_empty[vs], ((j / C::VS) & 1) ^ 1, 11);
+          uint8_t* vd = smem + C::OFF_V + vs * C::KV_BYTES;
+          mbar_expect_tx(&v_full[vs], C::KV_BYTES);
+          tma_load_2d(vd, &p.tmV[s], &v_full[vs], head * HD, row);
+          tma_load_2d(vd + C::KV_PANEL, &p.tmV[s], &v_full[vs], head * HD + 64, row);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(QT, BN, p.f16 == 0, false, false);
+      const uint32_t idesc_o = make_idesc_f16(QT, HD, p.f16 == 0, false, true);
+      auto issue_s = [&](int w, int ks) {
+        const uint32_t qa = smem_u32(smem + w * C::Q_BYTES);
+        const uint32_t ka = smem_u32(smem + C::OFF_K + ks * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint64_t ad = make_smem_desc(qa + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024, SWZ_128B);
+          const uint64_t bd = make_smem_desc(ka + (k / 4) * C::KV_PANEL + (k % 4) * 32, 16, 1024, SWZ_128B);
+          umma_f16_ss<1>(tmem_base + w * 128, ad, bd, idesc_s, k ? 1u : 0u);
+        }
+        umma_commit(&s_ready[w]);
+      };
+      auto issue_pv = [&](int w, int vs, bool accumulate) {
+        const uint32_t va = smem_u32(smem + C::OFF_V + vs * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < BN / 16; ++k) {
+          const uint64_t bd = make_smem_desc(va + k * 2048, C::KV_PANEL, 1024, SWZ_128B);
+          umma_f16_ts(tmem_base + 256 + w * 128, tmem_base + w * 128 + k * 8, bd, idesc_o, (accumulate || k) ? 1u : 0u);
+        }
+      };
+      mbar_wait(&q_full[0], 0, 20);
+      mbar_wait(&k_full[0], 0, 21);
+      tc_fence_after();
+      issue_s(0, 0);
+      mbar_wait(&q_full[1], 0, 22);
+      tc_fence_after();
+      issue_s(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int vs = j % C::VS;
+        const int ksn = (j + 1) % C::KS;
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(&p_ready[w], j & 1, 23);
+          if (w == 0) mbar_wait(&v_full[vs], (j / C::VS) & 1, 24);
+          tc_fence_after();
+          issue_pv(w, vs, j > 0);
+          if (w == 1) umma_commit(&v_empty[vs]);
+          if (j + 1 < n_tiles) {
+            if (w == 0) mbar_wait(&k_full[ksn], ((j + 1) / C::KS) & 1, 25);
+            tc_fence_after();
+            issue_s(w, ksn);
+            if (w == 1) umma_commit(&k_empty[ksn]);
+          } else {
+            umma_commit(&o_done[w]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================================================ softmax warpgroups
+    const int w = warp >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_off + w * 128;
+    const uint32_t t_o = tmem_base + lane_off + 256 + w * 128;
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;  // m_run in the scaled (log2) domain
+    int j = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      const int tiles = (p.seg_len[s] + BN - 1) / BN;
+      for (int t = 0; t < tiles; ++t, ++j) {
+        const int nvalid = min(BN, p.seg_len[s] - t * BN);
+        mbar_wait(&s_ready[w], j & 1, 30);
+        tc_fence_after();
+        uint32_t v[4][32];
+        tmem_ld_32x32(t_s, v[0]);
+        tmem_ld_32x32(t_s + 32, v[1]);
+        tmem_ld_32x32(t_s + 64, v[2]);
+        tmem_ld_32x32(t_s + 96, v[3]);
+        tmem_ld_wait();
+        if (nvalid < BN) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= nvalid) v[c][i] = 0xff800000u;  // -inf: ignored by the max, exp2 -> 0
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
+        const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2);
+        // lazy rescale: keep the stale maximum while the new one is within 2^8 of it
+        const bool move = (m_new - m_run) > 8.0f;   // first tile: m_run = -inf -> true
+        const float m_use = move ? m_new : m_run;
+        const float alpha = move ? fast_exp2(m_run - m_new) : 1.0f;
+        const float neg_m = -m_use;
+        float rs[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[64];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_m));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_m));
+            rs[c] += p0 + p1;
+            pk[c * 16 + i] = apk2(p0, p1, p.f16);
+          }
+        }
+        // P (16-bit) back into the first 64 columns of the S region
+        tmem_st_32x32(t_s, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
+        tmem_st_32x32(t_s + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
+        if (j > 0 && __any_sync(0xffffffffu, move)) {
+          // rescale O (PV(j-1) has completed: s_ready(j) was committed after it)
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32(t_o + h * 64, o0);
+            tmem_ld_32x32(t_o + h * 64 + 32, o1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+              o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+            }
+            tmem_st_32x32(t_o + h * 64, o0);
+            tmem_st_32x32(t_o + h * 64 + 32, o1);
+          }
+        }
+        tmem_st_wait();
+        l_run = l_run * alpha + ((rs[0] + rs[1]) + (rs[2] + rs[3]));
+        m_run = m_use;
+        tc_fence_before();
+        mbar_arrive(&p_ready[w]);
+      }
+    }
+    // ---- finalize: O / l
+    mbar_wait(&o_done[w], 0, 32);
+    tc_fence_after();
+    const int qrow = q_blk0 + w * QT + row;
+    const bool ok = qrow < p.sq;
+    const float inv_l = 1.0f / l_run;
+    uint16_t* orow = p.o + ((long long)p.o_row0 + b * p.o_bs + qrow) * p.ldo + head * HD;
+    uint32_t o[4][32];
+    tmem_ld_32x32(t_o, o[0]);
+    tmem_ld_32x32(t_o + 32, o[1]);
+    tmem_ld_32x32(t_o + 64, o[2]);
+    tmem_ld_32x32(t_o + 96, o[3]);
+    tmem_ld_wait();
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 u;
+          u.x = apk2(__uint_as_float(o[c][8 * q4 + 0]) * inv_l, __uint_as_float(o[c][8 * q4 + 1]) * inv_l, p.f16);
+          u.y = apk2(__uint_as_float(o[c][8 * q4 + 2]) * inv_l, __uint_as_float(o[c][8 * q4 + 3]) * inv_l, p.f16);
+          u.z = apk2(__uint_as_float(o[c][8 * q4 + 4]) * inv_l, __uint_as_float(o[c][8 * q4 + 5]) * inv_l, p.f16);
+          u.w = apk2(__uint_as_float(o[c][8 * q4 + 6]) * inv_l, __uint_as_float(o[c][8 * q4 + 7]) * inv_l, p.f16);
+          *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
+}
+
+static bool fill_params(const AttnProblem& a, int BN, AttnKParams& p) {
   {
     uint64_t d[2] = {(uint64_t)a.ldq, (uint64_t)a.q_rows_total};
     uint64_t s[1] = {(uint64_t)a.ldq * 2};
     uint32_t bx[2] = {64, QT};
-    if (!make_tmap_bf16(&p.tmQ, a.q, 2, d, s, bx)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16(&p.tmQ, a.q, 2, d, s, bx)) return false;
   }
   for (int i = 0; i < a.num_segments; ++i) {
     const KVSegment& g = a.seg[i];
@@ -350,8 +614,8 @@ static cudaError_t launch_attn(const AttnProblem& a, cudaStream_t stream) {
     uint64_t dv[2] = {(uint64_t)g.ldv, (uint64_t)g.rows_total};
     uint64_t sv[1] = {(uint64_t)g.ldv * 2};
     uint32_t bx[2] = {64, (uint32_t)BN};
-    if (!make_tmap_bf16(&p.tmK[i], g.k, 2, dk, sk, bx)) return cudaErrorInvalidValue;
-    if (!make_tmap_bf16(&p.tmV[i], g.v, 2, dv, sv, bx)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16(&p.tmK[i], g.k, 2, dk, sk, bx)) return false;
+    if (!make_tmap_bf16(&p.tmV[i], g.v, 2, dv, sv, bx)) return false;
     p.seg_row0[i] = g.row0;
     p.seg_len[i] = g.len;
     p.seg_bs[i] = g.batch_stride;
@@ -367,6 +631,28 @@ static cudaError_t launch_attn(const AttnProblem& a, cudaStream_t stream) {
   p.ldo = a.ldo;
   p.o_row0 = a.o_row0;
   p.o_bs = a.o_batch_stride;
+  return true;
+}
+
+static cudaError_t launch_attn_v3(const AttnProblem& a, cudaStream_t stream) {
+  AttnKParams p{};
+  if (!fill_params(a, A3::BN, p)) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, A3::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((a.sq + 2 * QT - 1) / (2 * QT), a.num_heads, a.batch);
+  attn_kernel_v3<<<grid, 320, A3::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int BN, bool kPTmem>
+static cudaError_t launch_attn(const AttnProblem& a, cudaStream_t stream) {
+  using C = ACfg<BN, kPTmem>;
+  AttnKParams p{};
+  if (!fill_params(a, BN, p)) return cudaErrorInvalidValue;
 
   auto kern = attn_kernel<BN, kPTmem>;
   static bool attr_set = false;
@@ -388,7 +674,8 @@ cudaError_t attention_launch(const AttnProblem& a, cudaStream_t stream) {
   if (total <= 0 || a.num_segments < 1 || a.num_segments > 3) return cudaErrorInvalidValue;
   for (int i = 0; i < a.num_segments; ++i)
     if (a.seg[i].len <= 0) return cudaErrorInvalidValue;
-  const int variant = a.variant ? a.variant : 1;
+  const int variant = a.variant ? a.variant : 3;
+  if (variant == 3) return launch_attn_v3(a, stream);
   if (variant == 2) return launch_attn<128, true>(a, stream);
   return launch_attn<64, false>(a, stream);
 }

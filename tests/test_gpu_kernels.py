@@ -96,7 +96,7 @@ def _attn_ref(qkv, B, S, H):
     return torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * S, D)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("B,S,H", [(1, 256, 2), (2, 328, 2), (1, 77, 1), (1, 768, 3), (1, 4608, 4)])
 def test_attention(ctx, B, S, H, variant):
     qkv = torch.randn(B * S, 3 * H * 128, generator=torch.Generator().manual_seed(S + H)).to(torch.bfloat16).cuda()
@@ -112,7 +112,7 @@ def test_attention_f16_and_large_logits(ctx_f16):
     qkv = torch.randn(B * S, 3 * H * 128, generator=torch.Generator().manual_seed(9))
     qkv[:, :2 * H * 128] *= 4.0
     qkv = qkv.to(torch.float16).cuda()
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         out = ctx_f16.op_attention(qkv, B, S, H, variant=variant)
         ctx_f16.synchronize()
         assert rel_l2(out, _attn_ref(qkv, B, S, H)) < 2e-3

@@ -206,6 +206,11 @@ PROBES = {
     "attn_v2_tail": lambda: probe_attention(2, 328, 2, 2),
     "attn_v1_big": lambda: probe_attention(1, 4608, 24, 1),
     "attn_v2_big": lambda: probe_attention(1, 4608, 24, 2),
+    "attn_v3_big": lambda: probe_attention(1, 4608, 24, 3),
+    "attn_v3_small": lambda: probe_attention(1, 256, 2, 3),
+    "attn_v3_tail": lambda: probe_attention(2, 328, 2, 3),
+    "attn_v3_k9": lambda: probe_attention(1, 4608, 32, 3),
+    "attn_v3_dev16k": lambda: probe_attention(1, 16896, 6, 3),
     "conv3_cg1": lambda: probe_conv(1, 32, 32, 64, 64, 3, 1),
     "conv3_c96_cg1": lambda: probe_conv(1, 40, 24, 96, 96, 3, 1, residual=True),
     "conv1_cg1": lambda: probe_conv(2, 16, 16, 32, 32, 1, 1),

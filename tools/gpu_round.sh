@@ -28,6 +28,10 @@ for w in $WHAT; do
       timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \
         -k regex:'gemm_kernel|attn_kernel' -s 40 -c 8 -o gpurun_out/prof_full -f python bench.py --profile-one > gpurun_out/ncu_full.log 2>&1
       echo "ncu full rc=$?"; ls -la gpurun_out/*.ncu-rep ;;
+    probe_attn)
+      timeout 900 python tools/gpu_probe.py attn_v > gpurun_out/probe_attn.log 2>&1; tail -n 20 gpurun_out/probe_attn.log ;;
+    tests_attn)
+      timeout 900 python -m pytest tests -m gpu -q -x -k "attention or dit_forward or denoise or kv" > gpurun_out/pytest_attn.log 2>&1; tail -n 15 gpurun_out/pytest_attn.log ;;
     probe)
       timeout 1500 python tools/gpu_probe.py gemm_big gemm_ffin gemm_out attn_v1_big attn_v2_big conv3_big > gpurun_out/probe.log 2>&1; tail -n 20 gpurun_out/probe.log ;;
   esac
