@@ -19,6 +19,7 @@
 #include "attention.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <string>
 
 namespace f2b {
@@ -54,6 +55,9 @@ struct AttnKParams {
   int seg_row0[3];
   int seg_len[3];
   long long seg_bs[3];
+  int o_rows_per_peer, o_col0;
+  uint16_t* o_peer[8];
+  int dbg;  // FLUX2B_ATTN_TIMELINE=1: CTA (0,0,0) prints its softmax / MMA time line (debug aid, off by default)
 };
 
 template <int BN, bool kPTmem>
@@ -356,6 +360,7 @@ struct A3 {
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
+template <bool kF16>
 __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__ AttnKParams p) {
   using C = A3;
   constexpr int BN = C::BN;
@@ -435,57 +440,69 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
     __syncwarp();
   } else if (warp == 9) {
     // ============================================================ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_f16(QT, BN, p.f16 == 0, false, false);
-      const uint32_t idesc_o = make_idesc_f16(QT, HD, p.f16 == 0, false, true);
-      auto issue_s = [&](int w, int ks) {
-        const uint32_t qa = smem_u32(smem + w * C::Q_BYTES);
-        const uint32_t ka = smem_u32(smem + C::OFF_K + ks * C::KV_BYTES);
+    // The whole warp walks the loop (warp-uniform control flow, barrier waits by all lanes) and one elected lane issues:
+    // inside an `if (lane == 0)` region ptxas wraps every tcgen05.mma in an elect / broadcast loop and reloads its
+    // operands from the stack (~25 instructions per MMA), which is slower than the 64 clk a 128x128x16 MMA takes.
+    // The 512-column allocation starts at TMEM address 0 (checked below), so accumulator addresses are immediates, and
+    // descriptors are (constant high word, 32-bit low word = address field + constants).
+    if (tmem_base != 0) __trap();
+    const uint32_t idesc_s = make_idesc_f16(QT, BN, !kF16, false, false);
+    const uint32_t idesc_o = make_idesc_f16(QT, HD, !kF16, false, true);
+    const uint32_t smem_base = smem_u32(smem);
+    // K-major operands (Q, K): LBO 16 B, SBO 1024 B; V (MN-major): LBO = panel stride, SBO 1024 B
+    const uint64_t desc_kmajor = make_smem_desc(0, 16, 1024, SWZ_128B);
+    const uint64_t desc_v = make_smem_desc(0, C::KV_PANEL, 1024, SWZ_128B);
+    auto issue_s = [&](int w, int ks) {
+      const uint32_t qa = (smem_base + w * C::Q_BYTES) >> 4;
+      const uint32_t ka = (smem_base + C::OFF_K + ks * C::KV_BYTES) >> 4;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint64_t ad = make_smem_desc(qa + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024, SWZ_128B);
-          const uint64_t bd = make_smem_desc(ka + (k / 4) * C::KV_PANEL + (k % 4) * 32, 16, 1024, SWZ_128B);
-          umma_f16_ss<1>(tmem_base + w * 128, ad, bd, idesc_s, k ? 1u : 0u);
-        }
-        umma_commit(&s_ready[w]);
-      };
-      auto issue_pv = [&](int w, int vs, bool accumulate) {
-        const uint32_t va = smem_u32(smem + C::OFF_V + vs * C::KV_BYTES);
+      for (int k = 0; k < HD / 16; ++k) {
+        const uint32_t off_q = ((k / 4) * (QT * 128) + (k % 4) * 32) >> 4;
+        const uint32_t off_k = ((k / 4) * C::KV_PANEL + (k % 4) * 32) >> 4;
+        umma_f16_ss<1>(w * 128, desc_kmajor + (qa + off_q), desc_kmajor + (ka + off_k), idesc_s, k ? 1u : 0u);
+      }
+      umma_commit(&s_ready[w]);
+    };
+    auto issue_pv = [&](int w, int vs, bool accumulate) {
+      const uint32_t va = (smem_base + C::OFF_V + vs * C::KV_BYTES) >> 4;
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k) {
-          const uint64_t bd = make_smem_desc(va + k * 2048, C::KV_PANEL, 1024, SWZ_128B);
-          umma_f16_ts(tmem_base + 256 + w * 128, tmem_base + w * 128 + k * 8, bd, idesc_o, (accumulate || k) ? 1u : 0u);
+      for (int k = 0; k < BN / 16; ++k)
+        umma_f16_ts(256 + w * 128, w * 128 + k * 8, desc_v + (va + k * (2048 >> 4)), idesc_o, (accumulate || k) ? 1u : 0u);
+    };
+    mbar_wait(&q_full[0], 0, 20);
+    mbar_wait(&k_full[0], 0, 21);
+    tc_fence_after();
+    if (elect_one()) issue_s(0, 0);
+    __syncwarp();
+    mbar_wait(&q_full[1], 0, 22);
+    tc_fence_after();
+    if (elect_one()) { issue_s(1, 0); umma_commit(&k_empty[0]); }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int vs = j % C::VS;
+      const int ksn = (j + 1) % C::KS;
+      const bool more = j + 1 < n_tiles;
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        mbar_wait(&p_ready[w], j & 1, 23);
+        if (w == 0) {
+          mbar_wait(&v_full[vs], (j / C::VS) & 1, 24);
+          if (more) mbar_wait(&k_full[ksn], ((j + 1) / C::KS) & 1, 25);
         }
-      };
-      mbar_wait(&q_full[0], 0, 20);
-      mbar_wait(&k_full[0], 0, 21);
-      tc_fence_after();
-      issue_s(0, 0);
-      mbar_wait(&q_full[1], 0, 22);
-      tc_fence_after();
-      issue_s(1, 0);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int vs = j % C::VS;
-        const int ksn = (j + 1) % C::KS;
-        for (int w = 0; w < 2; ++w) {
-          mbar_wait(&p_ready[w], j & 1, 23);
-          if (w == 0) mbar_wait(&v_full[vs], (j / C::VS) & 1, 24);
-          tc_fence_after();
+        tc_fence_after();
+        if (elect_one()) {
           issue_pv(w, vs, j > 0);
           if (w == 1) umma_commit(&v_empty[vs]);
-          if (j + 1 < n_tiles) {
-            if (w == 0) mbar_wait(&k_full[ksn], ((j + 1) / C::KS) & 1, 25);
-            tc_fence_after();
+          if (more) {
             issue_s(w, ksn);
             if (w == 1) umma_commit(&k_empty[ksn]);
           } else {
             umma_commit(&o_done[w]);
           }
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ============================================================ softmax warpgroups
     const int w = warp >> 2;
@@ -496,12 +513,16 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
     const uint32_t t_o = tmem_base + lane_off + 256 + w * 128;
     const float sl2 = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;  // m_run in the scaled (log2) domain
+    const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 127) == 0;
+    const long long t_start = dbg ? clock64() : 0;
+    int tl_wake[16], tl_done[16];
     int j = 0;
     for (int s = 0; s < p.nseg; ++s) {
       const int tiles = (p.seg_len[s] + BN - 1) / BN;
       for (int t = 0; t < tiles; ++t, ++j) {
         const int nvalid = min(BN, p.seg_len[s] - t * BN);
         mbar_wait(&s_ready[w], j & 1, 30);
+        long long t_wake = dbg ? clock64() : 0;
         tc_fence_after();
         uint32_t v[4][32];
         tmem_ld_32x32(t_s, v[0]);
@@ -536,7 +557,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
             const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_m));
             const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_m));
             rs[c] += p0 + p1;
-            pk[c * 16 + i] = apk2(p0, p1, p.f16);
+            pk[c * 16 + i] = apk2(p0, p1, kF16 ? 1 : 0);
           }
         }
         // P (16-bit) back into the first 64 columns of the S region
@@ -564,8 +585,13 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
         m_run = m_use;
         tc_fence_before();
         mbar_arrive(&p_ready[w]);
+        if (dbg && j < 16) { tl_wake[j] = (int)(t_wake - t_start); tl_done[j] = (int)(clock64() - t_start); }
       }
     }
+    if (dbg)
+      for (int i = 0; i < 16 && i < j; ++i)
+        printf("[attn timeline] wg %d tile %2d  S ready at %6d  P handed over at %6d  (softmax %5d)\n", w, i, tl_wake[i], tl_done[i],
+               tl_done[i] - tl_wake[i]);
     // ---- finalize: O / l
     mbar_wait(&o_done[w], 0, 32);
     tc_fence_after();
@@ -573,6 +599,11 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
     const bool ok = qrow < p.sq;
     const float inv_l = 1.0f / l_run;
     uint16_t* orow = p.o + ((long long)p.o_row0 + b * p.o_bs + qrow) * p.ldo + head * HD;
+    if (p.o_rows_per_peer > 0 && ok) {
+      // sequence parallel: this query row lives on rank `dest`; store its heads straight into that rank's buffer
+      const int dest = qrow / p.o_rows_per_peer;
+      orow = p.o_peer[dest] + (long long)(qrow - dest * p.o_rows_per_peer) * p.ldo + p.o_col0 + head * HD;
+    }
     uint32_t o[4][32];
     tmem_ld_32x32(t_o, o[0]);
     tmem_ld_32x32(t_o + 32, o[1]);
@@ -585,10 +616,10 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           uint4 u;
-          u.x = apk2(__uint_as_float(o[c][8 * q4 + 0]) * inv_l, __uint_as_float(o[c][8 * q4 + 1]) * inv_l, p.f16);
-          u.y = apk2(__uint_as_float(o[c][8 * q4 + 2]) * inv_l, __uint_as_float(o[c][8 * q4 + 3]) * inv_l, p.f16);
-          u.z = apk2(__uint_as_float(o[c][8 * q4 + 4]) * inv_l, __uint_as_float(o[c][8 * q4 + 5]) * inv_l, p.f16);
-          u.w = apk2(__uint_as_float(o[c][8 * q4 + 6]) * inv_l, __uint_as_float(o[c][8 * q4 + 7]) * inv_l, p.f16);
+          u.x = apk2(__uint_as_float(o[c][8 * q4 + 0]) * inv_l, __uint_as_float(o[c][8 * q4 + 1]) * inv_l, kF16 ? 1 : 0);
+          u.y = apk2(__uint_as_float(o[c][8 * q4 + 2]) * inv_l, __uint_as_float(o[c][8 * q4 + 3]) * inv_l, kF16 ? 1 : 0);
+          u.z = apk2(__uint_as_float(o[c][8 * q4 + 4]) * inv_l, __uint_as_float(o[c][8 * q4 + 5]) * inv_l, kF16 ? 1 : 0);
+          u.w = apk2(__uint_as_float(o[c][8 * q4 + 6]) * inv_l, __uint_as_float(o[c][8 * q4 + 7]) * inv_l, kF16 ? 1 : 0);
           *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = u;
         }
       }
@@ -631,6 +662,11 @@ static bool fill_params(const AttnProblem& a, int BN, AttnKParams& p) {
   p.ldo = a.ldo;
   p.o_row0 = a.o_row0;
   p.o_bs = a.o_batch_stride;
+  p.o_rows_per_peer = a.o_rows_per_peer;
+  p.o_col0 = a.o_col0;
+  for (int i = 0; i < 8; ++i) p.o_peer[i] = reinterpret_cast<uint16_t*>(a.o_peer[i]);
+  static const bool timeline = getenv("FLUX2B_ATTN_TIMELINE") != nullptr;
+  p.dbg = timeline ? 1 : 0;
   return true;
 }
 
@@ -639,12 +675,14 @@ static cudaError_t launch_attn_v3(const AttnProblem& a, cudaStream_t stream) {
   if (!fill_params(a, A3::BN, p)) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, A3::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((a.sq + 2 * QT - 1) / (2 * QT), a.num_heads, a.batch);
-  attn_kernel_v3<<<grid, 320, A3::SMEM_BYTES, stream>>>(p);
+  if (a.f16) attn_kernel_v3<true><<<grid, 320, A3::SMEM_BYTES, stream>>>(p);
+  else attn_kernel_v3<false><<<grid, 320, A3::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -675,6 +713,7 @@ cudaError_t attention_launch(const AttnProblem& a, cudaStream_t stream) {
   for (int i = 0; i < a.num_segments; ++i)
     if (a.seg[i].len <= 0) return cudaErrorInvalidValue;
   const int variant = a.variant ? a.variant : 3;
+  if (a.o_rows_per_peer > 0 && variant != 3) return cudaErrorInvalidValue;
   if (variant == 3) return launch_attn_v3(a, stream);
   if (variant == 2) return launch_attn<128, true>(a, stream);
   return launch_attn<64, false>(a, stream);

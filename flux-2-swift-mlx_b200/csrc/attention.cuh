@@ -34,6 +34,11 @@ struct AttnProblem {
   float scale = 0.08838834764831845f;
   int num_segments = 1;
   KVSegment seg[3];
+  // Ulysses peer-memory output (variant 3 only): query row r belongs to rank r / o_rows_per_peer; its output goes to
+  // o_peer[that rank] + (r % o_rows_per_peer) * ldo + o_col0 + head * 128 (a buffer mapped over NVLink). 0 = off.
+  int o_rows_per_peer = 0;
+  int o_col0 = 0;
+  void* o_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int f16 = 0;      // 16-bit storage type: 0 = bf16, 1 = f16
   int variant = 0;  // 0 = auto, 1 = P through shared memory (64-key tiles), 2 = P kept in TMEM (128-key tiles)
 };

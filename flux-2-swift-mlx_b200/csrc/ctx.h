@@ -115,6 +115,21 @@ struct VaeW {
   bool has_bn = false;
 };
 
+// Ulysses sequence-parallel state (sp.cu). world == 1: off.
+struct SpState {
+  int world = 1, rank = 0;
+  void* comm = nullptr;          // ncclComm_t
+  int mode = 0;                  // 0 = NCCL all-to-all, 1 = peer-memory stores fused into the producing kernels
+  // peer mappings (mode 1): [rank] -> base of that rank's gather / CAT buffer and barrier flags in this process
+  void* gather_peer[8] = {};
+  void* cat_peer[8] = {};
+  uint32_t* flag_peer[8] = {};
+  void* gather_exported = nullptr;  // local buffers whose handles the peers currently hold
+  void* cat_exported = nullptr;
+  void* flag_exported = nullptr;
+  uint32_t epoch = 0;
+};
+
 struct ProfKind {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
   size_t used = 0;
@@ -170,6 +185,10 @@ struct flux2b_ctx {
     f2b::DevBuf& b = scratch[name];
     return b.ensure(bytes) == cudaSuccess ? b.p : nullptr;
   }
+
+  // ---- sequence parallelism
+  f2b::SpState sp;
+  f2b::DevBuf ws_sp_gather, ws_sp_o, ws_sp_orecv, ws_sp_flags;
 
   // ---- profiler
   bool prof_on = false;
@@ -227,6 +246,13 @@ struct DitIO {
   int S_ref = 0; const float* ref_hidden = nullptr; const int32_t* ref_ids = nullptr;
 };
 int dit_forward_device(flux2b_ctx* c, const DitIO& io);  // all pointers already on device
+
+// sequence parallelism (sp.cu)
+int sp_all_to_all(flux2b_ctx* c, const void* send, void* recv, size_t chunk_elems16);  // 16-bit elements per peer chunk
+int sp_all_gather_f32(flux2b_ctx* c, float* buf, size_t elems_per_rank);                // in place: rank r's slice at r * elems
+int sp_map_peers(flux2b_ctx* c);   // (re-)exchange cudaIpc handles of ws_sp_gather / ws_cat / flags when they changed (collective)
+int sp_barrier(flux2b_ctx* c);     // all ranks: everything enqueued before it on every rank is visible after it
+void sp_destroy(flux2b_ctx* c);
 int vae_decode_device(flux2b_ctx* c, int B, int h8, int w8, const void* latents_nhwc16, void** out_nhwc16, int* out_ld);
 
 }  // namespace f2b

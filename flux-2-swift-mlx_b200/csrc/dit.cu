@@ -73,7 +73,50 @@ static int record_block(flux2b_ctx* c, int idx, int S) {
   return 0;
 }
 
+// Ulysses attention for the local token shard (see sp.cu): QKV of the local rows is already in ws_qkv in the
+// [dest rank][token][q|k|v][Hp*128] layout (mode 0) or already sits in every peer's gather buffer (mode 1).
+static int sp_attention(flux2b_ctx* c, int Sl, void* o, int64_t ldo) {
+  const int P = c->sp.world, Hp = c->H / P, Dp = Hp * 128;
+  const size_t qkv_chunk = (size_t)Sl * 3 * Dp, o_chunk = (size_t)Sl * Dp;
+  const int S = Sl * P;
+  const bool p2p = c->sp.mode == 1;
+  if (p2p) F2B_TRY(sp_barrier(c));  // every rank's QKV epilogue stores have landed in my gather buffer
+  else F2B_TRY(sp_all_to_all(c, c->ws_qkv.p, c->ws_sp_gather.p, qkv_chunk));
+  uint16_t* G = c->ws_sp_gather.as<uint16_t>();
+  AttnProblem a;
+  a.q = G; a.ldq = 3 * Dp; a.q_rows_total = S; a.q_row0 = 0; a.sq = S;
+  a.o = c->ws_sp_o.p; a.ldo = Dp; a.o_row0 = 0;
+  a.num_heads = Hp; a.batch = 1;
+  a.scale = 1.0f / sqrtf(128.0f);
+  a.num_segments = 1;
+  a.seg[0].k = G + Dp; a.seg[0].v = G + 2 * Dp; a.seg[0].ldk = a.seg[0].ldv = 3 * Dp;
+  a.seg[0].rows_total = S; a.seg[0].row0 = 0; a.seg[0].len = S;
+  a.f16 = c->f16() ? 1 : 0;
+  a.variant = c->option("attn_variant", 0);
+  if (p2p) {
+    // the attention epilogue stores each query row's heads straight into the owning rank's attention-output buffer
+    a.variant = 3;
+    a.ldo = ldo; a.o_rows_per_peer = Sl; a.o_col0 = c->sp.rank * Dp;
+    const size_t off = reinterpret_cast<uint8_t*>(o) - reinterpret_cast<uint8_t*>(c->ws_cat.p);
+    for (int d = 0; d < P; ++d) a.o_peer[d] = reinterpret_cast<uint8_t*>(c->sp.cat_peer[d]) + off;
+  }
+  {
+    ProfScope ps(c, FLUX2B_PROF_ATTN, 4.0 * S * (double)S * Dp, 2.0 * (4.0 * S * Dp));
+    F2B_CUDA(attention_launch(a, c->stream));
+  }
+  if (p2p) return sp_barrier(c);  // all heads of my rows have arrived; peers are done reading their gather buffers
+  F2B_TRY(sp_all_to_all(c, c->ws_sp_o.p, c->ws_sp_orecv.p, o_chunk));
+  // heads of rank j land in columns [j*Dp, (j+1)*Dp) of the local attention output
+  for (int j = 0; j < P; ++j)
+    F2B_CUDA(cudaMemcpy2DAsync(reinterpret_cast<uint16_t*>(o) + (size_t)j * Dp, (size_t)ldo * 2,
+                               c->ws_sp_orecv.as<uint16_t>() + (size_t)j * o_chunk, (size_t)Dp * 2, (size_t)Dp * 2, Sl,
+                               cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
 // One batch item. hidden [S_img, in_ch] f32, enc [S_txt, joint] (dtype), t/g scalars on device, ids on device.
+// Under sequence parallelism every rank receives the FULL inputs and returns the FULL output; it computes the rows of
+// its own token shard and the [S_img, out_ch] prediction is all-gathered at the end.
 static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden, const void* enc, int enc_dtype,
                        const float* t, const float* g, const int32_t* img_ids, const int32_t* txt_ids, float* out,
                        int kv_mode, int S_ref, const float* ref_hidden, const int32_t* ref_ids) {
@@ -81,11 +124,32 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
   const int D = c->D, Hm = c->Hm;
   const bool f16 = c->f16();
   cudaStream_t st = c->stream;
+  const int P = c->sp.world;
+  float* out_full = out;
+  const int S_img_full = S_img;
+  if (P > 1) {
+    if (kv_mode) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "the KV-cached forward is not sequence-parallel");
+    if (!c->option("fuse_qk_rope", 1)) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "sequence parallelism needs fuse_qk_rope = 1");
+    flux2b_sp_layout_t L;
+    F2B_TRY(flux2b_sp_layout(P, c->sp.rank, S_txt, S_img, c->H, &L));
+    S_txt = L.txt_rows; S_img = L.img_rows;
+    hidden += (size_t)L.img_row0 * cfg.in_channels;
+    enc = reinterpret_cast<const uint8_t*>(enc) + (size_t)L.txt_row0 * cfg.joint_attention_dim * dtype_size(enc_dtype);
+    img_ids += (size_t)L.img_row0 * 4;
+    txt_ids += (size_t)L.txt_row0 * 4;
+    out += (size_t)L.img_row0 * cfg.out_channels;
+  }
   // token layout of this pass: [txt | (ref) | img]
   const int S_mid = (kv_mode == 1) ? S_ref : 0;
   const int S_im_all = S_mid + S_img;   // rows of the "image" stream
   const int S = S_txt + S_im_all;
   F2B_TRY(ensure_ws(c, S, S_im_all, S_txt));
+  if (P > 1) {
+    F2B_CUDA(c->ws_sp_gather.ensure((size_t)S * 3 * D * 2));
+    F2B_CUDA(c->ws_sp_o.ensure((size_t)S * D * 2));
+    F2B_CUDA(c->ws_sp_orecv.ensure((size_t)S * D * 2));
+    if (c->sp.mode == 1) F2B_TRY(sp_map_peers(c));
+  }
   float* X = c->ws_x.as<float>();
   float* Ximg = X + (size_t)S_txt * D;
   uint16_t* XN = c->ws_xn.as<uint16_t>();
@@ -173,6 +237,18 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
     if (fuse_qk) {
       e.mode = EPI_QKV_ROPE; e.cos = cosT + (size_t)row0 * 128; e.sin = sinT + (size_t)row0 * 128;
       e.norm_q = nq.as<float>(); e.norm_k = nk.as<float>(); e.dmodel = D; e.eps = 1e-6f;
+      if (P > 1) {
+        // all-to-all layout [dest][local token][q|k|v][Dp]; S is the local row count here
+        const int Hp = c->H / P, Dp = Hp * 128;
+        e.sp_hp = Hp; e.ldo = 3 * Dp;
+        if (c->sp.mode == 1) {
+          // fused projection + all-to-all: store into rank d's gather buffer, slab of THIS rank's tokens
+          for (int d = 0; d < P; ++d)
+            e.sp_base[d] = reinterpret_cast<uint16_t*>(c->sp.gather_peer[d]) + ((size_t)c->sp.rank * S + row0) * 3 * Dp;
+        } else {
+          for (int d = 0; d < P; ++d) e.sp_base[d] = QKV + ((size_t)d * S + row0) * 3 * Dp;
+        }
+      }
       F2B_TRY(run_gemm(c, a, D, W, rows, 0, nullptr, e));
     } else {
       e.mode = EPI_BF16;
@@ -202,6 +278,7 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
 
   // attention key segments for this pass
   auto full_attention = [&](int layer, void* o, int64_t ldo) -> int {
+    if (P > 1) return sp_attention(c, S, o, ldo);
     const int64_t rows_total = S;
     uint16_t* Kp = QKV + D;
     uint16_t* Vp = QKV + 2 * D;
@@ -275,6 +352,8 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
   F2B_TRY(ln_mod(Xout, S_img, mod_out + D, mod_out + 0, XN));
   Epilogue e; e.mode = EPI_F32; e.out = out; e.ldo = cfg.out_channels;
   F2B_TRY(run_gemm(c, XN, D, c->proj_out, S_img, 0, nullptr, e));
+  if (P > 1) F2B_TRY(sp_all_gather_f32(c, out_full, (size_t)S_img * cfg.out_channels));
+  (void)S_img_full;
   return 0;
 }
 

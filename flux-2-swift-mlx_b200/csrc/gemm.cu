@@ -145,7 +145,16 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
             pk[2 * j + 1] = pk2(x2 * cc.z - x3 * s4.z, x3 * cc.w + x2 * s4.w, e.f16);
           }
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + grow * e.ldo + hc + c * 32);
+        uint4* dst;
+        if (e.sp_hp > 0) {
+          const int which = hc / e.dmodel;                    // 0 q, 1 k, 2 v
+          const int hh = (hc - which * e.dmodel) >> 7;        // head index
+          const int dest = hh / e.sp_hp, hl = hh - dest * e.sp_hp;
+          dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.sp_base[dest]) + grow * e.ldo +
+                                         (which * e.sp_hp + hl) * 128 + c * 32);
+        } else {
+          dst = reinterpret_cast<uint4*>(out + grow * e.ldo + hc + c * 32);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
       }
@@ -332,8 +341,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    // The whole warp walks the loop (warp-uniform control flow, barrier waits by all lanes); one elected lane issues.
+    // Inside an `if (lane == 0)` region ptxas wraps every tcgen05.mma in an elect / broadcast loop with operand reloads,
+    // which costs more issue time than a narrow (BN <= 128) MMA takes to execute.
+    if (leader) {
       const uint32_t idesc = make_idesc_f16(BM * CG, BN, p.epi.f16 == 0, false, false);
+      const uint64_t desc_hi = make_smem_desc(0, 16, 1024, SWZ_128B);
+      const uint32_t a0 = smem_u32(smA) >> 4, b0 = smem_u32(smB) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -345,21 +359,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait<CG == 2>(&full[stage], phase, 3);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(smA + stage * C::A_BYTES), 16, 1024, SWZ_128B);
-          const uint64_t bdesc = make_smem_desc(smem_u32(smB + stage * C::B_BYTES), 16, 1024, SWZ_128B);
+          if (elect_one()) {
+            const uint64_t adesc = desc_hi + (a0 + stage * (C::A_BYTES >> 4));
+            const uint64_t bdesc = desc_hi + (b0 + stage * (C::B_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the 16 B-unit address field
-            umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the 16 B-unit address field
+              umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            }
+            if (CG == 1) umma_commit(&empty[stage]); else umma_commit_cg2_mc(&empty[stage], 0x3);
+            if (kb == p.num_kb - 1) {
+              if (CG == 1) umma_commit(&tfull[acc]); else umma_commit_cg2_mc(&tfull[acc], 0x3);
+            }
           }
-          if (CG == 1) umma_commit(&empty[stage]); else umma_commit_cg2_mc(&empty[stage], 0x3);
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (CG == 1) umma_commit(&tfull[acc]); else umma_commit_cg2_mc(&tfull[acc], 0x3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-    __syncwarp();
   } else {
     // ===================================================== epilogue warps (2..5): TMEM lane quarter = warp % 4
     const int quarter = warp & 3;

@@ -31,6 +31,12 @@ struct Epilogue {
   const float* norm_k = nullptr;  // [128]
   int dmodel = 0;                 // D: columns [0,D) = q, [D,2D) = k, [2D,3D) = v
   float eps = 1e-6f;
+  // EPI_QKV_ROPE under Ulysses sequence parallelism (sp_hp > 0): head h of q / k / v goes to rank h / sp_hp, i.e. the
+  // epilogue stores straight into the all-to-all layout [dest rank][local token][q | k | v][sp_hp * 128]. sp_base[d] is
+  // where rank d's slab for THIS rank's tokens starts (a local send buffer, or rank d's gather buffer mapped over
+  // NVLink: the projection and its all-to-all are then one kernel); `out` is unused, ldo = 3 * sp_hp * 128.
+  int sp_hp = 0;
+  void* sp_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct GemmProblem {

@@ -407,8 +407,4 @@ int flux2b_vae_decode_u8(flux2b_ctx* c, int B, int h8, int w8, const float* lat,
   return vae_decode_common(c, B, h8, w8, lat, nullptr, rgb);
 }
 
-// ------------------------------------------------------------------ sequence parallelism (wired in sp.cu when NCCL is linked)
-int flux2b_sp_unique_id(void*) { return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "sequence parallelism is not built into this library yet"); }
-int flux2b_sp_init(flux2b_ctx*, const void*, int, int) { return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "sequence parallelism is not built into this library yet"); }
-
 }  // extern "C"

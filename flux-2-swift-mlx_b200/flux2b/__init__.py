@@ -81,7 +81,7 @@ EXPORTS = [
     "flux2b_euler_step", "flux2b_scale_noise", "flux2b_pack_patchified_to_sequence", "flux2b_unpack_sequence_to_patchified",
     "flux2b_unpatchify_latents", "flux2b_pack_latents_to_patchified", "flux2b_bn_latents", "flux2b_image_position_ids",
     "flux2b_text_position_ids", "flux2b_reference_position_ids", "flux2b_vae_decode", "flux2b_vae_decode_u8",
-    "flux2b_denoise", "flux2b_generate", "flux2b_repaint_blend", "flux2b_sp_unique_id", "flux2b_sp_init",
+    "flux2b_denoise", "flux2b_generate", "flux2b_repaint_blend", "flux2b_sp_unique_id", "flux2b_sp_init", "flux2b_sp_layout",
     "flux2b_prof_enable", "flux2b_prof_reset", "flux2b_prof_get", "flux2b_launch_count", "flux2b_op_gemm",
     "flux2b_op_attention", "flux2b_op_ln_modulate", "flux2b_op_qk_norm_rope", "flux2b_op_rope_table",
     "flux2b_op_timestep_embedding", "flux2b_op_conv2d", "flux2b_op_groupnorm_silu",
@@ -217,6 +217,26 @@ def reference_position_ids(lat_h: Sequence[int], lat_w: Sequence[int], scale: in
     return out
 
 
+class SpLayoutC(ctypes.Structure):
+    _fields_ = [("txt_row0", ctypes.c_int), ("txt_rows", ctypes.c_int), ("img_row0", ctypes.c_int), ("img_rows", ctypes.c_int),
+                ("local_rows", ctypes.c_int), ("heads_per_rank", ctypes.c_int), ("qkv_chunk_elems", ctypes.c_int64),
+                ("o_chunk_elems", ctypes.c_int64)]
+
+
+def sp_layout(world: int, rank: int, S_txt: int, S_img: int, num_heads: int) -> SpLayoutC:
+    """How the joint sequence is sharded for Ulysses sequence parallelism (host-only)."""
+    out = SpLayoutC()
+    _ck(lib().flux2b_sp_layout(world, rank, S_txt, S_img, num_heads, ctypes.byref(out)))
+    return out
+
+
+def sp_unique_id() -> bytes:
+    """128-byte NCCL unique id; create on rank 0 and broadcast (torch.distributed / MPI / a file)."""
+    buf = ctypes.create_string_buffer(128)
+    _ck(lib().flux2b_sp_unique_id(buf))
+    return buf.raw
+
+
 def quant_params(quant: int):
     b, g, h, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     _ck(lib().flux2b_quant_params(quant, ctypes.byref(b), ctypes.byref(g), ctypes.byref(h), ctypes.byref(s)))
@@ -265,6 +285,11 @@ class Context:
 
     def synchronize(self):
         _ck(lib().flux2b_synchronize(self._h))
+
+    def sp_init(self, unique_id: bytes, rank: int, world: int):
+        """Join an Ulysses sequence-parallel group (one context per GPU / process)."""
+        assert len(unique_id) == 128
+        _ck(lib().flux2b_sp_init(self._h, ctypes.c_char_p(unique_id), rank, world))
 
     # -- weights
     def set_tensor(self, key: str, t):

@@ -196,7 +196,19 @@ int flux2b_repaint_blend(flux2b_ctx* ctx, float* x, const float* x0, const float
  * Ulysses sequence parallelism: tokens of each stream are sharded over `world` ranks; Q/K/V are exchanged by NCCL
  * all-to-all before the fused attention and O after it. nccl_unique_id: 128 bytes from flux2b_sp_unique_id on rank 0. */
 int flux2b_sp_unique_id(void* id128);
+/* option "sp_mode" (set before sp_init): 0 = NCCL all-to-all, 1 = peer-memory stores fused into the QKV GEMM / attention
+ * epilogues. After sp_init every rank calls flux2b_dit_forward / flux2b_denoise with the FULL inputs and receives the
+ * FULL output; the library computes the rows of its own token shard. */
 int flux2b_sp_init(flux2b_ctx* ctx, const void* id128, int rank, int world);
+/* host-only: how a joint sequence is sharded over `world` ranks (the single source of truth used by the forward).
+ * Rank r owns txt rows [txt_row0, txt_row0 + txt_rows) and img rows [img_row0, img_row0 + img_rows); after the first
+ * exchange it holds all S tokens (rank-major: [txt_0 | img_0 | txt_1 | img_1 | ...]) for heads
+ * [rank * heads_per_rank, (rank + 1) * heads_per_rank). Chunk sizes are 16-bit elements per peer message. */
+typedef struct {
+  int txt_row0, txt_rows, img_row0, img_rows, local_rows, heads_per_rank;
+  int64_t qkv_chunk_elems, o_chunk_elems;
+} flux2b_sp_layout_t;
+int flux2b_sp_layout(int world, int rank, int S_txt, int S_img, int num_heads, flux2b_sp_layout_t* out);
 
 /* ------------------------------------------------------------------ profiling (CUDA events on the context stream) */
 enum { FLUX2B_PROF_GEMM = 0, FLUX2B_PROF_ATTN = 1, FLUX2B_PROF_ELEMWISE = 2, FLUX2B_PROF_CONV = 3, FLUX2B_PROF_GEMV = 4,

@@ -28,6 +28,10 @@ for w in $WHAT; do
       timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \
         -k regex:'gemm_kernel|attn_kernel' -s 40 -c 8 -o gpurun_out/prof_full -f python bench.py --profile-one > gpurun_out/ncu_full.log 2>&1
       echo "ncu full rc=$?"; ls -la gpurun_out/*.ncu-rep ;;
+    prof_kernels)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_kernel|attn_kernel' -s 2 -c 20 \
+        -o gpurun_out/prof_kernels -f python tools/prof_kernels.py ${PROF_ARGS:-gemm_cg1 gemm_cg2 attn3} > gpurun_out/prof_kernels.log 2>&1
+      echo "prof_kernels rc=$?"; tail -n 3 gpurun_out/prof_kernels.log ;;
     probe_attn)
       timeout 900 python tools/gpu_probe.py attn_v > gpurun_out/probe_attn.log 2>&1; tail -n 20 gpurun_out/probe_attn.log ;;
     tests_attn)

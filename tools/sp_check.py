@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Ulysses sequence-parallel parity check, one process per GPU:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sp_check.py
+
+Every rank builds the same tiny DiT twice — a plain context and a sequence-parallel one — feeds both the same full
+inputs and checks (1) SP output == single-GPU output up to the key-order change in the softmax accumulation,
+(2) SP output vs the oracle within the bf16 tolerance, (3) a 3-step denoise loop. Prints one SP_CHECK line per rank.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "flux-2-swift-mlx_b200"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import flux2b  # noqa: E402
+from oracle import flux2_oracle as O  # noqa: E402  (checker)
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().flatten(), torch.as_tensor(b).double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    mode = int(os.environ.get("SP_MODE", "0"))
+    ids = [flux2b.sp_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    heads = 8 if world <= 8 else world
+    cfg = O.DiTConfig(num_layers=2, num_single_layers=2, num_attention_heads=heads, joint_attention_dim=256, guidance_embeds=True)
+    W = O.random_dit_weights(cfg, seed=0)
+    plain = flux2b.Context(dit=cfg, device=local)
+    plain.load_weights(W, dtype=torch.bfloat16); plain.finalize()
+    sp = flux2b.Context(dit=cfg, device=local, options={"sp_mode": mode})
+    sp.load_weights(W, dtype=torch.bfloat16); sp.finalize()
+    sp.sp_init(ids[0], rank, world)
+    S_img, S_txt, HW = 256, 64, 256
+    hidden = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(42))
+    enc = torch.randn(1, S_txt, cfg.joint_attention_dim, generator=torch.Generator().manual_seed(43))
+    t, gd = torch.tensor([0.7]), torch.tensor([4.0])
+    img_ids, txt_ids = O.image_position_ids(HW, HW), O.text_position_ids(S_txt)
+    args = (hidden.numpy(), enc.numpy(), t.numpy(), gd.numpy(), img_ids.numpy(), txt_ids.numpy())
+    out_plain = plain.dit_forward(*args)
+    out_sp = sp.dit_forward(*args)
+    ref = O.dit_forward(W, cfg, hidden, enc, t, gd, img_ids, txt_ids) if rank == 0 else None
+    res = {"rank": rank, "world": world, "mode": mode, "sp_vs_plain": rel_l2(out_sp, out_plain)}
+    if rank == 0:
+        res["sp_vs_oracle"] = rel_l2(out_sp, ref)
+        res["plain_vs_oracle"] = rel_l2(out_plain, ref)
+    # every rank must hold the same full output
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out_sp.tobytes())
+    res["ranks_agree"] = all(g == gathered[0] for g in gathered)
+    # denoise loop (3 steps) through the SP context
+    sched = flux2b.FlowMatchEulerScheduler(); sched.set_timesteps(3, S_img)
+    x_sp, x_pl = hidden.numpy().copy(), hidden.numpy().copy()
+    sp.denoise(x_sp, enc.numpy(), sched.sigmas, HW, HW, guidance=4.0)
+    plain.denoise(x_pl, enc.numpy(), sched.sigmas, HW, HW, guidance=4.0)
+    res["denoise_sp_vs_plain"] = rel_l2(x_sp, x_pl)
+    ok = res["sp_vs_plain"] < 1e-3 and res["ranks_agree"] and res["denoise_sp_vs_plain"] < 2e-3 and res.get("sp_vs_oracle", 0) < 4e-3
+    res["ok"] = bool(ok)
+    print("SP_CHECK " + json.dumps(res), flush=True)
+    dist.barrier()
+    sp.close(); plain.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
