@@ -118,8 +118,6 @@ int sp_map_peers(flux2b_ctx* c) {
   }
   if (sp.gather_exported == c->ws_sp_gather.p && sp.cat_exported == c->ws_cat.p && sp.flag_exported == c->ws_sp_flags.p) return 0;
   F2B_CUDA(cudaStreamSynchronize(c->stream));
-  const bool keep_flags = sp.flag_exported == c->ws_sp_flags.p;
-  (void)keep_flags;
   sp_unmap(c);
   struct Handles { cudaIpcMemHandle_t g, x, f; };
   Handles mine;
@@ -148,8 +146,6 @@ int sp_map_peers(flux2b_ctx* c) {
   // nobody may write into the new mappings before everyone has opened them; flags restart from a clean epoch
   F2B_CUDA(cudaMemsetAsync(c->ws_sp_flags.p, 0, 256, c->stream));
   sp.epoch = 0;
-  uint8_t token = 0;
-  (void)token;
   F2B_NCCL(g_nccl.AllGather(reinterpret_cast<uint8_t*>(dev.p) + sp.rank, dev.p, 1, ncclUint8, reinterpret_cast<ncclComm_t>(sp.comm), c->stream));
   F2B_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
