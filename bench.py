@@ -179,6 +179,88 @@ def make_weights_on_gpu(ctx, cfg, vcfg, device):
     ctx.load_weights(O.random_vae_weights(vcfg, seed=1))
 
 
+def run_sp(args, cfg, rank, local_rank, world, device, dist):
+    """BASELINE.json configs[3]: one denoising step of a large joint sequence, Ulysses sequence-parallel over all ranks.
+    Strong scaling: total work fixed, value = DiT steps/s of the whole job."""
+    import torch
+    import flux2b
+    H = W = args.res
+    S_img = (H // 16) * (W // 16)
+    ctx = flux2b.Context(dit=cfg, device=local_rank, options={"keep_raw_weights": 0, "sp_mode": args.sp_mode})
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    from oracle import flux2_oracle as O
+    g = torch.Generator(device=device).manual_seed(0)   # same seed on every rank: replicated weights
+    for k, (o, i) in O.dit_weight_shapes(cfg).items():
+        b = 1.0 / math.sqrt(i)
+        ctx.set_tensor(k, torch.empty(o, i, device=device, dtype=torch.float32).uniform_(-b, b, generator=g).to(torch.bfloat16))
+    ctx.finalize()
+    torch.cuda.empty_cache()
+    if world > 1:
+        ids = [flux2b.sp_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, device=device)
+        ctx.sp_init(ids[0], rank, world)
+    sched = flux2b.FlowMatchEulerScheduler()
+    sched.set_timesteps(28, S_img)
+    sig = sched.sigmas[:2]
+    lat = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(42)).to(device)
+    enc = torch.randn(1, S_TXT, cfg.joint_attention_dim, generator=torch.Generator().manual_seed(43)).to(torch.bfloat16).to(device)
+    guidance = 4.0 if cfg.guidance_embeds else None
+
+    def step():
+        x = lat.clone()
+        ctx.denoise(x, enc, sig, H, W, guidance=guidance)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.prof_enable(True); ctx.prof_reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    prof = {k: ctx.prof_get(i) for k, i in (("gemm", flux2b.PROF_GEMM), ("attn", flux2b.PROF_ATTN), ("elem", flux2b.PROF_ELEMWISE),
+                                            ("gemv", flux2b.PROF_GEMV), ("comm", flux2b.PROF_COMM))}
+    launches = ctx.launch_count()
+    clocks = sampler.stop() if rank == 0 else {}
+    barrier()
+    if rank == 0:
+        gemm_f, attn_f = dit_flops(cfg, S_img)
+        pk = peaks()
+        gp = prof["gemm"]
+        achieved = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] > 0 else 0.0
+        print(json.dumps({
+            "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.model} one denoising step at {H}x{W} ({S_img} img + {S_TXT} txt tokens), bf16, Ulysses "
+                                   f"sequence-parallel over {world} rank(s), transport mode {args.sp_mode}",
+                       "l2": "inputs larger than L2 (weights stream from HBM every step)"},
+            "tflops_total": (gemm_f + attn_f) * args.steps / (ms * 1e-3) / 1e12,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"]},
+            "kernel_classes_rank0": {k: {"ms_per_step": p["ms"] / args.steps, "launches_per_step": p["launches"] / args.steps}
+                                     for k, p in prof.items()},
+            "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +269,11 @@ def main():
     ap.add_argument("--impl", default="flux2b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="klein4b")
+    ap.add_argument("--sp", action="store_true",
+                    help="Ulysses sequence-parallel mode: all ranks cooperate on ONE denoising step (strong scaling); "
+                         "use with --model dev --res 2048 (BASELINE.json configs[3])")
+    ap.add_argument("--sp-mode", type=int, default=1, help="0 = NCCL all-to-all, 1 = peer-memory stores fused into the kernels")
+    ap.add_argument("--res", type=int, default=1024, help="square resolution in pixels (--sp mode)")
     ap.add_argument("--profile-one", action="store_true",
                     help="bracket ONE image with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`); prints no bench line")
     args = ap.parse_args()
@@ -214,6 +301,9 @@ def main():
 
     cfg = {"klein4b": O.klein_4b, "klein9b": O.klein_9b, "dev": O.flux2_dev}[args.model]()
     vcfg = O.vae_small_decoder()
+    if args.sp:
+        run_sp(args, cfg, rank, local_rank, world, device, dist)
+        return
     ctx = flux2b.Context(dit=cfg, vae=vcfg, device=local_rank, options={"keep_raw_weights": 0})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     make_weights_on_gpu(ctx, cfg, vcfg, device)

@@ -314,7 +314,6 @@ int flux2b_prof_enable(flux2b_ctx* c, int on) { if (!c) return -2; c->prof_on = 
 int flux2b_prof_reset(flux2b_ctx* c) {
   if (!c) return -2;
   cudaStreamSynchronize(c->stream);
-  sp_destroy(c);
   for (auto& pk : c->prof) { pk.used = 0; pk.flops = pk.bytes = 0; pk.launches = 0; }
   c->launches = 0;
   return 0;
