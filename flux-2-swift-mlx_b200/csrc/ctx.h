@@ -124,6 +124,9 @@ struct SpState {
   void* gather_peer[8] = {};
   void* cat_peer[8] = {};
   uint32_t* flag_peer[8] = {};
+  // side stream + events: the NCCL exchanges of a single-stream block run beside the MLP-in / MLP-part-of-out GEMMs
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
   void* gather_exported = nullptr;  // local buffers whose handles the peers currently hold
   void* cat_exported = nullptr;
   void* flag_exported = nullptr;
@@ -248,7 +251,9 @@ struct DitIO {
 int dit_forward_device(flux2b_ctx* c, const DitIO& io);  // all pointers already on device
 
 // sequence parallelism (sp.cu)
-int sp_all_to_all(flux2b_ctx* c, const void* send, void* recv, size_t chunk_elems16);  // 16-bit elements per peer chunk
+int sp_all_to_all(flux2b_ctx* c, const void* send, void* recv, size_t chunk_elems16, cudaStream_t stream = nullptr);  // 16-bit elements per peer chunk
+int sp_fork(flux2b_ctx* c);   // comm stream waits for everything enqueued on the context stream so far
+int sp_join(flux2b_ctx* c);   // context stream waits for everything enqueued on the comm stream so far
 int sp_all_gather_f32(flux2b_ctx* c, float* buf, size_t elems_per_rank);                // in place: rank r's slice at r * elems
 int sp_map_peers(flux2b_ctx* c);   // (re-)exchange cudaIpc handles of ws_sp_gather / ws_cat / flags when they changed (collective)
 int sp_barrier(flux2b_ctx* c);     // all ranks: everything enqueued before it on every rank is visible after it

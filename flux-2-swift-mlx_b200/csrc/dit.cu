@@ -16,11 +16,11 @@
 namespace f2b {
 
 static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int M, int N_override, const void* Bptr,
-                    Epilogue epi, int kind = FLUX2B_PROF_GEMM) {
+                    Epilogue epi, int kind = FLUX2B_PROF_GEMM, int K_override = 0) {
   GemmProblem g;
   g.A = A; g.lda = lda;
   g.B = Bptr ? Bptr : W.w.p; g.ldb = W.K;
-  g.M = M; g.N = N_override ? N_override : W.N; g.K = W.K;
+  g.M = M; g.N = N_override ? N_override : W.N; g.K = K_override ? K_override : W.K;
   epi.f16 = c->f16() ? 1 : 0;
   g.epi = epi;
   g.force_cta_group = c->option("gemm_cta_group", 0);
@@ -73,15 +73,22 @@ static int record_block(flux2b_ctx* c, int idx, int S) {
   return 0;
 }
 
-// Ulysses attention for the local token shard (see sp.cu): QKV of the local rows is already in ws_qkv in the
-// [dest rank][token][q|k|v][Hp*128] layout (mode 0) or already sits in every peer's gather buffer (mode 1).
-static int sp_attention(flux2b_ctx* c, int Sl, void* o, int64_t ldo) {
+// Ulysses attention for the local token shard (see sp.cu), in three phases so that a single-stream block can run its
+// MLP GEMMs beside the two exchanges:
+//   sp_exchange_qkv : QKV of the local rows ([dest rank][token][q|k|v][Hp*128], written by the GEMM epilogue) -> gather
+//   sp_attend       : attention over all S tokens for this rank's heads
+//   sp_exchange_o   : O back to the token owners, heads of rank j into columns [j*Dp, (j+1)*Dp) of `o`
+// `async` = run the NCCL exchange on the side stream (caller joins before consuming). Peer-memory mode (sp.mode 1) has
+// no exchange kernels at all: the producers already stored remotely, only flag barriers remain.
+static int sp_exchange_qkv(flux2b_ctx* c, int Sl, bool async) {
+  const int P = c->sp.world, Dp = (c->H / P) * 128;
+  if (c->sp.mode == 1) return sp_barrier(c);  // every rank's QKV epilogue stores have landed in my gather buffer
+  if (async) F2B_TRY(sp_fork(c));
+  return sp_all_to_all(c, c->ws_qkv.p, c->ws_sp_gather.p, (size_t)Sl * 3 * Dp, async ? c->sp.comm_stream : c->stream);
+}
+static int sp_attend(flux2b_ctx* c, int Sl, void* o, int64_t ldo) {
   const int P = c->sp.world, Hp = c->H / P, Dp = Hp * 128;
-  const size_t qkv_chunk = (size_t)Sl * 3 * Dp, o_chunk = (size_t)Sl * Dp;
   const int S = Sl * P;
-  const bool p2p = c->sp.mode == 1;
-  if (p2p) F2B_TRY(sp_barrier(c));  // every rank's QKV epilogue stores have landed in my gather buffer
-  else F2B_TRY(sp_all_to_all(c, c->ws_qkv.p, c->ws_sp_gather.p, qkv_chunk));
   uint16_t* G = c->ws_sp_gather.as<uint16_t>();
   AttnProblem a;
   a.q = G; a.ldq = 3 * Dp; a.q_rows_total = S; a.q_row0 = 0; a.sq = S;
@@ -93,25 +100,34 @@ static int sp_attention(flux2b_ctx* c, int Sl, void* o, int64_t ldo) {
   a.seg[0].rows_total = S; a.seg[0].row0 = 0; a.seg[0].len = S;
   a.f16 = c->f16() ? 1 : 0;
   a.variant = c->option("attn_variant", 0);
-  if (p2p) {
+  if (c->sp.mode == 1) {
     // the attention epilogue stores each query row's heads straight into the owning rank's attention-output buffer
     a.variant = 3;
     a.ldo = ldo; a.o_rows_per_peer = Sl; a.o_col0 = c->sp.rank * Dp;
     const size_t off = reinterpret_cast<uint8_t*>(o) - reinterpret_cast<uint8_t*>(c->ws_cat.p);
     for (int d = 0; d < P; ++d) a.o_peer[d] = reinterpret_cast<uint8_t*>(c->sp.cat_peer[d]) + off;
   }
-  {
-    ProfScope ps(c, FLUX2B_PROF_ATTN, 4.0 * S * (double)S * Dp, 2.0 * (4.0 * S * Dp));
-    F2B_CUDA(attention_launch(a, c->stream));
-  }
-  if (p2p) return sp_barrier(c);  // all heads of my rows have arrived; peers are done reading their gather buffers
-  F2B_TRY(sp_all_to_all(c, c->ws_sp_o.p, c->ws_sp_orecv.p, o_chunk));
-  // heads of rank j land in columns [j*Dp, (j+1)*Dp) of the local attention output
+  ProfScope ps(c, FLUX2B_PROF_ATTN, 4.0 * S * (double)S * Dp, 2.0 * (4.0 * S * Dp));
+  F2B_CUDA(attention_launch(a, c->stream));
+  return 0;
+}
+static int sp_exchange_o(flux2b_ctx* c, int Sl, void* o, int64_t ldo, bool async) {
+  const int P = c->sp.world, Dp = (c->H / P) * 128;
+  if (c->sp.mode == 1) return sp_barrier(c);  // all heads of my rows have arrived; peers are done with their gather buffers
+  const size_t o_chunk = (size_t)Sl * Dp;
+  if (async) F2B_TRY(sp_fork(c));
+  cudaStream_t st = async ? c->sp.comm_stream : c->stream;
+  F2B_TRY(sp_all_to_all(c, c->ws_sp_o.p, c->ws_sp_orecv.p, o_chunk, st));
   for (int j = 0; j < P; ++j)
     F2B_CUDA(cudaMemcpy2DAsync(reinterpret_cast<uint16_t*>(o) + (size_t)j * Dp, (size_t)ldo * 2,
                                c->ws_sp_orecv.as<uint16_t>() + (size_t)j * o_chunk, (size_t)Dp * 2, (size_t)Dp * 2, Sl,
-                               cudaMemcpyDeviceToDevice, c->stream));
+                               cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+static int sp_attention(flux2b_ctx* c, int Sl, void* o, int64_t ldo) {
+  F2B_TRY(sp_exchange_qkv(c, Sl, false));
+  F2B_TRY(sp_attend(c, Sl, o, ldo));
+  return sp_exchange_o(c, Sl, o, ldo, false);
 }
 
 // One batch item. hidden [S_img, in_ch] f32, enc [S_txt, joint] (dtype), t/g scalars on device, ids on device.
@@ -342,6 +358,26 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
     F2B_TRY(ln_mod(X, S, mod_sgl + 0, mod_sgl + D, XN));
     F2B_TRY(qkv_gemm(XN, b.qkv, S, 0, b.nq, b.nk));
     uint16_t* scratch = CAT + (size_t)S * ldc;  // [S, 2Hm] unfused fallback lives behind CAT (see ensure_ws)
+    if (P > 1 && c->sp.mode == 0 && c->option("sp_overlap", 1)) {
+      // NCCL transport: hide both exchanges behind the MLP GEMMs of the block.
+      //   QKV all-to-all  ||  MLP-in GEMM (SwiGLU)
+      //   attention
+      //   O all-to-all    ||  out GEMM over the MLP columns (K = Hm, no dependency on the attention)
+      //   out GEMM over the attention columns (K = D)
+      F2B_TRY(sp_exchange_qkv(c, S, true));
+      F2B_TRY(swiglu_gemm(XN, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
+      F2B_TRY(sp_join(c));
+      F2B_TRY(sp_attend(c, S, CAT, ldc));
+      F2B_TRY(sp_exchange_o(c, S, CAT, ldc, true));
+      {
+        Epilogue e; e.mode = EPI_GATE_RES; e.out = X; e.ldo = D; e.res = X; e.ldr = D; e.gate = mod_sgl + 2 * D;
+        F2B_TRY(run_gemm(c, CAT + D, ldc, b.out, S, 0, b.out.w.as<uint16_t>() + D, e, FLUX2B_PROF_GEMM, Hm));
+        F2B_TRY(sp_join(c));
+        F2B_TRY(run_gemm(c, CAT, ldc, b.out, S, 0, nullptr, e, FLUX2B_PROF_GEMM, D));
+      }
+      F2B_TRY(record_block(c, cfg.num_layers + i, S));
+      continue;
+    }
     F2B_TRY(swiglu_gemm(XN, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
     F2B_TRY(full_attention(cfg.num_layers + i, CAT, ldc));
     F2B_TRY(gate_res_gemm(CAT, ldc, b.out, S, X, mod_sgl + 2 * D));

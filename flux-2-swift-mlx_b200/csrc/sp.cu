@@ -73,16 +73,38 @@ static bool nccl_load() {
     if (_r != ncclSuccess) return fail(FLUX2B_ERR_CUDA, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
   } while (0)
 
-int sp_all_to_all(flux2b_ctx* c, const void* send, void* recv, size_t chunk_elems16) {
+int sp_fork(flux2b_ctx* c) {
+  SpState& sp = c->sp;
+  if (!sp.comm_stream) {
+    F2B_CUDA(cudaStreamCreateWithFlags(&sp.comm_stream, cudaStreamNonBlocking));
+    F2B_CUDA(cudaEventCreateWithFlags(&sp.ev_main, cudaEventDisableTiming));
+    F2B_CUDA(cudaEventCreateWithFlags(&sp.ev_comm, cudaEventDisableTiming));
+  }
+  F2B_CUDA(cudaEventRecord(sp.ev_main, c->stream));
+  F2B_CUDA(cudaStreamWaitEvent(sp.comm_stream, sp.ev_main, 0));
+  return 0;
+}
+int sp_join(flux2b_ctx* c) {
+  SpState& sp = c->sp;
+  F2B_CUDA(cudaEventRecord(sp.ev_comm, sp.comm_stream));
+  F2B_CUDA(cudaStreamWaitEvent(c->stream, sp.ev_comm, 0));
+  return 0;
+}
+
+int sp_all_to_all(flux2b_ctx* c, const void* send, void* recv, size_t chunk_elems16, cudaStream_t stream) {
+  if (!stream) stream = c->stream;
   ncclComm_t comm = reinterpret_cast<ncclComm_t>(c->sp.comm);
   const int P = c->sp.world;
   const uint16_t* s = reinterpret_cast<const uint16_t*>(send);
   uint16_t* r = reinterpret_cast<uint16_t*>(recv);
-  ProfScope ps(c, FLUX2B_PROF_COMM, 0, 2.0 * chunk_elems16 * 2 * (P - 1));
+  // (profiler events are recorded on the context stream, so an exchange on the side stream only counts launches / bytes)
+  c->launches++;
+  c->prof[FLUX2B_PROF_COMM].launches++;
+  c->prof[FLUX2B_PROF_COMM].bytes += 2.0 * chunk_elems16 * 2 * (P - 1);
   F2B_NCCL(g_nccl.GroupStart());
   for (int peer = 0; peer < P; ++peer) {
-    F2B_NCCL(g_nccl.Send(s + (size_t)peer * chunk_elems16, chunk_elems16, ncclBfloat16, peer, comm, c->stream));
-    F2B_NCCL(g_nccl.Recv(r + (size_t)peer * chunk_elems16, chunk_elems16, ncclBfloat16, peer, comm, c->stream));
+    F2B_NCCL(g_nccl.Send(s + (size_t)peer * chunk_elems16, chunk_elems16, ncclBfloat16, peer, comm, stream));
+    F2B_NCCL(g_nccl.Recv(r + (size_t)peer * chunk_elems16, chunk_elems16, ncclBfloat16, peer, comm, stream));
   }
   F2B_NCCL(g_nccl.GroupEnd());
   return 0;
@@ -179,6 +201,12 @@ int sp_barrier(flux2b_ctx* c) {
 
 void sp_destroy(flux2b_ctx* c) {
   sp_unmap(c);
+  if (c->sp.comm_stream) {
+    cudaStreamSynchronize(c->sp.comm_stream);
+    cudaEventDestroy(c->sp.ev_main); cudaEventDestroy(c->sp.ev_comm);
+    cudaStreamDestroy(c->sp.comm_stream);
+    c->sp.comm_stream = nullptr; c->sp.ev_main = c->sp.ev_comm = nullptr;
+  }
   if (c->sp.comm && g_nccl.ok) g_nccl.CommDestroy(reinterpret_cast<ncclComm_t>(c->sp.comm));
   c->sp.comm = nullptr;
   c->sp.world = 1;
