@@ -142,11 +142,11 @@ int flux2b_synchronize(flux2b_ctx* c) {
 int flux2b_set_option(flux2b_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "null argument");
   static const char* known[] = {"compute_f16", "fuse_qk_rope", "fuse_swiglu", "attn_variant", "gemm_cta_group",
-                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap"};
+                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx"};
   bool ok = false;
   for (const char* k : known) ok = ok || !strcmp(k, name);
   if (!ok) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string("unknown option: ") + name);
-  if (c->finalized && (!strcmp(name, "compute_f16") || !strcmp(name, "fuse_swiglu") || !strcmp(name, "vae_f16")))
+  if (c->finalized && (!strcmp(name, "compute_f16") || !strcmp(name, "fuse_swiglu") || !strcmp(name, "vae_f16") || !strcmp(name, "native_mx")))
     return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string(name) + " must be set before flux2b_finalize_weights");
   c->opt[name] = value;
   return 0;
@@ -363,6 +363,53 @@ int flux2b_op_gemm(flux2b_ctx* c, const void* a16, const void* w16, int M, int N
   }
   F2B_TRY(finish_out(c, out, dout, obytes, ho));
   return end_call(c, false);
+}
+
+__global__ void sf_untile_kernel(const uint8_t* __restrict__ sf, uint8_t* __restrict__ out, int M, int G) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * G) return;
+  const int64_t row = i / G, g = i % G;
+  out[i] = sf[((row >> 7) * (G / 4) + (g >> 2)) * 512 + (row & 31) * 16 + ((row & 127) >> 5) * 4 + (g & 3)];
+}
+
+int flux2b_op_gemm_mxfp8(flux2b_ctx* c, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N, int K,
+                         float* out, uint8_t* a8_out, uint8_t* sfa_out) {
+  F2B_TRY(check_ctx(c));
+  if (M < 1 || N % 128 || K % 128 || N < 128 || K < 128) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "mxfp8 GEMM needs N % 128 == 0 and K % 128 == 0");
+  const void *da, *dw, *ds;
+  F2B_TRY(dev_in(c, a16, (size_t)M * K * 2, &da));
+  F2B_TRY(dev_in(c, w_packed, (size_t)N * K, &dw));
+  F2B_TRY(dev_in(c, w_scales, (size_t)N * (K / 32), &ds));
+  void* dout; bool ho;
+  F2B_TRY(dev_out(c, out, (size_t)M * N * 4, &dout, &ho));
+  DevBuf w8, sfb, a8, sfa, sfa_plain;
+  F2B_CUDA(w8.alloc((size_t)N * K));
+  F2B_CUDA(sfb.alloc(mx8_sf_bytes(N, K)));
+  F2B_CUDA(a8.alloc((size_t)M * K));
+  F2B_CUDA(sfa.alloc(mx8_sf_bytes(M, K)));
+  F2B_CUDA(mx8_copy_rows((const uint8_t*)dw, (const uint8_t*)ds, 0, w8.as<uint8_t>(), sfb.as<uint8_t>(), 0, N, K, false, 0, c->stream));
+  {
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 3.0 * M * K);
+    F2B_CUDA(mx8_quantize_act(da, K, M, K, c->f16(), a8.as<uint8_t>(), sfa.as<uint8_t>(), c->stream));
+  }
+  GemmProblem g;
+  g.A = a8.p; g.lda = K; g.B = w8.p; g.ldb = K; g.M = M; g.N = N; g.K = K;
+  g.mx8 = 1; g.sfa = sfa.as<uint8_t>(); g.sfb = sfb.as<uint8_t>();
+  g.epi.mode = EPI_F32; g.epi.out = dout; g.epi.ldo = N;
+  {
+    ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * M * N * (double)K, (double)M * K + (double)N * K + 4.0 * M * N);
+    F2B_CUDA(gemm_launch(g, c->stream));
+  }
+  F2B_TRY(finish_out(c, out, dout, (size_t)M * N * 4, ho));
+  if (a8_out) F2B_CUDA(cudaMemcpyAsync(a8_out, a8.p, (size_t)M * K, is_device_ptr(a8_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  if (sfa_out) {
+    F2B_CUDA(sfa_plain.alloc((size_t)M * (K / 32)));
+    const int64_t n = (int64_t)M * (K / 32);
+    sf_untile_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(sfa.as<uint8_t>(), sfa_plain.as<uint8_t>(), M, K / 32);
+    F2B_CUDA(cudaGetLastError());
+    F2B_CUDA(cudaMemcpyAsync(sfa_out, sfa_plain.p, (size_t)n, is_device_ptr(sfa_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  }
+  return end_call(c, true);
 }
 
 int flux2b_op_attention(flux2b_ctx* c, const void* qkv16, int B, int S, int H, void* out16, int variant) {

@@ -82,6 +82,9 @@ struct Tensor {
 struct Lin {
   DevBuf w;
   int N = 0, K = 0;
+  // native block-scaled path (quant = mxfp8, option "native_mx"): E4M3 bytes [N, K] exactly as MLX packs them and the
+  // E8M0 group scales re-tiled into the tcgen05 scale-factor layout [N/128][K/128][32 x 16 B]
+  DevBuf w8, sfb;
 };
 struct DoubleBlockW {
   Lin qkv_img, qkv_txt, out_img, out_txt, ff_in_img, ff_out_img, ff_in_txt, ff_out_txt;
@@ -163,6 +166,7 @@ struct flux2b_ctx {
 
   // ---- workspaces (grown on demand)
   f2b::DevBuf ws_x, ws_xn, ws_qkv, ws_cat, ws_cos, ws_sin, ws_ids, ws_small, ws_hid16, ws_enc16, ws_out;
+  f2b::DevBuf ws_a8, ws_sfa;  // on-the-fly mxfp8 activations (native block-scaled path)
   f2b::DevBuf ws_rec;  // recorded block outputs
   int rec_S = 0, rec_count = 0;
   std::vector<f2b::DevBuf> vae_ws;

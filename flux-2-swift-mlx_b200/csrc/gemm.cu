@@ -37,18 +37,27 @@ struct KParams {
   // conv
   int taps, H, W, Cin, batch, tiles_x, tiles_y, kb_per_tap;
   Epilogue epi;
+  const uint8_t* sfa;  // mxfp8: scale factors of A [ceil(M/128)][K/128][512], of B [N/128][K/128][512]
+  const uint8_t* sfb;
   int dbg;  // FLUX2B_GEMM_TIMELINE=1: cluster 0 prints where its producer / issuer / epilogue warps waited (debug aid)
 };
 
-template <int BN, int CG>
+template <int BN, int CG, bool MX8 = false>
 struct Cfg {
   static constexpr int B_ROWS = BN / CG;
-  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int A_BYTES = BM * BK * 2;      // 128 rows x 128 B: 64 bf16 or 128 fp8 elements along K
   static constexpr int B_BYTES = B_ROWS * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SFA_BYTES = MX8 ? 512 : 0;                  // one 128-row x 4-group block
+  static constexpr int SFB_BYTES = MX8 ? (BN / 128) * 512 : 0;
+  static constexpr int SF_BYTES = SFA_BYTES + SFB_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + SF_BYTES;
   static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // accumulator stages in TMEM: two, except the 256-wide block-scaled tile, whose scale factors need columns too
+  static constexpr int ACC_STAGES = (MX8 && BN == 256) ? 1 : 2;
+  static constexpr int SF_COL0 = ACC_STAGES * BN;                  // SFA: 4 columns, SFB: BN / 32 columns behind them
+  static constexpr int COLS_NEEDED = ACC_STAGES * BN + (MX8 ? 4 + BN / 32 : 0);
+  static constexpr int TMEM_COLS = (COLS_NEEDED <= 32) ? 32 : (COLS_NEEDED <= 64) ? 64 : (COLS_NEEDED <= 128) ? 128 : (COLS_NEEDED <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
 };
@@ -241,19 +250,21 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN, int CG, bool CONV>
+template <int BN, int CG, bool CONV, bool MX8 = false>
 __global__ void __launch_bounds__(192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, MX8>;
+  static_assert(!MX8 || (CG == 1 && !CONV && (BN == 128 || BN == 256)), "block-scaled tiles: single CTA, BN 128 / 256");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;
   uint8_t* smB = smem + C::STAGES * C::A_BYTES;
+  uint8_t* smSF = smB + C::STAGES * C::B_BYTES;  // [STAGES][SFA 512 | SFB (BN/128) x 512]   (MX8 only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
   uint64_t* empty = bars + C::STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tfull = bars + 2 * C::STAGES;   // [2]       MMA -> epilogue
-  uint64_t* tempty = tfull + 2;             // [2]       epilogue -> MMA
+  uint64_t* tempty = tfull + 2;             // [2]       epilogue -> MMA   (only ACC_STAGES of each are used)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -321,8 +332,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_4d(a_dst, &tmA, &full[stage], c0, x0 + kx, y0 + ky, img);
               tma_load_3d(b_dst, &tmB, &full[stage], c0, tap, nrow0);
             } else {
-              tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_blk * BM);
-              tma_load_2d(b_dst, &tmB, &full[stage], kb * BK, nrow0);
+              // (tensor-map coordinates are in elements: 64 bf16 or 128 fp8 per 128 B row)
+              tma_load_2d(a_dst, &tmA, &full[stage], kb * (MX8 ? 2 * BK : BK), m_blk * BM);
+              tma_load_2d(b_dst, &tmB, &full[stage], kb * (MX8 ? 2 * BK : BK), nrow0);
+              if (MX8) {
+                uint8_t* sf = smSF + stage * C::SF_BYTES;
+                bulk_load(sf, p.sfa + ((size_t)m_blk * p.num_kb + kb) * 512, 512, &full[stage]);
+#pragma unroll
+                for (int i = 0; i < BN / 128; ++i)
+                  bulk_load(sf + 512 + i * 512, p.sfb + ((size_t)(n_blk * (BN / 128) + i) * p.num_kb + kb) * 512, 512, &full[stage]);
+              }
             }
           } else {
             const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
@@ -355,7 +374,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (leader) {
       const uint32_t idesc = make_idesc_f16(BM * CG, BN, p.epi.f16 == 0, false, false);
       const uint64_t desc_hi = make_smem_desc(0, 16, 1024, SWZ_128B);
-      const uint32_t a0 = smem_u32(smA) >> 4, b0 = smem_u32(smB) >> 4;
+      const uint64_t desc_sf = make_smem_desc(0, 0, 128, SWZ_NONE);  // 32 x 16 B block: 8-row atoms 128 B apart
+      const uint32_t a0 = smem_u32(smA) >> 4, b0 = smem_u32(smB) >> 4, sf0 = smem_u32(smSF) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -376,10 +396,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (elect_one()) {
             const uint64_t adesc = desc_hi + (a0 + stage * (C::A_BYTES >> 4));
             const uint64_t bdesc = desc_hi + (b0 + stage * (C::B_BYTES >> 4));
+            if constexpr (MX8) {
+              // stage this k-block's scale factors: SFA -> 4 columns, SFB -> 4 columns per 128 weight rows. tcgen05.cp
+              // and tcgen05.mma of one thread execute in issue order, so the single SF region needs no extra barrier.
+              const uint32_t t_sfa = tmem_base + C::SF_COL0, t_sfb = t_sfa + 4;
+              const uint32_t sfs = sf0 + stage * (C::SF_BYTES >> 4);
+              tmem_cp_32x128b_warpx4(t_sfa, desc_sf + sfs);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the 16 B-unit address field
-              umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              for (int i = 0; i < BN / 128; ++i) tmem_cp_32x128b_warpx4(t_sfb + 4 * i, desc_sf + (sfs + 32 + 32 * i));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)  // 32 fp8 elements (32 B) per MMA; scale-factor byte k of the staged columns
+                umma_mxf8_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf8(BM, BN, k), t_sfa, t_sfb, (kb | k) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the 16 B-unit address field
+                umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+              }
             }
             if (CG == 1) umma_commit(&empty[stage]); else umma_commit_cg2_mc(&empty[stage], 0x3);
             if (kb == p.num_kb - 1) {
@@ -389,7 +422,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
       if (dbg && lane == 0)
         printf("[gemm timeline] issuer: total %lld clk, waited on operands %lld clk, on accumulator drain %lld clk (%d k-blocks / tile)\n",
@@ -428,7 +461,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (CG == 1) mbar_arrive(&tempty[acc]);
         else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -461,14 +494,20 @@ bool gemm_init() {
   return g_encode != nullptr && g_num_sms > 0;
 }
 
+static bool make_tmap(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box);
 bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box) {
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+static bool make_tmap(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box) {
   cuuint64_t gd[5];
   cuuint64_t gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = g_encode(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -478,9 +517,9 @@ bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* 
   return true;
 }
 
-template <int BN, int CG, bool CONV>
+template <int BN, int CG, bool CONV, bool MX8 = false>
 static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, MX8>;
   KParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.epi = g.epi;
@@ -505,6 +544,18 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     uint64_t bs[3] = {(uint64_t)g.Cin * 2, (uint64_t)g.Cin * 2 * g.conv_taps, (uint64_t)g.Cin * 2 * g.conv_taps * g.N};
     uint32_t bb[4] = {BK, 1, (uint32_t)C::B_ROWS, 1};
     if (!make_tmap_bf16(&tmB, g.B, CG == 2 ? 4 : 3, bd, bs, bb)) return cudaErrorInvalidValue;
+  } else if (MX8) {
+    p.num_kb = g.K / 128;
+    p.sfa = g.sfa; p.sfb = g.sfb;
+    num_m_blks = (g.M + BM - 1) / BM;
+    uint64_t ad[2] = {(uint64_t)g.K, (uint64_t)g.M};
+    uint64_t as[1] = {(uint64_t)g.lda};
+    uint32_t ab[2] = {128, BM};
+    if (!make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, g.A, 2, ad, as, ab)) return cudaErrorInvalidValue;
+    uint64_t bd[2] = {(uint64_t)g.K, (uint64_t)g.N};
+    uint64_t bs[1] = {(uint64_t)g.ldb};
+    uint32_t bb[2] = {128, (uint32_t)C::B_ROWS};
+    if (!make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, g.B, 2, bd, bs, bb)) return cudaErrorInvalidValue;
   } else {
     p.num_kb = (g.K + BK - 1) / BK;
     num_m_blks = (g.M + BM - 1) / BM;
@@ -523,7 +574,7 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   const int max_units = g_num_sms / CG;
   const int units = std::min(total, max_units);
 
-  auto kern = gemm_kernel<BN, CG, CONV>;
+  auto kern = gemm_kernel<BN, CG, CONV, MX8>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -568,6 +619,15 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
   }
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaSuccess;
   const bool conv = g.conv_taps != 0;
+  if (g.mx8) {
+    if (conv || g.K % 128 || g.N % 128 || g.lda % 16 || g.ldb % 16 || !g.sfa || !g.sfb) {
+      g_err = "mxfp8 GEMM needs K % 128 == 0, N % 128 == 0, 16 B row strides and both scale-factor tensors";
+      return cudaErrorInvalidValue;
+    }
+    if (g.epi.mode == EPI_SWIGLU && g.N % 256) { g_err = "SwiGLU epilogue needs N % 256 == 0"; return cudaErrorInvalidValue; }
+    const bool wide = g.N % 256 == 0 && g.force_bn != 128;
+    return wide ? launch_cfg<256, 1, false, true>(g, stream) : launch_cfg<128, 1, false, true>(g, stream);
+  }
   if (!conv && (g.lda % 8 || g.ldb % 8)) { g_err = "lda/ldb must be multiples of 8 elements (TMA 16 B stride)"; return cudaErrorInvalidValue; }
   if (conv && (g.Cin % 8 || g.lda % 8)) { g_err = "conv Cin / pixel stride must be multiples of 8"; return cudaErrorInvalidValue; }
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) { g_err = "A/B must be 16 B aligned"; return cudaErrorInvalidValue; }

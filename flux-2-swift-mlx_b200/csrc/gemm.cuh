@@ -50,6 +50,11 @@ struct GemmProblem {
   int conv_taps = 0;  // 0 = plain GEMM, 1 = 1x1, 9 = 3x3 (pad 1)
   int batch = 1, H = 0, W = 0, Cin = 0;
   Epilogue epi;
+  // native block-scaled mxfp8 (tcgen05.mma.kind::mxf8f6f4.block_scale): A, B are E4M3 bytes (lda / ldb in elements = bytes),
+  // sfa / sfb the E8M0 group scales in the tcgen05 scale-factor layout (quant.cuh); K % 128 == 0, single-CTA tiles
+  int mx8 = 0;
+  const uint8_t* sfa = nullptr;
+  const uint8_t* sfb = nullptr;
   int force_cta_group = 0;  // 0 = auto, 1, 2
   int force_bn = 0;         // 0 = auto
 };

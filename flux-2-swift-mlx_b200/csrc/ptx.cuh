@@ -165,6 +165,12 @@ __device__ __forceinline__ void tma_load_4d_cg2(void* dst, const CUtensorMap* m,
       "l"((uint64_t)m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// plain (non-tensor) bulk copy global -> shared, completion on an mbarrier (used for the 512 B scale-factor blocks)
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // smem -> global tiled store (bulk group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)m),
@@ -239,6 +245,26 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+// Instruction descriptor for kind::mxf8f6f4.block_scale with E4M3 x E4M3 operands and E8M0 scale factors (fp32 accumulate):
+//  [4,6) B scale-factor id | [7,10) A fmt (0 = E4M3) | [10,13) B fmt | [15] A major | [16] B major | [17,23) N>>3
+//  [23] scale fmt (1 = E8M0) | [24,29) M>>4 | [29,31) A scale-factor id  (id = which byte of the 32-bit TMEM column)
+__host__ __device__ constexpr uint32_t make_idesc_mxf8(int M, int N, uint32_t sf_id) {
+  return (sf_id << 4) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24) | (sf_id << 29);
+}
+// D[tmem] (+)= (A[smem] * SFA[tmem]) * (B[smem] * SFB[tmem]), K = 32 fp8 elements, one scale per operand row
+__device__ __forceinline__ void umma_mxf8_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t tmem_sfa,
+                                             uint32_t tmem_sfb, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+// smem (32 rows x 16 B, described by a no-swizzle K-major descriptor) -> TMEM lanes 0..31 x 4 columns, replicated into all
+// four lane quarters: the scale-factor staging copy. Executes in issue order with the tcgen05.mma of the same thread.
+__device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,

@@ -10,6 +10,7 @@
 // All fp32 steps use explicit _rn intrinsics so that no FMA contraction can make the device disagree with the
 // C oracle (oracle/quant_oracle.c) by an ulp.
 #include "quant.cuh"
+#include <cuda_fp8.h>
 #include "ptx.cuh"
 
 namespace f2b {
@@ -262,6 +263,84 @@ cudaError_t lora_add(void* W, int w_dtype, const float* A, const float* B, int64
   const int64_t n = out_dim * in_dim;
   if (n <= 0) return cudaSuccess;
   lora_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(W, w_dtype, A, B, out_dim, in_dim, rank, scale);
+  return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------ native mxfp8 operands
+size_t mx8_sf_bytes(int64_t rows, int64_t K) { return (size_t)((rows + 127) / 128) * (K / 128) * 512; }
+__device__ __forceinline__ int64_t sf_offset(int64_t row, int64_t g, int64_t kb4) {
+  return ((row >> 7) * kb4 + (g >> 2)) * 512 + (row & 31) * 16 + ((row & 127) >> 5) * 4 + (g & 3);
+}
+__global__ void mx8_copy_rows_kernel(const uint8_t* __restrict__ src_w, const uint8_t* __restrict__ src_s, int64_t src_row0,
+                                     uint8_t* __restrict__ dst_w, uint8_t* __restrict__ dst_sf, int64_t dst_row0,
+                                     int64_t nrows, int64_t K, int tiled, int64_t Hm) {
+  const int64_t vec_per_row = K / 16;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows * vec_per_row) return;
+  const int64_t r = i / vec_per_row, v = i % vec_per_row;
+  int64_t sr = r;
+  if (tiled) {
+    const int64_t tile = r / 256, j = r % 256;
+    sr = (j < 128) ? tile * 128 + j : Hm + tile * 128 + (j - 128);
+  }
+  *reinterpret_cast<uint4*>(dst_w + (dst_row0 + r) * K + v * 16) = *reinterpret_cast<const uint4*>(src_w + (src_row0 + sr) * K + v * 16);
+  if ((v & 1) == 0) {  // one scale per 32 elements = per two 16 B vectors
+    const int64_t g = v >> 1;
+    dst_sf[sf_offset(dst_row0 + r, g, K / 128)] = src_s[(src_row0 + sr) * (K / 32) + g];
+  }
+}
+cudaError_t mx8_copy_rows(const uint8_t* src_w, const uint8_t* src_s, int64_t src_row0, uint8_t* dst_w, uint8_t* dst_sf,
+                          int64_t dst_row0, int64_t nrows, int64_t K, bool tiled, int64_t Hm, cudaStream_t s) {
+  if (K % 128) return cudaErrorInvalidValue;
+  const int64_t n = nrows * (K / 16);
+  if (n <= 0) return cudaSuccess;
+  mx8_copy_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src_w, src_s, src_row0, dst_w, dst_sf, dst_row0, nrows, K, tiled ? 1 : 0, Hm);
+  return cudaGetLastError();
+}
+// one warp per (row, 128-element K block): lane owns 4 consecutive elements, 8 lanes share a 32-element group
+__global__ void __launch_bounds__(256) mx8_quantize_act_kernel(const void* __restrict__ x, int64_t ldx, int M, int K, bool f16,
+                                                              uint8_t* __restrict__ a8, uint8_t* __restrict__ sfa) {
+  const int kb4 = K / 128;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t Mpad = ((int64_t)M + 127) / 128 * 128;
+  if (wid >= Mpad * kb4) return;
+  const int64_t row = wid / kb4;
+  const int kb = (int)(wid % kb4);
+  if (row >= M) {  // padding rows of the last 128-row block: scale 1.0 (never multiplied with anything but zeros)
+    if (lane < 4) sfa[sf_offset(row, kb * 4 + lane, kb4)] = 127;
+    return;
+  }
+  const uint16_t* xr = reinterpret_cast<const uint16_t*>(x) + row * ldx + kb * 128 + lane * 4;
+  const uint2 raw = *reinterpret_cast<const uint2*>(xr);
+  float2 a, b;
+  if (f16) { a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)); b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y)); }
+  else { a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x)); b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y)); }
+  float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y)));
+#pragma unroll
+  for (int o = 4; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));  // 8 lanes = one 32-element group
+  // smallest power of two s with amax / s <= 448  (exponent arithmetic only)
+  int e = -127;
+  if (amax > 0.f) {
+    const float q = amax * (1.0f / 448.0f);
+    const uint32_t u = __float_as_uint(q);
+    e = (int)((u >> 23) & 0xff) - 127 + ((u & 0x7fffff) ? 1 : 0);
+    e = e < -127 ? -127 : (e > 127 ? 127 : e);
+  }
+  const uint32_t ebits = (uint32_t)(127 - e);                                      // biased exponent of 2^-e, in [0, 254]
+  const float inv = __uint_as_float(ebits ? (ebits << 23) : 0x00400000u);          // 2^-e (2^-127 is subnormal)
+  const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a.x * inv, a.y * inv), __NV_SATFINITE, __NV_E4M3);
+  const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(b.x * inv, b.y * inv), __NV_SATFINITE, __NV_E4M3);
+  *reinterpret_cast<uint32_t*>(a8 + row * K + kb * 128 + lane * 4) = (uint32_t)lo | ((uint32_t)hi << 16);
+  if ((lane & 7) == 0) sfa[sf_offset(row, kb * 4 + (lane >> 3), kb4)] = (uint8_t)(e + 127);
+}
+cudaError_t mx8_quantize_act(const void* x16, int64_t ldx, int M, int K, bool f16, uint8_t* a8, uint8_t* sfa, cudaStream_t s) {
+  if (K % 128 || ldx % 4) return cudaErrorInvalidValue;
+  const int64_t Mpad = ((int64_t)M + 127) / 128 * 128;
+  const int64_t warps = Mpad * (K / 128);
+  if (warps <= 0) return cudaSuccess;
+  mx8_quantize_act_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(x16, ldx, M, K, f16, a8, sfa);
   return cudaGetLastError();
 }
 

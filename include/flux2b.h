@@ -79,7 +79,10 @@ int flux2b_set_stream(flux2b_ctx* ctx, void* cuda_stream);
 int flux2b_synchronize(flux2b_ctx* ctx);
 /* options: "compute_f16" (0 = bf16 activations [default], 1 = f16), "fuse_qk_rope" (1), "fuse_swiglu" (1),
  * "attn_variant" (0 auto | 1 | 2), "gemm_cta_group" (0 auto | 1 | 2), "keep_raw_weights" (1), "vae_f16" (1),
- * "uint8_round" (0 = truncate like MLX asType(.uint8) [default], 1 = round to nearest) */
+ * "uint8_round" (0 = truncate like MLX asType(.uint8) [default], 1 = round to nearest),
+ * "native_mx" (0 = W-only: x · dequant(W)^T through the 16-bit GEMM [default, matches the reference's arithmetic];
+ *  1 = with quant = mxfp8 the block linears run on tcgen05 block-scaled MMA with on-the-fly mxfp8 activations: faster,
+ *  but activations carry E4M3 precision — set before flux2b_finalize_weights) */
 int flux2b_set_option(flux2b_ctx* ctx, const char* name, int value);
 
 /* ------------------------------------------------------------------ weights (Loading/WeightLoader.swift:567-623)
@@ -224,6 +227,12 @@ int64_t flux2b_launch_count(flux2b_ctx* ctx);
  * 0 = store 16-bit (+bias), 1 = store f32 (+bias), 2 = out_f32 = res + gate*acc, 3 = SwiGLU (W rows pre-tiled), */
 int flux2b_op_gemm(flux2b_ctx* ctx, const void* a16, const void* w16, int M, int N, int K, int epilogue, void* out,
                    const float* bias, const float* gate, const float* res, int cta_group, int bn);
+/* native block-scaled GEMM (tcgen05.mma.kind::mxf8f6f4.block_scale): C[M,N] f32 = mxfp8(A)[M,K] · W[N,K]^T where W arrives
+ * exactly as MLX packs an mxfp8 Linear (weight uint32 [N, K/4] = E4M3 bytes, scales uint8 [N, K/32] E8M0) and A (16-bit)
+ * is quantised on the fly to E4M3 with one E8M0 scale per 32 elements. K % 128 == 0, N % 128 == 0.
+ * a8_out / sfa_out (optional, host or device): the quantised activation bytes [M, K] and their scales [M, K/32]. */
+int flux2b_op_gemm_mxfp8(flux2b_ctx* ctx, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N, int K,
+                         float* out, uint8_t* a8_out, uint8_t* sfa_out);
 int flux2b_op_attention(flux2b_ctx* ctx, const void* qkv16 /* [B*S, 3*H*128] */, int B, int S, int H, void* out16 /* [B*S, H*128] */,
                         int variant);
 int flux2b_op_ln_modulate(flux2b_ctx* ctx, const float* x, int rows, int D, const float* shift, const float* scale, void* out16);

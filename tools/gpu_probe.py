@@ -147,6 +147,37 @@ def probe_dit(name, fuse_qk=1, fuse_swiglu=1, attn_variant=0, cg=0, f16=0, S_img
                 "gpu_s_first_call": round(t_gpu, 3), "cpu_oracle_s": round(t_cpu, 2)}
 
 
+def probe_gemm_mx8(M, N, K, iters=5):
+    """native block-scaled mxfp8 GEMM: exact check against decode(a8) * 2^(sfa-127) @ dequant(W)^T in fp64."""
+    import numpy as np
+    import torch
+    import flux2b
+    from oracle import quant_oracle as Q
+    ctx = flux2b.Context()
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, K // 32, generator=g)).repeat_interleave(32, dim=1)
+    a = a.to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.05).half().numpy()
+    packed, scales, _ = Q.quantize(3, w)
+    out, a8, sfa = ctx.op_gemm_mxfp8(a.cuda(), packed, scales, return_quantized=True)
+    ctx.synchronize()
+    L = Q.lib()
+    tab = np.array([L.oracle_from_e4m3(i) for i in range(256)], dtype=np.float64)
+    A_deq = tab[a8] * np.exp2(sfa.astype(np.float64).repeat(32, axis=1) - 127.0)
+    W_deq = Q.dequantize(3, packed, scales, None, K).astype(np.float64)
+    ref = A_deq @ W_deq.T
+    err = rel_l2(out.cpu(), torch.from_numpy(ref))
+    qerr = rel_l2(torch.from_numpy(A_deq), a.double())
+    amax_ok = bool(np.all(np.abs(tab[a8]) <= 448))
+    ctx.prof_enable(True); ctx.prof_reset()
+    for _ in range(iters):
+        ctx.op_gemm_mxfp8(a.cuda(), packed, scales)
+    p = ctx.prof_get(flux2b.PROF_GEMM)
+    tf = p["flops"] / (p["ms"] * 1e-3) / 1e12 if p["ms"] > 0 else 0
+    return err < 1e-5 and qerr < 0.05 and amax_ok, {"rel_l2_vs_exact_emulation": err, "activation_quant_rel_err": qerr,
+                                                    "tflops": round(tf, 1), "ms": round(p["ms"] / iters, 4)}
+
+
 def probe_quant(quant):
     import numpy as np
     import torch
@@ -200,6 +231,11 @@ PROBES = {
     "gemm_ffin_cg2": lambda: probe_gemm(4608, 18432, 3072, 3, 2),
     "gemm_out_cg1": lambda: probe_gemm(4608, 3072, 12288, 2, 1),
     "gemm_out_cg2": lambda: probe_gemm(4608, 3072, 12288, 2, 2),
+    "mx8_small": lambda: probe_gemm_mx8(128, 128, 128),
+    "mx8_k512": lambda: probe_gemm_mx8(256, 256, 512),
+    "mx8_tail": lambda: probe_gemm_mx8(300, 384, 256),
+    "mx8_big": lambda: probe_gemm_mx8(4608, 3072, 3072, iters=3),
+    "mx8_ffin": lambda: probe_gemm_mx8(4608, 18432, 3072, iters=2),
     "attn_v1_small": lambda: probe_attention(1, 256, 2, 1),
     "attn_v2_small": lambda: probe_attention(1, 256, 2, 2),
     "attn_v1_tail": lambda: probe_attention(2, 328, 2, 1),
