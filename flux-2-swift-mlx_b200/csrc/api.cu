@@ -365,51 +365,52 @@ int flux2b_op_gemm(flux2b_ctx* c, const void* a16, const void* w16, int M, int N
   return end_call(c, false);
 }
 
-__global__ void sf_untile_kernel(const uint8_t* __restrict__ sf, uint8_t* __restrict__ out, int M, int G) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)M * G) return;
-  const int64_t row = i / G, g = i % G;
-  out[i] = sf[((row >> 7) * (G / 4) + (g >> 2)) * 512 + (row & 31) * 16 + ((row & 127) >> 5) * 4 + (g & 3)];
-}
-
-int flux2b_op_gemm_mxfp8(flux2b_ctx* c, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N, int K,
-                         float* out, uint8_t* a8_out, uint8_t* sfa_out) {
+int flux2b_op_gemm_mx(flux2b_ctx* c, int quant, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N,
+                      int K, float* out, uint8_t* aq_out, uint8_t* sfa_out, int bn) {
   F2B_TRY(check_ctx(c));
-  if (M < 1 || N % 128 || K % 128 || N < 128 || K < 128) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "mxfp8 GEMM needs N % 128 == 0 and K % 128 == 0");
+  const int kind = mx_kind_of_quant(quant);
+  if (!kind) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "block-scaled GEMM: quant must be mxfp8, mxfp4 or nvfp4");
+  const int kbe = kind == 1 ? 128 : 256, group = kind == 3 ? 16 : 32, bits = kind == 1 ? 8 : 4;
+  if (M < 1 || N % 128 || K % kbe || N < 128 || K < kbe)
+    return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "block-scaled GEMM needs N % 128 == 0 and K % 128 (fp8) / 256 (fp4) == 0");
+  const size_t wrow = (size_t)K * bits / 8, G = (size_t)K / group;
   const void *da, *dw, *ds;
   F2B_TRY(dev_in(c, a16, (size_t)M * K * 2, &da));
-  F2B_TRY(dev_in(c, w_packed, (size_t)N * K, &dw));
-  F2B_TRY(dev_in(c, w_scales, (size_t)N * (K / 32), &ds));
+  F2B_TRY(dev_in(c, w_packed, (size_t)N * wrow, &dw));
+  F2B_TRY(dev_in(c, w_scales, (size_t)N * G, &ds));
   void* dout; bool ho;
   F2B_TRY(dev_out(c, out, (size_t)M * N * 4, &dout, &ho));
-  DevBuf w8, sfb, a8, sfa, sfa_plain;
-  F2B_CUDA(w8.alloc((size_t)N * K));
-  F2B_CUDA(sfb.alloc(mx8_sf_bytes(N, K)));
-  F2B_CUDA(a8.alloc((size_t)M * K));
-  F2B_CUDA(sfa.alloc(mx8_sf_bytes(M, K)));
-  F2B_CUDA(mx8_copy_rows((const uint8_t*)dw, (const uint8_t*)ds, 0, w8.as<uint8_t>(), sfb.as<uint8_t>(), 0, N, K, false, 0, c->stream));
+  DevBuf wq, sfb, aq, sfa, sfa_plain;
+  F2B_CUDA(wq.alloc((size_t)N * wrow));
+  F2B_CUDA(sfb.alloc(mx_sf_bytes(kind, N, K)));
+  F2B_CUDA(aq.alloc((size_t)M * wrow));
+  F2B_CUDA(sfa.alloc(mx_sf_bytes(kind, M, K)));
+  F2B_CUDA(mx_copy_rows(kind, (const uint8_t*)dw, (const uint8_t*)ds, 0, wq.as<uint8_t>(), sfb.as<uint8_t>(), 0, N, K, false, 0, c->stream));
   {
-    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 3.0 * M * K);
-    F2B_CUDA(mx8_quantize_act(da, K, M, K, c->f16(), a8.as<uint8_t>(), sfa.as<uint8_t>(), c->stream));
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (2.0 + bits / 8.0) * M * K);
+    F2B_CUDA(mx_quantize_act(kind, da, K, M, K, c->f16(), aq.as<uint8_t>(), (int64_t)wrow, sfa.as<uint8_t>(), mx_sf_ld(kind, K), 0, c->stream));
   }
   GemmProblem g;
-  g.A = a8.p; g.lda = K; g.B = w8.p; g.ldb = K; g.M = M; g.N = N; g.K = K;
-  g.mx8 = 1; g.sfa = sfa.as<uint8_t>(); g.sfb = sfb.as<uint8_t>();
+  g.A = aq.p; g.lda = (int64_t)wrow; g.B = wq.p; g.ldb = (int64_t)wrow; g.M = M; g.N = N; g.K = K;
+  g.mx = kind; g.sfa = sfa.as<uint8_t>(); g.sfb = sfb.as<uint8_t>();
   g.epi.mode = EPI_F32; g.epi.out = dout; g.epi.ldo = N;
+  g.force_bn = bn;
   {
-    ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * M * N * (double)K, (double)M * K + (double)N * K + 4.0 * M * N);
+    ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * M * N * (double)K, ((double)M + N) * wrow + 4.0 * M * N);
     F2B_CUDA(gemm_launch(g, c->stream));
   }
   F2B_TRY(finish_out(c, out, dout, (size_t)M * N * 4, ho));
-  if (a8_out) F2B_CUDA(cudaMemcpyAsync(a8_out, a8.p, (size_t)M * K, is_device_ptr(a8_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  if (aq_out) F2B_CUDA(cudaMemcpyAsync(aq_out, aq.p, (size_t)M * wrow, is_device_ptr(aq_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
   if (sfa_out) {
-    F2B_CUDA(sfa_plain.alloc((size_t)M * (K / 32)));
-    const int64_t n = (int64_t)M * (K / 32);
-    sf_untile_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(sfa.as<uint8_t>(), sfa_plain.as<uint8_t>(), M, K / 32);
-    F2B_CUDA(cudaGetLastError());
-    F2B_CUDA(cudaMemcpyAsync(sfa_out, sfa_plain.p, (size_t)n, is_device_ptr(sfa_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    F2B_CUDA(sfa_plain.alloc((size_t)M * G));
+    F2B_CUDA(mx_sf_untile(sfa.as<uint8_t>(), sfa_plain.as<uint8_t>(), M, (int64_t)G, c->stream));
+    F2B_CUDA(cudaMemcpyAsync(sfa_out, sfa_plain.p, (size_t)M * G, is_device_ptr(sfa_out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
   }
   return end_call(c, true);
+}
+int flux2b_op_gemm_mxfp8(flux2b_ctx* c, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N, int K,
+                         float* out, uint8_t* a8_out, uint8_t* sfa_out) {
+  return flux2b_op_gemm_mx(c, FLUX2B_MXFP8, a16, w_packed, w_scales, M, N, K, out, a8_out, sfa_out, 0);
 }
 
 int flux2b_op_attention(flux2b_ctx* c, const void* qkv16, int B, int S, int H, void* out16, int variant) {

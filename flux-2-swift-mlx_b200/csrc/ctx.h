@@ -82,9 +82,11 @@ struct Tensor {
 struct Lin {
   DevBuf w;
   int N = 0, K = 0;
-  // native block-scaled path (quant = mxfp8, option "native_mx"): E4M3 bytes [N, K] exactly as MLX packs them and the
-  // E8M0 group scales re-tiled into the tcgen05 scale-factor layout [N/128][K/128][32 x 16 B]
-  DevBuf w8, sfb;
+  // native block-scaled path (quant = mxfp8 / mxfp4 / nvfp4 with option "native_mx"): the element bytes [N, K*bits/8]
+  // exactly as MLX packs them (rows fused / re-tiled like `w`) and the group scales re-tiled into the tcgen05 scale-factor
+  // layout (quant.cuh). `w` is then not materialised.
+  DevBuf wq, sfb;
+  int mx = 0;  // 0 = dense 16-bit operand in `w`; 1 / 2 / 3 = mxfp8 / mxfp4 / nvfp4 operand in `wq` + `sfb`
 };
 struct DoubleBlockW {
   Lin qkv_img, qkv_txt, out_img, out_txt, ff_in_img, ff_out_img, ff_in_txt, ff_out_txt;
@@ -166,7 +168,10 @@ struct flux2b_ctx {
 
   // ---- workspaces (grown on demand)
   f2b::DevBuf ws_x, ws_xn, ws_qkv, ws_cat, ws_cos, ws_sin, ws_ids, ws_small, ws_hid16, ws_enc16, ws_out;
-  f2b::DevBuf ws_a8, ws_sfa;  // on-the-fly mxfp8 activations (native block-scaled path)
+  // on-the-fly block-scaled activations (native path): quantised XN and CAT, and their scale factors per row range
+  // (0 = text rows of XN, 1 = image rows / whole sequence of XN, 2 and 3 likewise for CAT)
+  f2b::DevBuf ws_aq_xn, ws_aq_cat, ws_sfa[4];
+  int mx_kind = 0;  // block-scaled kind the DiT block linears run in (0 = 16-bit operands); fixed at finalize
   f2b::DevBuf ws_rec;  // recorded block outputs
   int rec_S = 0, rec_count = 0;
   std::vector<f2b::DevBuf> vae_ws;

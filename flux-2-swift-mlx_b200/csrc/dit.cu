@@ -15,18 +15,39 @@
 
 namespace f2b {
 
-static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int M, int N_override, const void* Bptr,
-                    Epilogue epi, int kind = FLUX2B_PROF_GEMM, int K_override = 0) {
+// quantised view of an activation operand (native block-scaled path): element bytes + scale factors (quant.cuh layout)
+struct QView {
+  const uint8_t* q = nullptr;   // [rows, ldq bytes]
+  int64_t ldq = 0;
+  const uint8_t* sf = nullptr;  // first 512 B block of the operand's K range
+  int sf_ld = 0;                // blocks per 128-row block
+};
+
+// C = A · W^T (+ epilogue). k_off / K_override select a K-slice of W (the single-stream out projection split under SP).
+// Weights in block-scaled form (W.mx) need the activation's QView; the 16-bit A pointer is then unused.
+static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int M, Epilogue epi, const QView* qa = nullptr,
+                    int64_t k_off = 0, int K_override = 0) {
   GemmProblem g;
-  g.A = A; g.lda = lda;
-  g.B = Bptr ? Bptr : W.w.p; g.ldb = W.K;
-  g.M = M; g.N = N_override ? N_override : W.N; g.K = K_override ? K_override : W.K;
+  g.M = M; g.N = W.N; g.K = K_override ? K_override : W.K;
   epi.f16 = c->f16() ? 1 : 0;
   g.epi = epi;
-  g.force_cta_group = c->option("gemm_cta_group", 0);
+  double bytes;
+  if (W.mx) {
+    if (!qa || !qa->q) return fail(FLUX2B_ERR_GENERATION_FAILED, "internal: block-scaled weight without a quantised activation");
+    const int bits = W.mx == 1 ? 8 : 4, group = W.mx == 3 ? 16 : 32;
+    g.mx = W.mx;
+    g.A = qa->q; g.lda = qa->ldq; g.sfa = qa->sf; g.sfa_ld = qa->sf_ld;
+    g.B = W.wq.as<uint8_t>() + k_off * bits / 8; g.ldb = (int64_t)W.K * bits / 8;
+    g.sfb = W.sfb.as<uint8_t>() + (k_off / group / 4) * 512; g.sfb_ld = W.K / group / 4;
+    bytes = ((double)M + g.N) * g.K * bits / 8 + 2.0 * M * g.N;
+  } else {
+    g.A = A; g.lda = lda;
+    g.B = W.w.as<uint16_t>() + k_off; g.ldb = W.K;
+    g.force_cta_group = c->option("gemm_cta_group", 0);
+    bytes = 2.0 * ((double)M * g.K + (double)g.N * g.K + (double)M * g.N);
+  }
   const double flops = 2.0 * M * (double)g.N * g.K;
-  const double bytes = 2.0 * ((double)M * g.K + (double)g.N * g.K + (double)M * g.N);
-  ProfScope ps(c, kind, flops, bytes);
+  ProfScope ps(c, FLUX2B_PROF_GEMM, flops, bytes);
   F2B_CUDA(gemm_launch(g, c->stream));
   return 0;
 }
@@ -43,6 +64,12 @@ static int ensure_ws(flux2b_ctx* c, int S, int S_img, int S_txt) {
   F2B_CUDA(c->ws_small.ensure((size_t)(32 * D + 1024) * 4));
   F2B_CUDA(c->ws_hid16.ensure((size_t)S_img * c->dit.in_channels * 2));
   F2B_CUDA(c->ws_enc16.ensure((size_t)S_txt * c->dit.joint_attention_dim * 2));
+  if (c->mx_kind) {
+    const int bits = c->mx_kind == 1 ? 8 : 4;
+    F2B_CUDA(c->ws_aq_xn.ensure((size_t)S * D * bits / 8));
+    F2B_CUDA(c->ws_aq_cat.ensure((size_t)S * (D + Hm) * bits / 8));
+    for (int i = 0; i < 4; ++i) F2B_CUDA(c->ws_sfa[i].ensure(mx_sf_bytes(c->mx_kind, S, D + Hm)));
+  }
   return 0;
 }
 
@@ -229,7 +256,7 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
                          cfg.in_channels, f16, st));
     }
     Epilogue e; e.mode = EPI_F32; e.out = Ximg; e.ldo = D;
-    F2B_TRY(run_gemm(c, hid16, cfg.in_channels, c->x_embed, S_im_all, 0, nullptr, e));
+    F2B_TRY(run_gemm(c, hid16, cfg.in_channels, c->x_embed, S_im_all, e));
     uint16_t* enc16 = c->ws_enc16.as<uint16_t>();
     {
       ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)S_txt * cfg.joint_attention_dim * 6);
@@ -238,16 +265,39 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
       else F2B_CUDA(any16_to_16(enc, enc_dtype == FLUX2B_F16, enc16, f16, n, st));
     }
     Epilogue e2; e2.mode = EPI_F32; e2.out = X; e2.ldo = D;
-    F2B_TRY(run_gemm(c, enc16, cfg.joint_attention_dim, c->ctx_embed, S_txt, 0, nullptr, e2));
+    F2B_TRY(run_gemm(c, enc16, cfg.joint_attention_dim, c->ctx_embed, S_txt, e2));
   }
 
   const bool fuse_qk = c->option("fuse_qk_rope", 1) != 0;
-  auto ln_mod = [&](const float* x, int rows, const float* shift, const float* scale, uint16_t* o) -> int {
-    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * D * 6);
-    F2B_CUDA(ln_modulate(x, D, o, D, rows, D, shift, scale, 0, rows, 1e-6f, f16, st));
+  // ---- native block-scaled path: every block linear consumes its activation quantised on the fly to the weight's format.
+  // slot 0 / 1 = text rows / image rows (or the whole sequence) of XN, 2 / 3 likewise of CAT; `src` rows are quantised into
+  // the same row range of the slot's byte buffer, scale factors into the slot's own tile space (row 0 = first row of `src`).
+  const int mxk = c->mx_kind;
+  const int mx_bits = mxk == 1 ? 8 : 4, mx_grp = mxk == 3 ? 16 : 32;
+  auto quantize = [&](const uint16_t* src, int64_t ld, int rows, int K, int slot, int64_t row0, int64_t Ktot, int64_t col0,
+                      QView* qv) -> int {
+    if (!mxk) return 0;
+    uint8_t* base = (slot < 2 ? c->ws_aq_xn : c->ws_aq_cat).as<uint8_t>();
+    const int64_t ldq = Ktot * mx_bits / 8;
+    uint8_t* q = base + row0 * ldq + col0 * mx_bits / 8;
+    uint8_t* sf = c->ws_sfa[slot].as<uint8_t>();
+    const int sf_ld = (int)(Ktot / mx_grp / 4);
+    {
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * K * (2.0 + mx_bits / 8.0));
+      F2B_CUDA(mx_quantize_act(mxk, src, ld, rows, K, f16, q, ldq, sf, sf_ld, col0, st));
+    }
+    qv->q = q; qv->ldq = ldq; qv->sf = sf + (col0 / mx_grp / 4) * 512; qv->sf_ld = sf_ld;
     return 0;
   };
-  auto qkv_gemm = [&](const uint16_t* a, const Lin& W, int rows, int row0, const DevBuf& nq, const DevBuf& nk) -> int {
+  // LN + modulate of `rows` rows starting at XN row `row0` (slot 0 = text range, 1 = image range / everything)
+  auto ln_mod = [&](const float* x, int rows, const float* shift, const float* scale, uint16_t* o, int slot, QView* qv) -> int {
+    {
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * D * 6);
+      F2B_CUDA(ln_modulate(x, D, o, D, rows, D, shift, scale, 0, rows, 1e-6f, f16, st));
+    }
+    return quantize(o, D, rows, D, slot, (o - XN) / D, D, 0, qv);
+  };
+  auto qkv_gemm = [&](const uint16_t* a, const QView* qa, const Lin& W, int rows, int row0, const DevBuf& nq, const DevBuf& nk) -> int {
     Epilogue e;
     e.out = QKV + (size_t)row0 * 3 * D; e.ldo = 3 * D;
     if (fuse_qk) {
@@ -265,28 +315,28 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
           for (int d = 0; d < P; ++d) e.sp_base[d] = QKV + ((size_t)d * S + row0) * 3 * Dp;
         }
       }
-      F2B_TRY(run_gemm(c, a, D, W, rows, 0, nullptr, e));
+      F2B_TRY(run_gemm(c, a, D, W, rows, e, qa));
     } else {
       e.mode = EPI_BF16;
-      F2B_TRY(run_gemm(c, a, D, W, rows, 0, nullptr, e));
+      F2B_TRY(run_gemm(c, a, D, W, rows, e, qa));
       ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * D * 8);
       F2B_CUDA(qk_norm_rope(QKV + (size_t)row0 * 3 * D, 3 * D, rows, D, nq.as<float>(), nk.as<float>(),
                             cosT + (size_t)row0 * 128, sinT + (size_t)row0 * 128, 1e-6f, f16, st));
     }
     return 0;
   };
-  auto gate_res_gemm = [&](const uint16_t* a, int64_t lda, const Lin& W, int rows, float* x, const float* gate) -> int {
+  auto gate_res_gemm = [&](const uint16_t* a, int64_t lda, const QView* qa, const Lin& W, int rows, float* x, const float* gate) -> int {
     Epilogue e; e.mode = EPI_GATE_RES; e.out = x; e.ldo = D; e.res = x; e.ldr = D; e.gate = gate;
-    return run_gemm(c, a, lda, W, rows, 0, nullptr, e);
+    return run_gemm(c, a, lda, W, rows, e, qa);
   };
   // SwiGLU producer: out[rows, Hm] (leading dim ldo) = silu(gate) * value
-  auto swiglu_gemm = [&](const uint16_t* a, const Lin& W, bool tiled, int rows, uint16_t* o, int64_t ldo, uint16_t* scratch) -> int {
+  auto swiglu_gemm = [&](const uint16_t* a, const QView* qa, const Lin& W, bool tiled, int rows, uint16_t* o, int64_t ldo, uint16_t* scratch) -> int {
     if (tiled) {
       Epilogue e; e.mode = EPI_SWIGLU; e.out = o; e.ldo = (int)ldo;
-      return run_gemm(c, a, D, W, rows, 0, nullptr, e);
+      return run_gemm(c, a, D, W, rows, e, qa);
     }
     Epilogue e; e.mode = EPI_BF16; e.out = scratch; e.ldo = 2 * Hm;
-    F2B_TRY(run_gemm(c, a, D, W, rows, 0, nullptr, e));
+    F2B_TRY(run_gemm(c, a, D, W, rows, e, qa));
     ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * Hm * 6);
     F2B_CUDA(swiglu(scratch, 2 * Hm, o, ldo, rows, Hm, f16, st));
     return 0;
@@ -332,31 +382,37 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
   };
 
   // ---- double-stream blocks (Flux2TransformerBlock.swift:80-168)
+  QView q_img, q_txt, q_all, q_mlp;
   for (int i = 0; i < cfg.num_layers; ++i) {
     DoubleBlockW& b = c->dbl[i];
-    F2B_TRY(ln_mod(Ximg, S_im_all, mod_img + 0, mod_img + D, XN + (size_t)S_txt * D));
-    F2B_TRY(ln_mod(X, S_txt, mod_txt + 0, mod_txt + D, XN));
-    F2B_TRY(qkv_gemm(XN + (size_t)S_txt * D, b.qkv_img, S_im_all, S_txt, b.nq_img, b.nk_img));
-    F2B_TRY(qkv_gemm(XN, b.qkv_txt, S_txt, 0, b.nq_txt, b.nk_txt));
+    uint16_t* XNi = XN + (size_t)S_txt * D;
+    F2B_TRY(ln_mod(Ximg, S_im_all, mod_img + 0, mod_img + D, XNi, 1, &q_img));
+    F2B_TRY(ln_mod(X, S_txt, mod_txt + 0, mod_txt + D, XN, 0, &q_txt));
+    F2B_TRY(qkv_gemm(XNi, &q_img, b.qkv_img, S_im_all, S_txt, b.nq_img, b.nk_img));
+    F2B_TRY(qkv_gemm(XN, &q_txt, b.qkv_txt, S_txt, 0, b.nq_txt, b.nk_txt));
     F2B_TRY(full_attention(i, CAT, D));
-    F2B_TRY(gate_res_gemm(CAT + (size_t)S_txt * D, D, b.out_img, S_im_all, Ximg, mod_img + 2 * D));
-    F2B_TRY(gate_res_gemm(CAT, D, b.out_txt, S_txt, X, mod_txt + 2 * D));
-    F2B_TRY(ln_mod(Ximg, S_im_all, mod_img + 3 * D, mod_img + 4 * D, XN + (size_t)S_txt * D));
-    F2B_TRY(ln_mod(X, S_txt, mod_txt + 3 * D, mod_txt + 4 * D, XN));
+    F2B_TRY(quantize(CAT + (size_t)S_txt * D, D, S_im_all, D, 3, S_txt, D, 0, &q_img));
+    F2B_TRY(quantize(CAT, D, S_txt, D, 2, 0, D, 0, &q_txt));
+    F2B_TRY(gate_res_gemm(CAT + (size_t)S_txt * D, D, &q_img, b.out_img, S_im_all, Ximg, mod_img + 2 * D));
+    F2B_TRY(gate_res_gemm(CAT, D, &q_txt, b.out_txt, S_txt, X, mod_txt + 2 * D));
+    F2B_TRY(ln_mod(Ximg, S_im_all, mod_img + 3 * D, mod_img + 4 * D, XNi, 1, &q_img));
+    F2B_TRY(ln_mod(X, S_txt, mod_txt + 3 * D, mod_txt + 4 * D, XN, 0, &q_txt));
     uint16_t* Hbuf = CAT;                       // [S, Hm]
     uint16_t* scratch = CAT + (size_t)S * Hm;   // [S, 2Hm] unfused fallback
-    F2B_TRY(swiglu_gemm(XN + (size_t)S_txt * D, b.ff_in_img, b.ff_tiled, S_im_all, Hbuf + (size_t)S_txt * Hm, Hm, scratch));
-    F2B_TRY(gate_res_gemm(Hbuf + (size_t)S_txt * Hm, Hm, b.ff_out_img, S_im_all, Ximg, mod_img + 5 * D));
-    F2B_TRY(swiglu_gemm(XN, b.ff_in_txt, b.ff_tiled, S_txt, Hbuf, Hm, scratch));
-    F2B_TRY(gate_res_gemm(Hbuf, Hm, b.ff_out_txt, S_txt, X, mod_txt + 5 * D));
+    F2B_TRY(swiglu_gemm(XNi, &q_img, b.ff_in_img, b.ff_tiled, S_im_all, Hbuf + (size_t)S_txt * Hm, Hm, scratch));
+    F2B_TRY(quantize(Hbuf + (size_t)S_txt * Hm, Hm, S_im_all, Hm, 3, S_txt, Hm, 0, &q_img));
+    F2B_TRY(gate_res_gemm(Hbuf + (size_t)S_txt * Hm, Hm, &q_img, b.ff_out_img, S_im_all, Ximg, mod_img + 5 * D));
+    F2B_TRY(swiglu_gemm(XN, &q_txt, b.ff_in_txt, b.ff_tiled, S_txt, Hbuf, Hm, scratch));
+    F2B_TRY(quantize(Hbuf, Hm, S_txt, Hm, 2, 0, Hm, 0, &q_txt));
+    F2B_TRY(gate_res_gemm(Hbuf, Hm, &q_txt, b.ff_out_txt, S_txt, X, mod_txt + 5 * D));
     F2B_TRY(record_block(c, i, S));
   }
   // ---- single-stream blocks (Flux2SingleBlock.swift:59-98, Flux2ParallelAttention.swift:72-123)
   const int ldc = D + Hm;
   for (int i = 0; i < cfg.num_single_layers; ++i) {
     SingleBlockW& b = c->sgl[i];
-    F2B_TRY(ln_mod(X, S, mod_sgl + 0, mod_sgl + D, XN));
-    F2B_TRY(qkv_gemm(XN, b.qkv, S, 0, b.nq, b.nk));
+    F2B_TRY(ln_mod(X, S, mod_sgl + 0, mod_sgl + D, XN, 1, &q_all));
+    F2B_TRY(qkv_gemm(XN, &q_all, b.qkv, S, 0, b.nq, b.nk));
     uint16_t* scratch = CAT + (size_t)S * ldc;  // [S, 2Hm] unfused fallback lives behind CAT (see ensure_ws)
     if (P > 1 && c->sp.mode == 0 && c->option("sp_overlap", 1)) {
       // NCCL transport: hide both exchanges behind the MLP GEMMs of the block.
@@ -365,29 +421,35 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
       //   O all-to-all    ||  out GEMM over the MLP columns (K = Hm, no dependency on the attention)
       //   out GEMM over the attention columns (K = D)
       F2B_TRY(sp_exchange_qkv(c, S, true));
-      F2B_TRY(swiglu_gemm(XN, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
+      F2B_TRY(swiglu_gemm(XN, &q_all, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
+      F2B_TRY(quantize(CAT + D, ldc, S, Hm, 3, 0, ldc, D, &q_mlp));
       F2B_TRY(sp_join(c));
       F2B_TRY(sp_attend(c, S, CAT, ldc));
       F2B_TRY(sp_exchange_o(c, S, CAT, ldc, true));
       {
         Epilogue e; e.mode = EPI_GATE_RES; e.out = X; e.ldo = D; e.res = X; e.ldr = D; e.gate = mod_sgl + 2 * D;
-        F2B_TRY(run_gemm(c, CAT + D, ldc, b.out, S, 0, b.out.w.as<uint16_t>() + D, e, FLUX2B_PROF_GEMM, Hm));
+        F2B_TRY(run_gemm(c, CAT + D, ldc, b.out, S, e, &q_mlp, D, Hm));
         F2B_TRY(sp_join(c));
-        F2B_TRY(run_gemm(c, CAT, ldc, b.out, S, 0, nullptr, e, FLUX2B_PROF_GEMM, D));
+        F2B_TRY(quantize(CAT, ldc, S, D, 3, 0, ldc, 0, &q_all));
+        F2B_TRY(run_gemm(c, CAT, ldc, b.out, S, e, &q_all, 0, D));
       }
       F2B_TRY(record_block(c, cfg.num_layers + i, S));
       continue;
     }
-    F2B_TRY(swiglu_gemm(XN, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
+    F2B_TRY(swiglu_gemm(XN, &q_all, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
     F2B_TRY(full_attention(cfg.num_layers + i, CAT, ldc));
-    F2B_TRY(gate_res_gemm(CAT, ldc, b.out, S, X, mod_sgl + 2 * D));
+    F2B_TRY(quantize(CAT, ldc, S, ldc, 3, 0, ldc, 0, &q_all));
+    F2B_TRY(gate_res_gemm(CAT, ldc, &q_all, b.out, S, X, mod_sgl + 2 * D));
     F2B_TRY(record_block(c, cfg.num_layers + i, S));
   }
   // ---- output: AdaLayerNormContinuous (scale first, Flux2Modulation.swift:146-148) + projOut (:321-324)
   float* Xout = X + (size_t)(S_txt + S_mid) * D;
-  F2B_TRY(ln_mod(Xout, S_img, mod_out + D, mod_out + 0, XN));
+  {
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)S_img * D * 6);
+    F2B_CUDA(ln_modulate(Xout, D, XN, D, S_img, D, mod_out + D, mod_out + 0, 0, S_img, 1e-6f, f16, st));
+  }
   Epilogue e; e.mode = EPI_F32; e.out = out; e.ldo = cfg.out_channels;
-  F2B_TRY(run_gemm(c, XN, D, c->proj_out, S_img, 0, nullptr, e));
+  F2B_TRY(run_gemm(c, XN, D, c->proj_out, S_img, e));
   if (P > 1) F2B_TRY(sp_all_gather_f32(c, out_full, (size_t)S_img * cfg.out_channels));
   (void)S_img_full;
   return 0;

@@ -37,26 +37,34 @@ struct KParams {
   // conv
   int taps, H, W, Cin, batch, tiles_x, tiles_y, kb_per_tap;
   Epilogue epi;
-  const uint8_t* sfa;  // mxfp8: scale factors of A [ceil(M/128)][K/128][512], of B [N/128][K/128][512]
+  // block-scaled kinds: scale factors of A [ceil(M/128)][sfa_ld][512 B], of B [N/128][sfb_ld][512 B]; one 512 B block =
+  // 128 rows x 4 scale bytes in the tcgen05 layout (quant.cuh); *_ld = blocks per 128-row block (the full K extent)
+  const uint8_t* sfa;
   const uint8_t* sfb;
+  int sfa_ld, sfb_ld;
   int dbg;  // FLUX2B_GEMM_TIMELINE=1: cluster 0 prints where its producer / issuer / epilogue warps waited (debug aid)
 };
 
-template <int BN, int CG, bool MX8 = false>
+// MXK: 0 = 16-bit operands, 1 = mxfp8 (E4M3, E8M0 scale / 32), 2 = mxfp4 (E2M1, E8M0 / 32), 3 = nvfp4 (E2M1, E4M3 / 16)
+template <int BN, int CG, int MXK = 0>
 struct Cfg {
   static constexpr int B_ROWS = BN / CG;
-  static constexpr int A_BYTES = BM * BK * 2;      // 128 rows x 128 B: 64 bf16 or 128 fp8 elements along K
+  static constexpr int A_BYTES = BM * BK * 2;      // 128 rows x 128 B: 64 bf16, 128 fp8 or 256 fp4 elements along K
   static constexpr int B_BYTES = B_ROWS * BK * 2;
-  static constexpr int SFA_BYTES = MX8 ? 512 : 0;                  // one 128-row x 4-group block
-  static constexpr int SFB_BYTES = MX8 ? (BN / 128) * 512 : 0;
+  static constexpr int KB_ELEMS = MXK == 0 ? BK : MXK == 1 ? 128 : 256;   // K elements per pipeline stage
+  // 512 B scale-factor blocks (128 rows x 4 scale bytes) per 128 operand rows per stage
+  static constexpr int SFPK = MXK == 0 ? 0 : MXK == 1 ? 1 : MXK == 2 ? 2 : 4;
+  static constexpr int SFA_BYTES = 512 * SFPK;
+  static constexpr int SFB_BYTES = (BN / 128) * 512 * SFPK;
   static constexpr int SF_BYTES = SFA_BYTES + SFB_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + SF_BYTES;
   static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // accumulator stages in TMEM: two, except the 256-wide block-scaled tile, whose scale factors need columns too
-  static constexpr int ACC_STAGES = (MX8 && BN == 256) ? 1 : 2;
-  static constexpr int SF_COL0 = ACC_STAGES * BN;                  // SFA: 4 columns, SFB: BN / 32 columns behind them
-  static constexpr int COLS_NEEDED = ACC_STAGES * BN + (MX8 ? 4 + BN / 32 : 0);
+  static constexpr int ACC_STAGES = (MXK && BN == 256) ? 1 : 2;
+  static constexpr int SF_COL0 = ACC_STAGES * BN;  // SFA: 4 columns per block, SFB: 4 per block per 128 rows, behind them
+  static constexpr int SF_COLS = MXK ? 4 * SFPK * (1 + BN / 128) : 0;
+  static constexpr int COLS_NEEDED = ACC_STAGES * BN + SF_COLS;
   static constexpr int TMEM_COLS = (COLS_NEEDED <= 32) ? 32 : (COLS_NEEDED <= 64) ? 64 : (COLS_NEEDED <= 128) ? 128 : (COLS_NEEDED <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
@@ -250,16 +258,16 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN, int CG, bool CONV, bool MX8 = false>
+template <int BN, int CG, bool CONV, int MXK = 0>
 __global__ void __launch_bounds__(192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
-  using C = Cfg<BN, CG, MX8>;
-  static_assert(!MX8 || (CG == 1 && !CONV && (BN == 128 || BN == 256)), "block-scaled tiles: single CTA, BN 128 / 256");
+  using C = Cfg<BN, CG, MXK>;
+  static_assert(!MXK || (CG == 1 && !CONV && (BN == 128 || BN == 256)), "block-scaled tiles: single CTA, BN 128 / 256");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;
   uint8_t* smB = smem + C::STAGES * C::A_BYTES;
-  uint8_t* smSF = smB + C::STAGES * C::B_BYTES;  // [STAGES][SFA 512 | SFB (BN/128) x 512]   (MX8 only)
+  uint8_t* smSF = smB + C::STAGES * C::B_BYTES;  // [STAGES][SFA SFPK x 512 | SFB (BN/128) x SFPK x 512]   (block-scaled only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
   uint64_t* empty = bars + C::STAGES;       // [STAGES]  MMA -> TMA
@@ -332,15 +340,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_4d(a_dst, &tmA, &full[stage], c0, x0 + kx, y0 + ky, img);
               tma_load_3d(b_dst, &tmB, &full[stage], c0, tap, nrow0);
             } else {
-              // (tensor-map coordinates are in elements: 64 bf16 or 128 fp8 per 128 B row)
-              tma_load_2d(a_dst, &tmA, &full[stage], kb * (MX8 ? 2 * BK : BK), m_blk * BM);
-              tma_load_2d(b_dst, &tmB, &full[stage], kb * (MX8 ? 2 * BK : BK), nrow0);
-              if (MX8) {
+              // (tensor-map coordinates are in elements: 64 bf16, or 128 bytes of fp8 / packed fp4, per 128 B row)
+              tma_load_2d(a_dst, &tmA, &full[stage], kb * (MXK ? 2 * BK : BK), m_blk * BM);
+              tma_load_2d(b_dst, &tmB, &full[stage], kb * (MXK ? 2 * BK : BK), nrow0);
+              if (MXK) {
                 uint8_t* sf = smSF + stage * C::SF_BYTES;
-                bulk_load(sf, p.sfa + ((size_t)m_blk * p.num_kb + kb) * 512, 512, &full[stage]);
+                bulk_load(sf, p.sfa + ((size_t)m_blk * p.sfa_ld + kb * C::SFPK) * 512, C::SFA_BYTES, &full[stage]);
 #pragma unroll
                 for (int i = 0; i < BN / 128; ++i)
-                  bulk_load(sf + 512 + i * 512, p.sfb + ((size_t)(n_blk * (BN / 128) + i) * p.num_kb + kb) * 512, 512, &full[stage]);
+                  bulk_load(sf + C::SFA_BYTES + i * C::SFPK * 512,
+                            p.sfb + ((size_t)(n_blk * (BN / 128) + i) * p.sfb_ld + kb * C::SFPK) * 512, C::SFPK * 512, &full[stage]);
               }
             }
           } else {
@@ -396,17 +405,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (elect_one()) {
             const uint64_t adesc = desc_hi + (a0 + stage * (C::A_BYTES >> 4));
             const uint64_t bdesc = desc_hi + (b0 + stage * (C::B_BYTES >> 4));
-            if constexpr (MX8) {
-              // stage this k-block's scale factors: SFA -> 4 columns, SFB -> 4 columns per 128 weight rows. tcgen05.cp
-              // and tcgen05.mma of one thread execute in issue order, so the single SF region needs no extra barrier.
-              const uint32_t t_sfa = tmem_base + C::SF_COL0, t_sfb = t_sfa + 4;
+            if constexpr (MXK != 0) {
+              // stage this k-block's scale factors: every 512 B block -> 4 TMEM columns (SFA: block j at +4j; SFB: block j
+              // of weight rows [128 i, 128 i + 128) at +4 (j * BN/128 + i), so the columns one MMA reads are adjacent).
+              // tcgen05.cp and tcgen05.mma of one thread execute in issue order: the single SF region needs no barrier.
+              constexpr int NB = BN / 128;
+              const uint32_t t_sfa = tmem_base + C::SF_COL0, t_sfb = t_sfa + 4 * C::SFPK;
               const uint32_t sfs = sf0 + stage * (C::SF_BYTES >> 4);
-              tmem_cp_32x128b_warpx4(t_sfa, desc_sf + sfs);
 #pragma unroll
-              for (int i = 0; i < BN / 128; ++i) tmem_cp_32x128b_warpx4(t_sfb + 4 * i, desc_sf + (sfs + 32 + 32 * i));
+              for (int j = 0; j < C::SFPK; ++j) tmem_cp_32x128b_warpx4(t_sfa + 4 * j, desc_sf + (sfs + 32 * j));
 #pragma unroll
-              for (int k = 0; k < 4; ++k)  // 32 fp8 elements (32 B) per MMA; scale-factor byte k of the staged columns
-                umma_mxf8_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf8(BM, BN, k), t_sfa, t_sfb, (kb | k) ? 1u : 0u);
+              for (int i = 0; i < NB; ++i)
+#pragma unroll
+                for (int j = 0; j < C::SFPK; ++j)
+                  tmem_cp_32x128b_warpx4(t_sfb + 4 * (j * NB + i), desc_sf + (sfs + 32 * C::SFPK + 32 * (i * C::SFPK + j)));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // 32 B of K per MMA: 32 fp8 or 64 fp4 elements
+                const uint32_t accum = (kb | k) ? 1u : 0u;
+                if constexpr (MXK == 1)       // one scale per row per MMA: byte k of the staged columns
+                  umma_mxf8_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf8(BM, BN, k), t_sfa, t_sfb, accum);
+                else if constexpr (MXK == 2)  // two scales (bytes 0,1 or 2,3) of block k / 2
+                  umma_mxf4_ss<false>(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf4(BM, BN, true, (k & 1) * 2),
+                                      t_sfa + 4 * (k >> 1), t_sfb + 4 * NB * (k >> 1), accum);
+                else                          // four scales = the whole column of block k
+                  umma_mxf4_ss<true>(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf4(BM, BN, false, 0),
+                                     t_sfa + 4 * k, t_sfb + 4 * NB * k, accum);
+              }
             } else {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
@@ -517,9 +541,9 @@ static bool make_tmap(CUtensorMap* m, CUtensorMapDataType dtype, const void* bas
   return true;
 }
 
-template <int BN, int CG, bool CONV, bool MX8 = false>
+template <int BN, int CG, bool CONV, int MXK = 0>
 static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
-  using C = Cfg<BN, CG, MX8>;
+  using C = Cfg<BN, CG, MXK>;
   KParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.epi = g.epi;
@@ -544,15 +568,18 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     uint64_t bs[3] = {(uint64_t)g.Cin * 2, (uint64_t)g.Cin * 2 * g.conv_taps, (uint64_t)g.Cin * 2 * g.conv_taps * g.N};
     uint32_t bb[4] = {BK, 1, (uint32_t)C::B_ROWS, 1};
     if (!make_tmap_bf16(&tmB, g.B, CG == 2 ? 4 : 3, bd, bs, bb)) return cudaErrorInvalidValue;
-  } else if (MX8) {
-    p.num_kb = g.K / 128;
+  } else if (MXK) {
+    p.num_kb = g.K / C::KB_ELEMS;
     p.sfa = g.sfa; p.sfb = g.sfb;
+    p.sfa_ld = g.sfa_ld ? g.sfa_ld : p.num_kb * C::SFPK;
+    p.sfb_ld = g.sfb_ld ? g.sfb_ld : p.num_kb * C::SFPK;
     num_m_blks = (g.M + BM - 1) / BM;
-    uint64_t ad[2] = {(uint64_t)g.K, (uint64_t)g.M};
+    const uint64_t kbytes = (MXK == 1) ? (uint64_t)g.K : (uint64_t)g.K / 2;  // fp4: two elements per byte, dense
+    uint64_t ad[2] = {kbytes, (uint64_t)g.M};
     uint64_t as[1] = {(uint64_t)g.lda};
     uint32_t ab[2] = {128, BM};
     if (!make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, g.A, 2, ad, as, ab)) return cudaErrorInvalidValue;
-    uint64_t bd[2] = {(uint64_t)g.K, (uint64_t)g.N};
+    uint64_t bd[2] = {kbytes, (uint64_t)g.N};
     uint64_t bs[1] = {(uint64_t)g.ldb};
     uint32_t bb[2] = {128, (uint32_t)C::B_ROWS};
     if (!make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, g.B, 2, bd, bs, bb)) return cudaErrorInvalidValue;
@@ -574,7 +601,7 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   const int max_units = g_num_sms / CG;
   const int units = std::min(total, max_units);
 
-  auto kern = gemm_kernel<BN, CG, CONV, MX8>;
+  auto kern = gemm_kernel<BN, CG, CONV, MXK>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -619,14 +646,23 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
   }
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaSuccess;
   const bool conv = g.conv_taps != 0;
-  if (g.mx8) {
-    if (conv || g.K % 128 || g.N % 128 || g.lda % 16 || g.ldb % 16 || !g.sfa || !g.sfb) {
-      g_err = "mxfp8 GEMM needs K % 128 == 0, N % 128 == 0, 16 B row strides and both scale-factor tensors";
+  if (g.mx) {
+    const int kb_elems = g.mx == 1 ? 128 : 256;
+    if (g.mx < 1 || g.mx > 3 || conv || g.K % kb_elems || g.N % 128 || g.lda % 16 || g.ldb % 16 || !g.sfa || !g.sfb ||
+        (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) {
+      g_err = "block-scaled GEMM needs K % 128 (fp8) / 256 (fp4) == 0, N % 128 == 0, 16 B aligned rows and both scale-factor tensors";
       return cudaErrorInvalidValue;
     }
     if (g.epi.mode == EPI_SWIGLU && g.N % 256) { g_err = "SwiGLU epilogue needs N % 256 == 0"; return cudaErrorInvalidValue; }
     const bool wide = g.N % 256 == 0 && g.force_bn != 128;
-    return wide ? launch_cfg<256, 1, false, true>(g, stream) : launch_cfg<128, 1, false, true>(g, stream);
+    switch (g.mx * 2 + (wide ? 1 : 0)) {
+      case 2: return launch_cfg<128, 1, false, 1>(g, stream);
+      case 3: return launch_cfg<256, 1, false, 1>(g, stream);
+      case 4: return launch_cfg<128, 1, false, 2>(g, stream);
+      case 5: return launch_cfg<256, 1, false, 2>(g, stream);
+      case 6: return launch_cfg<128, 1, false, 3>(g, stream);
+      default: return launch_cfg<256, 1, false, 3>(g, stream);
+    }
   }
   if (!conv && (g.lda % 8 || g.ldb % 8)) { g_err = "lda/ldb must be multiples of 8 elements (TMA 16 B stride)"; return cudaErrorInvalidValue; }
   if (conv && (g.Cin % 8 || g.lda % 8)) { g_err = "conv Cin / pixel stride must be multiples of 8"; return cudaErrorInvalidValue; }

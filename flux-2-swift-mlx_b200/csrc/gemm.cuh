@@ -50,11 +50,17 @@ struct GemmProblem {
   int conv_taps = 0;  // 0 = plain GEMM, 1 = 1x1, 9 = 3x3 (pad 1)
   int batch = 1, H = 0, W = 0, Cin = 0;
   Epilogue epi;
-  // native block-scaled mxfp8 (tcgen05.mma.kind::mxf8f6f4.block_scale): A, B are E4M3 bytes (lda / ldb in elements = bytes),
-  // sfa / sfb the E8M0 group scales in the tcgen05 scale-factor layout (quant.cuh); K % 128 == 0, single-CTA tiles
-  int mx8 = 0;
+  // native block-scaled operands (tcgen05.mma.kind::mxf8f6f4 / mxf4nvf4 .block_scale), single-CTA tiles:
+  //   mx = 1 mxfp8: E4M3 bytes, E8M0 scale per 32 elements, K % 128 == 0
+  //   mx = 2 mxfp4: E2M1 nibbles (two per byte, low nibble first), E8M0 scale per 32 elements, K % 256 == 0
+  //   mx = 3 nvfp4: E2M1 nibbles, E4M3 scale per 16 elements, K % 256 == 0
+  // A, B hold the element bytes exactly as MLX packs them (lda / ldb in BYTES); sfa / sfb are the group scales in the
+  // tcgen05 scale-factor layout (quant.cuh) and sfa_ld / sfb_ld their 512 B blocks per 128-row block (0 = K / (4 groups),
+  // larger when A / B is a K-slice of a wider matrix and sfa / sfb point at the slice's first block)
+  int mx = 0;
   const uint8_t* sfa = nullptr;
   const uint8_t* sfb = nullptr;
+  int sfa_ld = 0, sfb_ld = 0;
   int force_cta_group = 0;  // 0 = auto, 1, 2
   int force_bn = 0;         // 0 = auto
 };

@@ -261,6 +261,32 @@ __device__ __forceinline__ void umma_mxf8_ss(uint32_t tmem_d, uint64_t adesc, ui
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
       : "memory");
 }
+// Instruction descriptor for kind::mxf4nvf4.block_scale with E2M1 x E2M1 operands (K = 64 per instruction, fp32 accumulate):
+// same fields as above; A / B fmt 1 = E2M1 (packed, two per byte); [23] scale fmt: 0 = UE4M3 (nvfp4, one scale per 16
+// elements = all four bytes of the scale-factor column, sf_id 0), 1 = UE8M0 (mxfp4, one scale per 32 elements = two bytes of
+// the column, sf_id 0 or 2)
+__host__ __device__ constexpr uint32_t make_idesc_mxf4(int M, int N, bool ue8m0, uint32_t sf_id) {
+  return (sf_id << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((ue8m0 ? 1u : 0u) << 23) |
+         ((uint32_t)(M >> 4) << 24) | (sf_id << 29);
+}
+// D[tmem] (+)= (A * SFA) * (B * SFB), K = 64 fp4 elements; kBlock16: one scale per 16 elements (nvfp4), else per 32 (mxfp4)
+template <bool kBlock16>
+__device__ __forceinline__ void umma_mxf4_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t tmem_sfa,
+                                             uint32_t tmem_sfb, uint32_t accumulate) {
+  if constexpr (kBlock16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.scale_vec::4X [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+  }
+}
 // smem (32 rows x 16 B, described by a no-swizzle K-major descriptor) -> TMEM lanes 0..31 x 4 columns, replicated into all
 // four lane quarters: the scale-factor staging copy. Executes in issue order with the tcgen05.mma of the same thread.
 __device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {

@@ -11,6 +11,7 @@
 // C oracle (oracle/quant_oracle.c) by an ulp.
 #include "quant.cuh"
 #include <cuda_fp8.h>
+#include <algorithm>
 #include "ptx.cuh"
 
 namespace f2b {
@@ -267,40 +268,61 @@ cudaError_t lora_add(void* W, int w_dtype, const float* A, const float* B, int64
 }
 
 
-// ------------------------------------------------------------------ native mxfp8 operands
-size_t mx8_sf_bytes(int64_t rows, int64_t K) { return (size_t)((rows + 127) / 128) * (K / 128) * 512; }
-__device__ __forceinline__ int64_t sf_offset(int64_t row, int64_t g, int64_t kb4) {
-  return ((row >> 7) * kb4 + (g >> 2)) * 512 + (row & 31) * 16 + ((row & 127) >> 5) * 4 + (g & 3);
+// ------------------------------------------------------------------ native block-scaled operands (mxfp8 / mxfp4 / nvfp4)
+__host__ __device__ inline int mx_group(int kind) { return kind == 3 ? 16 : 32; }
+__host__ __device__ inline int mx_bits(int kind) { return kind == 1 ? 8 : 4; }
+int mx_kind_of_quant(int quant) { return quant == 3 ? 1 : quant == 4 ? 2 : quant == 5 ? 3 : 0; }
+int64_t mx_sf_ld(int kind, int64_t K) { return K / mx_group(kind) / 4; }
+size_t mx_sf_bytes(int kind, int64_t rows, int64_t K) { return (size_t)((rows + 127) / 128) * mx_sf_ld(kind, K) * 512; }
+__device__ __forceinline__ int64_t sf_offset(int64_t row, int64_t g, int64_t ld_blocks) {
+  return ((row >> 7) * ld_blocks + (g >> 2)) * 512 + (row & 31) * 16 + ((row & 127) >> 5) * 4 + (g & 3);
 }
-__global__ void mx8_copy_rows_kernel(const uint8_t* __restrict__ src_w, const uint8_t* __restrict__ src_s, int64_t src_row0,
-                                     uint8_t* __restrict__ dst_w, uint8_t* __restrict__ dst_sf, int64_t dst_row0,
-                                     int64_t nrows, int64_t K, int tiled, int64_t Hm) {
-  const int64_t vec_per_row = K / 16;
+__global__ void mx_copy_rows_kernel(const uint8_t* __restrict__ src_w, const uint8_t* __restrict__ src_s, int64_t src_row0,
+                                    uint8_t* __restrict__ dst_w, uint8_t* __restrict__ dst_sf, int64_t dst_row0,
+                                    int64_t nrows, int64_t row_bytes, int64_t G, int tiled, int64_t Hm) {
+  const int64_t vec_per_row = row_bytes / 16;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nrows * vec_per_row) return;
-  const int64_t r = i / vec_per_row, v = i % vec_per_row;
-  int64_t sr = r;
-  if (tiled) {
+  auto src_row = [&](int64_t r) {
+    if (!tiled) return r;
     const int64_t tile = r / 256, j = r % 256;
-    sr = (j < 128) ? tile * 128 + j : Hm + tile * 128 + (j - 128);
+    return (j < 128) ? tile * 128 + j : Hm + tile * 128 + (j - 128);
+  };
+  if (i < nrows * vec_per_row) {
+    const int64_t r = i / vec_per_row, v = i % vec_per_row;
+    *reinterpret_cast<uint4*>(dst_w + (dst_row0 + r) * row_bytes + v * 16) =
+        *reinterpret_cast<const uint4*>(src_w + (src_row0 + src_row(r)) * row_bytes + v * 16);
   }
-  *reinterpret_cast<uint4*>(dst_w + (dst_row0 + r) * K + v * 16) = *reinterpret_cast<const uint4*>(src_w + (src_row0 + sr) * K + v * 16);
-  if ((v & 1) == 0) {  // one scale per 32 elements = per two 16 B vectors
-    const int64_t g = v >> 1;
-    dst_sf[sf_offset(dst_row0 + r, g, K / 128)] = src_s[(src_row0 + sr) * (K / 32) + g];
+  if (i < nrows * G) {
+    const int64_t r = i / G, g = i % G;
+    dst_sf[sf_offset(dst_row0 + r, g, G / 4)] = src_s[(src_row0 + src_row(r)) * G + g];
   }
 }
-cudaError_t mx8_copy_rows(const uint8_t* src_w, const uint8_t* src_s, int64_t src_row0, uint8_t* dst_w, uint8_t* dst_sf,
-                          int64_t dst_row0, int64_t nrows, int64_t K, bool tiled, int64_t Hm, cudaStream_t s) {
-  if (K % 128) return cudaErrorInvalidValue;
-  const int64_t n = nrows * (K / 16);
+cudaError_t mx_copy_rows(int kind, const uint8_t* src_w, const uint8_t* src_s, int64_t src_row0, uint8_t* dst_w, uint8_t* dst_sf,
+                         int64_t dst_row0, int64_t nrows, int64_t K, bool tiled, int64_t Hm, cudaStream_t s) {
+  if (kind < 1 || kind > 3 || K % (kind == 1 ? 128 : 256)) return cudaErrorInvalidValue;
+  const int64_t row_bytes = K * mx_bits(kind) / 8, G = K / mx_group(kind);
+  const int64_t n = nrows * std::max(row_bytes / 16, G);
   if (n <= 0) return cudaSuccess;
-  mx8_copy_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src_w, src_s, src_row0, dst_w, dst_sf, dst_row0, nrows, K, tiled ? 1 : 0, Hm);
+  mx_copy_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src_w, src_s, src_row0, dst_w, dst_sf, dst_row0, nrows, row_bytes, G,
+                                                                  tiled ? 1 : 0, Hm);
   return cudaGetLastError();
 }
-// one warp per (row, 128-element K block): lane owns 4 consecutive elements, 8 lanes share a 32-element group
+
+__device__ __forceinline__ void unpack8(const uint4 raw, bool f16, float (&v)[8]) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = f16 ? __half22float2(*reinterpret_cast<const __half2*>(&w[j]))
+                         : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    v[2 * j] = f.x; v[2 * j + 1] = f.y;
+  }
+}
+// mxfp8: one warp per (row, 128-element K block): lane owns 4 consecutive elements, 8 lanes share a 32-element group.
+// The scale is 2^ceil(log2(amax / 448)) (nothing saturates) — an activation is quantised once and consumed at once, so it
+// need not follow the weight packer's round-to-nearest exponent rule.
 __global__ void __launch_bounds__(256) mx8_quantize_act_kernel(const void* __restrict__ x, int64_t ldx, int M, int K, bool f16,
-                                                              uint8_t* __restrict__ a8, uint8_t* __restrict__ sfa) {
+                                                              uint8_t* __restrict__ a8, int64_t lda, uint8_t* __restrict__ sfa,
+                                                              int64_t sf_ld, int g0) {
   const int kb4 = K / 128;
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -309,7 +331,7 @@ __global__ void __launch_bounds__(256) mx8_quantize_act_kernel(const void* __res
   const int64_t row = wid / kb4;
   const int kb = (int)(wid % kb4);
   if (row >= M) {  // padding rows of the last 128-row block: scale 1.0 (never multiplied with anything but zeros)
-    if (lane < 4) sfa[sf_offset(row, kb * 4 + lane, kb4)] = 127;
+    if (lane < 4) sfa[sf_offset(row, g0 + kb * 4 + lane, sf_ld)] = 127;
     return;
   }
   const uint16_t* xr = reinterpret_cast<const uint16_t*>(x) + row * ldx + kb * 128 + lane * 4;
@@ -332,15 +354,74 @@ __global__ void __launch_bounds__(256) mx8_quantize_act_kernel(const void* __res
   const float inv = __uint_as_float(ebits ? (ebits << 23) : 0x00400000u);          // 2^-e (2^-127 is subnormal)
   const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a.x * inv, a.y * inv), __NV_SATFINITE, __NV_E4M3);
   const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(b.x * inv, b.y * inv), __NV_SATFINITE, __NV_E4M3);
-  *reinterpret_cast<uint32_t*>(a8 + row * K + kb * 128 + lane * 4) = (uint32_t)lo | ((uint32_t)hi << 16);
-  if ((lane & 7) == 0) sfa[sf_offset(row, kb * 4 + (lane >> 3), kb4)] = (uint8_t)(e + 127);
+  *reinterpret_cast<uint32_t*>(a8 + row * lda + kb * 128 + lane * 4) = (uint32_t)lo | ((uint32_t)hi << 16);
+  if ((lane & 7) == 0) sfa[sf_offset(row, g0 + kb * 4 + (lane >> 3), sf_ld)] = (uint8_t)(e + 127);
 }
-cudaError_t mx8_quantize_act(const void* x16, int64_t ldx, int M, int K, bool f16, uint8_t* a8, uint8_t* sfa, cudaStream_t s) {
-  if (K % 128 || ldx % 4) return cudaErrorInvalidValue;
+// fp4 kinds: one warp per (row, 256-element K block): lane owns 8 consecutive elements (16 B in, 4 B out); a 16-element
+// nvfp4 group is 2 lanes, a 32-element mxfp4 group 4 lanes. Same arithmetic as the weight packer above (amax / 6 -> E4M3 or
+// E8M0 scale, x / scale -> E2M1 RNE), so the result is bit-identical to quantize_kernel / the C oracle on the same matrix.
+template <bool kNv>
+__global__ void __launch_bounds__(256) mx4_quantize_act_kernel(const void* __restrict__ x, int64_t ldx, int M, int K, bool f16,
+                                                              uint8_t* __restrict__ a4, int64_t lda, uint8_t* __restrict__ sfa,
+                                                              int64_t sf_ld, int g0) {
+  constexpr int GPB = kNv ? 16 : 8;  // groups per 256-element block
+  const int kbn = K / 256;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   const int64_t Mpad = ((int64_t)M + 127) / 128 * 128;
-  const int64_t warps = Mpad * (K / 128);
+  if (wid >= Mpad * kbn) return;
+  const int64_t row = wid / kbn;
+  const int kb = (int)(wid % kbn);
+  if (row >= M) {  // padding rows: scale 1.0
+    if (lane < GPB) sfa[sf_offset(row, g0 + kb * GPB + lane, sf_ld)] = kNv ? 0x38 : 127;
+    return;
+  }
+  const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(x) + row * ldx + kb * 256 + lane * 8);
+  float v[8];
+  unpack8(raw, f16, v);
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
+  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+  if (!kNv) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+  float scale = __fdiv_rn(amax, 6.0f);
+  uint8_t sb;
+  if (kNv) { sb = to_e4m3(scale); scale = from_e4m3(sb); }
+  else { sb = to_e8m0(scale); scale = from_e8m0(sb); }
+  uint32_t word = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float q = (scale == 0.f) ? 0.f : __fdiv_rn(v[j], scale);
+    word |= (uint32_t)to_e2m1(q) << (4 * j);
+  }
+  *reinterpret_cast<uint32_t*>(a4 + row * lda + kb * 128 + lane * 4) = word;
+  constexpr int LPG = kNv ? 2 : 4;  // lanes per group
+  if ((lane % LPG) == 0) sfa[sf_offset(row, g0 + kb * GPB + lane / LPG, sf_ld)] = sb;
+}
+cudaError_t mx_quantize_act(int kind, const void* x16, int64_t ldx, int M, int K, bool f16, uint8_t* aq, int64_t lda_bytes,
+                            uint8_t* sfa, int64_t sf_ld, int64_t col0, cudaStream_t s) {
+  const int kb_elems = kind == 1 ? 128 : 256;
+  if (kind < 1 || kind > 3 || K % kb_elems || col0 % kb_elems || ldx % 8 || lda_bytes % 4) return cudaErrorInvalidValue;
+  const int64_t Mpad = ((int64_t)M + 127) / 128 * 128;
+  const int64_t warps = Mpad * (K / kb_elems);
   if (warps <= 0) return cudaSuccess;
-  mx8_quantize_act_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(x16, ldx, M, K, f16, a8, sfa);
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  const int g0 = (int)(col0 / mx_group(kind));
+  if (kind == 1) mx8_quantize_act_kernel<<<blocks, 256, 0, s>>>(x16, ldx, M, K, f16, aq, lda_bytes, sfa, sf_ld, g0);
+  else if (kind == 2) mx4_quantize_act_kernel<false><<<blocks, 256, 0, s>>>(x16, ldx, M, K, f16, aq, lda_bytes, sfa, sf_ld, g0);
+  else mx4_quantize_act_kernel<true><<<blocks, 256, 0, s>>>(x16, ldx, M, K, f16, aq, lda_bytes, sfa, sf_ld, g0);
+  return cudaGetLastError();
+}
+// scale factors back from the tcgen05 layout to row-major [M, G] (tests / debugging)
+__global__ void sf_untile_kernel(const uint8_t* __restrict__ sf, uint8_t* __restrict__ out, int64_t M, int64_t G) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * G) return;
+  out[i] = sf[sf_offset(i / G, i % G, G / 4)];
+}
+cudaError_t mx_sf_untile(const uint8_t* sf, uint8_t* out, int64_t M, int64_t G, cudaStream_t s) {
+  const int64_t n = M * G;
+  if (n <= 0) return cudaSuccess;
+  sf_untile_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sf, out, M, G);
   return cudaGetLastError();
 }
 

@@ -13,15 +13,24 @@ cudaError_t dequantize_matrix(int quant, const uint32_t* packed, const void* sca
 cudaError_t lora_add(void* W, int w_dtype, const float* A, const float* B, int64_t out_dim, int64_t in_dim, int rank,
                      float scale, cudaStream_t s);
 
-// ---- native block-scaled (mxfp8) operands: tcgen05 scale-factor layout, one 512 B block per (128 rows x 128 K):
-//      offset(row, g) = ((row / 128) * (K / 128) + g / 4) * 512 + (row % 32) * 16 + ((row % 128) / 32) * 4 + g % 4,  g = k / 32
-// rows of an MLX-packed mxfp8 weight (bytes [*, K], scales [*, K/32]) -> rows [dst_row0, dst_row0 + nrows) of the
+// ---- native block-scaled operands. kind: 1 = mxfp8 (E4M3, E8M0 / 32), 2 = mxfp4 (E2M1, E8M0 / 32), 3 = nvfp4 (E2M1, E4M3 / 16).
+// Element bytes stay exactly as MLX packs them (row-major, fp4 two per byte, low nibble first). Group scales are re-tiled into
+// the tcgen05 scale-factor layout: one 512 B block per (128 rows x 4 groups), blocks row-block-major with `ld` blocks per row block:
+//      offset(row, g) = ((row / 128) * ld + g / 4) * 512 + (row % 32) * 16 + ((row % 128) / 32) * 4 + g % 4,   g = k / group
+int mx_kind_of_quant(int quant);                       // flux2b_quant -> kind (0 for bf16 / affine modes)
+int64_t mx_sf_ld(int kind, int64_t K);                 // blocks per row block for a [*, K] operand
+size_t mx_sf_bytes(int kind, int64_t rows, int64_t K);
+// rows of an MLX-packed weight (bytes [*, K*bits/8], scales [*, K/group]) -> rows [dst_row0, dst_row0 + nrows) of the
 // working copy; `tiled` applies the SwiGLU [128 gate | 128 value] interleave of weights.cu
-cudaError_t mx8_copy_rows(const uint8_t* src_w, const uint8_t* src_s, int64_t src_row0, uint8_t* dst_w, uint8_t* dst_sf,
-                          int64_t dst_row0, int64_t nrows, int64_t K, bool tiled, int64_t Hm, cudaStream_t s);
-// 16-bit activations [M, K] (leading dim ldx) -> E4M3 bytes [M, K] + E8M0 scales (scale = 2^ceil(log2(amax / 448)), so
-// nothing saturates); scale-factor rows up to the next multiple of 128 are filled with 1.0
-cudaError_t mx8_quantize_act(const void* x16, int64_t ldx, int M, int K, bool f16, uint8_t* a8, uint8_t* sfa, cudaStream_t s);
-size_t mx8_sf_bytes(int64_t rows, int64_t K);
+cudaError_t mx_copy_rows(int kind, const uint8_t* src_w, const uint8_t* src_s, int64_t src_row0, uint8_t* dst_w, uint8_t* dst_sf,
+                         int64_t dst_row0, int64_t nrows, int64_t K, bool tiled, int64_t Hm, cudaStream_t s);
+// 16-bit activations x16[M, K] (leading dim ldx elements) -> quantised bytes aq[M, K*bits/8] (leading dim lda_bytes) + group
+// scales written at group offset col0 / group of a scale-factor tensor with `sf_ld` blocks per row block (so a column slice
+// [col0, col0 + K) of a wider activation can be quantised on its own). fp4 kinds use the weight packer's arithmetic
+// (bit-identical to quantize_matrix); mxfp8 uses scale = 2^ceil(log2(amax / 448)). Scale rows up to the next multiple of
+// 128 are filled with 1.0.
+cudaError_t mx_quantize_act(int kind, const void* x16, int64_t ldx, int M, int K, bool f16, uint8_t* aq, int64_t lda_bytes,
+                            uint8_t* sfa, int64_t sf_ld, int64_t col0, cudaStream_t s);
+cudaError_t mx_sf_untile(const uint8_t* sf, uint8_t* out, int64_t M, int64_t G, cudaStream_t s);
 
 }  // namespace f2b

@@ -81,6 +81,34 @@ int vector_f32_from_key(flux2b_ctx* c, const std::string& key, DevBuf* out, int6
   return 0;
 }
 
+// Linear `base` held as float -> MLX's packed form in place (weight uint32, scales, biases), exactly like quantize(model:)
+// (Flux2Pipeline.swift:567-578). Already packed layers are left alone (docs/knowledge/pitfalls/quantize-skips-quantized.md).
+int ensure_packed(flux2b_ctx* c, const std::string& base) {
+  Tensor* w = find(c, base + ".weight");
+  if (!w) return fail(FLUX2B_ERR_WEIGHT_LOADING, "missing tensor: " + base + ".weight");
+  if (w->dtype == FLUX2B_U32) return 0;
+  if (!is_float_dtype(w->dtype)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "unsupported weight dtype for " + base);
+  int bits, group, has_b, sdt;
+  if (!quant_params(c->quant, &bits, &group, &has_b, &sdt)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "context quantization is bf16");
+  const int64_t rows = w->shape.empty() ? 0 : w->shape[0];
+  const int64_t cols = rows ? w->numel() / rows : 0;
+  if (cols % group) return fail(FLUX2B_ERR_WEIGHT_LOADING, "input dim not divisible by group size: " + base);
+  Tensor packed, scales, biases;
+  packed.dtype = FLUX2B_U32; packed.shape = {rows, cols * bits / 32};
+  scales.dtype = sdt; scales.shape = {rows, cols / group};
+  biases.dtype = FLUX2B_F16; biases.shape = {rows, cols / group};
+  F2B_CUDA(packed.buf.alloc((size_t)packed.numel() * 4));
+  F2B_CUDA(scales.buf.alloc((size_t)scales.numel() * dtype_size(sdt)));
+  if (has_b) F2B_CUDA(biases.buf.alloc((size_t)biases.numel() * 2));
+  F2B_CUDA(quantize_matrix(c->quant, w->buf.p, w->dtype, rows, cols, packed.buf.as<uint32_t>(), scales.buf.p,
+                           has_b ? biases.buf.p : nullptr, c->stream));
+  F2B_CUDA(cudaStreamSynchronize(c->stream));  // the float weight is released below
+  c->tensors[base + ".weight"] = std::move(packed);
+  c->tensors[base + ".scales"] = std::move(scales);
+  if (has_b) c->tensors[base + ".biases"] = std::move(biases);
+  return 0;
+}
+
 // Dense [N, K] working copy (compute dtype) of Linear `base` — quantizing on the fly / dequantizing as configured.
 // quantize_ok=false keeps the layer dense (VAE linears / convs are never quantized by the reference).
 int dense16_from_key_ex(flux2b_ctx* c, const std::string& base, DevBuf* out, int* N, int* K, bool quantize_ok) {
@@ -108,27 +136,8 @@ int dense16_from_key_ex(flux2b_ctx* c, const std::string& base, DevBuf* out, int
   int64_t rows = w->shape.empty() ? 0 : w->shape[0];
   int64_t cols = rows ? w->numel() / rows : 0;
   if (quantize_ok && c->quant != FLUX2B_BF16) {
-    int bits, group, has_b, sdt;
-    quant_params(c->quant, &bits, &group, &has_b, &sdt);
-    if (cols % group) return fail(FLUX2B_ERR_WEIGHT_LOADING, "input dim not divisible by group size: " + base);
-    Tensor packed, scales, biases;
-    packed.dtype = FLUX2B_U32; packed.shape = {rows, cols * bits / 32};
-    scales.dtype = sdt; scales.shape = {rows, cols / group};
-    biases.dtype = FLUX2B_F16; biases.shape = {rows, cols / group};
-    F2B_CUDA(packed.buf.alloc((size_t)packed.numel() * 4));
-    F2B_CUDA(scales.buf.alloc((size_t)scales.numel() * dtype_size(sdt)));
-    if (has_b) F2B_CUDA(biases.buf.alloc((size_t)biases.numel() * 2));
-    F2B_CUDA(quantize_matrix(c->quant, w->buf.p, w->dtype, rows, cols, packed.buf.as<uint32_t>(), scales.buf.p,
-                             has_b ? biases.buf.p : nullptr, c->stream));
-    F2B_CUDA(out->alloc((size_t)rows * cols * 2));
-    F2B_CUDA(dequantize_matrix(c->quant, packed.buf.as<uint32_t>(), scales.buf.p, has_b ? biases.buf.p : nullptr, rows,
-                               cols, out->p, f16 ? FLUX2B_F16 : FLUX2B_BF16_T, c->stream));
-    F2B_CUDA(cudaStreamSynchronize(c->stream));  // the float weight is released below
-    c->tensors[base + ".weight"] = std::move(packed);
-    c->tensors[base + ".scales"] = std::move(scales);
-    if (has_b) c->tensors[base + ".biases"] = std::move(biases);
-    *N = (int)rows; *K = (int)cols;
-    return 0;
+    F2B_TRY(ensure_packed(c, base));
+    return dense16_from_key_ex(c, base, out, N, K, quantize_ok);  // now takes the packed branch above
   }
   F2B_CUDA(out->alloc((size_t)rows * cols * 2));
   const int64_t n = rows * cols;
@@ -178,6 +187,33 @@ static int build_swiglu(flux2b_ctx* c, const void* dense, int64_t ld, int64_t ro
   return 0;
 }
 
+// native block-scaled operand: rows [src_row0, src_row0 + nrows) of the packed Linear `base` (shape [eN, eK]) become rows
+// [dst_row0, dst_row0 + nrows) of L (N_total rows, allocated on first use); the bytes are MLX's, only the row order (fusion /
+// SwiGLU tile interleave) and the scale-factor tiling change.
+static int mx_rows(flux2b_ctx* c, const std::string& base, int eN, int eK, int64_t src_row0, int64_t nrows, Lin* L, int N_total,
+                   int64_t dst_row0, bool tiled, int Hm) {
+  const int kind = c->mx_kind;
+  F2B_TRY(ensure_packed(c, base));
+  Tensor* w = find(c, base + ".weight");
+  Tensor* s = find(c, base + ".scales");
+  int bits, group, has_b, sdt;
+  quant_params(c->quant, &bits, &group, &has_b, &sdt);
+  if (!w || !s || w->dtype != FLUX2B_U32 || w->shape.size() != 2) return fail(FLUX2B_ERR_WEIGHT_LOADING, "packed weight / scales expected for " + base);
+  F2B_TRY(expect_shape(base, (int)w->shape[0], (int)(w->shape[1] * 32 / bits), eN, eK));
+  if (s->numel() != (int64_t)eN * (eK / group)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "scales shape mismatch: " + base);
+  if (eK % (kind == 1 ? 128 : 256) || N_total % 128)
+    return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "native_mx needs in-features % 128 (fp8) / 256 (fp4) == 0 and out-features % 128 == 0: " + base);
+  if (!L->wq.p || L->N != N_total || L->K != eK || L->mx != kind) {
+    F2B_CUDA(L->wq.alloc((size_t)N_total * eK * bits / 8));
+    F2B_CUDA(L->sfb.alloc(mx_sf_bytes(kind, N_total, eK)));
+    L->w.release();
+    L->N = N_total; L->K = eK; L->mx = kind;
+  }
+  F2B_CUDA(mx_copy_rows(kind, w->buf.as<uint8_t>(), s->buf.as<uint8_t>(), src_row0, L->wq.as<uint8_t>(), L->sfb.as<uint8_t>(), dst_row0,
+                        nrows, eK, tiled, Hm, c->stream));
+  return 0;
+}
+
 int finalize_dit(flux2b_ctx* c) {
   const flux2b_dit_config& g = c->dit;
   const int D = g.num_attention_heads * g.attention_head_dim;
@@ -203,30 +239,48 @@ int finalize_dit(flux2b_ctx* c) {
   F2B_TRY(build_lin(c, "normOut.linear", &c->norm_out, 2 * D, D));
   F2B_TRY(build_lin(c, "projOut", &c->proj_out, g.out_channels, D));
 
+  // block linears: dense 16-bit operands, or (option native_mx with an mx* / nvfp4 quantization) MLX's packed bytes as they are
+  c->mx_kind = c->option("native_mx", 0) ? mx_kind_of_quant(c->quant) : 0;
+  if (c->option("native_mx", 0) && !c->mx_kind)
+    return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "native_mx needs quantization mxfp8, mxfp4 or nvfp4");
+  const bool mx = c->mx_kind != 0;
+  const bool tile_ok = (Hm % 128 == 0) && c->option("fuse_swiglu", 1);
+  auto lin = [&](const std::string& base, Lin* L, int eN, int eK) -> int {
+    if (mx) return mx_rows(c, base, eN, eK, 0, eN, L, eN, 0, false, 0);
+    return build_lin(c, base, L, eN, eK);
+  };
+  auto stacked = [&](const std::vector<std::string>& bases, Lin* L, int eN_each, int eK) -> int {
+    if (!mx) return build_stacked(c, bases, L, eN_each, eK);
+    for (size_t i = 0; i < bases.size(); ++i)
+      F2B_TRY(mx_rows(c, bases[i], eN_each, eK, 0, eN_each, L, (int)bases.size() * eN_each, (int64_t)i * eN_each, false, 0));
+    return 0;
+  };
+  // SwiGLU producer = rows [row0, row0 + 2 Hm) of `base` ([eN, D])
+  auto swiglu_lin = [&](const std::string& base, int eN, int64_t row0, Lin* L, bool* tiled) -> int {
+    if (mx) {
+      *tiled = tile_ok;
+      return mx_rows(c, base, eN, D, row0, 2 * (int64_t)Hm, L, 2 * Hm, 0, tile_ok, Hm);
+    }
+    DevBuf tmp; int N, K;
+    F2B_TRY(dense16_from_key(c, base, &tmp, &N, &K));
+    F2B_TRY(expect_shape(base, N, K, eN, D));
+    F2B_TRY(build_swiglu(c, tmp.p, K, row0, L, Hm, D, tiled));
+    F2B_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  };
+
   c->dbl.clear(); c->dbl.resize(g.num_layers);
   for (int i = 0; i < g.num_layers; ++i) {
     const std::string p = "transformerBlocks." + std::to_string(i) + ".";
     DoubleBlockW& b = c->dbl[i];
-    F2B_TRY(build_stacked(c, {p + "attn.toQ", p + "attn.toK", p + "attn.toV"}, &b.qkv_img, D, D));
-    F2B_TRY(build_stacked(c, {p + "attn.addQProj", p + "attn.addKProj", p + "attn.addVProj"}, &b.qkv_txt, D, D));
-    F2B_TRY(build_lin(c, p + "attn.toOut", &b.out_img, D, D));
-    F2B_TRY(build_lin(c, p + "attn.toAddOut", &b.out_txt, D, D));
-    {
-      DevBuf tmp; int N, K;
-      F2B_TRY(dense16_from_key(c, p + "ff.activation.proj", &tmp, &N, &K));
-      F2B_TRY(expect_shape(p + "ff.activation.proj", N, K, 2 * Hm, D));
-      F2B_TRY(build_swiglu(c, tmp.p, K, 0, &b.ff_in_img, Hm, D, &b.ff_tiled));
-      F2B_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    {
-      DevBuf tmp; int N, K;
-      F2B_TRY(dense16_from_key(c, p + "ffContext.activation.proj", &tmp, &N, &K));
-      F2B_TRY(expect_shape(p + "ffContext.activation.proj", N, K, 2 * Hm, D));
-      F2B_TRY(build_swiglu(c, tmp.p, K, 0, &b.ff_in_txt, Hm, D, &b.ff_tiled));
-      F2B_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    F2B_TRY(build_lin(c, p + "ff.linearOut", &b.ff_out_img, D, Hm));
-    F2B_TRY(build_lin(c, p + "ffContext.linearOut", &b.ff_out_txt, D, Hm));
+    F2B_TRY(stacked({p + "attn.toQ", p + "attn.toK", p + "attn.toV"}, &b.qkv_img, D, D));
+    F2B_TRY(stacked({p + "attn.addQProj", p + "attn.addKProj", p + "attn.addVProj"}, &b.qkv_txt, D, D));
+    F2B_TRY(lin(p + "attn.toOut", &b.out_img, D, D));
+    F2B_TRY(lin(p + "attn.toAddOut", &b.out_txt, D, D));
+    F2B_TRY(swiglu_lin(p + "ff.activation.proj", 2 * Hm, 0, &b.ff_in_img, &b.ff_tiled));
+    F2B_TRY(swiglu_lin(p + "ffContext.activation.proj", 2 * Hm, 0, &b.ff_in_txt, &b.ff_tiled));
+    F2B_TRY(lin(p + "ff.linearOut", &b.ff_out_img, D, Hm));
+    F2B_TRY(lin(p + "ffContext.linearOut", &b.ff_out_txt, D, Hm));
     F2B_TRY(vector_f32_from_key(c, p + "attn.normQ.weight", &b.nq_img, 128, false, 1.f));
     F2B_TRY(vector_f32_from_key(c, p + "attn.normK.weight", &b.nk_img, 128, false, 1.f));
     F2B_TRY(vector_f32_from_key(c, p + "attn.normAddedQ.weight", &b.nq_txt, 128, false, 1.f));
@@ -236,16 +290,20 @@ int finalize_dit(flux2b_ctx* c) {
   for (int i = 0; i < g.num_single_layers; ++i) {
     const std::string p = "singleTransformerBlocks." + std::to_string(i) + ".";
     SingleBlockW& b = c->sgl[i];
-    DevBuf tmp; int N, K;
     // fused projection column order q | k | v | gate | up, widths D,D,D,Hm,Hm (Flux2ParallelAttention.swift:56,83-87)
-    F2B_TRY(dense16_from_key(c, p + "attn.toQkvMlp", &tmp, &N, &K));
-    F2B_TRY(expect_shape(p + "attn.toQkvMlp", N, K, 3 * D + 2 * Hm, D));
-    F2B_CUDA(b.qkv.w.alloc((size_t)3 * D * D * 2));
-    F2B_TRY(copy_rows16(c, tmp.p, K, 0, b.qkv.w.p, K, 0, 3 * (int64_t)D, K, false, 0));
-    b.qkv.N = 3 * D; b.qkv.K = D;
-    F2B_TRY(build_swiglu(c, tmp.p, K, 3 * (int64_t)D, &b.mlp, Hm, D, &b.mlp_tiled));
-    F2B_CUDA(cudaStreamSynchronize(c->stream));
-    F2B_TRY(build_lin(c, p + "attn.toOut", &b.out, D, D + Hm));
+    if (mx) {
+      F2B_TRY(mx_rows(c, p + "attn.toQkvMlp", 3 * D + 2 * Hm, D, 0, 3 * (int64_t)D, &b.qkv, 3 * D, 0, false, 0));
+    } else {
+      DevBuf tmp; int N, K;
+      F2B_TRY(dense16_from_key(c, p + "attn.toQkvMlp", &tmp, &N, &K));
+      F2B_TRY(expect_shape(p + "attn.toQkvMlp", N, K, 3 * D + 2 * Hm, D));
+      F2B_CUDA(b.qkv.w.alloc((size_t)3 * D * D * 2));
+      F2B_TRY(copy_rows16(c, tmp.p, K, 0, b.qkv.w.p, K, 0, 3 * (int64_t)D, K, false, 0));
+      b.qkv.N = 3 * D; b.qkv.K = D;
+      F2B_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    F2B_TRY(swiglu_lin(p + "attn.toQkvMlp", 3 * D + 2 * Hm, 3 * (int64_t)D, &b.mlp, &b.mlp_tiled));
+    F2B_TRY(lin(p + "attn.toOut", &b.out, D, D + Hm));
     F2B_TRY(vector_f32_from_key(c, p + "attn.normQ.weight", &b.nq, 128, false, 1.f));
     F2B_TRY(vector_f32_from_key(c, p + "attn.normK.weight", &b.nk, 128, false, 1.f));
   }

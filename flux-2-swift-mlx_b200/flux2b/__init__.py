@@ -82,7 +82,7 @@ EXPORTS = [
     "flux2b_unpatchify_latents", "flux2b_pack_latents_to_patchified", "flux2b_bn_latents", "flux2b_image_position_ids",
     "flux2b_text_position_ids", "flux2b_reference_position_ids", "flux2b_vae_decode", "flux2b_vae_decode_u8",
     "flux2b_denoise", "flux2b_generate", "flux2b_repaint_blend", "flux2b_sp_unique_id", "flux2b_sp_init", "flux2b_sp_layout",
-    "flux2b_prof_enable", "flux2b_prof_reset", "flux2b_prof_get", "flux2b_launch_count", "flux2b_op_gemm", "flux2b_op_gemm_mxfp8",
+    "flux2b_prof_enable", "flux2b_prof_reset", "flux2b_prof_get", "flux2b_launch_count", "flux2b_op_gemm", "flux2b_op_gemm_mx", "flux2b_op_gemm_mxfp8",
     "flux2b_op_attention", "flux2b_op_ln_modulate", "flux2b_op_qk_norm_rope", "flux2b_op_rope_table",
     "flux2b_op_timestep_embedding", "flux2b_op_conv2d", "flux2b_op_groupnorm_silu",
 ]
@@ -495,16 +495,23 @@ class Context:
                                  _ptr(res), cta_group, bn))
         return out
 
-    def op_gemm_mxfp8(self, a16, w_packed, w_scales, return_quantized=False):
-        """a16 [M,K] 16-bit torch tensor; w_packed uint32 [N, K/4], w_scales uint8 [N, K/32] (MLX mxfp8 layout) -> f32 [M, N]."""
+    def op_gemm_mx(self, quant, a16, w_packed, w_scales, return_quantized=False, bn=0):
+        """Native block-scaled GEMM. a16 [M,K] 16-bit torch tensor; w_packed uint32 [N, K*bits/32], w_scales uint8 [N, K/group]
+        (the MLX layout of quant mode `quant` = "mxfp8" | "mxfp4" | "nvfp4") -> f32 [M, N]
+        (+ quantised activation bytes [M, K*bits/8] and their scales [M, K/group] with return_quantized)."""
         import torch
+        q = QUANT[quant] if isinstance(quant, str) else int(quant)
+        bits, group = {3: (8, 32), 4: (4, 32), 5: (4, 16)}[q]
         M, K = a16.shape
         N = w_packed.shape[0]
         out = torch.empty((M, N), dtype=torch.float32, device=a16.device)
-        a8 = np.zeros((M, K), dtype=np.uint8) if return_quantized else None
-        sfa = np.zeros((M, K // 32), dtype=np.uint8) if return_quantized else None
-        _ck(lib().flux2b_op_gemm_mxfp8(self._h, _ptr(a16), _ptr(w_packed), _ptr(w_scales), M, N, K, _ptr(out), _ptr(a8), _ptr(sfa)))
-        return (out, a8, sfa) if return_quantized else out
+        aq = np.zeros((M, K * bits // 8), dtype=np.uint8) if return_quantized else None
+        sfa = np.zeros((M, K // group), dtype=np.uint8) if return_quantized else None
+        _ck(lib().flux2b_op_gemm_mx(self._h, q, _ptr(a16), _ptr(w_packed), _ptr(w_scales), M, N, K, _ptr(out), _ptr(aq), _ptr(sfa), bn))
+        return (out, aq, sfa) if return_quantized else out
+
+    def op_gemm_mxfp8(self, a16, w_packed, w_scales, return_quantized=False):
+        return self.op_gemm_mx(3, a16, w_packed, w_scales, return_quantized)
 
     def op_attention(self, qkv16, B, S, H, variant=0):
         import torch

@@ -227,10 +227,16 @@ int64_t flux2b_launch_count(flux2b_ctx* ctx);
  * 0 = store 16-bit (+bias), 1 = store f32 (+bias), 2 = out_f32 = res + gate*acc, 3 = SwiGLU (W rows pre-tiled), */
 int flux2b_op_gemm(flux2b_ctx* ctx, const void* a16, const void* w16, int M, int N, int K, int epilogue, void* out,
                    const float* bias, const float* gate, const float* res, int cta_group, int bn);
-/* native block-scaled GEMM (tcgen05.mma.kind::mxf8f6f4.block_scale): C[M,N] f32 = mxfp8(A)[M,K] · W[N,K]^T where W arrives
- * exactly as MLX packs an mxfp8 Linear (weight uint32 [N, K/4] = E4M3 bytes, scales uint8 [N, K/32] E8M0) and A (16-bit)
- * is quantised on the fly to E4M3 with one E8M0 scale per 32 elements. K % 128 == 0, N % 128 == 0.
- * a8_out / sfa_out (optional, host or device): the quantised activation bytes [M, K] and their scales [M, K/32]. */
+/* native block-scaled GEMM (tcgen05.mma.kind::mxf8f6f4 / mxf4nvf4 .block_scale): C[M,N] f32 = q(A)[M,K] · W[N,K]^T where W arrives
+ * exactly as MLX packs a quantized Linear of mode `quant` (QuantizedLinear weight / scales, Flux2Pipeline.swift:567-578):
+ *   FLUX2B_MXFP8: weight uint32 [N, K/4] = E4M3 bytes,   scales uint8 [N, K/32] E8M0;  K % 128 == 0
+ *   FLUX2B_MXFP4: weight uint32 [N, K/8] = E2M1 nibbles, scales uint8 [N, K/32] E8M0;  K % 256 == 0
+ *   FLUX2B_NVFP4: weight uint32 [N, K/8] = E2M1 nibbles, scales uint8 [N, K/16] E4M3;  K % 256 == 0
+ * and A (16-bit) is quantised on the fly to the same element / scale format. N % 128 == 0; bn = 0 (auto) | 128 | 256.
+ * aq_out / sfa_out (optional, host or device): the quantised activation bytes [M, K*bits/8] and their scales [M, K/group]. */
+int flux2b_op_gemm_mx(flux2b_ctx* ctx, int quant, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N,
+                      int K, float* out, uint8_t* aq_out, uint8_t* sfa_out, int bn);
+/* = flux2b_op_gemm_mx(ctx, FLUX2B_MXFP8, ..., 0) */
 int flux2b_op_gemm_mxfp8(flux2b_ctx* ctx, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N, int K,
                          float* out, uint8_t* a8_out, uint8_t* sfa_out);
 int flux2b_op_attention(flux2b_ctx* ctx, const void* qkv16 /* [B*S, 3*H*128] */, int B, int S, int H, void* out16 /* [B*S, H*128] */,

@@ -255,6 +255,33 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
     return F.linear(x, w, b)
 
 
+# Checker-side model of the product's OPTIONAL native block-scaled mode (option "native_mx"; not a reference behaviour: the
+# reference computes x_fp32 · dequant(W)^T): the linears inside the transformer blocks see their input activation rounded
+# to the 16-bit operand type and then quantised to the weight's mx / nv format. `fn` maps an fp32 tensor [..., K] to its
+# fake-quantised fp32 version (oracle/quant_oracle.py: fake_quant_activation).
+_BLOCK_ACT_QUANT = None
+
+
+class block_activation_quant:
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __enter__(self):
+        global _BLOCK_ACT_QUANT
+        self.prev, _BLOCK_ACT_QUANT = _BLOCK_ACT_QUANT, self.fn
+        return self
+
+    def __exit__(self, *exc):
+        global _BLOCK_ACT_QUANT
+        _BLOCK_ACT_QUANT = self.prev
+        return False
+
+
+def block_linear(x: Tensor, w: Tensor) -> Tensor:
+    """A Linear inside a double- / single-stream block (no bias, Flux2Attention.swift:77-94)."""
+    return F.linear(_BLOCK_ACT_QUANT(x) if _BLOCK_ACT_QUANT is not None else x, w)
+
+
 def timestep_embedding(W: Dict[str, Tensor], prefix: str, x: Tensor) -> Tensor:
     """Flux2Embeddings.swift:74-79: Linear -> SiLU -> Linear, no bias."""
     return linear(F.silu(linear(x, W[prefix + ".linear1.weight"])), W[prefix + ".linear2.weight"])
@@ -351,8 +378,8 @@ def joint_attention(W, p, cfg: DiTConfig, img: Tensor, txt: Tensor, cos: Tensor,
     """Flux2Attention.callAsFunction (Flux2Attention.swift:103-193); KV variants :245-414."""
     H = cfg.num_attention_heads
     S_txt = txt.shape[1]
-    q, k, v = (to_heads(linear(img, W[p + n + ".weight"]), H) for n in ("attn.toQ", "attn.toK", "attn.toV"))
-    aq, ak, av = (to_heads(linear(txt, W[p + n + ".weight"]), H) for n in ("attn.addQProj", "attn.addKProj", "attn.addVProj"))
+    q, k, v = (to_heads(block_linear(img, W[p + n + ".weight"]), H) for n in ("attn.toQ", "attn.toK", "attn.toV"))
+    aq, ak, av = (to_heads(block_linear(txt, W[p + n + ".weight"]), H) for n in ("attn.addQProj", "attn.addKProj", "attn.addVProj"))
     one = torch.ones(cfg.attention_head_dim)
     q = rms_norm(q, W.get(p + "attn.normQ.weight", one))
     k = rms_norm(k, W.get(p + "attn.normK.weight", one))
@@ -370,14 +397,14 @@ def joint_attention(W, p, cfg: DiTConfig, img: Tensor, txt: Tensor, cos: Tensor,
         V = torch.cat([av, v], dim=2)
     o = from_heads(sdpa(Q, K, V, mask))
     txt_o, img_o = o[:, :S_txt], o[:, S_txt:]                                                     # :178-179
-    return linear(img_o, W[p + "attn.toOut.weight"]), linear(txt_o, W[p + "attn.toAddOut.weight"]), kv_ref
+    return block_linear(img_o, W[p + "attn.toOut.weight"]), block_linear(txt_o, W[p + "attn.toAddOut.weight"]), kv_ref
 
 
 def feed_forward(W, p: str, x: Tensor) -> Tensor:
     """Flux2FeedForward.swift:59-67,102-108: Linear D->2Hm, split (gate, value), silu(gate)*value, Linear Hm->D."""
-    h = linear(x, W[p + ".activation.proj.weight"])
+    h = block_linear(x, W[p + ".activation.proj.weight"])
     gate, value = h.chunk(2, dim=-1)
-    return linear(F.silu(gate) * value, W[p + ".linearOut.weight"])
+    return block_linear(F.silu(gate) * value, W[p + ".linearOut.weight"])
 
 
 def double_block(W, i: int, cfg: DiTConfig, img, txt, img_mod, txt_mod, cos, sin, mask=None, extra_kv=None, return_kv_ref=0):
@@ -401,7 +428,7 @@ def single_block(W, i: int, cfg: DiTConfig, x: Tensor, mod, cos, sin, mask=None,
     p = f"singleTransformerBlocks.{i}."
     D, Hm, H = cfg.inner_dim, cfg.mlp_hidden, cfg.num_attention_heads
     xn = apply_modulation(layer_norm(x), mod[0][0], mod[0][1])
-    proj = linear(xn, W[p + "attn.toQkvMlp.weight"])                       # q | k | v | gate | up  (:83-87)
+    proj = block_linear(xn, W[p + "attn.toQkvMlp.weight"])                       # q | k | v | gate | up  (:83-87)
     q, k, v = (to_heads(proj[..., j * D:(j + 1) * D], H) for j in range(3))
     gate, up = proj[..., 3 * D:3 * D + Hm], proj[..., 3 * D + Hm:]
     one = torch.ones(cfg.attention_head_dim)
@@ -418,7 +445,7 @@ def single_block(W, i: int, cfg: DiTConfig, x: Tensor, mod, cos, sin, mask=None,
         K, V = k, v
         kv = (k[:, :, kv_slice[0]:kv_slice[1]], v[:, :, kv_slice[0]:kv_slice[1]]) if kv_slice else None
     attn = from_heads(sdpa(q, K, V, mask))
-    out = linear(torch.cat([attn, F.silu(gate) * up], dim=-1), W[p + "attn.toOut.weight"])   # :116-122
+    out = block_linear(torch.cat([attn, F.silu(gate) * up], dim=-1), W[p + "attn.toOut.weight"])   # :116-122
     return x + apply_gate(out, mod[0][2]), kv                                             # Flux2SingleBlock.swift:91-97
 
 

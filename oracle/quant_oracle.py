@@ -84,3 +84,29 @@ def dequantize(quant: int, packed: np.ndarray, scales: np.ndarray, biases, cols:
     if rc != 0:
         raise ValueError("oracle_dequantize failed")
     return out
+
+
+def fake_quant_activation(quant: int, x, f16: bool = False):
+    """Checker model of the product's on-the-fly activation quantisation in native block-scaled mode (csrc/quant.cu:
+    mx_quantize_act): x (torch fp32 [..., K]) -> rounded to the 16-bit operand type -> quantised -> dequantised fp32.
+    mxfp4 / nvfp4 use exactly the weight packer above (groups along the last dim); mxfp8 uses E4M3 elements with the
+    scale 2^ceil(log2(amax / 448)) per 32 elements (nothing saturates)."""
+    import torch
+    shp = x.shape
+    K = shp[-1]
+    x16 = x.to(torch.float16 if f16 else torch.bfloat16).reshape(-1, K)
+    if quant in (4, 5):
+        raw = x16.view(torch.int16).numpy().view(np.uint16) if not f16 else x16.numpy()
+        p, s, _ = quantize(quant, raw)
+        return torch.from_numpy(dequantize(quant, p, s, None, K)).reshape(shp)
+    if quant != 3:
+        raise ValueError("native block-scaled modes are mxfp8, mxfp4, nvfp4")
+    g = x16.float().reshape(-1, K // 32, 32)
+    amax = g.abs().amax(dim=-1, keepdim=True)
+    qv = (amax * np.float32(1.0 / 448.0)).contiguous()
+    u = qv.view(torch.int32)
+    e = ((u >> 23) & 0xff) - 127 + ((u & 0x7fffff) != 0).to(torch.int32)
+    e = torch.where(amax > 0, e.clamp(-127, 127), torch.full_like(e, -127))
+    inv = torch.ldexp(torch.ones_like(amax), -e)
+    q8 = (g * inv).to(torch.float8_e4m3fn).float()
+    return (q8 * torch.ldexp(torch.ones_like(amax), e)).reshape(shp)

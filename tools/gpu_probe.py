@@ -147,35 +147,46 @@ def probe_dit(name, fuse_qk=1, fuse_swiglu=1, attn_variant=0, cg=0, f16=0, S_img
                 "gpu_s_first_call": round(t_gpu, 3), "cpu_oracle_s": round(t_cpu, 2)}
 
 
-def probe_gemm_mx8(M, N, K, iters=5):
-    """native block-scaled mxfp8 GEMM: exact check against decode(a8) * 2^(sfa-127) @ dequant(W)^T in fp64."""
+def probe_gemm_mx(quant, M, N, K, iters=5, bn=0):
+    """native block-scaled GEMM (mxfp8 / mxfp4 / nvfp4): exact check against dequant(aq, sfa) @ dequant(W)^T in fp64; for the
+    fp4 kinds the quantised activations must also be bit-identical to the oracle's weight packer run on the same matrix."""
     import numpy as np
     import torch
     import flux2b
     from oracle import quant_oracle as Q
+    qi = Q.QUANT[quant]
+    bits, group, _ = Q.params(qi)
     ctx = flux2b.Context()
     g = torch.Generator().manual_seed(11)
     a = torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, K // 32, generator=g)).repeat_interleave(32, dim=1)
     a = a.to(torch.bfloat16)
     w = (torch.randn(N, K, generator=g) * 0.05).half().numpy()
-    packed, scales, _ = Q.quantize(3, w)
-    out, a8, sfa = ctx.op_gemm_mxfp8(a.cuda(), packed, scales, return_quantized=True)
+    packed, scales, _ = Q.quantize(qi, w)
+    out, aq, sfa = ctx.op_gemm_mx(quant, a.cuda(), packed, scales, return_quantized=True, bn=bn)
     ctx.synchronize()
-    L = Q.lib()
-    tab = np.array([L.oracle_from_e4m3(i) for i in range(256)], dtype=np.float64)
-    A_deq = tab[a8] * np.exp2(sfa.astype(np.float64).repeat(32, axis=1) - 127.0)
-    W_deq = Q.dequantize(3, packed, scales, None, K).astype(np.float64)
+    A_deq = Q.dequantize(qi, np.ascontiguousarray(aq).view(np.uint32), sfa, None, K).astype(np.float64)
+    W_deq = Q.dequantize(qi, packed, scales, None, K).astype(np.float64)
     ref = A_deq @ W_deq.T
     err = rel_l2(out.cpu(), torch.from_numpy(ref))
     qerr = rel_l2(torch.from_numpy(A_deq), a.double())
-    amax_ok = bool(np.all(np.abs(tab[a8]) <= 448))
+    info = {"rel_l2_vs_exact_emulation": err, "activation_quant_rel_err": qerr}
+    ok = err < 1e-5 and qerr < (0.05 if bits == 8 else 0.2)
+    if bits == 4:
+        a_bits = a.view(torch.int16).numpy().view(np.uint16)   # raw bf16 bits
+        p_ref, s_ref, _ = Q.quantize(qi, a_bits)
+        info["act_packed_bit_exact"] = bool(np.array_equal(p_ref.view(np.uint8).reshape(M, -1), aq))
+        info["act_scales_bit_exact"] = bool(np.array_equal(s_ref, sfa))
+        ok = ok and info["act_packed_bit_exact"] and info["act_scales_bit_exact"]
     ctx.prof_enable(True); ctx.prof_reset()
+    ad = a.cuda()
     for _ in range(iters):
-        ctx.op_gemm_mxfp8(a.cuda(), packed, scales)
+        ctx.op_gemm_mx(quant, ad, packed, scales, bn=bn)
     p = ctx.prof_get(flux2b.PROF_GEMM)
+    e = ctx.prof_get(flux2b.PROF_ELEMWISE)
     tf = p["flops"] / (p["ms"] * 1e-3) / 1e12 if p["ms"] > 0 else 0
-    return err < 1e-5 and qerr < 0.05 and amax_ok, {"rel_l2_vs_exact_emulation": err, "activation_quant_rel_err": qerr,
-                                                    "tflops": round(tf, 1), "ms": round(p["ms"] / iters, 4)}
+    info.update({"tflops": round(tf, 1), "ms": round(p["ms"] / iters, 4), "act_quant_ms": round(e["ms"] / iters, 4),
+                 "act_quant_gbs": round(e["bytes"] / (e["ms"] * 1e-3) / 1e9, 1) if e["ms"] > 0 else None})
+    return ok, info
 
 
 def probe_quant(quant):
@@ -231,11 +242,22 @@ PROBES = {
     "gemm_ffin_cg2": lambda: probe_gemm(4608, 18432, 3072, 3, 2),
     "gemm_out_cg1": lambda: probe_gemm(4608, 3072, 12288, 2, 1),
     "gemm_out_cg2": lambda: probe_gemm(4608, 3072, 12288, 2, 2),
-    "mx8_small": lambda: probe_gemm_mx8(128, 128, 128),
-    "mx8_k512": lambda: probe_gemm_mx8(256, 256, 512),
-    "mx8_tail": lambda: probe_gemm_mx8(300, 384, 256),
-    "mx8_big": lambda: probe_gemm_mx8(4608, 3072, 3072, iters=3),
-    "mx8_ffin": lambda: probe_gemm_mx8(4608, 18432, 3072, iters=2),
+    "mx8_small": lambda: probe_gemm_mx("mxfp8", 128, 128, 128),
+    "mx8_k512": lambda: probe_gemm_mx("mxfp8", 256, 256, 512),
+    "mx8_tail": lambda: probe_gemm_mx("mxfp8", 300, 384, 256),
+    "mx8_big": lambda: probe_gemm_mx("mxfp8", 4608, 3072, 3072, iters=3),
+    "mx8_ffin": lambda: probe_gemm_mx("mxfp8", 4608, 18432, 3072, iters=2),
+    "mx8_ffin_bn128": lambda: probe_gemm_mx("mxfp8", 4608, 18432, 3072, iters=2, bn=128),
+    "nv4_small": lambda: probe_gemm_mx("nvfp4", 128, 128, 256),
+    "nv4_k1024": lambda: probe_gemm_mx("nvfp4", 256, 256, 1024),
+    "nv4_tail": lambda: probe_gemm_mx("nvfp4", 300, 384, 512),
+    "nv4_big": lambda: probe_gemm_mx("nvfp4", 4608, 4096, 4096, iters=3),
+    "nv4_ffin": lambda: probe_gemm_mx("nvfp4", 4608, 24576, 4096, iters=2),
+    "nv4_ffin_bn128": lambda: probe_gemm_mx("nvfp4", 4608, 24576, 4096, iters=2, bn=128),
+    "mx4_small": lambda: probe_gemm_mx("mxfp4", 128, 128, 256),
+    "mx4_k1024": lambda: probe_gemm_mx("mxfp4", 256, 256, 1024),
+    "mx4_tail": lambda: probe_gemm_mx("mxfp4", 300, 384, 512),
+    "mx4_ffin": lambda: probe_gemm_mx("mxfp4", 4608, 24576, 4096, iters=2),
     "attn_v1_small": lambda: probe_attention(1, 256, 2, 1),
     "attn_v2_small": lambda: probe_attention(1, 256, 2, 2),
     "attn_v1_tail": lambda: probe_attention(2, 328, 2, 1),
