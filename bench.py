@@ -38,13 +38,27 @@ METRIC = "dit_steps_per_sec"
 UNIT = "steps/s"
 
 
-def peaks():
+def peaks(rate_mult: int = 1):
+    """Roofline denominators. rate_mult: tensor-pipe rate of the operand type relative to bf16 (fp8 x2, fp4 x4) — there is no
+    measured fp8 / fp4 library number on this pool, so the block-scaled modes are normalised to the measured bf16 figure
+    scaled by the nominal rate ratio (said so in peak_source)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    mult = "" if rate_mult == 1 else f" x {rate_mult} (nominal fp{8 if rate_mult == 2 else 4} : bf16 tensor rate)"
     if os.path.exists(path):
         d = json.load(open(path))
-        return {"tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0)), "hbm": d.get("hbm_gbs", 6650.0),
-                "src": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"}
-    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md sustained figure)"}
+        return {"tflops": rate_mult * d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0)), "hbm": d.get("hbm_gbs", 6650.0),
+                "src": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" + mult}
+    return {"tflops": rate_mult * 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md sustained figure)" + mult}
+
+
+def measured_traffic(kernel_class: str):
+    """DRAM bytes per launch of a kernel class from the committed ncu pass (profiles/r01_traffic.json, written by
+    tools/summarize_ncu.py traffic from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`), else None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel_class)
+    except Exception:
+        return None
 
 
 def dit_flops(cfg, S_img, S_txt=512):
@@ -186,7 +200,8 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
     import flux2b
     H = W = args.res
     S_img = (H // 16) * (W // 16)
-    ctx = flux2b.Context(dit=cfg, device=local_rank, options={"keep_raw_weights": 0, "sp_mode": args.sp_mode})
+    ctx = flux2b.Context(dit=cfg, device=local_rank, quant=flux2b.QUANT[args.quant],
+                         options={"keep_raw_weights": 0, "sp_mode": args.sp_mode, "native_mx": args.native_mx, "mx_bn": args.mx_bn})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     from oracle import flux2_oracle as O
     g = torch.Generator(device=device).manual_seed(0)   # same seed on every rank: replicated weights
@@ -240,14 +255,14 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
     barrier()
     if rank == 0:
         gemm_f, attn_f = dit_flops(cfg, S_img)
-        pk = peaks()
+        pk = peaks(rate_mult(args))
         gp = prof["gemm"]
         achieved = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] > 0 else 0.0
         print(json.dumps({
             "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.model} one denoising step at {H}x{W} ({S_img} img + {S_TXT} txt tokens), bf16, Ulysses "
+            "vs_baseline": None, "dtype": dtype_name(args), "data": "synthetic",
+            "config": {"workload": f"{args.model} one denoising step at {H}x{W} ({S_img} img + {S_TXT} txt tokens), {dtype_name(args)}, Ulysses "
                                    f"sequence-parallel over {world} rank(s), transport mode {args.sp_mode}",
                        "l2": "inputs larger than L2 (weights stream from HBM every step)"},
             "tflops_total": (gemm_f + attn_f) * args.steps / (ms * 1e-3) / 1e12,
@@ -261,6 +276,21 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
         dist.destroy_process_group()
 
 
+def rate_mult(args) -> int:
+    if not args.native_mx:
+        return 1
+    return {"mxfp8": 2, "mxfp4": 4, "nvfp4": 4}.get(args.quant, 1)
+
+
+def dtype_name(args) -> str:
+    """arithmetic type of the dominant kernel's operands"""
+    if args.quant == "bf16":
+        return "bf16"
+    if args.native_mx:
+        return f"{args.quant} (block-scaled tcgen05 MMA, weights and on-the-fly activations)"
+    return f"bf16 x dequant({args.quant}) (W-only)"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,6 +299,12 @@ def main():
     ap.add_argument("--impl", default="flux2b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="klein4b")
+    ap.add_argument("--quant", default="bf16", choices=["bf16", "qint8", "int4", "mxfp8", "mxfp4", "nvfp4"],
+                    help="TransformerQuantization of the DiT linears (quantized on the fly by the bit-exact packer)")
+    ap.add_argument("--native-mx", type=int, default=0,
+                    help="1 = block linears on tcgen05 block-scaled MMA (mxfp8 / mxfp4 / nvfp4 weights consumed as packed, activations "
+                         "quantised on the fly); 0 = W-only x · dequant(W)^T through the 16-bit GEMM (the reference's arithmetic)")
+    ap.add_argument("--mx-bn", type=int, default=0, help="N tile of the block-scaled GEMM (0 = auto / 128 / 256)")
     ap.add_argument("--sp", action="store_true",
                     help="Ulysses sequence-parallel mode: all ranks cooperate on ONE denoising step (strong scaling); "
                          "use with --model dev --res 2048 (BASELINE.json configs[3])")
@@ -304,7 +340,8 @@ def main():
     if args.sp:
         run_sp(args, cfg, rank, local_rank, world, device, dist)
         return
-    ctx = flux2b.Context(dit=cfg, vae=vcfg, device=local_rank, options={"keep_raw_weights": 0})
+    ctx = flux2b.Context(dit=cfg, vae=vcfg, device=local_rank, quant=flux2b.QUANT[args.quant],
+                         options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     make_weights_on_gpu(ctx, cfg, vcfg, device)
     ctx.finalize()
@@ -394,7 +431,7 @@ def main():
     ms_per_image = ms / args.steps
     value = n_img * NUM_STEPS / (ms * 1e-3)
     e2e_value = n_img * NUM_STEPS / (ms_e2e * 1e-3)
-    pk = peaks()
+    pk = peaks(rate_mult(args))
     g = prof["gemm"]
     achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     gemm_f, attn_f = dit_flops(cfg, S_img)
@@ -402,8 +439,8 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_image, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.model} t2i {HEIGHT}x{WIDTH} ({S_img} img + {S_TXT} txt tokens), {NUM_STEPS} Euler steps bf16 + small-decoder "
+        "dtype": dtype_name(args), "data": "synthetic",
+        "config": {"workload": f"{args.model} t2i {HEIGHT}x{WIDTH} ({S_img} img + {S_TXT} txt tokens), {NUM_STEPS} Euler steps {dtype_name(args)} + small-decoder "
                                "VAE decode (f16) per image; random-init weights; one image per bench step; image-parallel over ranks",
                    "l2": "inputs larger than L2 (7.8 GB of weights stream through the 126 MB L2 every forward)",
                    "images_per_rank": args.steps},
@@ -416,7 +453,9 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 GEMM, all DiT linears)", "achieved": achieved,
                      "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"] if pk["tflops"] else None,
-                     "traffic": None, "peak_source": pk["src"], "launches": g["launches"],
+                     "traffic": measured_traffic("gemm") if args.quant == "bf16" and args.model == "klein4b" else None,
+                     "algorithmic_bytes_per_launch": g["bytes"] / g["launches"] if g["launches"] else None,
+                     "peak_source": pk["src"], "launches": g["launches"],
                      "share_of_kernel_time": g["ms"] / total_kernel_ms if total_kernel_ms else None},
         "kernel_classes": {k: {"ms_per_image": p["ms"] / args.steps, "launches_per_image": p["launches"] / args.steps,
                                "tflops": (p["flops"] / (p["ms"] * 1e-3) / 1e12) if p["ms"] > 0 and p["flops"] else None,

@@ -108,7 +108,10 @@ int flux2b_create(int device, const flux2b_dit_config* dit, const flux2b_vae_con
   c->quant = quant;
   if (dit) { c->dit = *dit; c->has_dit = true; }
   if (vae) { c->vae = *vae; c->has_vae = true; }
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+  // a blocking stream: ordered against the legacy default stream, so device buffers a caller produced there (e.g. a pageable
+  // cudaMemcpy whose DMA is still in flight when it returns) are complete before this context reads them, and results are
+  // visible to it afterwards. Callers that want full concurrency hand in their own stream (flux2b_set_stream).
+  if (cudaStreamCreate(&c->stream) != cudaSuccess)
     return fail(FLUX2B_ERR_CUDA, "cudaStreamCreate failed");
   c->own_stream = true;
   *out = c.release();
@@ -142,11 +145,11 @@ int flux2b_synchronize(flux2b_ctx* c) {
 int flux2b_set_option(flux2b_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "null argument");
   static const char* known[] = {"compute_f16", "fuse_qk_rope", "fuse_swiglu", "attn_variant", "gemm_cta_group",
-                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx"};
+                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant"};
   bool ok = false;
   for (const char* k : known) ok = ok || !strcmp(k, name);
   if (!ok) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string("unknown option: ") + name);
-  if (c->finalized && (!strcmp(name, "compute_f16") || !strcmp(name, "fuse_swiglu") || !strcmp(name, "vae_f16") || !strcmp(name, "native_mx")))
+  if (c->finalized && (!strcmp(name, "compute_f16") || !strcmp(name, "fuse_swiglu") || !strcmp(name, "vae_f16") || !strcmp(name, "native_mx") || !strcmp(name, "mx_bn")))
     return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string(name) + " must be set before flux2b_finalize_weights");
   c->opt[name] = value;
   return 0;
@@ -385,7 +388,7 @@ int flux2b_op_gemm_mx(flux2b_ctx* c, int quant, const void* a16, const uint32_t*
   F2B_CUDA(sfb.alloc(mx_sf_bytes(kind, N, K)));
   F2B_CUDA(aq.alloc((size_t)M * wrow));
   F2B_CUDA(sfa.alloc(mx_sf_bytes(kind, M, K)));
-  F2B_CUDA(mx_copy_rows(kind, (const uint8_t*)dw, (const uint8_t*)ds, 0, wq.as<uint8_t>(), sfb.as<uint8_t>(), 0, N, K, false, 0, c->stream));
+  F2B_CUDA(mx_copy_rows(kind, (const uint8_t*)dw, (const uint8_t*)ds, 0, wq.as<uint8_t>(), sfb.as<uint8_t>(), 0, N, K, 0, 0, c->stream));
   {
     ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (2.0 + bits / 8.0) * M * K);
     F2B_CUDA(mx_quantize_act(kind, da, K, M, K, c->f16(), aq.as<uint8_t>(), (int64_t)wrow, sfa.as<uint8_t>(), mx_sf_ld(kind, K), 0, c->stream));

@@ -87,6 +87,7 @@ struct Lin {
   // layout (quant.cuh). `w` is then not materialised.
   DevBuf wq, sfb;
   int mx = 0;  // 0 = dense 16-bit operand in `w`; 1 / 2 / 3 = mxfp8 / mxfp4 / nvfp4 operand in `wq` + `sfb`
+  int bn = 0;  // block-scaled operands: GEMM N tile (128 | 256); SwiGLU producers are row-interleaved per tile of this size
 };
 struct DoubleBlockW {
   Lin qkv_img, qkv_txt, out_img, out_txt, ff_in_img, ff_out_img, ff_in_txt, ff_out_txt;

@@ -35,7 +35,7 @@ static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int
   if (W.mx) {
     if (!qa || !qa->q) return fail(FLUX2B_ERR_GENERATION_FAILED, "internal: block-scaled weight without a quantised activation");
     const int bits = W.mx == 1 ? 8 : 4, group = W.mx == 3 ? 16 : 32;
-    g.mx = W.mx;
+    g.mx = W.mx; g.force_bn = W.bn;
     g.A = qa->q; g.lda = qa->ldq; g.sfa = qa->sf; g.sfa_ld = qa->sf_ld;
     g.B = W.wq.as<uint8_t>() + k_off * bits / 8; g.ldb = (int64_t)W.K * bits / 8;
     g.sfb = W.sfb.as<uint8_t>() + (k_off / group / 4) * 512; g.sfb_ld = W.K / group / 4;
@@ -274,23 +274,37 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
   // the same row range of the slot's byte buffer, scale factors into the slot's own tile space (row 0 = first row of `src`).
   const int mxk = c->mx_kind;
   const int mx_bits = mxk == 1 ? 8 : 4, mx_grp = mxk == 3 ? 16 : 32;
-  auto quantize = [&](const uint16_t* src, int64_t ld, int rows, int K, int slot, int64_t row0, int64_t Ktot, int64_t col0,
-                      QView* qv) -> int {
-    if (!mxk) return 0;
+  // where the quantised version of rows [row0, ...) x columns [col0, col0 + K) of a [*, Ktot] activation lives
+  auto qdest = [&](int slot, int64_t row0, int64_t Ktot, int64_t col0, QView* qv, MxOut* mo) {
     uint8_t* base = (slot < 2 ? c->ws_aq_xn : c->ws_aq_cat).as<uint8_t>();
     const int64_t ldq = Ktot * mx_bits / 8;
     uint8_t* q = base + row0 * ldq + col0 * mx_bits / 8;
     uint8_t* sf = c->ws_sfa[slot].as<uint8_t>();
     const int sf_ld = (int)(Ktot / mx_grp / 4);
-    {
-      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * K * (2.0 + mx_bits / 8.0));
-      F2B_CUDA(mx_quantize_act(mxk, src, ld, rows, K, f16, q, ldq, sf, sf_ld, col0, st));
-    }
     qv->q = q; qv->ldq = ldq; qv->sf = sf + (col0 / mx_grp / 4) * 512; qv->sf_ld = sf_ld;
+    mo->kind = mxk; mo->q = q; mo->ldq = ldq; mo->sf = sf; mo->sf_ld = sf_ld; mo->g0 = (int)(col0 / mx_grp);
+  };
+  auto quantize = [&](const uint16_t* src, int64_t ld, int rows, int K, int slot, int64_t row0, int64_t Ktot, int64_t col0,
+                      QView* qv) -> int {
+    if (!mxk) return 0;
+    MxOut mo;
+    qdest(slot, row0, Ktot, col0, qv, &mo);
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * K * (2.0 + mx_bits / 8.0));
+    F2B_CUDA(mx_quantize_act(mxk, src, ld, rows, K, f16, mo.q, mo.ldq, mo.sf, mo.sf_ld, col0, st));
     return 0;
   };
-  // LN + modulate of `rows` rows starting at XN row `row0` (slot 0 = text range, 1 = image range / everything)
+  // option mx_fuse_quant (default 1): LayerNorm + modulate and the SwiGLU epilogue emit the block-scaled operand themselves
+  // (no 16-bit XN / MLP activation is ever written); 0 = separate quantisation pass (same bits, kept as the cross-check)
+  const bool fuse_q = mxk && c->option("mx_fuse_quant", 1) != 0;
+  // LN + modulate of `rows` rows into XN rows starting at `o` (slot 0 = text range, 1 = image range / everything)
   auto ln_mod = [&](const float* x, int rows, const float* shift, const float* scale, uint16_t* o, int slot, QView* qv) -> int {
+    if (fuse_q) {
+      MxOut mo;
+      qdest(slot, (o - XN) / D, D, 0, qv, &mo);
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * D * (4.0 + mx_bits / 8.0));
+      F2B_CUDA(ln_modulate(x, D, o, D, rows, D, shift, scale, 0, rows, 1e-6f, f16, st, &mo));
+      return 0;
+    }
     {
       ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)rows * D * 6);
       F2B_CUDA(ln_modulate(x, D, o, D, rows, D, shift, scale, 0, rows, 1e-6f, f16, st));
@@ -330,9 +344,12 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
     return run_gemm(c, a, lda, W, rows, e, qa);
   };
   // SwiGLU producer: out[rows, Hm] (leading dim ldo) = silu(gate) * value
-  auto swiglu_gemm = [&](const uint16_t* a, const QView* qa, const Lin& W, bool tiled, int rows, uint16_t* o, int64_t ldo, uint16_t* scratch) -> int {
+  // With `mo` (native path, fused quantisation) the 16-bit result is not stored; the epilogue emits the block-scaled operand.
+  auto swiglu_gemm = [&](const uint16_t* a, const QView* qa, const Lin& W, bool tiled, int rows, uint16_t* o, int64_t ldo, uint16_t* scratch,
+                         const MxOut* mo = nullptr) -> int {
     if (tiled) {
       Epilogue e; e.mode = EPI_SWIGLU; e.out = o; e.ldo = (int)ldo;
+      if (mo) e.mxo = *mo;
       return run_gemm(c, a, D, W, rows, e, qa);
     }
     Epilogue e; e.mode = EPI_BF16; e.out = scratch; e.ldo = 2 * Hm;
@@ -399,12 +416,22 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
     F2B_TRY(ln_mod(X, S_txt, mod_txt + 3 * D, mod_txt + 4 * D, XN, 0, &q_txt));
     uint16_t* Hbuf = CAT;                       // [S, Hm]
     uint16_t* scratch = CAT + (size_t)S * Hm;   // [S, 2Hm] unfused fallback
-    F2B_TRY(swiglu_gemm(XNi, &q_img, b.ff_in_img, b.ff_tiled, S_im_all, Hbuf + (size_t)S_txt * Hm, Hm, scratch));
-    F2B_TRY(quantize(Hbuf + (size_t)S_txt * Hm, Hm, S_im_all, Hm, 3, S_txt, Hm, 0, &q_img));
-    F2B_TRY(gate_res_gemm(Hbuf + (size_t)S_txt * Hm, Hm, &q_img, b.ff_out_img, S_im_all, Ximg, mod_img + 5 * D));
-    F2B_TRY(swiglu_gemm(XN, &q_txt, b.ff_in_txt, b.ff_tiled, S_txt, Hbuf, Hm, scratch));
-    F2B_TRY(quantize(Hbuf, Hm, S_txt, Hm, 2, 0, Hm, 0, &q_txt));
-    F2B_TRY(gate_res_gemm(Hbuf, Hm, &q_txt, b.ff_out_txt, S_txt, X, mod_txt + 5 * D));
+    if (fuse_q && b.ff_tiled) {
+      MxOut mo; QView q_h;
+      qdest(3, S_txt, Hm, 0, &q_h, &mo);
+      F2B_TRY(swiglu_gemm(XNi, &q_img, b.ff_in_img, true, S_im_all, nullptr, Hm, nullptr, &mo));
+      F2B_TRY(gate_res_gemm(nullptr, Hm, &q_h, b.ff_out_img, S_im_all, Ximg, mod_img + 5 * D));
+      qdest(2, 0, Hm, 0, &q_h, &mo);
+      F2B_TRY(swiglu_gemm(XN, &q_txt, b.ff_in_txt, true, S_txt, nullptr, Hm, nullptr, &mo));
+      F2B_TRY(gate_res_gemm(nullptr, Hm, &q_h, b.ff_out_txt, S_txt, X, mod_txt + 5 * D));
+    } else {
+      F2B_TRY(swiglu_gemm(XNi, &q_img, b.ff_in_img, b.ff_tiled, S_im_all, Hbuf + (size_t)S_txt * Hm, Hm, scratch));
+      F2B_TRY(quantize(Hbuf + (size_t)S_txt * Hm, Hm, S_im_all, Hm, 3, S_txt, Hm, 0, &q_img));
+      F2B_TRY(gate_res_gemm(Hbuf + (size_t)S_txt * Hm, Hm, &q_img, b.ff_out_img, S_im_all, Ximg, mod_img + 5 * D));
+      F2B_TRY(swiglu_gemm(XN, &q_txt, b.ff_in_txt, b.ff_tiled, S_txt, Hbuf, Hm, scratch));
+      F2B_TRY(quantize(Hbuf, Hm, S_txt, Hm, 2, 0, Hm, 0, &q_txt));
+      F2B_TRY(gate_res_gemm(Hbuf, Hm, &q_txt, b.ff_out_txt, S_txt, X, mod_txt + 5 * D));
+    }
     F2B_TRY(record_block(c, i, S));
   }
   // ---- single-stream blocks (Flux2SingleBlock.swift:59-98, Flux2ParallelAttention.swift:72-123)
@@ -421,8 +448,14 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
       //   O all-to-all    ||  out GEMM over the MLP columns (K = Hm, no dependency on the attention)
       //   out GEMM over the attention columns (K = D)
       F2B_TRY(sp_exchange_qkv(c, S, true));
-      F2B_TRY(swiglu_gemm(XN, &q_all, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
-      F2B_TRY(quantize(CAT + D, ldc, S, Hm, 3, 0, ldc, D, &q_mlp));
+      if (fuse_q && b.mlp_tiled) {
+        MxOut mo;
+        qdest(3, 0, ldc, D, &q_mlp, &mo);
+        F2B_TRY(swiglu_gemm(XN, &q_all, b.mlp, true, S, nullptr, ldc, nullptr, &mo));
+      } else {
+        F2B_TRY(swiglu_gemm(XN, &q_all, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
+        F2B_TRY(quantize(CAT + D, ldc, S, Hm, 3, 0, ldc, D, &q_mlp));
+      }
       F2B_TRY(sp_join(c));
       F2B_TRY(sp_attend(c, S, CAT, ldc));
       F2B_TRY(sp_exchange_o(c, S, CAT, ldc, true));
@@ -436,9 +469,19 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
       F2B_TRY(record_block(c, cfg.num_layers + i, S));
       continue;
     }
-    F2B_TRY(swiglu_gemm(XN, &q_all, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
-    F2B_TRY(full_attention(cfg.num_layers + i, CAT, ldc));
-    F2B_TRY(quantize(CAT, ldc, S, ldc, 3, 0, ldc, 0, &q_all));
+    if (fuse_q && b.mlp_tiled) {
+      // MLP columns [D, D + Hm) of the out-projection operand come quantised from the SwiGLU epilogue; only the attention
+      // columns [0, D) need the separate pass
+      MxOut mo;
+      qdest(3, 0, ldc, D, &q_mlp, &mo);
+      F2B_TRY(swiglu_gemm(XN, &q_all, b.mlp, true, S, nullptr, ldc, nullptr, &mo));
+      F2B_TRY(full_attention(cfg.num_layers + i, CAT, ldc));
+      F2B_TRY(quantize(CAT, ldc, S, D, 3, 0, ldc, 0, &q_all));
+    } else {
+      F2B_TRY(swiglu_gemm(XN, &q_all, b.mlp, b.mlp_tiled, S, CAT + D, ldc, b.mlp_tiled ? nullptr : scratch));
+      F2B_TRY(full_attention(cfg.num_layers + i, CAT, ldc));
+      F2B_TRY(quantize(CAT, ldc, S, ldc, 3, 0, ldc, 0, &q_all));
+    }
     F2B_TRY(gate_res_gemm(CAT, ldc, &q_all, b.out, S, X, mod_sgl + 2 * D));
     F2B_TRY(record_block(c, cfg.num_layers + i, S));
   }

@@ -3,6 +3,7 @@
 // oversubscribe the 148 SMs).
 #include "elementwise.cuh"
 #include "ptx.cuh"
+#include "quant_dev.cuh"
 #include <algorithm>
 
 namespace f2b {
@@ -46,13 +47,23 @@ __device__ __forceinline__ float block_sum(float v, float* sm) {
 
 // ------------------------------------------------------------------ LayerNorm + modulate
 // one CTA (256 threads) per row; the row stays in registers across the mean / variance reductions.
-template <int MAXV>  // float4 vectors per thread
+// KIND != 0 (native block-scaled path): the result is rounded to the 16-bit operand type and quantised in the same pass to
+// mxfp8 / mxfp4 / nvfp4 (element bytes + tcgen05-layout scale factors, bit-identical to mx_quantize_act on the 16-bit
+// output) — a thread owns 4 consecutive elements, a 16 / 32-element group is 4 / 8 adjacent lanes. CTAs of rows >= `rows`
+// (up to the next multiple of 128) only fill their scale-factor row with 1.0.
+template <int MAXV, int KIND>  // float4 vectors per thread
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, int64_t ldx, void* __restrict__ out,
-                                                          int64_t ldo, int D, const float* __restrict__ shift,
+                                                          int64_t ldo, int rows, int D, const float* __restrict__ shift,
                                                           const float* __restrict__ scale, int64_t mod_bs,
-                                                          int rows_per_batch, float eps, bool f16) {
+                                                          int rows_per_batch, float eps, bool f16, MxOut mx) {
   __shared__ float sm[8];
+  constexpr int GROUP = KIND == 3 ? 16 : 32;
+  constexpr int LPG = GROUP / 4;
   const int row = blockIdx.x;
+  if (KIND != 0 && row >= rows) {
+    for (int g = threadIdx.x; g < D / GROUP; g += 256) mx.sf[sf_offset(row, mx.g0 + g, mx.sf_ld)] = mx_scale_one(KIND);
+    return;
+  }
   const int b = row / rows_per_batch;
   const float* xr = x + (int64_t)row * ldx;
   float4 v[MAXV];
@@ -81,30 +92,65 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
   const float* sh = shift + b * mod_bs;
   const float* sc = scale + b * mod_bs;
   uint16_t* orow = reinterpret_cast<uint16_t*>(out) + (int64_t)row * ldo;
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = (i * 256 + threadIdx.x) * 4;
-    if (c < D) {
+    if (c < D) {  // warp-uniform in the quantising variant (D % 128 == 0)
       const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + c));
       const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc + c));
       const float o0 = (v[i].x - mean) * rstd * (1.f + c4.x) + h4.x;
       const float o1 = (v[i].y - mean) * rstd * (1.f + c4.y) + h4.y;
       const float o2 = (v[i].z - mean) * rstd * (1.f + c4.z) + h4.z;
       const float o3 = (v[i].w - mean) * rstd * (1.f + c4.w) + h4.w;
-      *reinterpret_cast<uint2*>(orow + c) = make_uint2(pack2(o0, o1, f16), pack2(o2, o3, f16));
+      const uint32_t p01 = pack2(o0, o1, f16), p23 = pack2(o2, o3, f16);
+      if constexpr (KIND == 0) {
+        *reinterpret_cast<uint2*>(orow + c) = make_uint2(p01, p23);
+      } else {
+        const float2 a = unpack2(p01, f16), bb = unpack2(p23, f16);
+        float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(bb.x), fabsf(bb.y)));
+#pragma unroll
+        for (int o = 1; o < LPG; o <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const MxScale ms = mx_scale<KIND>(amax);
+        const uint32_t pk = mx_pack4<KIND>(a.x, a.y, bb.x, bb.y, ms.mul);
+        uint8_t* qrow = mx.q + (int64_t)row * mx.ldq;
+        if constexpr (KIND == 1) *reinterpret_cast<uint32_t*>(qrow + c) = pk;
+        else *reinterpret_cast<uint16_t*>(qrow + (c >> 1)) = (uint16_t)pk;
+        uint32_t w = ms.sb | (__shfl_down_sync(0xffffffffu, ms.sb, LPG) << 8);
+        w |= __shfl_down_sync(0xffffffffu, w, 2 * LPG) << 16;
+        if ((lane % (4 * LPG)) == 0) *reinterpret_cast<uint32_t*>(mx.sf + sf_offset(row, mx.g0 + c / GROUP, mx.sf_ld)) = w;
+      }
     }
   }
 }
 
+template <int KIND>
+static void ln_launch(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int grid_rows, int D, const float* shift,
+                      const float* scale, int64_t mod_bs, int rows_per_batch, float eps, bool f16, const MxOut& mx, cudaStream_t s) {
+#define F2B_LN(V) ln_modulate_kernel<V, KIND><<<grid_rows, 256, 0, s>>>(x, ldx, out16, ldo, rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, mx)
+  if (D <= 1024) F2B_LN(1);
+  else if (D <= 3072) F2B_LN(3);
+  else if (D <= 4096) F2B_LN(4);
+  else if (D <= 6144) F2B_LN(6);
+  else F2B_LN(8);
+#undef F2B_LN
+}
 cudaError_t ln_modulate(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int D, const float* shift,
-                        const float* scale, int64_t mod_bs, int rows_per_batch, float eps, bool f16, cudaStream_t s) {
+                        const float* scale, int64_t mod_bs, int rows_per_batch, float eps, bool f16, cudaStream_t s,
+                        const MxOut* mx) {
   if (rows <= 0) return cudaSuccess;
   if (D % 4 || D > 8192 || ldx % 4 || ldo % 4) return cudaErrorInvalidValue;
-  if (D <= 1024) ln_modulate_kernel<1><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
-  else if (D <= 3072) ln_modulate_kernel<3><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
-  else if (D <= 4096) ln_modulate_kernel<4><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
-  else if (D <= 6144) ln_modulate_kernel<6><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
-  else ln_modulate_kernel<8><<<rows, 256, 0, s>>>(x, ldx, out16, ldo, D, shift, scale, mod_bs, rows_per_batch, eps, f16);
+  MxOut m;
+  if (mx) m = *mx;
+  if (m.kind) {
+    if (D % 128 || !m.q || !m.sf || m.g0 % 4 || m.ldq % 4) return cudaErrorInvalidValue;
+    const int grid_rows = (rows + 127) / 128 * 128;
+    if (m.kind == 1) ln_launch<1>(x, ldx, out16, ldo, rows, grid_rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, m, s);
+    else if (m.kind == 2) ln_launch<2>(x, ldx, out16, ldo, rows, grid_rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, m, s);
+    else ln_launch<3>(x, ldx, out16, ldo, rows, grid_rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, m, s);
+  } else {
+    ln_launch<0>(x, ldx, out16, ldo, rows, rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, m, s);
+  }
   return cudaGetLastError();
 }
 

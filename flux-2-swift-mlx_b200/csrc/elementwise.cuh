@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "quant.cuh"
+
 namespace f2b {
 
 // 16-bit activation storage: bf16 (default) or f16, selected at run time (same kernels, different pack/unpack).
@@ -10,7 +12,9 @@ namespace f2b {
 // LayerNorm: biased variance, eps, no affine (Flux2TransformerBlock.swift:56-61; Flux2Modulation.swift:96-112).
 cudaError_t ln_modulate(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int D, const float* shift,
                         const float* scale, int64_t mod_batch_stride, int rows_per_batch, float eps, bool f16,
-                        cudaStream_t s);
+                        cudaStream_t s, const MxOut* mx = nullptr);
+// With mx->kind != 0 (native block-scaled path) out16 is not written: the 16-bit result is quantised in the same pass to
+// mxfp8 / mxfp4 / nvfp4 (bit-identical to mx_quantize_act applied to the 16-bit output); D % 128 == 0.
 
 // y[b, n] = sum_k act(x[b, k]) * W[n, k] ; W 16-bit [N, K] row-major; act = SiLU if silu_in. B <= 8.
 cudaError_t gemv(const float* x, int64_t ldx, const void* W16, int64_t ldw, float* y, int64_t ldy, int B, int N, int K,

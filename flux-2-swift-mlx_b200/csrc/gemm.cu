@@ -18,6 +18,7 @@
 // loads its 128 rows of A and half of B, the leader CTA issues, commits are multicast to both CTAs.
 #include "gemm.cuh"
 #include "ptx.cuh"
+#include "quant_dev.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -82,6 +83,62 @@ __device__ __forceinline__ float2 upk2(uint32_t u, int f16) {
   if (f16) return __half22float2(*reinterpret_cast<__half2*>(&u));
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
+// 32 consecutive 16-bit results of row `grow` starting at output column `col` -> block-scaled bytes + group scale(s)
+template <int KIND>
+__device__ __forceinline__ void store_quantised32(const Epilogue& e, const uint32_t (&pk)[16], bool row_ok, int64_t grow, int col) {
+  const MxOut& m = e.mxo;
+  constexpr int GROUP = KIND == 3 ? 16 : 32;
+  uint8_t* sp = m.sf + sf_offset(grow, m.g0 + col / GROUP, m.sf_ld);
+  if (!row_ok) {  // padding row of the last 128-row block: scale 1.0
+    if constexpr (KIND == 3) *reinterpret_cast<uint16_t*>(sp) = 0x3838; else *sp = 127;
+    return;
+  }
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float2 t = upk2(pk[j], e.f16);
+    f[2 * j] = t.x; f[2 * j + 1] = t.y;
+  }
+  if constexpr (KIND == 3) {
+    uint32_t w[4], sb2 = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float amax = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(f[16 * h + j]));
+      const MxScale sc = mx_scale<3>(amax);
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        w[2 * h + q] = mx_pack4<3>(f[16 * h + 8 * q], f[16 * h + 8 * q + 1], f[16 * h + 8 * q + 2], f[16 * h + 8 * q + 3], sc.mul) |
+                       (mx_pack4<3>(f[16 * h + 8 * q + 4], f[16 * h + 8 * q + 5], f[16 * h + 8 * q + 6], f[16 * h + 8 * q + 7], sc.mul) << 16);
+      sb2 |= sc.sb << (8 * h);
+    }
+    *reinterpret_cast<uint4*>(m.q + grow * m.ldq + (col >> 1)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint16_t*>(sp) = (uint16_t)sb2;
+  } else {
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(f[j]));
+    const MxScale sc = mx_scale<KIND>(amax);
+    if constexpr (KIND == 2) {
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        w[q] = mx_pack4<2>(f[8 * q], f[8 * q + 1], f[8 * q + 2], f[8 * q + 3], sc.mul) |
+               (mx_pack4<2>(f[8 * q + 4], f[8 * q + 5], f[8 * q + 6], f[8 * q + 7], sc.mul) << 16);
+      *reinterpret_cast<uint4*>(m.q + grow * m.ldq + (col >> 1)) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      uint32_t w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) w[q] = mx_pack4<1>(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3], sc.mul);
+      uint4* dst = reinterpret_cast<uint4*>(m.q + grow * m.ldq + col);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    *sp = (uint8_t)sc.sb;
+  }
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int quarter, int lane, bool row_ok,
                                               int64_t grow, int n0) {
@@ -100,7 +157,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
       tmem_ld_32x32(tq + HALF + c * 32, u);
       tmem_ld_wait();
       const int oc = n0 / 2 + c * 32;
-      if (row_ok && oc < p.N / 2) {
+      if ((row_ok || e.mxo.kind) && oc < p.N / 2) {
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -108,9 +165,17 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
           float u0 = __uint_as_float(u[2 * j]), u1 = __uint_as_float(u[2 * j + 1]);
           pk[j] = pk2(silu_f(g0) * u0, silu_f(g1) * u1, e.f16);
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + grow * e.ldo + oc);
+        if (e.mxo.kind == 0) {
+          uint4* dst = reinterpret_cast<uint4*>(out + grow * e.ldo + oc);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        } else if (e.mxo.kind == 1) {
+          store_quantised32<1>(e, pk, row_ok, grow, oc);
+        } else if (e.mxo.kind == 2) {
+          store_quantised32<2>(e, pk, row_ok, grow, oc);
+        } else {
+          store_quantised32<3>(e, pk, row_ok, grow, oc);
+        }
       }
     }
     return;
@@ -653,8 +718,11 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
       g_err = "block-scaled GEMM needs K % 128 (fp8) / 256 (fp4) == 0, N % 128 == 0, 16 B aligned rows and both scale-factor tensors";
       return cudaErrorInvalidValue;
     }
-    if (g.epi.mode == EPI_SWIGLU && g.N % 256) { g_err = "SwiGLU epilogue needs N % 256 == 0"; return cudaErrorInvalidValue; }
-    const bool wide = g.N % 256 == 0 && g.force_bn != 128;
+    // N tile: 128 by default (two accumulator stages fit next to the scale-factor columns in TMEM, so the epilogue of one
+    // tile overlaps the MMAs of the next); 256 on request. A SwiGLU producer must be launched with the tile its weight
+    // rows were interleaved for (force_bn).
+    const bool wide = g.force_bn == 256 && g.N % 256 == 0;
+    if (g.epi.mode == EPI_SWIGLU && !g.force_bn) { g_err = "block-scaled SwiGLU epilogue needs the weight's tile size (force_bn)"; return cudaErrorInvalidValue; }
     switch (g.mx * 2 + (wide ? 1 : 0)) {
       case 2: return launch_cfg<128, 1, false, 1>(g, stream);
       case 3: return launch_cfg<256, 1, false, 1>(g, stream);

@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "quant.cuh"
+
 namespace f2b {
 
 enum EpiMode : int {
@@ -37,6 +39,10 @@ struct Epilogue {
   // NVLink: the projection and its all-to-all are then one kernel); `out` is unused, ldo = 3 * sp_hp * 128.
   int sp_hp = 0;
   void* sp_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // EPI_SWIGLU on the native block-scaled path (mxo.kind != 0): the 16-bit result is not stored; it is quantised in the
+  // epilogue (a thread owns 32 consecutive output columns = whole groups) to the format the next GEMM consumes, bit-identical
+  // to mx_quantize_act on the 16-bit output. Rows of the last M tile beyond M get scale 1.0.
+  MxOut mxo;
 };
 
 struct GemmProblem {

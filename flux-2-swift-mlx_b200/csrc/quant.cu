@@ -10,7 +10,9 @@
 // All fp32 steps use explicit _rn intrinsics so that no FMA contraction can make the device disagree with the
 // C oracle (oracle/quant_oracle.c) by an ulp.
 #include "quant.cuh"
+#include "quant_dev.cuh"
 #include <cuda_fp8.h>
+#include <cuda_fp4.h>
 #include <algorithm>
 #include "ptx.cuh"
 
@@ -46,84 +48,6 @@ __device__ __forceinline__ void store_o(void* o, int dtype, int64_t i, float v) 
   if (dtype == 0) reinterpret_cast<float*>(o)[i] = v;
   else if (dtype == 1) reinterpret_cast<__half*>(o)[i] = __float2half_rn(v);
   else reinterpret_cast<__nv_bfloat16*>(o)[i] = __float2bfloat16(v);
-}
-
-// ---- scalar format conversions (integer / compare logic only: deterministic everywhere)
-// round(log2(x)) for x > 0 without libm: exponent + (mantissa >= sqrt(2))
-__device__ __forceinline__ int round_log2_pos(float x) {
-  uint32_t u = __float_as_uint(x);
-  int e = (int)((u >> 23) & 0xff);
-  uint32_t m = u & 0x7fffff;
-  if (e == 0) {  // subnormal: below 2^-126, clamps to -127 anyway
-    return -127;
-  }
-  return (e - 127) + (m >= 0x3504F4u ? 1 : 0);
-}
-__device__ __forceinline__ uint8_t to_e8m0(float x) {
-  if (!(x > 0.f)) return 0;  // zero / negative / NaN -> smallest scale (NaN cannot occur for finite weights)
-  if (isinf(x)) return 0xFF;
-  int n = round_log2_pos(x);
-  n = n < -127 ? -127 : n;
-  n = n > 127 ? 127 : n;
-  return (uint8_t)(n + 127);
-}
-__device__ __forceinline__ float from_e8m0(uint8_t b) {
-  // 2^(b-127); b = 0 -> 2^-127 (subnormal), b = 255 treated as 2^128 -> inf
-  if (b == 0) return __uint_as_float(0x00400000u);
-  if (b == 255) return __uint_as_float(0x7f800000u);
-  return __uint_as_float((uint32_t)b << 23);
-}
-// fp32 -> E4M3 (fn: no inf, max 448), round-to-nearest-even, saturating; sign kept
-__device__ __forceinline__ uint8_t to_e4m3(float x) {
-  uint32_t u = __float_as_uint(x);
-  uint8_t sign = (u >> 31) ? 0x80 : 0;
-  float a = fabsf(x);
-  if (a != a) return sign | 0x7F;
-  if (a >= 448.f) return sign | 0x7E;  // saturate (covers inf)
-  if (a < 0.015625f) {
-    // subnormal range: multiples of 2^-9, RNE
-    float q = rintf(__fmul_rn(a, 512.f));  // exact scaling by a power of two
-    return sign | (uint8_t)q;              // q in [0,8]; 8 == smallest normal 0x08
-  }
-  uint32_t au = __float_as_uint(a);
-  int e = (int)(au >> 23) - 127;   // [-6, 8]
-  uint32_t m = au & 0x7fffff;
-  uint32_t keep = m >> 20;         // 3 mantissa bits
-  uint32_t rem = m & 0xfffff;
-  uint32_t half = 0x80000;
-  if (rem > half || (rem == half && (keep & 1))) ++keep;
-  if (keep == 8) { keep = 0; ++e; }
-  uint32_t code = ((uint32_t)(e + 7) << 3) | keep;
-  if (code > 0x7E) code = 0x7E;
-  return sign | (uint8_t)code;
-}
-__device__ __forceinline__ float from_e4m3(uint8_t b) {
-  const float sgn = (b & 0x80) ? -1.f : 1.f;
-  const int e = (b >> 3) & 0xF;
-  const int m = b & 7;
-  if (e == 0) return sgn * (float)m * 0.001953125f;  // m * 2^-9
-  if (e == 15 && m == 7) return __uint_as_float(0x7fc00000u);
-  return sgn * __uint_as_float((uint32_t)(e - 7 + 127) << 23) * (1.f + (float)m * 0.125f);
-}
-__device__ __forceinline__ uint8_t to_e2m1(float x) {
-  const uint8_t sign = (__float_as_uint(x) >> 31) ? 0x8 : 0x0;
-  const float a = fabsf(x);
-  uint8_t b;
-  if (a != a) b = 0x7;
-  else if (a > 5.0f) b = 0x7;
-  else if (a >= 3.5f) b = 0x6;
-  else if (a > 2.5f) b = 0x5;
-  else if (a >= 1.75f) b = 0x4;
-  else if (a > 1.25f) b = 0x3;
-  else if (a >= 0.75f) b = 0x2;
-  else if (a > 0.25f) b = 0x1;
-  else b = 0x0;
-  return b | sign;
-}
-__device__ __forceinline__ float from_e2m1(uint8_t b) {
-  const float tab[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
-  const float v = tab[b & 7];
-  return (b & 8) ? -v : v;
 }
 
 // ---- one thread per group
@@ -274,18 +198,15 @@ __host__ __device__ inline int mx_bits(int kind) { return kind == 1 ? 8 : 4; }
 int mx_kind_of_quant(int quant) { return quant == 3 ? 1 : quant == 4 ? 2 : quant == 5 ? 3 : 0; }
 int64_t mx_sf_ld(int kind, int64_t K) { return K / mx_group(kind) / 4; }
 size_t mx_sf_bytes(int kind, int64_t rows, int64_t K) { return (size_t)((rows + 127) / 128) * mx_sf_ld(kind, K) * 512; }
-__device__ __forceinline__ int64_t sf_offset(int64_t row, int64_t g, int64_t ld_blocks) {
-  return ((row >> 7) * ld_blocks + (g >> 2)) * 512 + (row & 31) * 16 + ((row & 127) >> 5) * 4 + (g & 3);
-}
 __global__ void mx_copy_rows_kernel(const uint8_t* __restrict__ src_w, const uint8_t* __restrict__ src_s, int64_t src_row0,
                                     uint8_t* __restrict__ dst_w, uint8_t* __restrict__ dst_sf, int64_t dst_row0,
-                                    int64_t nrows, int64_t row_bytes, int64_t G, int tiled, int64_t Hm) {
+                                    int64_t nrows, int64_t row_bytes, int64_t G, int tile, int64_t Hm) {
   const int64_t vec_per_row = row_bytes / 16;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  auto src_row = [&](int64_t r) {
-    if (!tiled) return r;
-    const int64_t tile = r / 256, j = r % 256;
-    return (j < 128) ? tile * 128 + j : Hm + tile * 128 + (j - 128);
+  auto src_row = [&](int64_t r) {  // SwiGLU interleave: every `tile` rows = [tile/2 gate rows | tile/2 value rows]
+    if (!tile) return r;
+    const int64_t h = tile / 2, t = r / tile, j = r % tile;
+    return (j < h) ? t * h + j : Hm + t * h + (j - h);
   };
   if (i < nrows * vec_per_row) {
     const int64_t r = i / vec_per_row, v = i % vec_per_row;
@@ -298,118 +219,94 @@ __global__ void mx_copy_rows_kernel(const uint8_t* __restrict__ src_w, const uin
   }
 }
 cudaError_t mx_copy_rows(int kind, const uint8_t* src_w, const uint8_t* src_s, int64_t src_row0, uint8_t* dst_w, uint8_t* dst_sf,
-                         int64_t dst_row0, int64_t nrows, int64_t K, bool tiled, int64_t Hm, cudaStream_t s) {
-  if (kind < 1 || kind > 3 || K % (kind == 1 ? 128 : 256)) return cudaErrorInvalidValue;
+                         int64_t dst_row0, int64_t nrows, int64_t K, int tile, int64_t Hm, cudaStream_t s) {
+  if (kind < 1 || kind > 3 || K % (kind == 1 ? 128 : 256) || (tile && (nrows % tile || Hm % (tile / 2)))) return cudaErrorInvalidValue;
   const int64_t row_bytes = K * mx_bits(kind) / 8, G = K / mx_group(kind);
   const int64_t n = nrows * std::max(row_bytes / 16, G);
   if (n <= 0) return cudaSuccess;
   mx_copy_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src_w, src_s, src_row0, dst_w, dst_sf, dst_row0, nrows, row_bytes, G,
-                                                                  tiled ? 1 : 0, Hm);
+                                                                  tile, Hm);
   return cudaGetLastError();
 }
 
-__device__ __forceinline__ void unpack8(const uint4 raw, bool f16, float (&v)[8]) {
-  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = f16 ? __half22float2(*reinterpret_cast<const __half2*>(&w[j]))
-                         : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-    v[2 * j] = f.x; v[2 * j + 1] = f.y;
-  }
-}
-// mxfp8: one warp per (row, 128-element K block): lane owns 4 consecutive elements, 8 lanes share a 32-element group.
-// The scale is 2^ceil(log2(amax / 448)) (nothing saturates) — an activation is quantised once and consumed at once, so it
-// need not follow the weight packer's round-to-nearest exponent rule.
-__global__ void __launch_bounds__(256) mx8_quantize_act_kernel(const void* __restrict__ x, int64_t ldx, int M, int K, bool f16,
-                                                              uint8_t* __restrict__ a8, int64_t lda, uint8_t* __restrict__ sfa,
-                                                              int64_t sf_ld, int g0) {
-  const int kb4 = K / 128;
+// On-the-fly activation quantiser. A warp owns up to kIters x 256 consecutive elements of one row: lane = 8 consecutive
+// elements per iteration (16 B in; 8 B of E4M3 or 4 B of E2M1 out), all loads of a warp issued before any arithmetic.
+// A 32-element group is 4 lanes, a 16-element nvfp4 group 2 lanes; the four scale bytes of one 512 B-block row are gathered
+// by shuffles and stored as one word.
+//   mxfp8: scale = 2^ceil(log2(amax / 448)) (nothing saturates; an activation is quantised once and consumed at once, so it
+//          need not follow the weight packer's round-to-nearest exponent rule), elements by cvt.rn.satfinite.e4m3x2.
+//   mxfp4 / nvfp4: the weight packer's rule (amax / 6 -> E8M0 / E4M3 scale, x / scale -> E2M1 RNE, saturating), evaluated as
+//          cvt.rn.satfinite.e2m1x2(f16(x * (1 / scale))). That is bit-identical to quantize_kernel / the C oracle for 16-bit
+//          inputs: x (<= 11 significant bits) and threshold * scale (<= 7 bits) are dyadic rationals that either coincide or
+//          differ by >= 2^-12 relative, the product carries <= 2^-22 error and the f16 rounding snaps an exact tie back onto
+//          its threshold, where RNE picks the even code exactly like to_e2m1() above.
+template <int KIND>
+__global__ void __launch_bounds__(256) mx_quantize_act_kernel(const void* __restrict__ x, int64_t ldx, int M, int K, bool f16,
+                                                             uint8_t* __restrict__ aq, int64_t lda, uint8_t* __restrict__ sfa,
+                                                             int64_t sf_ld, int g0) {
+  constexpr int kIters = 4;
+  constexpr int GROUP = KIND == 3 ? 16 : 32;
+  constexpr int LPG = GROUP / 8;        // lanes per group
+  const int chunks = (K + kIters * 256 - 1) / (kIters * 256);
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t Mpad = ((int64_t)M + 127) / 128 * 128;
-  if (wid >= Mpad * kb4) return;
-  const int64_t row = wid / kb4;
-  const int kb = (int)(wid % kb4);
-  if (row >= M) {  // padding rows of the last 128-row block: scale 1.0 (never multiplied with anything but zeros)
-    if (lane < 4) sfa[sf_offset(row, g0 + kb * 4 + lane, sf_ld)] = 127;
+  if (wid >= Mpad * chunks) return;
+  const int64_t row = wid / chunks;
+  const int k_begin = (int)(wid % chunks) * kIters * 256;
+  if (row >= M) {  // padding rows of the last 128-row block: scale 1.0 (only ever multiplied with TMA zero fill)
+    const int g_end = min(K, k_begin + kIters * 256) / GROUP;
+    for (int g = k_begin / GROUP + lane; g < g_end; g += 32) sfa[sf_offset(row, g0 + g, sf_ld)] = (KIND == 3) ? 0x38 : 127;
     return;
   }
-  const uint16_t* xr = reinterpret_cast<const uint16_t*>(x) + row * ldx + kb * 128 + lane * 4;
-  const uint2 raw = *reinterpret_cast<const uint2*>(xr);
-  float2 a, b;
-  if (f16) { a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)); b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y)); }
-  else { a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x)); b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y)); }
-  float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y)));
+  const uint16_t* xr = reinterpret_cast<const uint16_t*>(x) + row * ldx;
+  uint4 raw[kIters];
 #pragma unroll
-  for (int o = 4; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));  // 8 lanes = one 32-element group
-  // smallest power of two s with amax / s <= 448  (exponent arithmetic only)
-  int e = -127;
-  if (amax > 0.f) {
-    const float q = amax * (1.0f / 448.0f);
-    const uint32_t u = __float_as_uint(q);
-    e = (int)((u >> 23) & 0xff) - 127 + ((u & 0x7fffff) ? 1 : 0);
-    e = e < -127 ? -127 : (e > 127 ? 127 : e);
+  for (int i = 0; i < kIters; ++i) {
+    const int k = k_begin + i * 256 + lane * 8;
+    raw[i] = (k < K) ? *reinterpret_cast<const uint4*>(xr + k) : make_uint4(0, 0, 0, 0);
   }
-  const uint32_t ebits = (uint32_t)(127 - e);                                      // biased exponent of 2^-e, in [0, 254]
-  const float inv = __uint_as_float(ebits ? (ebits << 23) : 0x00400000u);          // 2^-e (2^-127 is subnormal)
-  const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a.x * inv, a.y * inv), __NV_SATFINITE, __NV_E4M3);
-  const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(b.x * inv, b.y * inv), __NV_SATFINITE, __NV_E4M3);
-  *reinterpret_cast<uint32_t*>(a8 + row * lda + kb * 128 + lane * 4) = (uint32_t)lo | ((uint32_t)hi << 16);
-  if ((lane & 7) == 0) sfa[sf_offset(row, g0 + kb * 4 + (lane >> 3), sf_ld)] = (uint8_t)(e + 127);
-}
-// fp4 kinds: one warp per (row, 256-element K block): lane owns 8 consecutive elements (16 B in, 4 B out); a 16-element
-// nvfp4 group is 2 lanes, a 32-element mxfp4 group 4 lanes. Same arithmetic as the weight packer above (amax / 6 -> E4M3 or
-// E8M0 scale, x / scale -> E2M1 RNE), so the result is bit-identical to quantize_kernel / the C oracle on the same matrix.
-template <bool kNv>
-__global__ void __launch_bounds__(256) mx4_quantize_act_kernel(const void* __restrict__ x, int64_t ldx, int M, int K, bool f16,
-                                                              uint8_t* __restrict__ a4, int64_t lda, uint8_t* __restrict__ sfa,
-                                                              int64_t sf_ld, int g0) {
-  constexpr int GPB = kNv ? 16 : 8;  // groups per 256-element block
-  const int kbn = K / 256;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int64_t Mpad = ((int64_t)M + 127) / 128 * 128;
-  if (wid >= Mpad * kbn) return;
-  const int64_t row = wid / kbn;
-  const int kb = (int)(wid % kbn);
-  if (row >= M) {  // padding rows: scale 1.0
-    if (lane < GPB) sfa[sf_offset(row, g0 + kb * GPB + lane, sf_ld)] = kNv ? 0x38 : 127;
-    return;
-  }
-  const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(x) + row * ldx + kb * 256 + lane * 8);
-  float v[8];
-  unpack8(raw, f16, v);
-  float amax = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
-  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-  if (!kNv) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-  float scale = __fdiv_rn(amax, 6.0f);
-  uint8_t sb;
-  if (kNv) { sb = to_e4m3(scale); scale = from_e4m3(sb); }
-  else { sb = to_e8m0(scale); scale = from_e8m0(sb); }
-  uint32_t word = 0;
+  for (int i = 0; i < kIters; ++i) {
+    const int k = k_begin + i * 256 + lane * 8;
+    if (k_begin + i * 256 >= K) break;  // warp-uniform
+    float v[8];
+    unpack8(raw[i], f16, v);
+    float amax = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float q = (scale == 0.f) ? 0.f : __fdiv_rn(v[j], scale);
-    word |= (uint32_t)to_e2m1(q) << (4 * j);
+    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    if (LPG == 4) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    const MxScale sc = mx_scale<KIND>(amax);
+    const uint32_t sb = sc.sb;
+    if constexpr (KIND == 1) {
+      if (k < K) *reinterpret_cast<uint2*>(aq + row * lda + k) =
+          make_uint2(mx_pack4<1>(v[0], v[1], v[2], v[3], sc.mul), mx_pack4<1>(v[4], v[5], v[6], v[7], sc.mul));
+    } else {
+      if (k < K) *reinterpret_cast<uint32_t*>(aq + row * lda + (k >> 1)) =
+          mx_pack4<KIND>(v[0], v[1], v[2], v[3], sc.mul) | (mx_pack4<KIND>(v[4], v[5], v[6], v[7], sc.mul) << 16);
+    }
+    // four consecutive group scales -> one 32-bit store (lane of the first group of each 4-group block)
+    uint32_t w = sb | (__shfl_down_sync(0xffffffffu, sb, LPG) << 8);
+    w |= __shfl_down_sync(0xffffffffu, w, 2 * LPG) << 16;
+    if ((lane % (4 * LPG)) == 0 && k < K)
+      *reinterpret_cast<uint32_t*>(sfa + sf_offset(row, g0 + k / GROUP, sf_ld)) = w;
   }
-  *reinterpret_cast<uint32_t*>(a4 + row * lda + kb * 128 + lane * 4) = word;
-  constexpr int LPG = kNv ? 2 : 4;  // lanes per group
-  if ((lane % LPG) == 0) sfa[sf_offset(row, g0 + kb * GPB + lane / LPG, sf_ld)] = sb;
 }
 cudaError_t mx_quantize_act(int kind, const void* x16, int64_t ldx, int M, int K, bool f16, uint8_t* aq, int64_t lda_bytes,
                             uint8_t* sfa, int64_t sf_ld, int64_t col0, cudaStream_t s) {
   const int kb_elems = kind == 1 ? 128 : 256;
-  if (kind < 1 || kind > 3 || K % kb_elems || col0 % kb_elems || ldx % 8 || lda_bytes % 4) return cudaErrorInvalidValue;
+  if (kind < 1 || kind > 3 || K % kb_elems || col0 % kb_elems || ldx % 8 || lda_bytes % 8 ||
+      (reinterpret_cast<uintptr_t>(x16) & 15) || (reinterpret_cast<uintptr_t>(aq) & 7))
+    return cudaErrorInvalidValue;
   const int64_t Mpad = ((int64_t)M + 127) / 128 * 128;
-  const int64_t warps = Mpad * (K / kb_elems);
+  const int64_t warps = Mpad * ((K + 1023) / 1024);
   if (warps <= 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
   const int g0 = (int)(col0 / mx_group(kind));
-  if (kind == 1) mx8_quantize_act_kernel<<<blocks, 256, 0, s>>>(x16, ldx, M, K, f16, aq, lda_bytes, sfa, sf_ld, g0);
-  else if (kind == 2) mx4_quantize_act_kernel<false><<<blocks, 256, 0, s>>>(x16, ldx, M, K, f16, aq, lda_bytes, sfa, sf_ld, g0);
-  else mx4_quantize_act_kernel<true><<<blocks, 256, 0, s>>>(x16, ldx, M, K, f16, aq, lda_bytes, sfa, sf_ld, g0);
+  if (kind == 1) mx_quantize_act_kernel<1><<<blocks, 256, 0, s>>>(x16, ldx, M, K, f16, aq, lda_bytes, sfa, sf_ld, g0);
+  else if (kind == 2) mx_quantize_act_kernel<2><<<blocks, 256, 0, s>>>(x16, ldx, M, K, f16, aq, lda_bytes, sfa, sf_ld, g0);
+  else mx_quantize_act_kernel<3><<<blocks, 256, 0, s>>>(x16, ldx, M, K, f16, aq, lda_bytes, sfa, sf_ld, g0);
   return cudaGetLastError();
 }
 // scale factors back from the tcgen05 layout to row-major [M, G] (tests / debugging)

@@ -21,9 +21,9 @@ int mx_kind_of_quant(int quant);                       // flux2b_quant -> kind (
 int64_t mx_sf_ld(int kind, int64_t K);                 // blocks per row block for a [*, K] operand
 size_t mx_sf_bytes(int kind, int64_t rows, int64_t K);
 // rows of an MLX-packed weight (bytes [*, K*bits/8], scales [*, K/group]) -> rows [dst_row0, dst_row0 + nrows) of the
-// working copy; `tiled` applies the SwiGLU [128 gate | 128 value] interleave of weights.cu
+// working copy; tile = 256 / 128 applies the SwiGLU interleave ([tile/2 gate | tile/2 value] rows per GEMM N tile), 0 = none
 cudaError_t mx_copy_rows(int kind, const uint8_t* src_w, const uint8_t* src_s, int64_t src_row0, uint8_t* dst_w, uint8_t* dst_sf,
-                         int64_t dst_row0, int64_t nrows, int64_t K, bool tiled, int64_t Hm, cudaStream_t s);
+                         int64_t dst_row0, int64_t nrows, int64_t K, int tile, int64_t Hm, cudaStream_t s);
 // 16-bit activations x16[M, K] (leading dim ldx elements) -> quantised bytes aq[M, K*bits/8] (leading dim lda_bytes) + group
 // scales written at group offset col0 / group of a scale-factor tensor with `sf_ld` blocks per row block (so a column slice
 // [col0, col0 + K) of a wider activation can be quantised on its own). fp4 kinds use the weight packer's arithmetic
@@ -31,6 +31,17 @@ cudaError_t mx_copy_rows(int kind, const uint8_t* src_w, const uint8_t* src_s, i
 // 128 are filled with 1.0.
 cudaError_t mx_quantize_act(int kind, const void* x16, int64_t ldx, int M, int K, bool f16, uint8_t* aq, int64_t lda_bytes,
                             uint8_t* sfa, int64_t sf_ld, int64_t col0, cudaStream_t s);
+// Destination of an activation quantisation fused into the producing kernel (LayerNorm + modulate, SwiGLU GEMM epilogue):
+// row r, column c of the producer's output goes to q[r * ldq + c * bits / 8] and its group scale to group g0 + c / group of
+// row r in the scale-factor tensor `sf` (sf_ld blocks per 128-row block). kind 0 = off.
+struct MxOut {
+  int kind = 0;
+  uint8_t* q = nullptr;
+  int64_t ldq = 0;
+  uint8_t* sf = nullptr;
+  int64_t sf_ld = 0;
+  int g0 = 0;
+};
 cudaError_t mx_sf_untile(const uint8_t* sf, uint8_t* out, int64_t M, int64_t G, cudaStream_t s);
 
 }  // namespace f2b

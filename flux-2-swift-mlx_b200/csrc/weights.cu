@@ -193,6 +193,8 @@ static int build_swiglu(flux2b_ctx* c, const void* dense, int64_t ld, int64_t ro
 static int mx_rows(flux2b_ctx* c, const std::string& base, int eN, int eK, int64_t src_row0, int64_t nrows, Lin* L, int N_total,
                    int64_t dst_row0, bool tiled, int Hm) {
   const int kind = c->mx_kind;
+  // N tile of the block-scaled GEMM: 128 keeps two accumulator stages next to the scale-factor columns in TMEM
+  const int bn = (c->option("mx_bn", 0) == 256 && N_total % 256 == 0) ? 256 : 128;
   F2B_TRY(ensure_packed(c, base));
   Tensor* w = find(c, base + ".weight");
   Tensor* s = find(c, base + ".scales");
@@ -203,14 +205,15 @@ static int mx_rows(flux2b_ctx* c, const std::string& base, int eN, int eK, int64
   if (s->numel() != (int64_t)eN * (eK / group)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "scales shape mismatch: " + base);
   if (eK % (kind == 1 ? 128 : 256) || N_total % 128)
     return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "native_mx needs in-features % 128 (fp8) / 256 (fp4) == 0 and out-features % 128 == 0: " + base);
-  if (!L->wq.p || L->N != N_total || L->K != eK || L->mx != kind) {
+  if (!L->wq.p || L->N != N_total || L->K != eK || L->mx != kind || L->bn != bn) {
     F2B_CUDA(L->wq.alloc((size_t)N_total * eK * bits / 8));
     F2B_CUDA(L->sfb.alloc(mx_sf_bytes(kind, N_total, eK)));
     L->w.release();
-    L->N = N_total; L->K = eK; L->mx = kind;
+    L->N = N_total; L->K = eK; L->mx = kind; L->bn = bn;
   }
+  if (tiled && (nrows % bn || Hm % (bn / 2))) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "SwiGLU tile does not divide the MLP width: " + base);
   F2B_CUDA(mx_copy_rows(kind, w->buf.as<uint8_t>(), s->buf.as<uint8_t>(), src_row0, L->wq.as<uint8_t>(), L->sfb.as<uint8_t>(), dst_row0,
-                        nrows, eK, tiled, Hm, c->stream));
+                        nrows, eK, tiled ? bn : 0, Hm, c->stream));
   return 0;
 }
 

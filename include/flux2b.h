@@ -74,7 +74,9 @@ int flux2b_device_count(void);
  * (Pipeline/Flux2Pipeline.swift:299-316,483-610,692-735) */
 int flux2b_create(int device, const flux2b_dit_config* dit, const flux2b_vae_config* vae, int quant, flux2b_ctx** out);
 void flux2b_destroy(flux2b_ctx* ctx);
-/* run on the caller's CUDA stream (cudaStream_t) instead of the context's own */
+/* run on the caller's CUDA stream (cudaStream_t) instead of the context's own. The context's own stream is a blocking
+ * stream (ordered against the legacy default stream); device pointers handed to any call must be ready with respect to the
+ * stream the context runs on — that ordering is the caller's responsibility when it supplies a non-blocking stream. */
 int flux2b_set_stream(flux2b_ctx* ctx, void* cuda_stream);
 int flux2b_synchronize(flux2b_ctx* ctx);
 /* options: "compute_f16" (0 = bf16 activations [default], 1 = f16), "fuse_qk_rope" (1), "fuse_swiglu" (1),

@@ -119,7 +119,13 @@ def test_dit_forward_native_block_scaled(flux2b, name):
     assert np.array_equal(out, out2)
     # deterministic
     assert np.array_equal(out, ctx.dit_forward(*args))
-    ctx.close(); ctx_w.close(); ctx2.close()
+    # the quantisation fused into LayerNorm + modulate and the SwiGLU epilogue produces the same bits as the separate pass
+    ctx3 = make_ctx(flux2b, cfg, W, quant=q, dtype=torch.float16, opts={"native_mx": 1, "mx_fuse_quant": 0})
+    assert np.array_equal(out, ctx3.dit_forward(*args))
+    # 256-wide N tiles (one accumulator stage, SwiGLU rows interleaved per 256): same arithmetic
+    ctx4 = make_ctx(flux2b, cfg, W, quant=q, dtype=torch.float16, opts={"native_mx": 1, "mx_bn": 256})
+    assert rel_l2(ctx4.dit_forward(*args), out) < 1e-5
+    ctx.close(); ctx_w.close(); ctx2.close(); ctx3.close(); ctx4.close()
 
 
 def test_native_mx_ragged_and_batch(flux2b):

@@ -23,6 +23,18 @@ for w in $WHAT; do
       timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 2000 --csv \
         --log-file gpurun_out/launches.csv python bench.py --profile-one > gpurun_out/ncu_launches.log 2>&1
       echo "ncu launches rc=$?"; wc -l gpurun_out/launches.csv ;;
+    traffic)
+      # DRAM bytes of EVERY launch of one image (cheap pass: two counters, no --set full)
+      timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --profile-from-start off \
+        -c 2000 --csv --log-file gpurun_out/traffic.csv python bench.py --profile-one > gpurun_out/ncu_traffic.log 2>&1
+      echo "ncu traffic rc=$?"; wc -l gpurun_out/traffic.csv ;;
+    bench_k9)
+      # BASELINE.json configs[2] on one GPU: Klein 9B nvfp4, W-only and native block-scaled
+      for nm in 0 1; do
+        timeout 900 python bench.py --model klein9b --quant nvfp4 --native-mx $nm --steps 3 --warmup 3 --no-cpu-baseline \
+          > gpurun_out/bench_k9_nvfp4_native$nm.json 2> gpurun_out/bench_k9_$nm.err
+        echo "bench k9 native=$nm rc=$?"; tail -c 2500 gpurun_out/bench_k9_nvfp4_native$nm.json; tail -n 3 gpurun_out/bench_k9_$nm.err
+      done ;;
     full)
       # top kernels, full sections (few launches each)
       timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \

@@ -60,5 +60,35 @@ def full(src, dst):
     print(open(dst).read()[:6000])
 
 
+def traffic(src, dst):
+    """ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over every launch of one image -> mean DRAM bytes per launch
+    per kernel class (json read by bench.py for roofline.traffic)."""
+    import json
+    lines = [l for l in open(src) if l.startswith('"')]
+    r = csv.reader(lines)
+    hdr = next(r)
+    ki, ii, mi, vi, ui = (hdr.index(k) for k in ("Kernel Name", "ID", "Metric Name", "Metric Value", "Metric Unit"))
+    per = collections.OrderedDict()
+    for row in r:
+        if not row[mi].startswith("dram__bytes"):
+            continue
+        v = float(row[vi].replace(",", ""))
+        v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row[ui], 1.0)
+        name = re.sub(r"\(.*", "", row[ki]).replace("void ", "")
+        per.setdefault((row[ii], name), 0.0)
+        per[(row[ii], name)] += v
+    cls = collections.OrderedDict()
+    for (_, name), v in per.items():
+        c = ("conv" if re.search(r"gemm_kernel<\d+, \d+, 1", name) else "gemm" if name.startswith("gemm_kernel") else
+             "attn" if name.startswith("attn_kernel") else name)
+        a = cls.setdefault(c, [0, 0.0])
+        a[0] += 1; a[1] += v
+    out = {c: a[1] / a[0] for c, a in cls.items()}
+    out["_launches"] = {c: a[0] for c, a in cls.items()}
+    out["_source"] = "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one klein4b 1024x1024 image (bench.py --profile-one); mean bytes per launch"
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1)[:3000])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
