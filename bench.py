@@ -201,7 +201,8 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
     H = W = args.res
     S_img = (H // 16) * (W // 16)
     ctx = flux2b.Context(dit=cfg, device=local_rank, quant=flux2b.QUANT[args.quant],
-                         options={"keep_raw_weights": 0, "sp_mode": args.sp_mode, "native_mx": args.native_mx, "mx_bn": args.mx_bn})
+                         options={"keep_raw_weights": 0, "sp_mode": args.sp_mode, "native_mx": args.native_mx, "mx_bn": args.mx_bn,
+                                  "gemm_cta_group": args.cta_group})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     from oracle import flux2_oracle as O
     g = torch.Generator(device=device).manual_seed(0)   # same seed on every rank: replicated weights
@@ -305,6 +306,7 @@ def main():
                     help="1 = block linears on tcgen05 block-scaled MMA (mxfp8 / mxfp4 / nvfp4 weights consumed as packed, activations "
                          "quantised on the fly); 0 = W-only x · dequant(W)^T through the 16-bit GEMM (the reference's arithmetic)")
     ap.add_argument("--mx-bn", type=int, default=0, help="N tile of the block-scaled GEMM (0 = auto / 128 / 256)")
+    ap.add_argument("--cta-group", type=int, default=0, help="GEMM CTA group (0 = auto: CTA pairs / 1 / 2)")
     ap.add_argument("--sp", action="store_true",
                     help="Ulysses sequence-parallel mode: all ranks cooperate on ONE denoising step (strong scaling); "
                          "use with --model dev --res 2048 (BASELINE.json configs[3])")
@@ -341,7 +343,8 @@ def main():
         run_sp(args, cfg, rank, local_rank, world, device, dist)
         return
     ctx = flux2b.Context(dit=cfg, vae=vcfg, device=local_rank, quant=flux2b.QUANT[args.quant],
-                         options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn})
+                         options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn,
+                                  "gemm_cta_group": args.cta_group})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     make_weights_on_gpu(ctx, cfg, vcfg, device)
     ctx.finalize()

@@ -369,7 +369,7 @@ int flux2b_op_gemm(flux2b_ctx* c, const void* a16, const void* w16, int M, int N
 }
 
 int flux2b_op_gemm_mx(flux2b_ctx* c, int quant, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N,
-                      int K, float* out, uint8_t* aq_out, uint8_t* sfa_out, int bn) {
+                      int K, float* out, uint8_t* aq_out, uint8_t* sfa_out, int bn, int cta_group) {
   F2B_TRY(check_ctx(c));
   const int kind = mx_kind_of_quant(quant);
   if (!kind) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "block-scaled GEMM: quant must be mxfp8, mxfp4 or nvfp4");
@@ -397,7 +397,7 @@ int flux2b_op_gemm_mx(flux2b_ctx* c, int quant, const void* a16, const uint32_t*
   g.A = aq.p; g.lda = (int64_t)wrow; g.B = wq.p; g.ldb = (int64_t)wrow; g.M = M; g.N = N; g.K = K;
   g.mx = kind; g.sfa = sfa.as<uint8_t>(); g.sfb = sfb.as<uint8_t>();
   g.epi.mode = EPI_F32; g.epi.out = dout; g.epi.ldo = N;
-  g.force_bn = bn;
+  g.force_bn = bn; g.force_cta_group = cta_group;
   {
     ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * M * N * (double)K, ((double)M + N) * wrow + 4.0 * M * N);
     F2B_CUDA(gemm_launch(g, c->stream));
@@ -413,7 +413,7 @@ int flux2b_op_gemm_mx(flux2b_ctx* c, int quant, const void* a16, const uint32_t*
 }
 int flux2b_op_gemm_mxfp8(flux2b_ctx* c, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N, int K,
                          float* out, uint8_t* a8_out, uint8_t* sfa_out) {
-  return flux2b_op_gemm_mx(c, FLUX2B_MXFP8, a16, w_packed, w_scales, M, N, K, out, a8_out, sfa_out, 0);
+  return flux2b_op_gemm_mx(c, FLUX2B_MXFP8, a16, w_packed, w_scales, M, N, K, out, a8_out, sfa_out, 0, 0);
 }
 
 int flux2b_op_attention(flux2b_ctx* c, const void* qkv16, int B, int S, int H, void* out16, int variant) {

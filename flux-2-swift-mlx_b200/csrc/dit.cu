@@ -36,6 +36,7 @@ static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int
     if (!qa || !qa->q) return fail(FLUX2B_ERR_GENERATION_FAILED, "internal: block-scaled weight without a quantised activation");
     const int bits = W.mx == 1 ? 8 : 4, group = W.mx == 3 ? 16 : 32;
     g.mx = W.mx; g.force_bn = W.bn;
+    g.force_cta_group = c->option("gemm_cta_group", 0);
     g.A = qa->q; g.lda = qa->ldq; g.sfa = qa->sf; g.sfa_ld = qa->sf_ld;
     g.B = W.wq.as<uint8_t>() + k_off * bits / 8; g.ldb = (int64_t)W.K * bits / 8;
     g.sfb = W.sfb.as<uint8_t>() + (k_off / group / 4) * 512; g.sfb_ld = W.K / group / 4;

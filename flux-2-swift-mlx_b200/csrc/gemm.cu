@@ -325,9 +325,10 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
 // ------------------------------------------------------------------------------------------------ kernel
 template <int BN, int CG, bool CONV, int MXK = 0>
 __global__ void __launch_bounds__(192, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmSFA, const __grid_constant__ CUtensorMap tmSFB, const KParams p) {
   using C = Cfg<BN, CG, MXK>;
-  static_assert(!MXK || (CG == 1 && !CONV && (BN == 128 || BN == 256)), "block-scaled tiles: single CTA, BN 128 / 256");
+  static_assert(!MXK || (!CONV && (BN == 128 || (BN == 256 && CG == 1))), "block-scaled tiles: BN 128 (1 or 2 CTAs) / 256 (1 CTA)");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;
@@ -429,8 +430,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               // 3-D weight box through the cta_group::2 path is expressed as 4-D with a unit outer dim
               tma_load_4d_cg2(b_dst, &tmB, lbar, c0, tap, nrow0, 0);
             } else {
-              tma_load_2d_cg2(a_dst, &tmA, lbar, kb * BK, m_blk * BM);
-              tma_load_2d_cg2(b_dst, &tmB, lbar, kb * BK, nrow0);
+              tma_load_2d_cg2(a_dst, &tmA, lbar, kb * (MXK ? 2 * BK : BK), m_blk * BM);
+              tma_load_2d_cg2(b_dst, &tmB, lbar, kb * (MXK ? 2 * BK : BK), nrow0);
+              if (MXK) {
+                // scale factors through tensor maps ([blocks][128 x u32]): a plain bulk copy cannot signal the leader's barrier.
+                // Each CTA stages the scales of its own 128 A rows and of ALL BN weight rows of the tile.
+                uint8_t* sf = smSF + stage * C::SF_BYTES;
+                tma_load_2d_cg2(sf, &tmSFA, lbar, 0, m_blk * p.sfa_ld + kb * C::SFPK);
+#pragma unroll
+                for (int i = 0; i < BN / 128; ++i)
+                  tma_load_2d_cg2(sf + C::SFA_BYTES + i * C::SFPK * 512, &tmSFB, lbar, 0,
+                                  (n_blk * (BN / 128) + i) * p.sfb_ld + kb * C::SFPK);
+              }
             }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -478,22 +489,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const uint32_t t_sfa = tmem_base + C::SF_COL0, t_sfb = t_sfa + 4 * C::SFPK;
               const uint32_t sfs = sf0 + stage * (C::SF_BYTES >> 4);
 #pragma unroll
-              for (int j = 0; j < C::SFPK; ++j) tmem_cp_32x128b_warpx4(t_sfa + 4 * j, desc_sf + (sfs + 32 * j));
+              for (int j = 0; j < C::SFPK; ++j) tmem_cp_32x128b_warpx4<CG>(t_sfa + 4 * j, desc_sf + (sfs + 32 * j));
 #pragma unroll
               for (int i = 0; i < NB; ++i)
 #pragma unroll
                 for (int j = 0; j < C::SFPK; ++j)
-                  tmem_cp_32x128b_warpx4(t_sfb + 4 * (j * NB + i), desc_sf + (sfs + 32 * C::SFPK + 32 * (i * C::SFPK + j)));
+                  tmem_cp_32x128b_warpx4<CG>(t_sfb + 4 * (j * NB + i), desc_sf + (sfs + 32 * C::SFPK + 32 * (i * C::SFPK + j)));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {  // 32 B of K per MMA: 32 fp8 or 64 fp4 elements
                 const uint32_t accum = (kb | k) ? 1u : 0u;
                 if constexpr (MXK == 1)       // one scale per row per MMA: byte k of the staged columns
-                  umma_mxf8_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf8(BM, BN, k), t_sfa, t_sfb, accum);
+                  umma_mxf8_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf8(BM * CG, BN, k), t_sfa, t_sfb, accum);
                 else if constexpr (MXK == 2)  // two scales (bytes 0,1 or 2,3) of block k / 2
-                  umma_mxf4_ss<false>(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf4(BM, BN, true, (k & 1) * 2),
+                  umma_mxf4_ss<false, CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf4(BM * CG, BN, true, (k & 1) * 2),
                                       t_sfa + 4 * (k >> 1), t_sfb + 4 * NB * (k >> 1), accum);
                 else                          // four scales = the whole column of block k
-                  umma_mxf4_ss<true>(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf4(BM, BN, false, 0),
+                  umma_mxf4_ss<true, CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, make_idesc_mxf4(BM * CG, BN, false, 0),
                                      t_sfa + 4 * k, t_sfb + 4 * NB * k, accum);
               }
             } else {
@@ -584,20 +595,20 @@ bool gemm_init() {
 }
 
 static bool make_tmap(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box);
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);
 bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box) {
   return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
 }
 static bool make_tmap(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box) {
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   cuuint64_t gd[5];
   cuuint64_t gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = g_encode(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     g_err = "cuTensorMapEncodeTiled failed, CUresult=" + std::to_string((int)r);
@@ -614,7 +625,7 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   p.epi = g.epi;
   static const bool timeline = getenv("FLUX2B_GEMM_TIMELINE") != nullptr;
   p.dbg = timeline ? 1 : 0;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmSFA, tmSFB;
   int num_m_blks;
   if (CONV) {
     p.taps = g.conv_taps; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.batch = g.batch;
@@ -648,6 +659,16 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     uint64_t bs[1] = {(uint64_t)g.ldb};
     uint32_t bb[2] = {128, (uint32_t)C::B_ROWS};
     if (!make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, g.B, 2, bd, bs, bb)) return cudaErrorInvalidValue;
+    if (CG == 2) {
+      // scale factors as [512 B blocks][128 x u32]; extents are exact, so a block row past the operand (odd M-block count)
+      // is zero-filled: scale 0 (E4M3) / 2^-127 (E8M0) times the zero-filled operand rows
+      uint64_t sd[2] = {128, (uint64_t)(num_m_blks - 1) * p.sfa_ld + (uint64_t)p.num_kb * C::SFPK};
+      uint64_t ss[1] = {512};
+      uint32_t sb[2] = {128, (uint32_t)C::SFPK};
+      if (!make_tmap(&tmSFA, CU_TENSOR_MAP_DATA_TYPE_UINT32, g.sfa, 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
+      sd[1] = (uint64_t)(g.N / 128 - 1) * p.sfb_ld + (uint64_t)p.num_kb * C::SFPK;
+      if (!make_tmap(&tmSFB, CU_TENSOR_MAP_DATA_TYPE_UINT32, g.sfb, 2, sd, ss, sb, CU_TENSOR_MAP_SWIZZLE_NONE)) return cudaErrorInvalidValue;
+    }
   } else {
     p.num_kb = (g.K + BK - 1) / BK;
     num_m_blks = (g.M + BM - 1) / BM;
@@ -685,7 +706,8 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  if (!(MXK && CG == 2)) { tmSFA = tmA; tmSFB = tmA; }  // unused by those instantiations
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmSFA, tmSFB, p);
 }
 
 template <bool CONV>
@@ -723,13 +745,19 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
     // rows were interleaved for (force_bn).
     const bool wide = g.force_bn == 256 && g.N % 256 == 0;
     if (g.epi.mode == EPI_SWIGLU && !g.force_bn) { g_err = "block-scaled SwiGLU epilogue needs the weight's tile size (force_bn)"; return cudaErrorInvalidValue; }
-    switch (g.mx * 2 + (wide ? 1 : 0)) {
-      case 2: return launch_cfg<128, 1, false, 1>(g, stream);
-      case 3: return launch_cfg<256, 1, false, 1>(g, stream);
-      case 4: return launch_cfg<128, 1, false, 2>(g, stream);
-      case 5: return launch_cfg<256, 1, false, 2>(g, stream);
-      case 6: return launch_cfg<128, 1, false, 3>(g, stream);
-      default: return launch_cfg<256, 1, false, 3>(g, stream);
+    // CTA pairs (cta_group::2, 256 x 128 tiles) by default: per MMA each tensor core then reads 128 A rows + 64 B rows from
+    // shared memory instead of 128 + 128 — the single-CTA 128 x 128 tile sits exactly on the 128 B/clk smem read limit
+    const bool pair = !wide && g.force_cta_group != 1 && (g.M + BM - 1) / BM >= 2;
+    switch (g.mx * 4 + (wide ? 1 : 0) + (pair ? 2 : 0)) {
+      case 4: return launch_cfg<128, 1, false, 1>(g, stream);
+      case 5: return launch_cfg<256, 1, false, 1>(g, stream);
+      case 6: return launch_cfg<128, 2, false, 1>(g, stream);
+      case 8: return launch_cfg<128, 1, false, 2>(g, stream);
+      case 9: return launch_cfg<256, 1, false, 2>(g, stream);
+      case 10: return launch_cfg<128, 2, false, 2>(g, stream);
+      case 12: return launch_cfg<128, 1, false, 3>(g, stream);
+      case 13: return launch_cfg<256, 1, false, 3>(g, stream);
+      default: return launch_cfg<128, 2, false, 3>(g, stream);
     }
   }
   if (!conv && (g.lda % 8 || g.ldb % 8)) { g_err = "lda/ldb must be multiples of 8 elements (TMA 16 B stride)"; return cudaErrorInvalidValue; }

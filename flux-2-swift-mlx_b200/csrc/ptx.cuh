@@ -252,14 +252,25 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uin
 __host__ __device__ constexpr uint32_t make_idesc_mxf8(int M, int N, uint32_t sf_id) {
   return (sf_id << 4) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24) | (sf_id << 29);
 }
-// D[tmem] (+)= (A[smem] * SFA[tmem]) * (B[smem] * SFB[tmem]), K = 32 fp8 elements, one scale per operand row
+// D[tmem] (+)= (A[smem] * SFA[tmem]) * (B[smem] * SFB[tmem]), K = 32 fp8 elements, one scale per operand row.
+// kCtaGroup == 2: the CTA pair computes a 256-row tile; each CTA holds the scale factors of its own 128 A rows and of ALL B rows
+// in its own TMEM at the same column addresses.
+template <int kCtaGroup = 1>
 __device__ __forceinline__ void umma_mxf8_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t tmem_sfa,
                                              uint32_t tmem_sfb, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
-      : "memory");
+  if constexpr (kCtaGroup == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+  }
 }
 // Instruction descriptor for kind::mxf4nvf4.block_scale with E2M1 x E2M1 operands (K = 64 per instruction, fp32 accumulate):
 // same fields as above; A / B fmt 1 = E2M1 (packed, two per byte); [23] scale fmt: 0 = UE4M3 (nvfp4, one scale per 16
@@ -270,27 +281,30 @@ __host__ __device__ constexpr uint32_t make_idesc_mxf4(int M, int N, bool ue8m0,
          ((uint32_t)(M >> 4) << 24) | (sf_id << 29);
 }
 // D[tmem] (+)= (A * SFA) * (B * SFB), K = 64 fp4 elements; kBlock16: one scale per 16 elements (nvfp4), else per 32 (mxfp4)
-template <bool kBlock16>
+template <bool kBlock16, int kCtaGroup = 1>
 __device__ __forceinline__ void umma_mxf4_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t tmem_sfa,
                                              uint32_t tmem_sfb, uint32_t accumulate) {
+#define F2B_MXF4(CG_, VEC_)                                                                                              \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                        \
+               "tcgen05.mma.cta_group::" CG_ ".kind::mxf4nvf4.block_scale.scale_vec::" VEC_                               \
+               " [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),                                                 \
+               "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)                          \
+               : "memory")
   if constexpr (kBlock16) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.scale_vec::4X [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
-        : "memory");
+    if constexpr (kCtaGroup == 1) F2B_MXF4("1", "4X"); else F2B_MXF4("2", "4X");
   } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
-        : "memory");
+    if constexpr (kCtaGroup == 1) F2B_MXF4("1", "2X"); else F2B_MXF4("2", "2X");
   }
+#undef F2B_MXF4
 }
 // smem (32 rows x 16 B, described by a no-swizzle K-major descriptor) -> TMEM lanes 0..31 x 4 columns, replicated into all
 // four lane quarters: the scale-factor staging copy. Executes in issue order with the tcgen05.mma of the same thread.
+template <int kCtaGroup = 1>
 __device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
-  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+  if constexpr (kCtaGroup == 1)
+    asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+  else  // both CTAs of the pair copy from their own shared memory (same offset) into their own TMEM
+    asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem]
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,

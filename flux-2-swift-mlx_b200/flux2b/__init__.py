@@ -495,7 +495,7 @@ class Context:
                                  _ptr(res), cta_group, bn))
         return out
 
-    def op_gemm_mx(self, quant, a16, w_packed, w_scales, return_quantized=False, bn=0):
+    def op_gemm_mx(self, quant, a16, w_packed, w_scales, return_quantized=False, bn=0, cta_group=0):
         """Native block-scaled GEMM. a16 [M,K] 16-bit torch tensor; w_packed uint32 [N, K*bits/32], w_scales uint8 [N, K/group]
         (the MLX layout of quant mode `quant` = "mxfp8" | "mxfp4" | "nvfp4") -> f32 [M, N]
         (+ quantised activation bytes [M, K*bits/8] and their scales [M, K/group] with return_quantized)."""
@@ -507,7 +507,7 @@ class Context:
         out = torch.empty((M, N), dtype=torch.float32, device=a16.device)
         aq = np.zeros((M, K * bits // 8), dtype=np.uint8) if return_quantized else None
         sfa = np.zeros((M, K // group), dtype=np.uint8) if return_quantized else None
-        _ck(lib().flux2b_op_gemm_mx(self._h, q, _ptr(a16), _ptr(w_packed), _ptr(w_scales), M, N, K, _ptr(out), _ptr(aq), _ptr(sfa), bn))
+        _ck(lib().flux2b_op_gemm_mx(self._h, q, _ptr(a16), _ptr(w_packed), _ptr(w_scales), M, N, K, _ptr(out), _ptr(aq), _ptr(sfa), bn, cta_group))
         return (out, aq, sfa) if return_quantized else out
 
     def op_gemm_mxfp8(self, a16, w_packed, w_scales, return_quantized=False):

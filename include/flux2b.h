@@ -234,11 +234,12 @@ int flux2b_op_gemm(flux2b_ctx* ctx, const void* a16, const void* w16, int M, int
  *   FLUX2B_MXFP8: weight uint32 [N, K/4] = E4M3 bytes,   scales uint8 [N, K/32] E8M0;  K % 128 == 0
  *   FLUX2B_MXFP4: weight uint32 [N, K/8] = E2M1 nibbles, scales uint8 [N, K/32] E8M0;  K % 256 == 0
  *   FLUX2B_NVFP4: weight uint32 [N, K/8] = E2M1 nibbles, scales uint8 [N, K/16] E4M3;  K % 256 == 0
- * and A (16-bit) is quantised on the fly to the same element / scale format. N % 128 == 0; bn = 0 (auto) | 128 | 256.
+ * and A (16-bit) is quantised on the fly to the same element / scale format. N % 128 == 0; bn = 0 (auto = 128) | 128 | 256;
+ * cta_group = 0 (auto: CTA pairs, cta_group::2, for 128-wide tiles) | 1 | 2.
  * aq_out / sfa_out (optional, host or device): the quantised activation bytes [M, K*bits/8] and their scales [M, K/group]. */
 int flux2b_op_gemm_mx(flux2b_ctx* ctx, int quant, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N,
-                      int K, float* out, uint8_t* aq_out, uint8_t* sfa_out, int bn);
-/* = flux2b_op_gemm_mx(ctx, FLUX2B_MXFP8, ..., 0) */
+                      int K, float* out, uint8_t* aq_out, uint8_t* sfa_out, int bn, int cta_group);
+/* = flux2b_op_gemm_mx(ctx, FLUX2B_MXFP8, ..., 0, 0) */
 int flux2b_op_gemm_mxfp8(flux2b_ctx* ctx, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N, int K,
                          float* out, uint8_t* a8_out, uint8_t* sfa_out);
 int flux2b_op_attention(flux2b_ctx* ctx, const void* qkv16 /* [B*S, 3*H*128] */, int B, int S, int H, void* out16 /* [B*S, H*128] */,

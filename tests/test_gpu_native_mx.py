@@ -41,14 +41,14 @@ def test_block_scaled_gemm_exact(flux2b, name, shape):
     a = a.to(torch.bfloat16)
     w = (torch.randn(N, K, generator=g) * 0.05).half().numpy()
     packed, scales, _ = Q.quantize(q, w)
-    for bn in (0, 128):
-        out, aq, sfa = ctx.op_gemm_mx(name, a.cuda(), packed, scales, return_quantized=True, bn=bn)
+    for bn, cg in ((0, 0), (128, 1), (256, 1), (128, 2)):   # auto = 128-wide tiles on CTA pairs
+        out, aq, sfa = ctx.op_gemm_mx(name, a.cuda(), packed, scales, return_quantized=True, bn=bn, cta_group=cg)
         ctx.synchronize()
         A_deq = Q.dequantize(q, np.ascontiguousarray(aq).view(np.uint32), sfa, None, K).astype(np.float64)
         W_deq = Q.dequantize(q, packed, scales, None, K).astype(np.float64)
         ref = torch.from_numpy(A_deq @ W_deq.T)
         assert torch.isfinite(out).all()
-        assert rel_l2(out.cpu(), ref) < TOL_GEMM, (name, shape, bn)
+        assert rel_l2(out.cpu(), ref) < TOL_GEMM, (name, shape, bn, cg)
         # the activation quantiser against the checker
         want = Q.fake_quant_activation(q, a.float())
         assert np.array_equal(A_deq.astype(np.float32), want.numpy()), (name, shape)
@@ -122,10 +122,12 @@ def test_dit_forward_native_block_scaled(flux2b, name):
     # the quantisation fused into LayerNorm + modulate and the SwiGLU epilogue produces the same bits as the separate pass
     ctx3 = make_ctx(flux2b, cfg, W, quant=q, dtype=torch.float16, opts={"native_mx": 1, "mx_fuse_quant": 0})
     assert np.array_equal(out, ctx3.dit_forward(*args))
-    # 256-wide N tiles (one accumulator stage, SwiGLU rows interleaved per 256): same arithmetic
-    ctx4 = make_ctx(flux2b, cfg, W, quant=q, dtype=torch.float16, opts={"native_mx": 1, "mx_bn": 256})
-    assert rel_l2(ctx4.dit_forward(*args), out) < 1e-5
-    ctx.close(); ctx_w.close(); ctx2.close(); ctx3.close(); ctx4.close()
+    # 256-wide N tiles (one accumulator stage, SwiGLU rows interleaved per 256) / single-CTA tiles: same arithmetic
+    for o in ({"mx_bn": 256}, {"gemm_cta_group": 1}):
+        ctx4 = make_ctx(flux2b, cfg, W, quant=q, dtype=torch.float16, opts={"native_mx": 1, **o})
+        assert rel_l2(ctx4.dit_forward(*args), out) < 1e-5, o
+        ctx4.close()
+    ctx.close(); ctx_w.close(); ctx2.close(); ctx3.close()
 
 
 def test_native_mx_ragged_and_batch(flux2b):

@@ -147,7 +147,7 @@ def probe_dit(name, fuse_qk=1, fuse_swiglu=1, attn_variant=0, cg=0, f16=0, S_img
                 "gpu_s_first_call": round(t_gpu, 3), "cpu_oracle_s": round(t_cpu, 2)}
 
 
-def probe_gemm_mx(quant, M, N, K, iters=5, bn=0):
+def probe_gemm_mx(quant, M, N, K, iters=5, bn=0, cg=0):
     """native block-scaled GEMM (mxfp8 / mxfp4 / nvfp4): exact check against dequant(aq, sfa) @ dequant(W)^T in fp64; for the
     fp4 kinds the quantised activations must also be bit-identical to the oracle's weight packer run on the same matrix."""
     import numpy as np
@@ -162,7 +162,7 @@ def probe_gemm_mx(quant, M, N, K, iters=5, bn=0):
     a = a.to(torch.bfloat16)
     w = (torch.randn(N, K, generator=g) * 0.05).half().numpy()
     packed, scales, _ = Q.quantize(qi, w)
-    out, aq, sfa = ctx.op_gemm_mx(quant, a.cuda(), packed, scales, return_quantized=True, bn=bn)
+    out, aq, sfa = ctx.op_gemm_mx(quant, a.cuda(), packed, scales, return_quantized=True, bn=bn, cta_group=cg)
     ctx.synchronize()
     A_deq = Q.dequantize(qi, np.ascontiguousarray(aq).view(np.uint32), sfa, None, K).astype(np.float64)
     W_deq = Q.dequantize(qi, packed, scales, None, K).astype(np.float64)
@@ -180,7 +180,7 @@ def probe_gemm_mx(quant, M, N, K, iters=5, bn=0):
     ctx.prof_enable(True); ctx.prof_reset()
     ad = a.cuda()
     for _ in range(iters):
-        ctx.op_gemm_mx(quant, ad, packed, scales, bn=bn)
+        ctx.op_gemm_mx(quant, ad, packed, scales, bn=bn, cta_group=cg)
     p = ctx.prof_get(flux2b.PROF_GEMM)
     e = ctx.prof_get(flux2b.PROF_ELEMWISE)
     tf = p["flops"] / (p["ms"] * 1e-3) / 1e12 if p["ms"] > 0 else 0
@@ -247,13 +247,18 @@ PROBES = {
     "mx8_tail": lambda: probe_gemm_mx("mxfp8", 300, 384, 256),
     "mx8_big": lambda: probe_gemm_mx("mxfp8", 4608, 3072, 3072, iters=3),
     "mx8_ffin": lambda: probe_gemm_mx("mxfp8", 4608, 18432, 3072, iters=2),
-    "mx8_ffin_bn128": lambda: probe_gemm_mx("mxfp8", 4608, 18432, 3072, iters=2, bn=128),
+    "mx8_ffin_bn128": lambda: probe_gemm_mx("mxfp8", 4608, 18432, 3072, iters=2, bn=128, cg=1),
     "nv4_small": lambda: probe_gemm_mx("nvfp4", 128, 128, 256),
     "nv4_k1024": lambda: probe_gemm_mx("nvfp4", 256, 256, 1024),
     "nv4_tail": lambda: probe_gemm_mx("nvfp4", 300, 384, 512),
     "nv4_big": lambda: probe_gemm_mx("nvfp4", 4608, 4096, 4096, iters=3),
     "nv4_ffin": lambda: probe_gemm_mx("nvfp4", 4608, 24576, 4096, iters=2),
-    "nv4_ffin_bn128": lambda: probe_gemm_mx("nvfp4", 4608, 24576, 4096, iters=2, bn=128),
+    "nv4_ffin_bn128": lambda: probe_gemm_mx("nvfp4", 4608, 24576, 4096, iters=2, bn=128, cg=1),
+    "nv4_ffin_cg2": lambda: probe_gemm_mx("nvfp4", 4608, 24576, 4096, iters=2, bn=128, cg=2),
+    "nv4_small_cg2": lambda: probe_gemm_mx("nvfp4", 256, 128, 256, cg=2),
+    "nv4_tail_cg2": lambda: probe_gemm_mx("nvfp4", 300, 384, 512, cg=2),
+    "mx8_ffin_cg2": lambda: probe_gemm_mx("mxfp8", 4608, 18432, 3072, iters=2, bn=128, cg=2),
+    "mx4_ffin_cg2": lambda: probe_gemm_mx("mxfp4", 4608, 24576, 4096, iters=2, bn=128, cg=2),
     "mx4_small": lambda: probe_gemm_mx("mxfp4", 128, 128, 256),
     "mx4_k1024": lambda: probe_gemm_mx("mxfp4", 256, 256, 1024),
     "mx4_tail": lambda: probe_gemm_mx("mxfp4", 300, 384, 512),
