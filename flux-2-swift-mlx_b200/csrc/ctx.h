@@ -106,8 +106,24 @@ struct ConvW {
 };
 struct NormW { DevBuf gamma, beta; int C = 0; };
 struct ResnetW { NormW n1, n2; ConvW c1, c2, sc; bool has_sc = false; int cin = 0, cout = 0; };
+// VAE encoder (VAE/VAEEncoder.swift:26-115): optional, built when the "encoder.*" tensors are present
+struct VaeEncW {
+  bool ready = false;
+  ConvW conv_in;                            // Cin zero-padded 3 -> 8 (TMA rows are 16 B)
+  std::vector<std::vector<ResnetW>> down;   // [4][layers_per_block]
+  std::vector<ConvW> downconv;              // stride-2 3x3, pad bottom / right (ResnetBlock.swift:189-213)
+  std::vector<bool> has_down;
+  ResnetW mid1, mid2;
+  NormW attn_norm;
+  Lin attn_qkv, attn_out;
+  DevBuf attn_qkv_bias, attn_out_bias;
+  NormW norm_out;
+  ConvW conv_out, quant;
+  bool has_quant = false;
+};
 struct VaeW {
   bool ready = false;
+  VaeEncW enc;
   ConvW post_quant, conv_in, conv_out;
   ResnetW mid1, mid2;
   NormW attn_norm;
@@ -269,5 +285,7 @@ int sp_map_peers(flux2b_ctx* c);   // (re-)exchange cudaIpc handles of ws_sp_gat
 int sp_barrier(flux2b_ctx* c);     // all ranks: everything enqueued before it on every rank is visible after it
 void sp_destroy(flux2b_ctx* c);
 int vae_decode_device(flux2b_ctx* c, int B, int h8, int w8, const void* latents_nhwc16, void** out_nhwc16, int* out_ld);
+// image NHWC 16-bit [B, H, W, 8] (3 channels + zero padding) -> moments NHWC 16-bit [B, H/8, W/8, 2 * latent_ch] (after quantConv)
+int vae_encode_device(flux2b_ctx* c, int B, int H, int W, const void* image_nhwc16, void** out_nhwc16, int* out_ld);
 
 }  // namespace f2b

@@ -760,4 +760,39 @@ cudaError_t nchw_f32_to_nhwc16(const float* in, void* out16, int B, int64_t HW, 
   return cudaGetLastError();
 }
 
+// image NCHW fp32 [B, C, HW] -> NHWC 16-bit [B, HW, Cpad] with channels [C, Cpad) zero (VAE encoder input, VAEEncoder.swift:88)
+__global__ void nchw_to_nhwc16_pad_kernel(const float* __restrict__ in, void* __restrict__ out, int64_t HW, int C, int Cpad, bool f16,
+                                          int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % Cpad);
+  const int64_t p = (i / Cpad) % HW, b = i / (Cpad * HW);
+  store16(out, i, c < C ? in[(b * C + c) * HW + p] : 0.f, f16);
+}
+cudaError_t nchw_f32_to_nhwc16_pad(const float* in, void* out16, int B, int64_t HW, int C, int Cpad, bool f16, cudaStream_t s) {
+  const int64_t n = (int64_t)B * HW * Cpad;
+  if (n <= 0) return cudaSuccess;
+  nchw_to_nhwc16_pad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out16, HW, C, Cpad, f16, n);
+  return cudaGetLastError();
+}
+// posterior moments NHWC 16-bit [B, HW, 2L] = [mean | logvar] -> latent NCHW fp32 [B, L, HW]:
+// mean, or mean + exp(0.5 * logvar) * noise when noise (NCHW fp32) is given (AutoencoderKL.swift:101-111)
+__global__ void moments_to_latent_kernel(const void* __restrict__ m16, int64_t ldc, const float* __restrict__ noise, float* __restrict__ out,
+                                         int64_t HW, int L, bool f16, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = i % HW; const int c = (int)((i / HW) % L); const int64_t b = i / (HW * L);
+  const int64_t base = (b * HW + p) * ldc;
+  float v = load16(m16, base + c, f16);
+  if (noise) v = __fadd_rn(v, __fmul_rn(expf(__fmul_rn(0.5f, load16(m16, base + L + c, f16))), noise[i]));
+  out[i] = v;
+}
+cudaError_t moments_to_latent(const void* m16, int64_t ldc, const float* noise, float* out, int B, int64_t HW, int L, bool f16,
+                              cudaStream_t s) {
+  const int64_t n = (int64_t)B * L * HW;
+  if (n <= 0) return cudaSuccess;
+  moments_to_latent_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m16, ldc, noise, out, HW, L, f16, n);
+  return cudaGetLastError();
+}
+
 }  // namespace f2b

@@ -83,5 +83,10 @@ cudaError_t postprocess_u8(const void* x16, int64_t ldc, uint8_t* out, int64_t n
 cudaError_t nhwc16_to_nchw_f32(const void* x16, int64_t ldc, float* out, int B, int64_t HW, int C, bool f16,
                                cudaStream_t s);
 cudaError_t nchw_f32_to_nhwc16(const float* in, void* out16, int B, int64_t HW, int C, bool f16, cudaStream_t s);
+// the same with the channel count padded to Cpad with zeros (VAE encoder input: 3 -> 8 channels)
+cudaError_t nchw_f32_to_nhwc16_pad(const float* in, void* out16, int B, int64_t HW, int C, int Cpad, bool f16, cudaStream_t s);
+// posterior moments NHWC 16-bit [B, HW, ldc >= 2L] -> latent NCHW fp32: mean (noise == nullptr) or mean + exp(logvar / 2) * noise
+cudaError_t moments_to_latent(const void* m16, int64_t ldc, const float* noise, float* out, int B, int64_t HW, int L, bool f16,
+                              cudaStream_t s);
 
 }  // namespace f2b

@@ -36,7 +36,8 @@ struct KParams {
   int M, N, K;
   int num_m_units, num_n_blks, num_kb;
   // conv
-  int taps, H, W, Cin, batch, tiles_x, tiles_y, kb_per_tap;
+  int taps, H, W, Cin, batch, tiles_x, tiles_y, kb_per_tap;  // H, W: OUTPUT extent
+  int stride, tap_off;  // input coordinate of tap (ky, kx) for output (y, x): (y * stride + ky + tap_off, x * stride + kx + tap_off)
   Epilogue epi;
   // block-scaled kinds: scale factors of A [ceil(M/128)][sfa_ld][512 B], of B [N/128][sfb_ld][512 B]; one 512 B block =
   // 128 rows x 4 scale bytes in the tcgen05 layout (quant.cuh); *_ld = blocks per 128-row block (the full K extent)
@@ -401,9 +402,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (CONV) {
               const int tap = kb / p.kb_per_tap;
               const int c0 = (kb % p.kb_per_tap) * BK;
-              const int ky = (p.taps == 9) ? tap / 3 - 1 : 0;
-              const int kx = (p.taps == 9) ? tap % 3 - 1 : 0;
-              tma_load_4d(a_dst, &tmA, &full[stage], c0, x0 + kx, y0 + ky, img);
+              const int ky = (p.taps == 9) ? tap / 3 + p.tap_off : 0;
+              const int kx = (p.taps == 9) ? tap % 3 + p.tap_off : 0;
+              tma_load_4d(a_dst, &tmA, &full[stage], c0, x0 * p.stride + kx, y0 * p.stride + ky, img);
               tma_load_3d(b_dst, &tmB, &full[stage], c0, tap, nrow0);
             } else {
               // (tensor-map coordinates are in elements: 64 bf16, or 128 bytes of fp8 / packed fp4, per 128 B row)
@@ -424,9 +425,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (CONV) {
               const int tap = kb / p.kb_per_tap;
               const int c0 = (kb % p.kb_per_tap) * BK;
-              const int ky = (p.taps == 9) ? tap / 3 - 1 : 0;
-              const int kx = (p.taps == 9) ? tap % 3 - 1 : 0;
-              tma_load_4d_cg2(a_dst, &tmA, lbar, c0, x0 + kx, y0 + ky, img);
+              const int ky = (p.taps == 9) ? tap / 3 + p.tap_off : 0;
+              const int kx = (p.taps == 9) ? tap % 3 + p.tap_off : 0;
+              tma_load_4d_cg2(a_dst, &tmA, lbar, c0, x0 * p.stride + kx, y0 * p.stride + ky, img);
               // 3-D weight box through the cta_group::2 path is expressed as 4-D with a unit outer dim
               tma_load_4d_cg2(b_dst, &tmB, lbar, c0, tap, nrow0, 0);
             } else {
@@ -595,17 +596,19 @@ bool gemm_init() {
 }
 
 static bool make_tmap(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B,
+                      const uint32_t* elem_strides = nullptr);
 bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box) {
   return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
 }
 static bool make_tmap(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz, const uint32_t* elem_strides) {
   cuuint64_t gd[5];
   cuuint64_t gs[4];
   cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  // with an element stride s the box extent is given in traversed elements: s * (elements loaded)
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; es[i] = elem_strides ? elem_strides[i] : 1; bx[i] = box[i] * es[i]; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = g_encode(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -634,11 +637,17 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     p.kb_per_tap = (g.Cin + BK - 1) / BK;
     p.num_kb = g.conv_taps * p.kb_per_tap;
     num_m_blks = g.batch * p.tiles_x * p.tiles_y;
-    // activations NHWC: dims (C, W, H, N)
-    uint64_t ad[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.batch};
-    uint64_t as[3] = {(uint64_t)g.lda * 2, (uint64_t)g.lda * 2 * g.W, (uint64_t)g.lda * 2 * g.W * g.H};
+    // activations NHWC: dims (C, W_in, H_in, N). Stride-2 convolutions (VAE encoder downsample: pad bottom / right only,
+    // ResnetBlock.swift:203-213) traverse the input with element stride 2; out-of-bounds fill is the zero padding.
+    const int st = g.conv_stride > 1 ? g.conv_stride : 1;
+    const int Hin = g.Hin ? g.Hin : g.H * st, Win = g.Win ? g.Win : g.W * st;
+    p.stride = st;
+    p.tap_off = (g.conv_taps == 9 && st == 1) ? -1 : 0;
+    uint64_t ad[4] = {(uint64_t)g.Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)g.batch};
+    uint64_t as[3] = {(uint64_t)g.lda * 2, (uint64_t)g.lda * 2 * Win, (uint64_t)g.lda * 2 * Win * Hin};
     uint32_t ab[4] = {BK, CONV_TW, CONV_TH, 1};
-    if (!make_tmap_bf16(&tmA, g.A, 4, ad, as, ab)) return cudaErrorInvalidValue;
+    uint32_t ae[4] = {1, (uint32_t)st, (uint32_t)st, 1};
+    if (!make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.A, 4, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B, ae)) return cudaErrorInvalidValue;
     // weights OHWI: dims (Cin, taps, Cout[, 1])
     uint64_t bd[4] = {(uint64_t)g.Cin, (uint64_t)g.conv_taps, (uint64_t)g.N, 1};
     uint64_t bs[3] = {(uint64_t)g.Cin * 2, (uint64_t)g.Cin * 2 * g.conv_taps, (uint64_t)g.Cin * 2 * g.conv_taps * g.N};

@@ -53,8 +53,10 @@ struct GemmProblem {
   int64_t ldb = 0;
   int M = 0, N = 0, K = 0;
   // implicit-GEMM 3x3 / 1x1 convolution (NHWC activations, OHWI weights): M = batch*H*W, K = taps*Cin
-  int conv_taps = 0;  // 0 = plain GEMM, 1 = 1x1, 9 = 3x3 (pad 1)
-  int batch = 1, H = 0, W = 0, Cin = 0;
+  int conv_taps = 0;  // 0 = plain GEMM, 1 = 1x1, 9 = 3x3 (stride 1: pad 1; stride 2: pad 0 top / left, 1 bottom / right)
+  int batch = 1, H = 0, W = 0, Cin = 0;  // H, W = OUTPUT extent
+  int conv_stride = 1;                   // 1 | 2
+  int Hin = 0, Win = 0;                  // input extent (0 = H * stride, W * stride)
   Epilogue epi;
   // native block-scaled operands (tcgen05.mma.kind::mxf8f6f4 / mxf4nvf4 .block_scale), single-CTA tiles:
   //   mx = 1 mxfp8: E4M3 bytes, E8M0 scale per 32 elements, K % 128 == 0

@@ -407,4 +407,69 @@ int flux2b_vae_decode_u8(flux2b_ctx* c, int B, int h8, int w8, const float* lat,
   return vae_decode_common(c, B, h8, w8, lat, nullptr, rgb);
 }
 
+// ------------------------------------------------------------------ VAE encoder entry points
+// image (host or device) -> latent NCHW fp32 in the scratch buffer "vae.enc.lat"
+static int vae_encode_to_latent(flux2b_ctx* c, int B, int H, int W, const float* image, const float* noise, float** lat_out) {
+  F2B_TRY(check(c));
+  if (!c->vw.ready || !c->vw.enc.ready) return fail(FLUX2B_ERR_MODEL_NOT_LOADED, "VAE encoder weights not loaded (encoder.* tensors)");
+  if (B < 1 || H % 8 || W % 8 || H < 8 || W < 8) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "VAE encode: batch >= 1, height / width multiples of 8");
+  const int L = c->vae.latent_channels, Cin = c->vae.in_channels, Cpad = c->vw.enc.conv_in.cin;
+  const bool vf16 = c->option("vae_f16", 1) != 0;
+  const int h8 = H / 8, w8 = W / 8;
+  const void *di, *dn;
+  F2B_TRY(dev_in(c, image, (size_t)B * Cin * H * W * 4, &di));
+  F2B_TRY(dev_in(c, noise, (size_t)B * L * h8 * w8 * 4, &dn));
+  void* xp = c->scratch_buf("vae.enc.x", (size_t)B * H * W * Cpad * 2);
+  float* lat = (float*)c->scratch_buf("vae.enc.lat", (size_t)B * L * h8 * w8 * 4);
+  if (!xp || !lat) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "VAE encoder input allocation failed"); }
+  {
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)B * H * W * (4.0 * Cin + 2.0 * Cpad));
+    F2B_CUDA(nchw_f32_to_nhwc16_pad((const float*)di, xp, B, (int64_t)H * W, Cin, Cpad, vf16, c->stream));
+  }
+  void* m16; int ld;
+  F2B_TRY(vae_encode_device(c, B, H, W, xp, &m16, &ld));
+  {
+    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)B * h8 * w8 * L * 8.0);
+    F2B_CUDA(moments_to_latent(m16, ld, (const float*)dn, lat, B, (int64_t)h8 * w8, L, vf16, c->stream));
+  }
+  *lat_out = lat;
+  return 0;
+}
+int flux2b_vae_encode(flux2b_ctx* c, int B, int H, int W, const float* image, const float* noise, float* latents) {
+  float* lat;
+  F2B_TRY(vae_encode_to_latent(c, B, H, W, image, noise, &lat));
+  const size_t n = (size_t)B * c->vae.latent_channels * (H / 8) * (W / 8);
+  F2B_CUDA(cudaMemcpyAsync(latents, lat, n * 4, is_device_ptr(latents) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  return end_call(c, true);
+}
+int flux2b_encode_image_to_sequence(flux2b_ctx* c, int B, int H, int W, const float* image, const float* noise, float* seq) {
+  if (H % 16 || W % 16) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "encode to sequence: height / width must be multiples of 16");
+  float* lat;
+  F2B_TRY(vae_encode_to_latent(c, B, H, W, image, noise, &lat));
+  if (!c->vw.has_bn) return fail(FLUX2B_ERR_MODEL_NOT_LOADED, "latentBatchNorm.runningMean / runningVar not loaded");
+  const int L = c->vae.latent_channels, C4 = 4 * L, h8 = H / 8, w8 = W / 8, pH = h8 / 2, pW = w8 / 2;
+  const size_t n = (size_t)B * L * h8 * w8;
+  float* t1 = (float*)c->scratch_buf("vae.enc.t1", n * 4);
+  float* t2 = (float*)c->scratch_buf("vae.enc.t2", n * 4);
+  if (!t1 || !t2) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "VAE encoder scratch"); }
+  void* dout; bool ho;
+  F2B_TRY(dev_out(c, seq, n * 4, &dout, &ho));
+  ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 24.0 * n);
+  {  // packLatentsToPatchified (LatentUtils.swift:186-212): [B, L, h8, w8] -> [B, 4L, pH, pW], channel = c * 4 + ph * 2 + pw
+    const int p = 2;
+    const int os[6] = {B, L, p, p, pH, pW};
+    const int64_t is[6] = {(int64_t)L * h8 * w8, (int64_t)h8 * w8, w8, 1, (int64_t)p * w8, p};
+    F2B_CUDA(permute_f32(lat, t1, 6, os, is, c->stream));
+  }
+  // normalizeLatentsWithBatchNorm (:460-473): (x - mean) / sqrt(var + 1e-4)
+  F2B_CUDA(bn_affine_nchw(t1, t2, c->vw.bn_mean.as<float>(), c->vw.bn_var.as<float>(), 1e-4f, B, C4, (int64_t)pH * pW, false, c->stream));
+  {  // packPatchifiedToSequence (:76-86): [B, 4L, pH, pW] -> [B, pH * pW, 4L]
+    const int os[4] = {B, pH, pW, C4};
+    const int64_t is[4] = {(int64_t)C4 * pH * pW, pW, 1, (int64_t)pH * pW};
+    F2B_CUDA(permute_f32(t2, (float*)dout, 4, os, is, c->stream));
+  }
+  F2B_TRY(finish_out(c, seq, dout, n * 4, ho));
+  return end_call(c, true);
+}
+
 }  // extern "C"

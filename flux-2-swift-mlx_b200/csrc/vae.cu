@@ -19,11 +19,12 @@ struct VaeRun {
   }
 };
 
-static int conv(flux2b_ctx* c, bool f16, const ConvW& w, const void* x, void* y, const void* res, int B, int H, int W) {
+// H, W: OUTPUT extent; stride 2 = the encoder's downsample (input 2H x 2W, zero pad bottom / right only)
+static int conv(flux2b_ctx* c, bool f16, const ConvW& w, const void* x, void* y, const void* res, int B, int H, int W, int stride = 1) {
   GemmProblem g;
   g.A = x; g.lda = w.cin; g.B = w.w.p; g.ldb = (int64_t)w.taps * w.cin;
   g.M = B * H * W; g.N = w.cout; g.K = w.taps * w.cin;
-  g.conv_taps = w.taps; g.batch = B; g.H = H; g.W = W; g.Cin = w.cin;
+  g.conv_taps = w.taps; g.batch = B; g.H = H; g.W = W; g.Cin = w.cin; g.conv_stride = stride;
   g.epi.mode = EPI_BF16; g.epi.f16 = f16; g.epi.out = y; g.epi.ldo = w.cout; g.epi.bias = w.bias.as<float>();
   g.epi.res16 = res; g.epi.ldr = w.cout;
   g.force_cta_group = c->option("vae_conv_cta_group", 0);
@@ -59,9 +60,11 @@ static int resnet(VaeRun& r, const ResnetW& w, void*& x, int H, int W) {
   return 0;
 }
 
-static int mid_attention(VaeRun& r, void*& x, int H, int W) {
+struct VaeAttnRef {
+  const NormW& attn_norm; const Lin& attn_qkv; const DevBuf& attn_qkv_bias; const Lin& attn_out; const DevBuf& attn_out_bias;
+};
+static int mid_attention(VaeRun& r, const VaeAttnRef& v, void*& x, int H, int W) {
   flux2b_ctx* c = r.c;
-  const VaeW& v = c->vw;
   const int C = v.attn_norm.C;
   const int N = H * W;
   const bool f16 = r.f16;
@@ -138,7 +141,7 @@ int vae_decode_device(flux2b_ctx* c, int B, int h8, int w8, const void* z, void*
   F2B_TRY(conv(c, f16, v.conv_in, x, t, nullptr, B, H, W));      // VAEDecoder.swift:97
   x = t;
   F2B_TRY(resnet(r, v.mid1, x, H, W));
-  F2B_TRY(mid_attention(r, x, H, W));
+  F2B_TRY(mid_attention(r, VaeAttnRef{v.attn_norm, v.attn_qkv, v.attn_qkv_bias, v.attn_out, v.attn_out_bias}, x, H, W));
   F2B_TRY(resnet(r, v.mid2, x, H, W));
   for (int i = 0; i < 4; ++i) {
     for (const ResnetW& rw : v.up[i]) F2B_TRY(resnet(r, rw, x, H, W));
@@ -160,6 +163,57 @@ int vae_decode_device(flux2b_ctx* c, int B, int h8, int w8, const void* z, void*
   F2B_TRY(conv(c, f16, v.conv_out, n, y, nullptr, B, H, W));
   *out = y;
   *out_ld = g.out_channels;
+  return 0;
+}
+
+// VAEEncoder.callAsFunction (VAE/VAEEncoder.swift:85-115) + quantConv (VAE/AutoencoderKL.swift:94-99).
+// image NHWC 16-bit [B, H, W, 8] (channels 3..7 zero) -> moments NHWC 16-bit [B, H/8, W/8, 2 * latent_ch]
+int vae_encode_device(flux2b_ctx* c, int B, int H, int W, const void* image, void** out, int* out_ld) {
+  const VaeEncW& e = c->vw.enc;
+  if (!c->vw.ready || !e.ready) return fail(FLUX2B_ERR_MODEL_NOT_LOADED, "VAE encoder weights not loaded (encoder.* tensors)");
+  if (H % 8 || W % 8 || H < 8 || W < 8) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "VAE encode: height / width must be multiples of 8");
+  const bool f16 = c->option("vae_f16", 1) != 0;
+  // largest activation: full resolution x the widest of the first block's channels
+  size_t max_elems = 0;
+  {
+    int h = H, w = W, prev = e.conv_in.cout;
+    for (int i = 0; i < 4; ++i) {
+      const int co = e.down[i].empty() ? prev : e.down[i][0].cout;
+      max_elems = std::max(max_elems, (size_t)h * w * std::max(prev, co));
+      prev = co;
+      if (e.has_down[i]) { h /= 2; w /= 2; }
+    }
+    max_elems *= B;
+  }
+  if (c->vae_ws.size() != 5) { c->vae_ws.clear(); c->vae_ws.resize(5); }
+  for (auto& b : c->vae_ws) F2B_CUDA(b.ensure(max_elems * 2));
+  VaeRun r{c, f16, B, c->vae_ws};
+  int h = H, w = W;
+  void* x = r.pick();
+  F2B_TRY(conv(c, f16, e.conv_in, image, x, nullptr, B, h, w));
+  for (int i = 0; i < 4; ++i) {
+    for (const ResnetW& rw : e.down[i]) F2B_TRY(resnet(r, rw, x, h, w));
+    if (e.has_down[i]) {
+      h /= 2; w /= 2;
+      void* y = r.pick(x);
+      F2B_TRY(conv(c, f16, e.downconv[i], x, y, nullptr, B, h, w, 2));
+      x = y;
+    }
+  }
+  F2B_TRY(resnet(r, e.mid1, x, h, w));
+  F2B_TRY(mid_attention(r, VaeAttnRef{e.attn_norm, e.attn_qkv, e.attn_qkv_bias, e.attn_out, e.attn_out_bias}, x, h, w));
+  F2B_TRY(resnet(r, e.mid2, x, h, w));
+  void* n = r.pick(x);
+  F2B_TRY(gn(c, f16, e.norm_out, x, n, B, (int64_t)h * w, true));
+  void* y = r.pick(n);
+  F2B_TRY(conv(c, f16, e.conv_out, n, y, nullptr, B, h, w));
+  if (e.has_quant) {
+    void* q = r.pick(y);
+    F2B_TRY(conv(c, f16, e.quant, y, q, nullptr, B, h, w));
+    y = q;
+  }
+  *out = y;
+  *out_ld = e.conv_out.cout;
   return 0;
 }
 

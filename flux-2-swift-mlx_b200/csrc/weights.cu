@@ -354,6 +354,89 @@ static int build_resnet(flux2b_ctx* c, const std::string& base, ResnetW* r, int 
   return 0;
 }
 
+// single-head VAE attention: fuse toQ|toK|toV into one [3C, C] operand (ResnetBlock.swift:258-313)
+static int build_vae_attention(flux2b_ctx* c, const std::string& prefix, int C, Lin* qkv, DevBuf* qkv_bias, Lin* out, DevBuf* out_bias) {
+  qkv->N = 3 * C; qkv->K = C;
+  F2B_CUDA(qkv->w.alloc((size_t)3 * C * C * 2));
+  F2B_CUDA(qkv_bias->alloc(sizeof(float) * 3 * C));
+  const char* names[3] = {"toQ", "toK", "toV"};
+  for (int i = 0; i < 3; ++i) {
+    DevBuf tmp, b; int N, K;
+    const std::string base = prefix + "." + names[i];
+    F2B_TRY(dense16_from_key_ex(c, base, &tmp, &N, &K, false));
+    F2B_TRY(expect_shape(base, N, K, C, C));
+    F2B_TRY(copy_rows16(c, tmp.p, K, 0, qkv->w.p, K, (int64_t)i * C, C, C, false, 0));
+    F2B_TRY(vector_f32_from_key(c, base + ".bias", &b, C, false, 0.f));
+    F2B_CUDA(cudaMemcpyAsync(qkv_bias->as<float>() + (size_t)i * C, b.p, sizeof(float) * C, cudaMemcpyDeviceToDevice, c->stream));
+    F2B_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  int N, K;
+  F2B_TRY(dense16_from_key_ex(c, prefix + ".toOut", &out->w, &N, &K, false));
+  F2B_TRY(expect_shape(prefix + ".toOut", N, K, C, C));
+  out->N = C; out->K = C;
+  F2B_TRY(vector_f32_from_key(c, prefix + ".toOut.bias", out_bias, C, false, 0.f));
+  return 0;
+}
+
+__global__ void pad_cin_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t rows, int cin, int cpad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cpad) return;
+  const int64_t r = i / cpad; const int ch = (int)(i % cpad);
+  dst[i] = ch < cin ? src[r * cin + ch] : (uint16_t)0;
+}
+
+// VAE encoder (VAE/VAEEncoder.swift:26-83; key layout WeightLoader.swift:500-547): built when its tensors were handed over
+static int finalize_vae_encoder(flux2b_ctx* c) {
+  const flux2b_vae_config& g = c->vae;
+  VaeEncW& e = c->vw.enc;
+  e.ready = false;
+  if (!find(c, "encoder.convIn.weight")) return 0;
+  int ch[4];
+  for (int i = 0; i < 4; ++i) ch[i] = g.encoder_channels[i];
+  if (!ch[0]) { ch[0] = 128; ch[1] = 256; ch[2] = 512; ch[3] = 512; }
+  const int L2 = 2 * g.latent_channels;
+  {
+    // convIn: Cin = 3 is zero-padded to 8 input channels (the image arrives NHWC with 8 channels, 5 of them zero)
+    ConvW raw;
+    F2B_TRY(build_conv(c, "encoder.convIn", &raw, ch[0], g.in_channels, 3));
+    const int cpad = (g.in_channels + 7) / 8 * 8;
+    const int64_t rows = (int64_t)ch[0] * 9;
+    F2B_CUDA(e.conv_in.w.alloc((size_t)rows * cpad * 2));
+    pad_cin_kernel<<<(unsigned)((rows * cpad + 255) / 256), 256, 0, c->stream>>>(raw.w.as<uint16_t>(), e.conv_in.w.as<uint16_t>(), rows,
+                                                                                g.in_channels, cpad);
+    F2B_CUDA(cudaGetLastError());
+    F2B_CUDA(cudaStreamSynchronize(c->stream));
+    e.conv_in.bias = std::move(raw.bias);
+    e.conv_in.cin = cpad; e.conv_in.cout = ch[0]; e.conv_in.taps = 9;
+  }
+  e.down.clear(); e.downconv.clear(); e.has_down.clear();
+  e.down.resize(4); e.downconv.resize(4); e.has_down.assign(4, false);
+  int prev = ch[0];
+  for (int i = 0; i < 4; ++i) {
+    e.down[i].resize(g.layers_per_block);
+    for (int j = 0; j < g.layers_per_block; ++j) {
+      F2B_TRY(build_resnet(c, "encoder.downBlocks." + std::to_string(i) + ".0." + std::to_string(j), &e.down[i][j], prev, ch[i]));
+      prev = ch[i];
+    }
+    if (i < 3) {
+      F2B_TRY(build_conv(c, "encoder.downBlocks." + std::to_string(i) + ".1.conv", &e.downconv[i], ch[i], ch[i], 3));
+      e.has_down[i] = true;
+    }
+  }
+  const int C3 = ch[3];
+  F2B_TRY(build_resnet(c, "encoder.midBlock.0", &e.mid1, C3, C3));
+  F2B_TRY(build_norm(c, "encoder.midBlock.1.groupNorm", &e.attn_norm, C3));
+  F2B_TRY(build_vae_attention(c, "encoder.midBlock.1", C3, &e.attn_qkv, &e.attn_qkv_bias, &e.attn_out, &e.attn_out_bias));
+  F2B_TRY(build_resnet(c, "encoder.midBlock.2", &e.mid2, C3, C3));
+  F2B_TRY(build_norm(c, "encoder.convNormOut", &e.norm_out, C3));
+  F2B_TRY(build_conv(c, "encoder.convOut", &e.conv_out, L2, C3, 3));
+  e.has_quant = find(c, "quantConv.weight") != nullptr;   // optional (AutoencoderKL.swift:94-99)
+  if (e.has_quant) F2B_TRY(build_conv(c, "quantConv", &e.quant, L2, L2, 1));
+  F2B_CUDA(cudaStreamSynchronize(c->stream));
+  e.ready = true;
+  return 0;
+}
+
 int finalize_vae(flux2b_ctx* c) {
   const flux2b_vae_config& g = c->vae;
   VaeW& v = c->vw;
@@ -369,29 +452,7 @@ int finalize_vae(flux2b_ctx* c) {
     if ((rc = build_conv(c, "decoder.convIn", &v.conv_in, C3, g.latent_channels, 3))) break;
     if ((rc = build_resnet(c, "decoder.midBlock.0", &v.mid1, C3, C3))) break;
     if ((rc = build_norm(c, "decoder.midBlock.1.groupNorm", &v.attn_norm, C3))) break;
-    {
-      // single-head attention: fuse toQ|toK|toV into one [3C, C] operand (ResnetBlock.swift:258-313)
-      v.attn_qkv.N = 3 * C3; v.attn_qkv.K = C3;
-      if (cudaSuccess != v.attn_qkv.w.alloc((size_t)3 * C3 * C3 * 2)) { rc = fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "vae attn"); break; }
-      if (cudaSuccess != v.attn_qkv_bias.alloc(sizeof(float) * 3 * C3)) { rc = fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "vae attn"); break; }
-      const char* names[3] = {"toQ", "toK", "toV"};
-      for (int i = 0; i < 3 && !rc; ++i) {
-        DevBuf tmp, b; int N, K;
-        const std::string base = std::string("decoder.midBlock.1.") + names[i];
-        if ((rc = dense16_from_key_ex(c, base, &tmp, &N, &K, false))) break;
-        if ((rc = expect_shape(base, N, K, C3, C3))) break;
-        if ((rc = copy_rows16(c, tmp.p, K, 0, v.attn_qkv.w.p, K, (int64_t)i * C3, C3, C3, false, 0))) break;
-        if ((rc = vector_f32_from_key(c, base + ".bias", &b, C3, false, 0.f))) break;
-        cudaMemcpyAsync(v.attn_qkv_bias.as<float>() + (size_t)i * C3, b.p, sizeof(float) * C3, cudaMemcpyDeviceToDevice, c->stream);
-        cudaStreamSynchronize(c->stream);
-      }
-      if (rc) break;
-      int N, K;
-      if ((rc = dense16_from_key_ex(c, "decoder.midBlock.1.toOut", &v.attn_out.w, &N, &K, false))) break;
-      if ((rc = expect_shape("decoder.midBlock.1.toOut", N, K, C3, C3))) break;
-      v.attn_out.N = C3; v.attn_out.K = C3;
-      if ((rc = vector_f32_from_key(c, "decoder.midBlock.1.toOut.bias", &v.attn_out_bias, C3, false, 0.f))) break;
-    }
+    if ((rc = build_vae_attention(c, "decoder.midBlock.1", C3, &v.attn_qkv, &v.attn_qkv_bias, &v.attn_out, &v.attn_out_bias))) break;
     if ((rc = build_resnet(c, "decoder.midBlock.2", &v.mid2, C3, C3))) break;
     v.up.clear(); v.upconv.clear(); v.has_upconv.clear();
     v.up.resize(4); v.upconv.resize(4); v.has_upconv.assign(4, false);
@@ -418,6 +479,7 @@ int finalize_vae(flux2b_ctx* c) {
       if ((rc = vector_f32_from_key(c, "latentBatchNorm.runningMean", &v.bn_mean, n, true, 0.f))) break;
       if ((rc = vector_f32_from_key(c, "latentBatchNorm.runningVar", &v.bn_var, n, true, 1.f))) break;
     }
+    if ((rc = finalize_vae_encoder(c))) break;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(FLUX2B_ERR_CUDA, "sync after VAE weights"); break; }
     v.ready = true;
   } while (0);

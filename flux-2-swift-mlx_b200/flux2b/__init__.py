@@ -52,7 +52,7 @@ class DitConfigC(ctypes.Structure):
 class VaeConfigC(ctypes.Structure):
     _fields_ = [("in_channels", ctypes.c_int), ("out_channels", ctypes.c_int), ("latent_channels", ctypes.c_int),
                 ("layers_per_block", ctypes.c_int), ("norm_num_groups", ctypes.c_int),
-                ("decoder_channels", ctypes.c_int * 4), ("norm_eps", ctypes.c_float)]
+                ("decoder_channels", ctypes.c_int * 4), ("norm_eps", ctypes.c_float), ("encoder_channels", ctypes.c_int * 4)]
 
 
 class StepContextC(ctypes.Structure):
@@ -80,7 +80,7 @@ EXPORTS = [
     "flux2b_compute_empirical_mu", "flux2b_scheduler_set_timesteps", "flux2b_scheduler_set_custom_sigmas",
     "flux2b_euler_step", "flux2b_scale_noise", "flux2b_pack_patchified_to_sequence", "flux2b_unpack_sequence_to_patchified",
     "flux2b_unpatchify_latents", "flux2b_pack_latents_to_patchified", "flux2b_bn_latents", "flux2b_image_position_ids",
-    "flux2b_text_position_ids", "flux2b_reference_position_ids", "flux2b_vae_decode", "flux2b_vae_decode_u8",
+    "flux2b_text_position_ids", "flux2b_reference_position_ids", "flux2b_vae_decode", "flux2b_vae_decode_u8", "flux2b_vae_encode", "flux2b_encode_image_to_sequence",
     "flux2b_denoise", "flux2b_generate", "flux2b_repaint_blend", "flux2b_sp_unique_id", "flux2b_sp_init", "flux2b_sp_layout",
     "flux2b_prof_enable", "flux2b_prof_reset", "flux2b_prof_get", "flux2b_launch_count", "flux2b_op_gemm", "flux2b_op_gemm_mx", "flux2b_op_gemm_mxfp8",
     "flux2b_op_attention", "flux2b_op_ln_modulate", "flux2b_op_qk_norm_rope", "flux2b_op_rope_table",
@@ -258,7 +258,8 @@ class Context:
                             int(dit.guidance_embeds), (ctypes.c_int * 4)(*dit.axes_dims_rope), dit.rope_theta, dit.mlp_ratio)
         if vae is not None:
             vc = VaeConfigC(vae.in_channels, vae.out_channels, vae.latent_channels, vae.layers_per_block,
-                            vae.norm_num_groups, (ctypes.c_int * 4)(*vae.decoder_channels), vae.norm_eps)
+                            vae.norm_num_groups, (ctypes.c_int * 4)(*vae.decoder_channels), vae.norm_eps,
+                            (ctypes.c_int * 4)(*getattr(vae, "block_out_channels", (0, 0, 0, 0))))
         _ck(L.flux2b_create(device, ctypes.byref(dc) if dc else None, ctypes.byref(vc) if vc else None, quant,
                             ctypes.byref(self._h)))
         for k, v in (options or {}).items():
@@ -417,6 +418,22 @@ class Context:
         B, _, h8, w8 = latents.shape
         out = _empty_like_backend(latents, (B, self.vae_cfg.out_channels, 8 * h8, 8 * w8))
         _ck(lib().flux2b_vae_decode(self._h, B, h8, w8, _ptr(latents), _ptr(out)))
+        return out
+
+    def vae_encode(self, image, noise=None):
+        """AutoencoderKLFlux2.encode(_:samplePosterior:) (VAE/AutoencoderKL.swift:90-127). image [B,3,H,W] f32 in [-1,1];
+        noise None = samplePosterior false, else the standard-normal noise to use -> latents [B, latent_ch, H/8, W/8]."""
+        B, _, H, W = image.shape
+        out = _empty_like_backend(image, (B, self.vae_cfg.latent_channels, H // 8, W // 8))
+        _ck(lib().flux2b_vae_encode(self._h, B, H, W, _ptr(image), _ptr(noise), _ptr(out)))
+        return out
+
+    def encode_image_to_sequence(self, image, noise=None):
+        """encodeImageToPackedSequence (Flux2Pipeline+ChainHelpers.swift:75-101) on a preprocessed image [B,3,H,W] f32:
+        -> [B, (H/16)*(W/16), 4*latent_ch] BatchNorm-normalised packed latents."""
+        B, _, H, W = image.shape
+        out = _empty_like_backend(image, (B, (H // 16) * (W // 16), 4 * self.vae_cfg.latent_channels))
+        _ck(lib().flux2b_encode_image_to_sequence(self._h, B, H, W, _ptr(image), _ptr(noise), _ptr(out)))
         return out
 
     def vae_decode_u8(self, latents) -> np.ndarray:

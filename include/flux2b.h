@@ -57,12 +57,14 @@ typedef struct {
   float mlp_ratio;
 } flux2b_dit_config;
 
-/* == VAEConfig (Configuration/VAEConfig.swift:7-81); decoder_channels = effectiveDecoderChannels */
+/* == VAEConfig (Configuration/VAEConfig.swift:7-81); decoder_channels = effectiveDecoderChannels,
+ * encoder_channels = blockOutChannels (all zero = the default 128, 256, 512, 512) */
 typedef struct {
   int in_channels, out_channels, latent_channels;
   int layers_per_block, norm_num_groups;
   int decoder_channels[4];
   float norm_eps;
+  int encoder_channels[4];
 } flux2b_vae_config;
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -162,6 +164,18 @@ int flux2b_reference_position_ids(const int* lat_h, const int* lat_w, int n, int
 int flux2b_vae_decode(flux2b_ctx* ctx, int B, int h8, int w8, const float* latents_nchw, float* image_nchw);
 /* decode + postprocessVAEOutput (Pipeline/Flux2Pipeline.swift:2425-2468): uint8 [B, H, W, 3] */
 int flux2b_vae_decode_u8(flux2b_ctx* ctx, int B, int h8, int w8, const float* latents_nchw, uint8_t* rgb_hwc);
+
+/* ------------------------------------------------------------------ VAE encoder (needs the "encoder.*" / "quantConv.*" tensors)
+ * AutoencoderKLFlux2.encode (VAE/AutoencoderKL.swift:90-127; VAE/VAEEncoder.swift:85-115; asymmetric-pad stride-2 downsample
+ * VAE/ResnetBlock.swift:189-213): image [B, 3, H, W] f32 NCHW in [-1, 1] (H, W multiples of 8) -> latents
+ * [B, latent_ch, H/8, W/8] f32 NCHW. noise = NULL: samplePosterior false (the mean — what every pipeline call site uses,
+ * Flux2Pipeline.swift:2199); otherwise standard-normal noise [B, latent_ch, H/8, W/8] supplied by the caller (MLXRandom streams
+ * cannot be reproduced): mean + exp(0.5 * logvar) * noise. No scaling factor, no BatchNorm here (:113-123). */
+int flux2b_vae_encode(flux2b_ctx* ctx, int B, int H, int W, const float* image_nchw, const float* noise, float* latents_nchw);
+/* encodeImageToPackedSequence (Pipeline/Flux2Pipeline+ChainHelpers.swift:75-101) = the per-image body of encodeReferenceImages
+ * (Pipeline/Flux2Pipeline.swift:2196-2213): encode -> packLatentsToPatchified -> normalizeLatentsWithBatchNorm ->
+ * packPatchifiedToSequence. H, W multiples of 16. seq: [B, (H/16) * (W/16), 4 * latent_ch] f32. */
+int flux2b_encode_image_to_sequence(flux2b_ctx* ctx, int B, int H, int W, const float* image_nchw, const float* noise, float* seq);
 
 /* ------------------------------------------------------------------ denoise loop (Pipeline/Flux2Pipeline.swift:1933-2052)
  * Flux2StepHook (:64): called after the Euler update of every step with the output latents [1, seq, 128] in HOST

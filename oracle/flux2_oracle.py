@@ -622,8 +622,55 @@ def vae_decode(W: Dict[str, Tensor], cfg: VAEConfig, z: Tensor) -> Tensor:
     return x.permute(0, 3, 1, 2)
 
 
-def random_vae_weights(cfg: VAEConfig, seed: int = 1, round_to: Optional[torch.dtype] = torch.float16) -> Dict[str, Tensor]:
-    """Synthetic decoder weights: fan-in-scaled uniform convs / linears, GN gamma ~ 1, beta ~ 0, BN mean 0 var 1 (+noise)."""
+def downsample2d(W, p: str, x: Tensor) -> Tensor:
+    """Downsample2D (ResnetBlock.swift:189-213): zero-pad bottom / right by one pixel only, conv3x3 stride 2 without padding."""
+    x = F.pad(x, (0, 0, 0, 1, 0, 1))   # NHWC: (C: 0,0) (W: 0,1) (H: 0,1)
+    y = F.conv2d(x.permute(0, 3, 1, 2), W[p + ".conv.weight"].permute(0, 3, 1, 2), W[p + ".conv.bias"], stride=2, padding=0)
+    return y.permute(0, 2, 3, 1)
+
+
+def vae_encode_moments(W: Dict[str, Tensor], cfg: VAEConfig, img: Tensor) -> Tensor:
+    """VAEEncoder.callAsFunction (VAE/VAEEncoder.swift:85-115) + quantConv (VAE/AutoencoderKL.swift:94-99).
+    img [B, 3, H, W] NCHW in [-1, 1] -> posterior moments [B, 2 * latent, H/8, W/8] NCHW (mean | logvar)."""
+    g, eps = cfg.norm_num_groups, cfg.norm_eps
+    x = img.to(torch.float32).permute(0, 2, 3, 1)
+    x = conv2d_nhwc(x, W["encoder.convIn.weight"], W["encoder.convIn.bias"], 1)
+    for i in range(len(cfg.block_out_channels)):
+        for j in range(cfg.layers_per_block):
+            x = resnet_block(W, f"encoder.downBlocks.{i}.0.{j}", x, g, eps)
+        if i < len(cfg.block_out_channels) - 1:
+            x = downsample2d(W, f"encoder.downBlocks.{i}.1", x)
+    x = resnet_block(W, "encoder.midBlock.0", x, g, eps)
+    x = vae_attention_block(W, "encoder.midBlock.1", x, g, eps)
+    x = resnet_block(W, "encoder.midBlock.2", x, g, eps)
+    x = F.silu(group_norm_nhwc(x, W["encoder.convNormOut.weight"], W["encoder.convNormOut.bias"], g, eps))
+    x = conv2d_nhwc(x, W["encoder.convOut.weight"], W["encoder.convOut.bias"], 1)
+    if "quantConv.weight" in W:
+        x = conv2d_nhwc(x, W["quantConv.weight"], W["quantConv.bias"], 0)
+    return x.permute(0, 3, 1, 2)
+
+
+def vae_encode(W: Dict[str, Tensor], cfg: VAEConfig, img: Tensor, noise: Optional[Tensor] = None) -> Tensor:
+    """AutoencoderKLFlux2.encode (VAE/AutoencoderKL.swift:90-127): mean (samplePosterior false) or mean + exp(logvar / 2) * noise;
+    no scaling factor, no BatchNorm (:113-123)."""
+    h = vae_encode_moments(W, cfg, img)
+    L = cfg.latent_channels
+    mean, logvar = h[:, :L], h[:, L:]
+    return mean if noise is None else mean + torch.exp(0.5 * logvar) * noise
+
+
+def encode_image_to_packed_sequence(W: Dict[str, Tensor], cfg: VAEConfig, img: Tensor) -> Tensor:
+    """encodeImageToPackedSequence (Flux2Pipeline+ChainHelpers.swift:75-101) = per-image body of encodeReferenceImages
+    (Flux2Pipeline.swift:2196-2213), after image preprocessing."""
+    pat = pack_latents_to_patchified(vae_encode(W, cfg, img))
+    pat = normalize_latents_bn(pat, W["latentBatchNorm.runningMean"], W["latentBatchNorm.runningVar"], 1e-4)
+    return pack_patchified_to_sequence(pat)
+
+
+def random_vae_weights(cfg: VAEConfig, seed: int = 1, round_to: Optional[torch.dtype] = torch.float16,
+                       encoder: bool = False) -> Dict[str, Tensor]:
+    """Synthetic decoder (+ optionally encoder) weights: fan-in-scaled uniform convs / linears, GN gamma ~ 1, beta ~ 0,
+    BN mean 0 var 1 (+noise). The encoder tensors are drawn after all decoder tensors, so decoder fixtures do not change."""
     gen = torch.Generator().manual_seed(seed)
     W: Dict[str, Tensor] = {}
 
@@ -671,6 +718,24 @@ def random_vae_weights(cfg: VAEConfig, seed: int = 1, round_to: Optional[torch.d
     conv("decoder.convOut", cfg.out_channels, ch[0], 3)
     W["latentBatchNorm.runningMean"] = 0.1 * torch.randn(128, generator=gen)
     W["latentBatchNorm.runningVar"] = 1.0 + 0.1 * torch.rand(128, generator=gen)
+    if encoder:
+        ec = cfg.block_out_channels
+        conv("encoder.convIn", ec[0], cfg.in_channels, 3)
+        prev = ec[0]
+        for i, co in enumerate(ec):
+            for j in range(cfg.layers_per_block):
+                resnet(f"encoder.downBlocks.{i}.0.{j}", prev, co)
+                prev = co
+            if i < len(ec) - 1:
+                conv(f"encoder.downBlocks.{i}.1.conv", co, co, 3)
+        resnet("encoder.midBlock.0", ec[-1], ec[-1])
+        norm("encoder.midBlock.1.groupNorm", ec[-1])
+        for n in ("toQ", "toK", "toV", "toOut"):
+            lin("encoder.midBlock.1." + n, ec[-1], ec[-1])
+        resnet("encoder.midBlock.2", ec[-1], ec[-1])
+        norm("encoder.convNormOut", ec[-1])
+        conv("encoder.convOut", 2 * L, ec[-1], 3)
+        conv("quantConv", 2 * L, 2 * L, 1)
     return W
 
 

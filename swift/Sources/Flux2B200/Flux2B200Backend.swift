@@ -49,6 +49,8 @@ public final class Flux2B200Context: @unchecked Sendable {
             v.layers_per_block = Int32(c.layersPerBlock); v.norm_num_groups = Int32(c.normNumGroups); v.norm_eps = c.normEps
             let ch = c.effectiveDecoderChannels
             v.decoder_channels = (Int32(ch[0]), Int32(ch[1]), Int32(ch[2]), Int32(ch[3]))
+            let ec = c.blockOutChannels
+            v.encoder_channels = (Int32(ec[0]), Int32(ec[1]), Int32(ec[2]), Int32(ec[3]))
         }
         let q: Int32 = { switch quantization { case .bf16: return 0; case .qint8: return 1; case .int4: return 2
                                                 case .mxfp8: return 3; case .mxfp4: return 4; case .nvfp4: return 5 } }()
@@ -149,5 +151,25 @@ extension AutoencoderKLFlux2 {
         var img = [Float](repeating: 0, count: B * 3 * 64 * h * w)
         try f2bCheck(flux2b_vae_decode(ctx.handle, Int32(B), Int32(h), Int32(w), lat, &img))
         return MLXArray(img, [B, 3, 8 * h, 8 * w])
+    }
+
+    /// Body of `AutoencoderKLFlux2.encode(_:samplePosterior:)` (VAE/AutoencoderKL.swift:90). `noise` = nil is
+    /// `samplePosterior: false`; otherwise the caller draws `MLXRandom.normal(mean.shape)` and hands it over.
+    public func b200Encode(_ ctx: Flux2B200Context, _ x: MLXArray, noise: MLXArray? = nil) throws -> MLXArray {
+        let B = x.dim(0), H = x.dim(2), W = x.dim(3)
+        let img = x.asType(.float32).asArray(Float.self)
+        let nz = noise?.asType(.float32).asArray(Float.self)
+        var lat = [Float](repeating: 0, count: B * 32 * (H / 8) * (W / 8))
+        try f2bCheck(flux2b_vae_encode(ctx.handle, Int32(B), Int32(H), Int32(W), img, nz, &lat))
+        return MLXArray(lat, [B, 32, H / 8, W / 8])
+    }
+
+    /// `Flux2Pipeline.encodeImageToPackedSequence` after `preprocessImageForVAE` (Flux2Pipeline+ChainHelpers.swift:75-101).
+    public func b200EncodeToPackedSequence(_ ctx: Flux2B200Context, _ x: MLXArray) throws -> MLXArray {
+        let B = x.dim(0), H = x.dim(2), W = x.dim(3)
+        let img = x.asType(.float32).asArray(Float.self)
+        var seq = [Float](repeating: 0, count: B * (H / 16) * (W / 16) * 128)
+        try f2bCheck(flux2b_encode_image_to_sequence(ctx.handle, Int32(B), Int32(H), Int32(W), img, nil, &seq))
+        return MLXArray(seq, [B, (H / 16) * (W / 16), 128])
     }
 }

@@ -47,3 +47,26 @@ def test_dit_and_vae_fixtures(golden):
     VW = O.random_vae_weights(vcfg, seed=1)
     img = O.vae_decode(VW, vcfg, torch.from_numpy(golden["vae_z"]))
     np.testing.assert_allclose(img.numpy(), golden["vae_out"], rtol=1e-4, atol=1e-4)
+
+
+def test_vae_encoder_fixture():
+    g = dict(np.load(MG.GOLDEN_ENC))
+    vcfg = O.vae_small_decoder()
+    VW = O.random_vae_weights(vcfg, seed=3, encoder=True)
+    # adding the encoder tensors after the decoder ones leaves every decoder tensor as it was
+    VW0 = O.random_vae_weights(vcfg, seed=3)
+    assert all(torch.equal(VW[k], v) for k, v in VW0.items())
+    img = torch.from_numpy(g["img"])
+    np.testing.assert_allclose(O.vae_encode_moments(VW, vcfg, img).numpy(), g["moments"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(O.encode_image_to_packed_sequence(VW, vcfg, img).numpy(), g["seq"], rtol=1e-4, atol=1e-4)
+    # Downsample2D pads bottom / right only (ResnetBlock.swift:203-213): equals an explicit padded stride-2 correlation
+    x = torch.randn(1, 6, 8, 4)
+    W = {"d.conv.weight": torch.randn(5, 3, 3, 4), "d.conv.bias": torch.randn(5)}
+    y = O.downsample2d(W, "d", x)
+    xp = torch.zeros(1, 7, 9, 4); xp[:, :6, :8] = x
+    ref = torch.zeros(1, 3, 4, 5)
+    for oy in range(3):
+        for ox in range(4):
+            patch = xp[0, 2 * oy:2 * oy + 3, 2 * ox:2 * ox + 3]          # [3, 3, 4]
+            ref[0, oy, ox] = (W["d.conv.weight"] * patch[None]).sum(dim=(1, 2, 3)) + W["d.conv.bias"]
+    np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)

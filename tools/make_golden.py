@@ -22,6 +22,7 @@ from oracle import flux2_oracle as O  # noqa: E402
 from oracle import quant_oracle as Q  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden", "golden.npz")
+GOLDEN_ENC = os.path.join(ROOT, "tests", "golden", "golden_vae_encoder.npz")   # added later: kept apart so golden.npz never changes
 
 TINY = dict(num_layers=1, num_single_layers=2, num_attention_heads=2, joint_attention_dim=256, guidance_embeds=True)
 S_IMG, S_TXT, HW = 64, 64, 128  # 128x128 pixels -> 8x8 tokens
@@ -79,7 +80,23 @@ def main():
     os.makedirs(os.path.dirname(GOLDEN), exist_ok=True)
     np.savez_compressed(GOLDEN, **out)
     print(f"wrote {GOLDEN}: {os.path.getsize(GOLDEN) / 1024:.0f} KiB, {len(out)} arrays")
+    encoder_fixture()
+
+
+def encoder_fixture():
+    """VAE encoder: 32x48 image -> 4x6 latent -> 6 packed tokens; standard encoder widths."""
+    torch.set_num_threads(1)
+    vcfg = O.vae_small_decoder()
+    VW = O.random_vae_weights(vcfg, seed=3, encoder=True)
+    img = torch.rand(1, 3, 32, 48, generator=torch.Generator().manual_seed(11)) * 2 - 1
+    enc = {"img": img.numpy(), "moments": O.vae_encode_moments(VW, vcfg, img).numpy(),
+           "seq": O.encode_image_to_packed_sequence(VW, vcfg, img).numpy()}
+    np.savez_compressed(GOLDEN_ENC, **enc)
+    print(f"wrote {GOLDEN_ENC}: {os.path.getsize(GOLDEN_ENC) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder":
+        encoder_fixture()      # golden.npz untouched
+    else:
+        main()
