@@ -80,7 +80,8 @@ EXPORTS = [
     "flux2b_compute_empirical_mu", "flux2b_scheduler_set_timesteps", "flux2b_scheduler_set_custom_sigmas",
     "flux2b_euler_step", "flux2b_scale_noise", "flux2b_pack_patchified_to_sequence", "flux2b_unpack_sequence_to_patchified",
     "flux2b_unpatchify_latents", "flux2b_pack_latents_to_patchified", "flux2b_bn_latents", "flux2b_image_position_ids",
-    "flux2b_text_position_ids", "flux2b_reference_position_ids", "flux2b_vae_decode", "flux2b_vae_decode_u8", "flux2b_vae_encode", "flux2b_encode_image_to_sequence",
+    "flux2b_text_position_ids", "flux2b_reference_position_ids", "flux2b_vae_decode", "flux2b_vae_decode_u8", "flux2b_vae_encode", "flux2b_encode_image_to_sequence", "flux2b_load_safetensors", "flux2b_save_prequantized",
+    "flux2b_load_prequantized", "flux2b_prequantized_is_valid",
     "flux2b_denoise", "flux2b_generate", "flux2b_repaint_blend", "flux2b_sp_unique_id", "flux2b_sp_init", "flux2b_sp_layout",
     "flux2b_prof_enable", "flux2b_prof_reset", "flux2b_prof_get", "flux2b_launch_count", "flux2b_op_gemm", "flux2b_op_gemm_mx", "flux2b_op_gemm_mxfp8",
     "flux2b_op_attention", "flux2b_op_ln_modulate", "flux2b_op_qk_norm_rope", "flux2b_op_rope_table",
@@ -145,6 +146,17 @@ def _dtype_code(x) -> int:
 
 def device_count() -> int:
     return lib().flux2b_device_count()
+
+
+def last_error() -> str:
+    return (lib().flux2b_last_error() or b"").decode()
+
+
+def prequantized_is_valid(path: str, quant, source_name: Optional[str] = None, source_fingerprint: Optional[str] = None) -> bool:
+    """Flux2PrequantizedCheckpoint.isValid (PrequantizedCheckpoint.swift:150-166); runs without a GPU."""
+    q = QUANT[quant] if isinstance(quant, str) else int(quant)
+    return bool(lib().flux2b_prequantized_is_valid(path.encode(), q, source_name.encode() if source_name is not None else None,
+                                                   source_fingerprint.encode() if source_fingerprint is not None else None))
 
 
 # ------------------------------------------------------------------------------------------------ host-only helpers
@@ -280,6 +292,26 @@ class Context:
     # -- lifecycle / options
     def set_option(self, name: str, value: int):
         _ck(lib().flux2b_set_option(self._h, name.encode(), int(value)))
+
+    # -- safetensors / pre-quantized checkpoint (Loading/PrequantizedCheckpoint.swift)
+    def load_safetensors(self, path: str) -> int:
+        n = lib().flux2b_load_safetensors(self._h, path.encode())
+        if n < 0:
+            _ck(n)
+        return n
+
+    def save_prequantized(self, path: str, source_name: str = "", source_fingerprint: str = "unknown", lora_baked: bool = False):
+        """Flux2PrequantizedCheckpoint.save(model:sourceModelPath:quantization:component:loRABaked:)"""
+        _ck(lib().flux2b_save_prequantized(self._h, path.encode(), source_name.encode(), source_fingerprint.encode(), int(lora_baked)))
+
+    def load_prequantized(self, path: str, source_name: Optional[str] = None, source_fingerprint: Optional[str] = None) -> bool:
+        """Flux2PrequantizedCheckpoint.load(into:...): True = applied (finalize next); False = context untouched, fall back
+        to the standard load (reason: flux2b.last_error())."""
+        r = lib().flux2b_load_prequantized(self._h, path.encode(), source_name.encode() if source_name is not None else None,
+                                           source_fingerprint.encode() if source_fingerprint is not None else None)
+        if r < 0:
+            _ck(r)
+        return r == 0
 
     def set_stream(self, cuda_stream: int):
         _ck(lib().flux2b_set_stream(self._h, ctypes.c_void_p(cuda_stream)))

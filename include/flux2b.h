@@ -101,6 +101,26 @@ int64_t flux2b_get_tensor(flux2b_ctx* ctx, const char* key, void* dst, size_t ca
 /* build the internal fused / tiled working copies; on-the-fly quantization when quant != bf16 and the layer arrived
  * unquantized: == quantize(model:groupSize:bits:mode:) over every Linear (Pipeline/Flux2Pipeline.swift:567-578). */
 int flux2b_finalize_weights(flux2b_ctx* ctx);
+
+/* ------------------------------------------------------------------ safetensors + pre-quantized checkpoint (Loading/PrequantizedCheckpoint.swift)
+ * Hand every tensor of a safetensors file to flux2b_set_tensor under its own key. The file must already use the Swift module
+ * keys (a pre-quantized export; weights re-saved after WeightLoader's key mapping, WeightLoader.swift:99-204,397-547). The
+ * payload size is checked against the header's data_offsets first. Returns the number of tensors, or a negative status. */
+int flux2b_load_safetensors(flux2b_ctx* ctx, const char* path);
+/* Flux2PrequantizedCheckpoint.save (:225-281): the finalized, quantized transformer of this context — packed uint32 `weight`,
+ * `scales`, affine `biases`, and the float parameters — as "flux2-mlx-prequantized-v1" safetensors with the reference's metadata
+ * (format, quantization, bits, group_size, mode, component, source, source_fingerprint, created_by[, lora_baked]); written
+ * atomically (temporary file + rename). invalidConfiguration for a bf16 context (:234-237). */
+int flux2b_save_prequantized(flux2b_ctx* ctx, const char* path, const char* source_name, const char* source_fingerprint, int lora_baked);
+/* Flux2PrequantizedCheckpoint.load (:290-387). Everything is validated BEFORE the context is touched: payload integrity,
+ * metadata (source_name / source_fingerprint may be NULL = not checked), key set in both directions against the
+ * post-quantization manifest of the context's configuration, shapes and dtype categories (uint32 / uint8 exact, floats
+ * interchangeable). 0 = tensors handed over, call flux2b_finalize_weights next (no quantize pass runs); 1 = not applied, the
+ * context is untouched and the caller falls back to the standard load (reason in flux2b_last_error()); < 0 = misuse.
+ * A LoRA-baked export loads with a warning left in flux2b_last_error() (:322-325). */
+int flux2b_load_prequantized(flux2b_ctx* ctx, const char* path, const char* source_name, const char* source_fingerprint);
+/* Flux2PrequantizedCheckpoint.isValid (:150-166): payload integrity + header + metadata, no device needed. 1 valid, 0 not. */
+int flux2b_prequantized_is_valid(const char* path, int quant, const char* source_name, const char* source_fingerprint);
 /* W += scale * B·A, in the weight dtype, or dequantize -> add -> requantize for quantized layers
  * (Loading/WeightLoader.swift:736-856). layer_path e.g. "transformerBlocks.0.attn.toQ". A [rank,in], B [out,rank]. */
 int flux2b_merge_lora(flux2b_ctx* ctx, const char* layer_path, const void* A, const void* B, int rank, int dtype, float scale);
