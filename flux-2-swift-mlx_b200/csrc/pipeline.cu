@@ -295,6 +295,8 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
   F2B_TRY(dev_in(c, p->guidance, 4, &guid_d));
   std::vector<float> host_lat;
   const int steps = p->num_sigmas - 1;
+  const bool kv = p->kv_cache != 0 && S_ref > 0;
+  if (kv && p->enc_uncond) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "the KV-cached loop has no classical-CFG branch (as the reference)");
   for (int i = 0; i < steps; ++i) {
     const float sigma = p->sigmas[i], sigma_next = p->sigmas[i + 1];
     F2B_CUDA(cudaMemcpyAsync(hid.p, x.p, n_lat * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -302,6 +304,16 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
     io.B = 1; io.S_img = S_all; io.S_txt = p->S_txt; io.hidden = hid.as<float>(); io.enc = enc_d; io.enc_dtype = p->enc_dtype;
     io.timestep = tbuf.as<float>() + i; io.guidance = (const float*)guid_d;
     io.img_ids = ids_img.as<int32_t>(); io.txt_ids = ids_txt.as<int32_t>(); io.out = pred.as<float>();
+    if (kv) {
+      // klein-9b-kv (Flux2Pipeline.swift:1565-1644): the reference tokens enter the transformer once, at step 0
+      io.S_img = S_img;
+      io.kv_mode = i == 0 ? 1 : 2;
+      if (i == 0) {
+        io.S_ref = S_ref;
+        io.ref_hidden = hid.as<float>() + n_lat;
+        io.ref_ids = ids_img.as<int32_t>() + (size_t)S_img * 4;
+      }
+    }
     F2B_TRY(dit_forward_device(c, io));
     if (p->enc_uncond) {
       io.enc = encu_d; io.out = pred_u.as<float>();

@@ -69,7 +69,7 @@ class DenoiseParamsC(ctypes.Structure):
                 ("sigmas", ctypes.POINTER(ctypes.c_float)), ("guidance", ctypes.c_void_p), ("cfg_scale", ctypes.c_float),
                 ("enc", ctypes.c_void_p), ("enc_uncond", ctypes.c_void_p), ("enc_dtype", ctypes.c_int),
                 ("S_txt", ctypes.c_int), ("ref_latents", ctypes.c_void_p), ("ref_ids", ctypes.c_void_p),
-                ("S_ref", ctypes.c_int), ("hook", HOOK_T), ("hook_user", ctypes.c_void_p)]
+                ("S_ref", ctypes.c_int), ("hook", HOOK_T), ("hook_user", ctypes.c_void_p), ("kv_cache", ctypes.c_int)]
 
 
 EXPORTS = [
@@ -501,9 +501,11 @@ class Context:
         return p, keep
 
     def denoise(self, latents, enc, sigmas, height, width, guidance=None, enc_uncond=None, cfg_scale=1.0,
-                ref_latents=None, ref_ids=None, hook: Optional[Callable] = None):
-        """In place on `latents` [1, S_img, 128]; hook(step_context, latents_view) may edit the view (Flux2StepHook)."""
+                ref_latents=None, ref_ids=None, hook: Optional[Callable] = None, kv_cache: bool = False):
+        """In place on `latents` [1, S_img, 128]; hook(step_context, latents_view) may edit the view (Flux2StepHook).
+        kv_cache=True with ref_latents: the klein-9b-kv loop (extract at step 0, cached afterwards)."""
         p, keep = self._denoise_params(height, width, sigmas, enc, guidance, enc_uncond, cfg_scale, ref_latents, ref_ids, hook)
+        p.kv_cache = int(kv_cache)
         _ck(lib().flux2b_denoise(self._h, ctypes.byref(p), _ptr(latents)))
         return latents
 

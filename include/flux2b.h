@@ -223,6 +223,9 @@ typedef struct {
   int S_ref;
   flux2b_step_hook hook;         /* or NULL: no host round trip inside the loop */
   void* hook_user;
+  int kv_cache;                  /* with ref_latents: 1 = the klein-9b-kv loop (Flux2Pipeline.swift:1555-1683): step 0 is
+                                  * forwardKVExtract over [txt | refs | output], later steps forwardKVCached over [txt | output]
+                                  * against the cached reference K / V; 0 = the standard I2I loop ([output | refs] every step) */
 } flux2b_denoise_params;
 /* latents [1, S_img, 128] f32 in/out (packed sequence). */
 int flux2b_denoise(flux2b_ctx* ctx, const flux2b_denoise_params* p, float* latents_inout);

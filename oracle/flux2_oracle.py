@@ -749,8 +749,9 @@ def latents_to_image(W_vae, vcfg: VAEConfig, seq: Tensor, height: int, width: in
 
 def denoise(W, cfg: DiTConfig, latents: Tensor, enc: Tensor, sigmas: List[float], height: int, width: int,
             guidance: Optional[float] = None, enc_uncond: Optional[Tensor] = None, cfg_scale: float = 1.0,
-            hook=None, ref_latents: Optional[Tensor] = None, ref_ids: Optional[Tensor] = None) -> Tensor:
-    """The per-step body of Flux2Pipeline.generateWithResult (Flux2Pipeline.swift:1933-2001; I2I :1696-1767)."""
+            hook=None, ref_latents: Optional[Tensor] = None, ref_ids: Optional[Tensor] = None, kv_cache: bool = False) -> Tensor:
+    """The per-step body of Flux2Pipeline.generateWithResult (Flux2Pipeline.swift:1933-2001; I2I :1696-1767;
+    kv_cache=True: the klein-9b-kv loop :1565-1644 — forwardKVExtract at step 0, forwardKVCached afterwards)."""
     txt_ids = text_position_ids(enc.shape[1])
     img_ids = image_position_ids(height, width)
     S_img = latents.shape[1]
@@ -758,6 +759,16 @@ def denoise(W, cfg: DiTConfig, latents: Tensor, enc: Tensor, sigmas: List[float]
     g = torch.tensor([guidance], dtype=torch.float32) if guidance is not None else None
     for i in range(len(sigmas) - 1):
         t = torch.tensor([sigmas[i]], dtype=torch.float32)
+        if kv_cache and ref_latents is not None:
+            if i == 0:
+                pred, cache = dit_forward(W, cfg, x, enc, t, g, img_ids, txt_ids, kv_mode=1, ref_hidden=ref_latents, ref_ids=ref_ids)
+            else:
+                pred = dit_forward(W, cfg, x, enc, t, g, img_ids, txt_ids, kv_mode=2, kv_cache=cache)
+            dt = _f32(sigmas[i + 1]) - _f32(sigmas[i])
+            x = x + torch.tensor(dt, dtype=torch.float32) * pred
+            if hook is not None:
+                x = hook(i, len(sigmas) - 1, sigmas[i], sigmas[i + 1], x)
+            continue
         if ref_latents is not None:
             hid = torch.cat([x, ref_latents], dim=1)                 # [output | refs] (:1703)
             ids = torch.cat([img_ids, ref_ids], dim=0)               # (:1504)

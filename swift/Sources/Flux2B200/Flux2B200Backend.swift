@@ -94,11 +94,11 @@ extension Flux2Transformer2DModel {
 }
 
 extension Flux2Pipeline {
-    /// Replaces the T2I / I2I loop bodies (Flux2Pipeline.swift:1933-2052, 1696-1808): the whole loop runs on the device;
-    /// control returns to Swift only when a Flux2StepHook is installed.
+    /// Replaces the T2I / I2I / KV loop bodies (Flux2Pipeline.swift:1933-2052, 1696-1808, 1555-1683): the whole loop runs on the
+    /// device; control returns to Swift only when a Flux2StepHook is installed. `kvCache` = `model.supportsKVCache` (:1555).
     func b200Denoise(_ ctx: Flux2B200Context, latents: MLXArray, textEmbeddings: MLXArray, negativeEmbeddings: MLXArray?,
                      sigmas: [Float], guidance: Float?, cfgScale: Float, height: Int, width: Int,
-                     refLatents: MLXArray?, refIds: MLXArray?, onStep: Flux2StepHook?) throws -> MLXArray {
+                     refLatents: MLXArray?, refIds: MLXArray?, kvCache: Bool = false, onStep: Flux2StepHook?) throws -> MLXArray {
         var x = latents.asType(.float32).asArray(Float.self)
         let enc = textEmbeddings.asType(.float32).asArray(Float.self)
         let neg = negativeEmbeddings?.asType(.float32).asArray(Float.self)
@@ -125,6 +125,7 @@ extension Flux2Pipeline {
             p.height = Int32(height); p.width = Int32(width); p.num_sigmas = Int32(sigmas.count); p.sigmas = sp.baseAddress
             p.cfg_scale = cfgScale; p.enc_dtype = 0; p.S_txt = Int32(textEmbeddings.dim(1)); p.S_ref = Int32(refLatents?.dim(1) ?? 0)
             p.hook = cHook
+            p.kv_cache = kvCache ? 1 : 0
             p.hook_user = box.map { UnsafeMutableRawPointer(Unmanaged.passUnretained($0).toOpaque()) }
             try enc.withUnsafeBytes { e in
                 p.enc = e.baseAddress

@@ -312,6 +312,28 @@ def test_denoise_loop_variants(flux2b):
     ctx.denoise(x, enc.numpy(), sched.sigmas, HW, HW, ref_latents=ref_lat.numpy(), ref_ids=ref_ids.numpy())
     want = O.denoise(W, cfg, lat, enc, sched.sigmas, HW, HW, ref_latents=ref_lat, ref_ids=ref_ids)
     assert cosine(x, want) >= 0.999 and rel_l2(x, want) < TOL_OUT
+    # (3b) the klein-9b-kv loop (:1565-1644): extract at step 0, cached K / V afterwards; is_i2i is reported to the hook
+    seen_kv = []
+    x = lat.numpy().copy()
+    ctx.denoise(x, enc.numpy(), sched.sigmas, HW, HW, ref_latents=ref_lat.numpy(), ref_ids=ref_ids.numpy(), kv_cache=True,
+                hook=lambda sc, v: seen_kv.append((sc.step_idx, sc.is_i2i)) and None)
+    want = O.denoise(W, cfg, lat, enc, sched.sigmas, HW, HW, ref_latents=ref_lat, ref_ids=ref_ids, kv_cache=True)
+    assert cosine(x, want) >= 0.999 and rel_l2(x, want) < TOL_OUT
+    assert seen_kv == [(0, 1), (1, 1), (2, 1), (3, 1)]
+    # ... and equals the manual composition of the public KV calls, bit for bit
+    y = lat.numpy().copy()
+    ids, tids = O.image_position_ids(HW, HW).numpy(), O.text_position_ids(S_txt).numpy()
+    for i in range(4):
+        ts = np.array([sched.sigmas[i]], np.float32)
+        if i == 0:
+            pred = ctx.dit_forward_kv_extract(y, ref_lat.numpy(), enc.numpy(), ts, None, ids, ref_ids.numpy(), tids)
+        else:
+            pred = ctx.dit_forward_kv_cached(y, enc.numpy(), ts, None, ids, tids)
+        ctx.euler_step(y, pred, sched.sigmas[i], sched.sigmas[i + 1])
+    assert np.array_equal(x, y)
+    with pytest.raises(flux2b.Flux2Error):   # no classical-CFG branch in the KV loop
+        ctx.denoise(lat.numpy().copy(), enc.numpy(), sched.sigmas, HW, HW, ref_latents=ref_lat.numpy(), ref_ids=ref_ids.numpy(),
+                    kv_cache=True, enc_uncond=enc_u.numpy(), cfg_scale=2.0)
     # (4) Flux2StepHook: RePaint blend after every step incl. the last (sigma_next == 0), Flux2MaskedInpaintingChain.swift:399-403
     x0 = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(46))
     eps = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(47))
