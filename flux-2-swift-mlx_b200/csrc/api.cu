@@ -145,7 +145,7 @@ int flux2b_synchronize(flux2b_ctx* c) {
 int flux2b_set_option(flux2b_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "null argument");
   static const char* known[] = {"compute_f16", "fuse_qk_rope", "fuse_swiglu", "attn_variant", "gemm_cta_group",
-                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant"};
+                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant", "attn_poly"};
   bool ok = false;
   for (const char* k : known) ok = ok || !strcmp(k, name);
   if (!ok) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string("unknown option: ") + name);
@@ -432,7 +432,7 @@ int flux2b_op_attention(flux2b_ctx* c, const void* qkv16, int B, int S, int H, v
   a.seg[0].k = (const uint16_t*)dq + D; a.seg[0].v = (const uint16_t*)dq + 2 * D;
   a.seg[0].ldk = a.seg[0].ldv = 3 * D; a.seg[0].rows_total = (int64_t)B * S; a.seg[0].row0 = 0; a.seg[0].len = S;
   a.seg[0].batch_stride = S;
-  a.f16 = c->f16(); a.variant = variant;
+  a.f16 = c->f16(); a.variant = variant; a.poly = c->option("attn_poly", 0);
   {
     ProfScope ps(c, FLUX2B_PROF_ATTN, 4.0 * B * (double)S * S * D, 8.0 * B * (double)S * D);
     F2B_CUDA(attention_launch(a, c->stream));

@@ -43,6 +43,7 @@ struct AttnKParams {
   CUtensorMap tmK[3];
   CUtensorMap tmV[3];
   int sq, num_heads;
+  int spin;
   float scale_log2;
   int q_row0;
   long long q_bs;
@@ -360,7 +361,40 @@ struct A3 {
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
-template <bool kF16>
+// 2^x on the FMA / ALU pipes instead of the MUFU: round-to-nearest split x = n + f by the 1.5 * 2^23 trick, a degree-3
+// minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5 — far below the 16-bit rounding of P), n added into
+// the exponent field. x <= ~8 here (scores minus the running maximum); the clamp keeps -inf / very negative scores at 2^-126.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float r = fmaf(f, 0.0551716648f, 0.2426111251f);
+  r = fmaf(r, f, 0.6932609677f);
+  r = fmaf(r, f, 0.9999280572f);
+  return __uint_as_float(__float_as_uint(r) + (__float_as_uint(t) << 23));
+}
+
+__device__ __forceinline__ bool getenv_dbg2(const AttnKParams& p) { return p.dbg >= 2; }
+
+// two elements at a time with the packed fp32x2 instructions
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 r = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(r, make_float2(-1.0f, -1.0f), x);
+  float2 q = __ffma2_rn(f, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
+  q = __ffma2_rn(q, f, make_float2(0.6932609677f, 0.6932609677f));
+  q = __ffma2_rn(q, f, make_float2(0.9999280572f, 0.9999280572f));
+  return make_float2(__uint_as_float(__float_as_uint(q.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(t.y) << 23)));
+}
+
+// kPoly: 0 = every exponential on the MUFU (ex2.approx); n > 0 = one element in n takes exp2_poly. At head dim 128 the MUFU
+// (16 ex2 / clk / SM: 1024 clk per 128 x 128 tile) is as busy as the tensor pipe (QK^T + PV: 1024 clk), so moving a share of the
+// exponentials onto the otherwise idle FMA lanes is what lets the MMAs run closer to back to back.
+template <bool kF16, int kPoly>
 __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__ AttnKParams p) {
   using C = A3;
   constexpr int BN = C::BN;
@@ -402,14 +436,18 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<1>(tmem_slot, 512);
+  __shared__ long long t0_shared;   // common origin of the debug timeline (all warps of a CTA read the same SM clock)
+  if (threadIdx.x == 0) t0_shared = clock64();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool dbg0 = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
   if (warp == 8) {
     // ============================================================ TMA producer
     if (lane == 0) {
+      int pk_t[8], pv_w[8], pv_t[8];
       const int qrow = p.q_row0 + (int)(b * p.q_bs) + q_blk0;
       for (int w = 0; w < 2; ++w) {
         mbar_expect_tx(&q_full[w], C::Q_BYTES);
@@ -417,25 +455,43 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
         tma_load_2d(dst, &p.tmQ, &q_full[w], head * HD, qrow + w * QT);
         tma_load_2d(dst + QT * 128, &p.tmQ, &q_full[w], head * HD + 64, qrow + w * QT);
       }
-      int j = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const int tiles = (p.seg_len[s] + BN - 1) / BN;
-        const int row_base = p.seg_row0[s] + (int)(b * p.seg_bs[s]);
-        for (int t = 0; t < tiles; ++t, ++j) {
-          const int row = row_base + t * BN;
-          const int ks = j % C::KS, vs = j % C::VS;
-          mbar_wait(&k_empty[ks], ((j / C::KS) & 1) ^ 1, 10);
-          uint8_t* kd = smem + C::OFF_K + ks * C::KV_BYTES;
-          mbar_expect_tx(&k_full[ks], C::KV_BYTES);
-          tma_load_2d(kd, &p.tmK[s], &k_full[ks], head * HD, row);
-          tma_load_2d(kd + C::KV_PANEL, &p.tmK[s], &k_full[ks], head * HD + 64, row);
-          mbar_wait(&v_empty[vs], ((j / C::VS) & 1) ^ 1, 11);
-          uint8_t* vd = smem + C::OFF_V + vs * C::KV_BYTES;
-          mbar_expect_tx(&v_full[vs], C::KV_BYTES);
-          tma_load_2d(vd, &p.tmV[s], &v_full[vs], head * HD, row);
-          tma_load_2d(vd + C::KV_PANEL, &p.tmV[s], &v_full[vs], head * HD + 64, row);
+      // K runs one tile ahead of V: K(j + 1) is needed for S(j + 1), which is issued right behind PV(j), and its ring
+      // (3 stages) is free long before; waiting for V(j)'s slot (2 stages) first would hold it back by a whole period.
+      auto tile_at = [&](int j, int* seg, int* row) {
+        for (int s = 0; s < p.nseg; ++s) {
+          const int tiles = (p.seg_len[s] + BN - 1) / BN;
+          if (j < tiles) { *seg = s; *row = p.seg_row0[s] + (int)(b * p.seg_bs[s]) + j * BN; return; }
+          j -= tiles;
         }
+      };
+      auto load_k = [&](int j) {
+        int s = 0, row = 0;
+        tile_at(j, &s, &row);
+        const int ks = j % C::KS;
+        mbar_wait(&k_empty[ks], ((j / C::KS) & 1) ^ 1, 10);
+        uint8_t* kd = smem + C::OFF_K + ks * C::KV_BYTES;
+        mbar_expect_tx(&k_full[ks], C::KV_BYTES);
+        tma_load_2d(kd, &p.tmK[s], &k_full[ks], head * HD, row);
+        tma_load_2d(kd + C::KV_PANEL, &p.tmK[s], &k_full[ks], head * HD + 64, row);
+        if (dbg0 && j < 8) pk_t[j] = (int)(clock64() - t0_shared);
+      };
+      load_k(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) load_k(j + 1);
+        int s = 0, row = 0;
+        tile_at(j, &s, &row);
+        const int vs = j % C::VS;
+        if (dbg0 && j < 8) pv_w[j] = (int)(clock64() - t0_shared);
+        mbar_wait(&v_empty[vs], ((j / C::VS) & 1) ^ 1, 11);
+        uint8_t* vd = smem + C::OFF_V + vs * C::KV_BYTES;
+        mbar_expect_tx(&v_full[vs], C::KV_BYTES);
+        tma_load_2d(vd, &p.tmV[s], &v_full[vs], head * HD, row);
+        tma_load_2d(vd + C::KV_PANEL, &p.tmV[s], &v_full[vs], head * HD + 64, row);
+        if (dbg0 && j < 8) pv_t[j] = (int)(clock64() - t0_shared);
       }
+      if (dbg0)
+        for (int j = 0; j < 8 && j < n_tiles; ++j)
+          printf("[attn timeline] producer: tile %d  K issued at %6d  V slot awaited from %6d, V issued at %6d\n", j, pk_t[j], pv_w[j], pv_t[j]);
     }
     __syncwarp();
   } else if (warp == 9) {
@@ -478,17 +534,25 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
     tc_fence_after();
     if (elect_one()) { issue_s(1, 0); umma_commit(&k_empty[0]); }
     __syncwarp();
+    const bool mdbg = dbg0;
+    const long long mt0 = t0_shared;
+    int m_seen[2][8], m_kv[2][8], m_iss[2][8], m_v[8];
     for (int j = 0; j < n_tiles; ++j) {
       const int vs = j % C::VS;
       const int ksn = (j + 1) % C::KS;
       const bool more = j + 1 < n_tiles;
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        mbar_wait(&p_ready[w], j & 1, 23);
         if (w == 0) {
+          // operand barriers first: they completed long ago, but every mbarrier wait costs ~200 clk of latency, which
+          // must not sit between "P is ready" and the MMAs that consume it
           mbar_wait(&v_full[vs], (j / C::VS) & 1, 24);
+          if (mdbg && j < 8) m_v[j] = (int)(clock64() - mt0);
           if (more) mbar_wait(&k_full[ksn], ((j + 1) / C::KS) & 1, 25);
         }
+        if (p.spin) mbar_spin(&p_ready[w], j & 1, 23); else mbar_wait(&p_ready[w], j & 1, 23);
+        if (mdbg && j < 8) m_seen[w][j] = (int)(clock64() - mt0);
+        if (mdbg && j < 8) m_kv[w][j] = (int)(clock64() - mt0);
         tc_fence_after();
         if (elect_one()) {
           issue_pv(w, vs, j > 0);
@@ -501,8 +565,18 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
           }
         }
         __syncwarp();
+        if (mdbg && j < 8) m_iss[w][j] = (int)(clock64() - mt0);
+        if (mdbg && more && getenv_dbg2(p)) {  // debug level 2: block until the S MMAs just issued have completed (perturbs the schedule)
+          mbar_wait(&s_ready[w], (j + 1) & 1, 26);
+          if (j < 8) m_kv[w][j] = (int)(clock64() - mt0);   // reuse the slot: completion time
+        }
       }
     }
+    if (mdbg && lane == 0)
+      for (int j = 0; j < 8 && j < n_tiles; ++j)
+        for (int w = 0; w < 2; ++w)
+          printf("[attn timeline] mma warp: wg %d tile %d  P seen at %6d  V full at %6d  K/V ready at %6d  PV + next S issued at %6d\n",
+                 w, j, m_seen[w][j], w == 0 ? m_v[j] : 0, m_kv[w][j], m_iss[w][j]);
   } else {
     // ============================================================ softmax warpgroups
     const int w = warp >> 2;
@@ -514,14 +588,14 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
     const float sl2 = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;  // m_run in the scaled (log2) domain
     const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 127) == 0;
-    const long long t_start = dbg ? clock64() : 0;
-    int tl_wake[16], tl_done[16];
+    const long long t_start = t0_shared;
+    int tl_wake[16], tl_done[16], tl_ld[16], tl_max[16], tl_exp[16];
     int j = 0;
     for (int s = 0; s < p.nseg; ++s) {
       const int tiles = (p.seg_len[s] + BN - 1) / BN;
       for (int t = 0; t < tiles; ++t, ++j) {
         const int nvalid = min(BN, p.seg_len[s] - t * BN);
-        mbar_wait(&s_ready[w], j & 1, 30);
+        if (p.spin) mbar_spin(&s_ready[w], j & 1, 30); else mbar_wait(&s_ready[w], j & 1, 30);
         long long t_wake = dbg ? clock64() : 0;
         tc_fence_after();
         uint32_t v[4][32];
@@ -530,6 +604,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
         tmem_ld_32x32(t_s + 64, v[2]);
         tmem_ld_32x32(t_s + 96, v[3]);
         tmem_ld_wait();
+        const long long t_ld = dbg ? clock64() : 0;
         if (nvalid < BN) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -548,18 +623,27 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
         const float m_use = move ? m_new : m_run;
         const float alpha = move ? fast_exp2(m_run - m_new) : 1.0f;
         const float neg_m = -m_use;
-        float rs[4] = {0.f, 0.f, 0.f, 0.f};
+        const long long t_max = dbg ? clock64() : 0;
+        // packed fp32x2 arithmetic (FFMA2 / FADD2): the loop is bound by the issue rate of its single warp per scheduler
+        // as much as by the MUFU, so two elements per instruction wherever the ISA has it
+        const float2 sl2v = make_float2(sl2, sl2), nmv = make_float2(neg_m, neg_m);
+        float2 rs2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         uint32_t pk[64];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i]), sl2, neg_m));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[c][2 * i + 1]), sl2, neg_m));
-            rs[c] += p0 + p1;
-            pk[c * 16 + i] = apk2(p0, p1, kF16 ? 1 : 0);
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl2v, nmv);
+            constexpr int kMod = kPoly > 0 ? kPoly : 1;
+            float2 e;
+            if (kPoly > 0 && i % kMod == kMod - 1) e = exp2_poly2(x);
+            else e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+            rs2[c] = __fadd2_rn(rs2[c], e);
+            pk[c * 16 + i] = apk2(e.x, e.y, kF16 ? 1 : 0);
           }
         }
+        const float rs[4] = {rs2[0].x + rs2[0].y, rs2[1].x + rs2[1].y, rs2[2].x + rs2[2].y, rs2[3].x + rs2[3].y};
+        const long long t_exp = dbg ? clock64() : 0;
         // P (16-bit) back into the first 64 columns of the S region
         tmem_st_32x32(t_s, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
         tmem_st_32x32(t_s + 32, *reinterpret_cast<const uint32_t(*)[32]>(&pk[32]));
@@ -571,10 +655,13 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
             tmem_ld_32x32(t_o + h * 64, o0);
             tmem_ld_32x32(t_o + h * 64 + 32, o1);
             tmem_ld_wait();
+            const float2 av = make_float2(alpha, alpha);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
-              o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+            for (int i = 0; i < 32; i += 2) {
+              const float2 a0 = __fmul2_rn(make_float2(__uint_as_float(o0[i]), __uint_as_float(o0[i + 1])), av);
+              const float2 a1 = __fmul2_rn(make_float2(__uint_as_float(o1[i]), __uint_as_float(o1[i + 1])), av);
+              o0[i] = __float_as_uint(a0.x); o0[i + 1] = __float_as_uint(a0.y);
+              o1[i] = __float_as_uint(a1.x); o1[i + 1] = __float_as_uint(a1.y);
             }
             tmem_st_32x32(t_o + h * 64, o0);
             tmem_st_32x32(t_o + h * 64 + 32, o1);
@@ -585,13 +672,17 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
         m_run = m_use;
         tc_fence_before();
         mbar_arrive(&p_ready[w]);
-        if (dbg && j < 16) { tl_wake[j] = (int)(t_wake - t_start); tl_done[j] = (int)(clock64() - t_start); }
+        if (dbg && j < 16) {
+          tl_wake[j] = (int)(t_wake - t_start); tl_done[j] = (int)(clock64() - t_start);
+          tl_ld[j] = (int)(t_ld - t_wake); tl_max[j] = (int)(t_max - t_ld); tl_exp[j] = (int)(t_exp - t_max);
+        }
       }
     }
     if (dbg)
       for (int i = 0; i < 16 && i < j; ++i)
-        printf("[attn timeline] wg %d tile %2d  S ready at %6d  P handed over at %6d  (softmax %5d)\n", w, i, tl_wake[i], tl_done[i],
-               tl_done[i] - tl_wake[i]);
+        printf("[attn timeline] wg %d tile %2d  S ready at %6d  P handed over at %6d  (softmax %5d = tmem ld %4d + max %4d + exp %4d + st/rescale %4d)\n",
+               w, i, tl_wake[i], tl_done[i], tl_done[i] - tl_wake[i], tl_ld[i], tl_max[i], tl_exp[i],
+               tl_done[i] - tl_wake[i] - tl_ld[i] - tl_max[i] - tl_exp[i]);
     // ---- finalize: O / l
     mbar_wait(&o_done[w], 0, 32);
     tc_fence_after();
@@ -665,24 +756,35 @@ static bool fill_params(const AttnProblem& a, int BN, AttnKParams& p) {
   p.o_rows_per_peer = a.o_rows_per_peer;
   p.o_col0 = a.o_col0;
   for (int i = 0; i < 8; ++i) p.o_peer[i] = reinterpret_cast<uint16_t*>(a.o_peer[i]);
-  static const bool timeline = getenv("FLUX2B_ATTN_TIMELINE") != nullptr;
-  p.dbg = timeline ? 1 : 0;
+  static const int timeline = getenv("FLUX2B_ATTN_TIMELINE") ? atoi(getenv("FLUX2B_ATTN_TIMELINE")) : 0;
+  p.dbg = timeline;
+  static const int spin = getenv("FLUX2B_ATTN_SPIN") ? atoi(getenv("FLUX2B_ATTN_SPIN")) : 0;
+  p.spin = spin;
   return true;
 }
 
+#ifndef F2B_ATTN_POLY_DEFAULT
+#define F2B_ATTN_POLY_DEFAULT 4   // share of the exponentials on the FMA pipe when AttnProblem::poly == 0 (1 element in n; 0 = none)
+#endif
 static cudaError_t launch_attn_v3(const AttnProblem& a, cudaStream_t stream) {
   AttnKParams p{};
   if (!fill_params(a, A3::BN, p)) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3::SMEM_BYTES);
+    cudaError_t e = cudaSuccess;
+#define F2B_ATTR(F16_, POLY_) if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kernel_v3<F16_, POLY_>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3::SMEM_BYTES)
+    F2B_ATTR(false, 0); F2B_ATTR(false, 2); F2B_ATTR(false, 3); F2B_ATTR(false, 4);
+    F2B_ATTR(true, 0); F2B_ATTR(true, 2); F2B_ATTR(true, 3); F2B_ATTR(true, 4);
+#undef F2B_ATTR
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((a.sq + 2 * QT - 1) / (2 * QT), a.num_heads, a.batch);
-  if (a.f16) attn_kernel_v3<true><<<grid, 320, A3::SMEM_BYTES, stream>>>(p);
-  else attn_kernel_v3<false><<<grid, 320, A3::SMEM_BYTES, stream>>>(p);
+  const int poly = a.poly < 0 ? 0 : (a.poly == 0 ? F2B_ATTN_POLY_DEFAULT : a.poly);
+#define F2B_GO(F16_, POLY_) attn_kernel_v3<F16_, POLY_><<<grid, 320, A3::SMEM_BYTES, stream>>>(p)
+  if (a.f16) { if (poly == 2) F2B_GO(true, 2); else if (poly == 3) F2B_GO(true, 3); else if (poly == 4) F2B_GO(true, 4); else F2B_GO(true, 0); }
+  else { if (poly == 2) F2B_GO(false, 2); else if (poly == 3) F2B_GO(false, 3); else if (poly == 4) F2B_GO(false, 4); else F2B_GO(false, 0); }
+#undef F2B_GO
   return cudaGetLastError();
 }
 

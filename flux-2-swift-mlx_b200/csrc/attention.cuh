@@ -41,6 +41,7 @@ struct AttnProblem {
   void* o_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int f16 = 0;      // 16-bit storage type: 0 = bf16, 1 = f16
   int variant = 0;  // 0 = auto, 1 = P through shared memory (64-key tiles), 2 = P kept in TMEM (128-key tiles)
+  int poly = 0;     // variant 3: 0 = default, -1 = all exponentials on the MUFU, n in {2, 3, 4} = one element in n by polynomial on the FMA pipe
 };
 
 cudaError_t attention_launch(const AttnProblem& p, cudaStream_t stream);

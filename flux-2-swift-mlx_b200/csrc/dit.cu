@@ -86,6 +86,7 @@ static int attention(flux2b_ctx* c, int S_q, int q_row0, const KVSegment* segs, 
   for (int i = 0; i < nseg; ++i) { a.seg[i] = segs[i]; keys += segs[i].len; }
   a.f16 = c->f16() ? 1 : 0;
   a.variant = c->option("attn_variant", 0);
+  a.poly = c->option("attn_poly", 0);
   ProfScope ps(c, FLUX2B_PROF_ATTN, 4.0 * S_q * keys * c->D, 2.0 * (2.0 * S_q * c->D + 2.0 * keys * c->D));
   F2B_CUDA(attention_launch(a, c->stream));
   return 0;
@@ -128,6 +129,7 @@ static int sp_attend(flux2b_ctx* c, int Sl, void* o, int64_t ldo) {
   a.seg[0].rows_total = S; a.seg[0].row0 = 0; a.seg[0].len = S;
   a.f16 = c->f16() ? 1 : 0;
   a.variant = c->option("attn_variant", 0);
+  a.poly = c->option("attn_poly", 0);
   if (c->sp.mode == 1) {
     // the attention epilogue stores each query row's heads straight into the owning rank's attention-output buffer
     a.variant = 3;

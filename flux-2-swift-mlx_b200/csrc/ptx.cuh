@@ -86,6 +86,19 @@ __device__ __forceinline__ bool mbar_try_wait_cluster_acq(uint64_t* bar, uint32_
       : "memory");
   return ok != 0;
 }
+// non-suspending probe (mbarrier.test_wait): for the two waits on the attention kernel's critical path, where the wake-up
+// latency of a suspended try_wait (~200 clk) is paid once per key tile
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -108,6 +121,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
       else if (now - t0 > F2B_MBAR_TIMEOUT_NS) {
         printf("[flux2b] mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x, blockIdx.y,
                blockIdx.z, threadIdx.x, parity);
+        __trap();
+      }
+    }
+  }
+}
+
+// busy-polling wait (bounded like mbar_wait)
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 0xfff) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > F2B_MBAR_TIMEOUT_NS) {
+        printf("[flux2b] mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x, parity);
         __trap();
       }
     }

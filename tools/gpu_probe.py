@@ -57,11 +57,11 @@ def probe_gemm(M, N, K, epi, cg, bn=0, dtype="bf16"):
     return err < tol, {"rel_l2": err, "tflops": round(tf, 1), "ms": round(p["ms"] / 5, 4)}
 
 
-def probe_attention(B, S, H, variant, dtype="bf16"):
+def probe_attention(B, S, H, variant, dtype="bf16", poly=0):
     import torch
     import flux2b
     dt = torch.bfloat16 if dtype == "bf16" else torch.float16
-    ctx = flux2b.Context(options={"compute_f16": int(dtype == "f16")})
+    ctx = flux2b.Context(options={"compute_f16": int(dtype == "f16"), "attn_poly": poly})
     g = torch.Generator().manual_seed(2)
     D = H * 128
     qkv = torch.randn(B * S, 3 * D, generator=g).to(dt).cuda()
@@ -263,6 +263,12 @@ PROBES = {
     "mx4_k1024": lambda: probe_gemm_mx("mxfp4", 256, 256, 1024),
     "mx4_tail": lambda: probe_gemm_mx("mxfp4", 300, 384, 512),
     "mx4_ffin": lambda: probe_gemm_mx("mxfp4", 4608, 24576, 4096, iters=2),
+    "attn_poly0_big": lambda: probe_attention(1, 4608, 24, 3, poly=-1),
+    "attn_poly4_big": lambda: probe_attention(1, 4608, 24, 3, poly=4),
+    "attn_poly3_big": lambda: probe_attention(1, 4608, 24, 3, poly=3),
+    "attn_poly2_big": lambda: probe_attention(1, 4608, 24, 3, poly=2),
+    "attn_poly3_tail": lambda: probe_attention(2, 328, 2, 3, poly=3),
+    "attn_poly2_f16": lambda: probe_attention(1, 1024, 4, 3, dtype="f16", poly=2),
     "attn_v1_small": lambda: probe_attention(1, 256, 2, 1),
     "attn_v2_small": lambda: probe_attention(1, 256, 2, 2),
     "attn_v1_tail": lambda: probe_attention(2, 328, 2, 1),
