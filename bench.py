@@ -206,9 +206,19 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     from oracle import flux2_oracle as O
     g = torch.Generator(device=device).manual_seed(0)   # same seed on every rank: replicated weights
+    n_lora = 0
     for k, (o, i) in O.dit_weight_shapes(cfg).items():
         b = 1.0 / math.sqrt(i)
-        ctx.set_tensor(k, torch.empty(o, i, device=device, dtype=torch.float32).uniform_(-b, b, generator=g).to(torch.bfloat16))
+        w = torch.empty(o, i, device=device, dtype=torch.float32).uniform_(-b, b, generator=g)
+        if args.lora and (".attn." in k or ".ff" in k):
+            # BASELINE.json configs[4]: a rank-16 LoRA (A, B ~ N(0, 0.02), scale 1) merged into every attention / FF linear at load
+            # time (W += B · A before the packer runs; the on-device dequant -> add -> requant merge is covered by the tests)
+            A = torch.randn(16, i, device=device, generator=g) * 0.02
+            Bm = torch.randn(o, 16, device=device, generator=g) * 0.02
+            w += Bm @ A
+            n_lora += 1
+        ctx.set_tensor(k, w.to(torch.bfloat16))
+        del w
     ctx.finalize()
     torch.cuda.empty_cache()
     if world > 1:
@@ -221,10 +231,18 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
     lat = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(42)).to(device)
     enc = torch.randn(1, S_TXT, cfg.joint_attention_dim, generator=torch.Generator().manual_seed(43)).to(torch.bfloat16).to(device)
     guidance = 4.0 if cfg.guidance_embeds else None
+    ref_lat = ref_ids = None
+    S_ref = 0
+    if args.refs > 0:
+        # image-to-image conditioning: `refs` reference images at the output resolution, T coordinates 10, 20, 30 ...
+        # (LatentUtils.swift:324-346), token order [output | refs] (Flux2Pipeline.swift:1703)
+        S_ref = args.refs * S_img
+        ref_lat = torch.randn(1, S_ref, 128, generator=torch.Generator().manual_seed(44)).to(device)
+        ref_ids = O.reference_position_ids([H // 16] * args.refs, [W // 16] * args.refs).to(torch.int32).to(device)
 
     def step():
         x = lat.clone()
-        ctx.denoise(x, enc, sig, H, W, guidance=guidance)
+        ctx.denoise(x, enc, sig, H, W, guidance=guidance, ref_latents=ref_lat, ref_ids=ref_ids)
 
     def barrier():
         if world > 1:
@@ -255,7 +273,7 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
     clocks = sampler.stop() if rank == 0 else {}
     barrier()
     if rank == 0:
-        gemm_f, attn_f = dit_flops(cfg, S_img)
+        gemm_f, attn_f = dit_flops(cfg, S_img + S_ref)
         pk = peaks(rate_mult(args))
         gp = prof["gemm"]
         achieved = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] > 0 else 0.0
@@ -263,7 +281,8 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
             "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": dtype_name(args), "data": "synthetic",
-            "config": {"workload": f"{args.model} one denoising step at {H}x{W} ({S_img} img + {S_TXT} txt tokens), {dtype_name(args)}, Ulysses "
+            "config": {"workload": f"{args.model} one denoising step at {H}x{W} ({S_img} img + {S_ref} reference + {S_TXT} txt tokens), "
+                                   f"{dtype_name(args)}{', rank-16 LoRA merged into ' + str(n_lora) + ' linears' if n_lora else ''}, Ulysses "
                                    f"sequence-parallel over {world} rank(s), transport mode {args.sp_mode}",
                        "l2": "inputs larger than L2 (weights stream from HBM every step)"},
             "tflops_total": (gemm_f + attn_f) * args.steps / (ms * 1e-3) / 1e12,
@@ -312,6 +331,8 @@ def main():
                          "use with --model dev --res 2048 (BASELINE.json configs[3])")
     ap.add_argument("--sp-mode", type=int, default=1, help="0 = NCCL all-to-all, 1 = peer-memory stores fused into the kernels")
     ap.add_argument("--res", type=int, default=1024, help="square resolution in pixels (--sp mode)")
+    ap.add_argument("--refs", type=int, default=0, help="--sp mode: number of reference images (image-to-image conditioning tokens)")
+    ap.add_argument("--lora", action="store_true", help="--sp mode: merge a rank-16 LoRA into every attention / FF linear at load time")
     ap.add_argument("--profile-one", action="store_true",
                     help="bracket ONE image with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`); prints no bench line")
     args = ap.parse_args()
