@@ -331,7 +331,7 @@ def main():
                          "use with --model dev --res 2048 (BASELINE.json configs[3])")
     ap.add_argument("--sp-mode", type=int, default=1, help="0 = NCCL all-to-all, 1 = peer-memory stores fused into the kernels")
     ap.add_argument("--res", type=int, default=1024, help="square resolution in pixels (--sp mode)")
-    ap.add_argument("--refs", type=int, default=0, help="--sp mode: number of reference images (image-to-image conditioning tokens)")
+    ap.add_argument("--refs", type=int, default=0, help="number of reference images (image-to-image conditioning tokens); without --sp also times the KV-cached loop")
     ap.add_argument("--lora", action="store_true", help="--sp mode: merge a rank-16 LoRA into every attention / FF linear at load time")
     ap.add_argument("--profile-one", action="store_true",
                     help="bracket ONE image with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`); prints no bench line")
@@ -441,6 +441,22 @@ def main():
         ctx.denoise(x, enc_dev, sched.sigmas, HEIGHT, WIDTH, guidance=guidance)
     dit_only()
     ms_dit = timed(dit_only, args.steps)
+    i2i = None
+    if args.refs > 0:
+        # image-to-image with `refs` reference images: the standard loop re-processes the reference tokens
+        # every step ([output | refs], Flux2Pipeline.swift:1696-1767); the klein-9b-kv loop extracts their K / V once (:1565-1644)
+        S_ref = args.refs * S_img
+        ref_lat = torch.randn(1, S_ref, 128, generator=torch.Generator().manual_seed(44)).to(device)
+        ref_ids = O.reference_position_ids([HEIGHT // 16] * args.refs, [WIDTH // 16] * args.refs).to(torch.int32).to(device)
+        res = {}
+        for name, kv in (("standard", False), ("kv_cached", True)):
+            def run():
+                x = lat_dev0.clone()
+                ctx.denoise(x, enc_dev, sched.sigmas, HEIGHT, WIDTH, guidance=guidance, ref_latents=ref_lat, ref_ids=ref_ids, kv_cache=kv)
+            run()
+            res[name] = timed(run, args.steps) / args.steps
+        i2i = {"refs": args.refs, "S_ref": S_ref, "ms_per_image_standard": res["standard"], "ms_per_image_kv_cached": res["kv_cached"],
+               "kv_speedup": res["standard"] / res["kv_cached"], "steps": NUM_STEPS}
     for _ in range(2):
         one_image_host()
     ms_e2e = timed(one_image_host, args.steps)
@@ -487,6 +503,8 @@ def main():
                            for k, p in prof.items()},
         "clocks": clocks,
     }
+    if i2i is not None:
+        out["i2i"] = i2i
     if world == 1 and not args.no_cpu_baseline:
         c = cpu_sample(os.cpu_count() or 1)
         out["cpu_baseline"] = {"value": 1.0 / c["step_s"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
