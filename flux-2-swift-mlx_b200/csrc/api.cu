@@ -88,9 +88,7 @@ int flux2b_device_count(void) {
   return ok;
 }
 
-int flux2b_create(int device, const flux2b_dit_config* dit, const flux2b_vae_config* vae, int quant, flux2b_ctx** out) {
-  if (!out) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "out is null");
-  *out = nullptr;
+static int create_common(int device, int quant, std::unique_ptr<flux2b_ctx>* holder) {
   if (quant < FLUX2B_BF16 || quant > FLUX2B_NVFP4) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "unknown quantization");
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -106,14 +104,41 @@ int flux2b_create(int device, const flux2b_dit_config* dit, const flux2b_vae_con
   std::unique_ptr<flux2b_ctx> c(new flux2b_ctx());
   c->device = device;
   c->quant = quant;
-  if (dit) { c->dit = *dit; c->has_dit = true; }
-  if (vae) { c->vae = *vae; c->has_vae = true; }
   // a blocking stream: ordered against the legacy default stream, so device buffers a caller produced there (e.g. a pageable
   // cudaMemcpy whose DMA is still in flight when it returns) are complete before this context reads them, and results are
   // visible to it afterwards. Callers that want full concurrency hand in their own stream (flux2b_set_stream).
   if (cudaStreamCreate(&c->stream) != cudaSuccess)
     return fail(FLUX2B_ERR_CUDA, "cudaStreamCreate failed");
   c->own_stream = true;
+  *holder = std::move(c);
+  return 0;
+}
+
+int flux2b_create(int device, const flux2b_dit_config* dit, const flux2b_vae_config* vae, int quant, flux2b_ctx** out) {
+  if (!out) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "out is null");
+  *out = nullptr;
+  std::unique_ptr<flux2b_ctx> c;
+  F2B_TRY(create_common(device, quant, &c));
+  if (dit) { c->dit = *dit; c->has_dit = true; }
+  if (vae) { c->vae = *vae; c->has_vae = true; }
+  *out = c.release();
+  return 0;
+}
+
+int flux2b_te_create(int device, const flux2b_te_config* cfg, int quant, flux2b_ctx** out) {
+  if (!out) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "out is null");
+  *out = nullptr;
+  if (!cfg) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "text-encoder config is null");
+  // configuration errors are reported before the device is touched (CPU-testable)
+  if (cfg->head_dim != 128) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "text encoder head_dim must be 128");
+  if (cfg->vocab_size < 1 || cfg->num_layers < 1 || cfg->num_heads < 1 || cfg->num_kv_heads < 1 ||
+      cfg->num_heads % cfg->num_kv_heads != 0 || cfg->hidden_size < 8 || cfg->hidden_size % 8 != 0 || cfg->hidden_size > 8192 ||
+      cfg->intermediate_size < 8 || cfg->intermediate_size % 8 != 0 || !(cfg->rope_theta > 1.0f) || !(cfg->rms_norm_eps > 0.0f))
+    return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "inconsistent text-encoder configuration");
+  std::unique_ptr<flux2b_ctx> c;
+  F2B_TRY(create_common(device, quant, &c));
+  c->te = *cfg;
+  c->has_te = true;
   *out = c.release();
   return 0;
 }
@@ -189,6 +214,7 @@ int64_t flux2b_get_tensor(flux2b_ctx* c, const char* key, void* dst, size_t capa
 
 int flux2b_finalize_weights(flux2b_ctx* c) {
   F2B_TRY(check_ctx(c));
+  if (c->has_te) F2B_TRY(finalize_te(c));
   if (c->has_dit) F2B_TRY(finalize_dit(c));
   if (c->has_vae && c->tensors.count("decoder.convIn.weight")) F2B_TRY(finalize_vae(c));
   c->finalized = true;

@@ -58,6 +58,11 @@ struct AttnKParams {
   long long seg_bs[3];
   int o_rows_per_peer, o_col0;
   uint16_t* o_peer[8];
+  // variant 3 only — causal / padded / grouped-query mode of the text-encoder prefill (te.cu):
+  int causal;        // key j is visible to query i iff j <= i (query index == key index, one segment)
+  int kv_group;      // query head h reads K / V head h / kv_group
+  int key_lo, key_hi;  // keys outside [key_lo, key_hi) get the additive padding mask pad_bias (key_hi == 0: no padding mask)
+  float pad_raw;     // raw (pre-scale) score given to padded keys: -(2^k) with 2^k >= |pad_bias| / scale
   int dbg;  // FLUX2B_ATTN_TIMELINE=1: CTA (0,0,0) prints its softmax / MMA time line (debug aid, off by default)
 };
 
@@ -394,7 +399,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // kPoly: 0 = every exponential on the MUFU (ex2.approx); n > 0 = one element in n takes exp2_poly. At head dim 128 the MUFU
 // (16 ex2 / clk / SM: 1024 clk per 128 x 128 tile) is as busy as the tensor pipe (QK^T + PV: 1024 clk), so moving a share of the
 // exponentials onto the otherwise idle FMA lanes is what lets the MMAs run closer to back to back.
-template <bool kF16, int kPoly>
+template <bool kF16, int kPoly, bool kMask = false>
 __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__ AttnKParams p) {
   using C = A3;
   constexpr int BN = C::BN;
@@ -417,8 +422,20 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
   const int b = blockIdx.z;
   const int q_blk0 = blockIdx.x * 2 * QT;
 
+  // causal: this CTA's 256 query rows see keys [0, q_blk0 + 256) at most (tiles above the diagonal are never loaded)
+  // right padding (key_lo == 0): keys >= key_hi carry exactly zero weight for every row (key 0 is always visible), so they are not loaded either
+  // (kMask: the causal / padded / grouped-query mode is a separate instantiation; the DiT kernel carries none of it)
+  auto seg_len_of = [&](int s) {
+    int n = p.seg_len[s];
+    if constexpr (kMask) {
+      if (p.causal && s == 0) n = min(n, q_blk0 + 2 * QT);
+      if (p.key_hi > 0 && p.key_lo == 0 && s == 0) n = min(n, p.key_hi);
+    }
+    return n;
+  };
+  const int kv_col = kMask ? (head / p.kv_group) * HD : head * HD;
   int n_tiles = 0;
-  for (int s = 0; s < p.nseg; ++s) n_tiles += (p.seg_len[s] + BN - 1) / BN;
+  for (int s = 0; s < p.nseg; ++s) n_tiles += (seg_len_of(s) + BN - 1) / BN;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -459,7 +476,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
       // (3 stages) is free long before; waiting for V(j)'s slot (2 stages) first would hold it back by a whole period.
       auto tile_at = [&](int j, int* seg, int* row) {
         for (int s = 0; s < p.nseg; ++s) {
-          const int tiles = (p.seg_len[s] + BN - 1) / BN;
+          const int tiles = (seg_len_of(s) + BN - 1) / BN;
           if (j < tiles) { *seg = s; *row = p.seg_row0[s] + (int)(b * p.seg_bs[s]) + j * BN; return; }
           j -= tiles;
         }
@@ -471,8 +488,8 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
         mbar_wait(&k_empty[ks], ((j / C::KS) & 1) ^ 1, 10);
         uint8_t* kd = smem + C::OFF_K + ks * C::KV_BYTES;
         mbar_expect_tx(&k_full[ks], C::KV_BYTES);
-        tma_load_2d(kd, &p.tmK[s], &k_full[ks], head * HD, row);
-        tma_load_2d(kd + C::KV_PANEL, &p.tmK[s], &k_full[ks], head * HD + 64, row);
+        tma_load_2d(kd, &p.tmK[s], &k_full[ks], kv_col, row);
+        tma_load_2d(kd + C::KV_PANEL, &p.tmK[s], &k_full[ks], kv_col + 64, row);
         if (dbg0 && j < 8) pk_t[j] = (int)(clock64() - t0_shared);
       };
       load_k(0);
@@ -485,8 +502,8 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
         mbar_wait(&v_empty[vs], ((j / C::VS) & 1) ^ 1, 11);
         uint8_t* vd = smem + C::OFF_V + vs * C::KV_BYTES;
         mbar_expect_tx(&v_full[vs], C::KV_BYTES);
-        tma_load_2d(vd, &p.tmV[s], &v_full[vs], head * HD, row);
-        tma_load_2d(vd + C::KV_PANEL, &p.tmV[s], &v_full[vs], head * HD + 64, row);
+        tma_load_2d(vd, &p.tmV[s], &v_full[vs], kv_col, row);
+        tma_load_2d(vd + C::KV_PANEL, &p.tmV[s], &v_full[vs], kv_col + 64, row);
         if (dbg0 && j < 8) pv_t[j] = (int)(clock64() - t0_shared);
       }
       if (dbg0)
@@ -592,9 +609,9 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
     int tl_wake[16], tl_done[16], tl_ld[16], tl_max[16], tl_exp[16];
     int j = 0;
     for (int s = 0; s < p.nseg; ++s) {
-      const int tiles = (p.seg_len[s] + BN - 1) / BN;
+      const int tiles = (seg_len_of(s) + BN - 1) / BN;
       for (int t = 0; t < tiles; ++t, ++j) {
-        const int nvalid = min(BN, p.seg_len[s] - t * BN);
+        const int nvalid = min(BN, seg_len_of(s) - t * BN);
         if (p.spin) mbar_spin(&s_ready[w], j & 1, 30); else mbar_wait(&s_ready[w], j & 1, 30);
         long long t_wake = dbg ? clock64() : 0;
         tc_fence_after();
@@ -611,6 +628,28 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= nvalid) v[c][i] = 0xff800000u;  // -inf: ignored by the max, exp2 -> 0
+        }
+        if (kMask && p.key_hi > 0 && (t * BN < p.key_lo || t * BN + BN > p.key_hi)) {
+          // additive padding mask of the reference (createCausalMask: -1e9 on padded keys, added to the scaled score in fp32).
+          // ulp(1e9) = 64, so the score is absorbed: every padded key ends up with the SAME value, a row that sees real keys
+          // gives them weight exp(-1e9) = 0, and a row that sees nothing but padding (left padding) attends uniformly. That is
+          // reproduced with one constant for all padded keys: -2^k / scale-ish (pad_raw, a power of two so that pad_raw * sl2
+          // is exact and the maximum subtraction below yields exactly 0, i.e. P = 1, in bf16 and f16 alike).
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int kj = t * BN + c * 32 + i;
+              if (kj < p.key_lo || kj >= p.key_hi) v[c][i] = __float_as_uint(p.pad_raw);
+            }
+        }
+        if (kMask && p.causal && t * BN + BN - 1 > q_blk0 + w * QT + quarter * 32) {
+          const int qi = q_blk0 + w * QT + row;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (t * BN + c * 32 + i > qi) v[c][i] = 0xff800000u;
         }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -743,6 +782,10 @@ static bool fill_params(const AttnProblem& a, int BN, AttnKParams& p) {
     p.seg_bs[i] = g.batch_stride;
   }
   p.nseg = a.num_segments;
+  p.causal = a.causal;
+  p.kv_group = a.kv_group > 0 ? a.kv_group : 1;
+  p.key_lo = a.key_lo; p.key_hi = a.key_hi;
+  p.pad_raw = -exp2f(ceilf(log2f(fabsf(a.pad_bias) / a.scale)));
   p.sq = a.sq;
   p.num_heads = a.num_heads;
   p.scale_log2 = a.scale * 1.4426950408889634f;
@@ -776,11 +819,22 @@ static cudaError_t launch_attn_v3(const AttnProblem& a, cudaStream_t stream) {
     F2B_ATTR(false, 0); F2B_ATTR(false, 2); F2B_ATTR(false, 3); F2B_ATTR(false, 4);
     F2B_ATTR(true, 0); F2B_ATTR(true, 2); F2B_ATTR(true, 3); F2B_ATTR(true, 4);
 #undef F2B_ATTR
+#define F2B_ATTR_M(F16_, POLY_) if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kernel_v3<F16_, POLY_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3::SMEM_BYTES)
+    F2B_ATTR_M(false, 0); F2B_ATTR_M(false, 4); F2B_ATTR_M(true, 0); F2B_ATTR_M(true, 4);
+#undef F2B_ATTR_M
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((a.sq + 2 * QT - 1) / (2 * QT), a.num_heads, a.batch);
   const int poly = a.poly < 0 ? 0 : (a.poly == 0 ? F2B_ATTN_POLY_DEFAULT : a.poly);
+  if (a.causal || a.key_hi > 0 || a.kv_group > 1) {
+    // text-encoder mode: two exponential variants are enough (all on the MUFU, or the default one-in-four polynomial)
+#define F2B_GO_M(F16_, POLY_) attn_kernel_v3<F16_, POLY_, true><<<grid, 320, A3::SMEM_BYTES, stream>>>(p)
+    if (a.f16) { if (poly == 0) F2B_GO_M(true, 0); else F2B_GO_M(true, 4); }
+    else { if (poly == 0) F2B_GO_M(false, 0); else F2B_GO_M(false, 4); }
+#undef F2B_GO_M
+    return cudaGetLastError();
+  }
 #define F2B_GO(F16_, POLY_) attn_kernel_v3<F16_, POLY_><<<grid, 320, A3::SMEM_BYTES, stream>>>(p)
   if (a.f16) { if (poly == 2) F2B_GO(true, 2); else if (poly == 3) F2B_GO(true, 3); else if (poly == 4) F2B_GO(true, 4); else F2B_GO(true, 0); }
   else { if (poly == 2) F2B_GO(false, 2); else if (poly == 3) F2B_GO(false, 3); else if (poly == 4) F2B_GO(false, 4); else F2B_GO(false, 0); }
@@ -816,6 +870,7 @@ cudaError_t attention_launch(const AttnProblem& a, cudaStream_t stream) {
     if (a.seg[i].len <= 0) return cudaErrorInvalidValue;
   const int variant = a.variant ? a.variant : 3;
   if (a.o_rows_per_peer > 0 && variant != 3) return cudaErrorInvalidValue;
+  if ((a.causal || a.key_hi > 0 || a.kv_group > 1) && (variant != 3 || a.num_segments != 1 || a.seg[0].len != a.sq)) return cudaErrorInvalidValue;
   if (variant == 3) return launch_attn_v3(a, stream);
   if (variant == 2) return launch_attn<128, true>(a, stream);
   return launch_attn<64, false>(a, stream);

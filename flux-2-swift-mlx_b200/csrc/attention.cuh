@@ -39,6 +39,11 @@ struct AttnProblem {
   int o_rows_per_peer = 0;
   int o_col0 = 0;
   void* o_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // Text-encoder prefill (variant 3, one segment with len == sq; Qwen3Model.createCausalMask, Qwen3Model.swift:196-231):
+  int causal = 0;        // key j visible to query i iff j <= i
+  int kv_group = 1;      // grouped-query attention: query head h uses K / V head h / kv_group (Qwen3Attention.swift:133-145)
+  int key_lo = 0, key_hi = 0;  // attention_mask == 1 exactly on keys [key_lo, key_hi); the others get `pad_bias` added (0, 0 = no mask)
+  float pad_bias = -1e9f;
   int f16 = 0;      // 16-bit storage type: 0 = bf16, 1 = f16
   int variant = 0;  // 0 = auto, 1 = P through shared memory (64-key tiles), 2 = P kept in TMEM (128-key tiles)
   int poly = 0;     // variant 3: 0 = default, -1 = all exponentials on the MUFU, n in {2, 3, 4} = one element in n by polynomial on the FMA pipe

@@ -137,6 +137,17 @@ struct VaeW {
   bool has_bn = false;
 };
 
+// Text encoder (FluxTextEncoders/Model/Qwen3/*, Model/Mistral*): one decoder layer's working weights
+struct TeLayerW {
+  Lin qkv;       // q_proj | k_proj | v_proj stacked: [(Hq + 2 Hkv) * 128, hidden]
+  Lin o;         // o_proj [hidden, Hq * 128]
+  Lin gate_up;   // gate_proj | up_proj, rows interleaved per 256-row tile as [128 gate | 128 up] (SwiGLU epilogue)
+  Lin down;      // down_proj [hidden, intermediate]
+  DevBuf ln1, ln2;   // input_layernorm / post_attention_layernorm weights, fp32 [hidden]
+  DevBuf nq, nk;     // q_norm / k_norm weights, fp32 [128] (Qwen3 only)
+  bool mlp_tiled = false;
+};
+
 // Ulysses sequence-parallel state (sp.cu). world == 1: off.
 struct SpState {
   int world = 1, rank = 0;
@@ -182,6 +193,15 @@ struct flux2b_ctx {
   std::vector<f2b::DoubleBlockW> dbl;
   std::vector<f2b::SingleBlockW> sgl;
   f2b::VaeW vw;
+
+  // ---- text encoder (context made by flux2b_te_create)
+  bool has_te = false;
+  flux2b_te_config te{};
+  std::vector<f2b::TeLayerW> te_layers;
+  f2b::DevBuf te_embed;   // 16-bit [vocab, hidden] (dequantized when the checkpoint holds a QuantizedEmbedding)
+  f2b::DevBuf te_norm;    // final norm weight fp32 [hidden]
+  f2b::DevBuf te_ones;    // fp32 ones [hidden]: "gate" of the residual-add GEMM epilogue
+  int te_layers_built = 0;
 
   // ---- workspaces (grown on demand)
   f2b::DevBuf ws_x, ws_xn, ws_qkv, ws_cat, ws_cos, ws_sin, ws_ids, ws_small, ws_hid16, ws_enc16, ws_out;
@@ -262,6 +282,11 @@ bool is_device_ptr(const void* p);
 int dense16_from_key(flux2b_ctx* c, const std::string& base, DevBuf* out, int* N, int* K);
 int finalize_dit(flux2b_ctx* c);
 int finalize_vae(flux2b_ctx* c);
+int finalize_te(flux2b_ctx* c);
+// text-encoder prefill (te.cu): ids [S] int32 on the device; attention_mask == 1 exactly on [key_lo, key_hi) (key_hi == 0: no mask);
+// hidden states after layers `layers[i]` (0 = embeddings, num_layers = after the final norm) -> out_f32[:, i * hidden ...], row stride ldo
+int te_forward_device(flux2b_ctx* c, int S, const int32_t* ids, int key_lo, int key_hi, const int* layers, int n_layers,
+                      float* out_f32, int64_t ldo);
 
 // forward passes
 struct DitIO {

@@ -124,6 +124,116 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------ text-encoder kernels (te.cu)
+// RMSNorm over the hidden dimension with a learned weight (FluxTextEncoders/Model/RMSNorm.swift -> MLXFast.rmsNorm):
+// out = x * rsqrt(mean(x^2) + eps) * w. One CTA per row, the row stays in registers; 16-bit GEMM operand or fp32 out.
+template <int MAXV, bool OUT_F32>
+__global__ void __launch_bounds__(256) rms_norm_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                            void* __restrict__ out, int64_t ldo, int D, float eps, bool f16) {
+  __shared__ float sm[8];
+  const int row = blockIdx.x;
+  const float* xr = x + (int64_t)row * ldx;
+  float4 v[MAXV];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 256 + threadIdx.x) * 4;
+    if (c < D) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  const float rstd = rsqrtf(block_sum<256>(q, sm) / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 256 + threadIdx.x) * 4;
+    if (c < D) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
+      const float o0 = v[i].x * rstd * w4.x, o1 = v[i].y * rstd * w4.y, o2 = v[i].z * rstd * w4.z, o3 = v[i].w * rstd * w4.w;
+      if constexpr (OUT_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (int64_t)row * ldo + c) = make_float4(o0, o1, o2, o3);
+      else *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + (int64_t)row * ldo + c) = make_uint2(pack2(o0, o1, f16), pack2(o2, o3, f16));
+    }
+  }
+}
+cudaError_t rms_norm_rows(const float* x, int64_t ldx, const float* w, void* out, int64_t ldo, int rows, int D, float eps,
+                          bool out_f32, bool f16, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  if (D % 4 || D > 8192) return cudaErrorInvalidValue;
+#define F2B_RMS(V)                                                                                        \
+  do {                                                                                                    \
+    if (out_f32) rms_norm_rows_kernel<V, true><<<rows, 256, 0, s>>>(x, ldx, w, out, ldo, D, eps, f16);     \
+    else rms_norm_rows_kernel<V, false><<<rows, 256, 0, s>>>(x, ldx, w, out, ldo, D, eps, f16);            \
+  } while (0)
+  if (D <= 1024) F2B_RMS(1);
+  else if (D <= 3072) F2B_RMS(3);
+  else if (D <= 4096) F2B_RMS(4);
+  else if (D <= 6144) F2B_RMS(6);
+  else F2B_RMS(8);
+#undef F2B_RMS
+  return cudaGetLastError();
+}
+
+// Token embedding lookup (Qwen3Model.swift:66 embed_tokens): X[s, :] = table16[ids[s], :] widened to fp32. 8 elements per thread.
+__global__ void embed_rows_kernel(const int32_t* __restrict__ ids, const uint16_t* __restrict__ table, int64_t vocab, int D,
+                                  float* __restrict__ x, int64_t ldx, int rows, bool f16) {
+  const int vec = D / 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * vec) return;
+  const int r = (int)(i / vec), c = (int)(i % vec) * 8;
+  int64_t tok = ids[r];
+  tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);   // ids are validated on the host when they arrive from host memory
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(table + tok * D + c));
+  const float2 a = unpack2(u.x, f16), b = unpack2(u.y, f16), cc = unpack2(u.z, f16), d = unpack2(u.w, f16);
+  float4* o = reinterpret_cast<float4*>(x + (int64_t)r * ldx + c);
+  o[0] = make_float4(a.x, a.y, b.x, b.y);
+  o[1] = make_float4(cc.x, cc.y, d.x, d.y);
+}
+cudaError_t embed_rows(const int32_t* ids, const void* table16, int64_t vocab, int D, float* x, int64_t ldx, int rows, bool f16,
+                       cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  if (D % 8) return cudaErrorInvalidValue;
+  const int64_t n = (int64_t)rows * (D / 8);
+  embed_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, reinterpret_cast<const uint16_t*>(table16), vocab, D, x, ldx, rows, f16);
+  return cudaGetLastError();
+}
+
+// cos / sin [S, 128] fp32 for rotate-half RoPE at head dim 128 (MLXFast.RoPE traditional = false, scale 1): column j and
+// j + 64 hold the angle (pos0 + s) * base^(-j / 64), j < 64.
+__global__ void rope_half_table_kernel(int S, int pos0, float log2_base, float* __restrict__ cos_out, float* __restrict__ sin_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * 64) return;
+  const int s = i >> 6, j = i & 63;
+  const float inv_freq = exp2f(-(float)j * (1.0f / 64.0f) * log2_base);
+  const float ang = (float)(pos0 + s) * inv_freq;
+  float sn, cs;
+  sincosf(ang, &sn, &cs);
+  cos_out[(int64_t)s * 128 + j] = cs; cos_out[(int64_t)s * 128 + 64 + j] = cs;
+  sin_out[(int64_t)s * 128 + j] = sn; sin_out[(int64_t)s * 128 + 64 + j] = sn;
+}
+cudaError_t rope_half_table(int S, int pos0, float base, float* cos_out, float* sin_out, cudaStream_t s) {
+  if (S <= 0) return cudaSuccess;
+  rope_half_table_kernel<<<(S * 64 + 255) / 256, 256, 0, s>>>(S, pos0, log2f(base), cos_out, sin_out);
+  return cudaGetLastError();
+}
+
+// strided fp32 -> {fp32, bf16, f16} copy of a [rows, cols] block (hidden-state extraction: [S, H] slab of the [S, n*H] output)
+__global__ void copy_f32_to_any_kernel(const float* __restrict__ in, int64_t ldi, void* __restrict__ out, int64_t ldo, int rows,
+                                       int cols, int out_kind) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  const float v = in[(int64_t)r * ldi + c];
+  if (out_kind == 0) reinterpret_cast<float*>(out)[(int64_t)r * ldo + c] = v;
+  else if (out_kind == 1) reinterpret_cast<__half*>(out)[(int64_t)r * ldo + c] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(out)[(int64_t)r * ldo + c] = __float2bfloat16(v);
+}
+cudaError_t copy_f32_to_any(const float* in, int64_t ldi, void* out, int64_t ldo, int rows, int cols, int out_kind, cudaStream_t s) {
+  const int64_t n = (int64_t)rows * cols;
+  if (n <= 0) return cudaSuccess;
+  copy_f32_to_any_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, ldi, out, ldo, rows, cols, out_kind);
+  return cudaGetLastError();
+}
+
 template <int KIND>
 static void ln_launch(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int grid_rows, int D, const float* shift,
                       const float* scale, int64_t mod_bs, int rows_per_batch, float eps, bool f16, const MxOut& mx, cudaStream_t s) {

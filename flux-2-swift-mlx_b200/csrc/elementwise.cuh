@@ -16,6 +16,18 @@ cudaError_t ln_modulate(const float* x, int64_t ldx, void* out16, int64_t ldo, i
 // With mx->kind != 0 (native block-scaled path) out16 is not written: the 16-bit result is quantised in the same pass to
 // mxfp8 / mxfp4 / nvfp4 (bit-identical to mx_quantize_act applied to the 16-bit output); D % 128 == 0.
 
+// ---- text-encoder prefill (te.cu)
+// out[r, :] = x[r, :] * rsqrt(mean(x[r, :]^2) + eps) * w   (FluxTextEncoders/Model/RMSNorm.swift); 16-bit or fp32 output
+cudaError_t rms_norm_rows(const float* x, int64_t ldx, const float* w, void* out, int64_t ldo, int rows, int D, float eps,
+                          bool out_f32, bool f16, cudaStream_t s);
+// x[r, :] = float(table16[ids[r], :])   (Qwen3Model.swift:66)
+cudaError_t embed_rows(const int32_t* ids, const void* table16, int64_t vocab, int D, float* x, int64_t ldx, int rows, bool f16,
+                       cudaStream_t s);
+// rotate-half RoPE table at head dim 128: cos/sin [S, 128], columns j and j + 64 = angle (pos0 + s) * base^(-j/64)
+cudaError_t rope_half_table(int S, int pos0, float base, float* cos_out, float* sin_out, cudaStream_t s);
+// out_kind: 0 fp32, 1 f16, 2 bf16
+cudaError_t copy_f32_to_any(const float* in, int64_t ldi, void* out, int64_t ldo, int rows, int cols, int out_kind, cudaStream_t s);
+
 // y[b, n] = sum_k act(x[b, k]) * W[n, k] ; W 16-bit [N, K] row-major; act = SiLU if silu_in. B <= 8.
 cudaError_t gemv(const float* x, int64_t ldx, const void* W16, int64_t ldw, float* y, int64_t ldy, int B, int N, int K,
                  bool silu_in, bool accumulate, bool f16, cudaStream_t s);

@@ -188,9 +188,11 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
     for (int h = 0; h < BN / 128; ++h) {
       const int hc = n0 + h * 128;  // first column of this 128-wide head slab
       if (hc >= p.N) break;
-      const bool is_v = hc >= 2 * e.dmodel;
+      const int kc0 = e.k_col0 ? e.k_col0 : e.dmodel, vc0 = e.v_col0 ? e.v_col0 : 2 * e.dmodel;
+      const bool is_v = hc >= vc0;
+      const float* nw = (hc < kc0) ? e.norm_q : e.norm_k;
       float rstd = 1.0f;
-      if (!is_v) {
+      if (!is_v && nw) {
         float ss = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -204,7 +206,43 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
         }
         rstd = rsqrtf(ss * (1.0f / 128.0f) + e.eps);
       }
-      const float* nw = (hc < e.dmodel) ? e.norm_q : e.norm_k;
+      if (e.rope_half && !is_v) {
+        // rotate-half RoPE of the text encoders (MLXFast.RoPE traditional = false; Qwen3Attention.swift:29-35): element j < 64
+        // pairs with j + 64: (x1, x2) -> (x1 c - x2 s, x2 c + x1 s), angle table column j. Optional per-head RMSNorm first.
+        uint32_t u[32];
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_32x32(tq + h * 128 + c * 32, v);
+          tmem_ld_32x32(tq + h * 128 + 64 + c * 32, u);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          const float4* cs = reinterpret_cast<const float4*>(e.cos + grow * 128 + c * 32);
+          const float4* sn = reinterpret_cast<const float4*>(e.sin + grow * 128 + c * 32);
+          uint32_t p1[16], p2[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 cc = __ldg(cs + j), s4 = __ldg(sn + j);
+            float4 w1 = make_float4(1.f, 1.f, 1.f, 1.f), w2 = w1;
+            if (nw) { w1 = __ldg(reinterpret_cast<const float4*>(nw + c * 32) + j); w2 = __ldg(reinterpret_cast<const float4*>(nw + 64 + c * 32) + j); }
+            const float a0 = __uint_as_float(v[4 * j + 0]) * rstd * w1.x, b0 = __uint_as_float(u[4 * j + 0]) * rstd * w2.x;
+            const float a1 = __uint_as_float(v[4 * j + 1]) * rstd * w1.y, b1 = __uint_as_float(u[4 * j + 1]) * rstd * w2.y;
+            const float a2 = __uint_as_float(v[4 * j + 2]) * rstd * w1.z, b2 = __uint_as_float(u[4 * j + 2]) * rstd * w2.z;
+            const float a3 = __uint_as_float(v[4 * j + 3]) * rstd * w1.w, b3 = __uint_as_float(u[4 * j + 3]) * rstd * w2.w;
+            p1[2 * j] = pk2(a0 * cc.x - b0 * s4.x, a1 * cc.y - b1 * s4.y, e.f16);
+            p1[2 * j + 1] = pk2(a2 * cc.z - b2 * s4.z, a3 * cc.w - b3 * s4.w, e.f16);
+            p2[2 * j] = pk2(b0 * cc.x + a0 * s4.x, b1 * cc.y + a1 * s4.y, e.f16);
+            p2[2 * j + 1] = pk2(b2 * cc.z + a2 * s4.z, b3 * cc.w + a3 * s4.w, e.f16);
+          }
+          uint4* d1 = reinterpret_cast<uint4*>(out + grow * e.ldo + hc + c * 32);
+          uint4* d2 = reinterpret_cast<uint4*>(out + grow * e.ldo + hc + 64 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            d1[j] = make_uint4(p1[4 * j], p1[4 * j + 1], p1[4 * j + 2], p1[4 * j + 3]);
+            d2[j] = make_uint4(p2[4 * j], p2[4 * j + 1], p2[4 * j + 2], p2[4 * j + 3]);
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         tmem_ld_32x32(tq + h * 128 + c * 32, v);
@@ -220,7 +258,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
           const float4* w4 = reinterpret_cast<const float4*>(nw + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 cc = __ldg(cs + j), s4 = __ldg(sn + j), ww = __ldg(w4 + j);
+            float4 cc = __ldg(cs + j), s4 = __ldg(sn + j), ww = nw ? __ldg(w4 + j) : make_float4(1.f, 1.f, 1.f, 1.f);
             float x0 = __uint_as_float(v[4 * j + 0]) * rstd * ww.x;
             float x1 = __uint_as_float(v[4 * j + 1]) * rstd * ww.y;
             float x2 = __uint_as_float(v[4 * j + 2]) * rstd * ww.z;
@@ -782,6 +820,30 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
   if (!cg) cg = 2;
   const int m_blks = conv ? g.batch * ((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + CONV_TH - 1) / CONV_TH) : (g.M + BM - 1) / BM;
   if (cg == 2 && (m_blks < 2 || bn < 32)) cg = 1;
+  if (!conv && !g.force_bn && !g.force_cta_group && bn == 256 && g.epi.mode != EPI_SWIGLU && g.N % 128 == 0) {
+    // Few-row problems (the text encoder's M = 512 prefill: 256-wide tiles of an N = 2560 projection occupy 40 of 148 SMs):
+    // pick the narrower tile when a simple wave model says it is clearly faster. Per k-step of 16 a CTA needs
+    // max(MMA clocks = bn / 2, shared-memory operand reads = (128 + bn / cg) / 4) clocks; a wave costs ~3000 clocks of
+    // pipeline fill + epilogue on top. The DiT shapes (M = 4608, many waves) keep the measured-best 256 x 256 pair tile.
+    auto est = [&](int bn_, int cg_) {
+      const long units = (long)((g.M + BM * cg_ - 1) / (BM * cg_)) * ((g.N + bn_ - 1) / bn_);
+      const long slots = g_num_sms / cg_;
+      const double per = (g.K / 16.0) * std::max(bn_ / 2.0, (128.0 + bn_ / cg_) / 4.0) + 3000.0;
+      return (double)((units + slots - 1) / slots) * per;
+    };
+    const double cur = est(bn, cg);
+    int best_bn = bn, best_cg = cg;
+    double best = cur;
+    for (int cb : {128, 64}) {
+      if (g.epi.mode == EPI_QKV_ROPE && cb < 128) continue;
+      for (int cc : {2, 1}) {
+        if (cc == 2 && m_blks < 2) continue;
+        const double e = est(cb, cc);
+        if (e < best) { best = e; best_bn = cb; best_cg = cc; }
+      }
+    }
+    if (best < 0.8 * cur) { bn = best_bn; cg = best_cg; }
+  }
   return conv ? dispatch<true>(g, stream, bn, cg) : dispatch<false>(g, stream, bn, cg);
 }
 

@@ -33,6 +33,10 @@ struct Epilogue {
   const float* norm_k = nullptr;  // [128]
   int dmodel = 0;                 // D: columns [0,D) = q, [D,2D) = k, [2D,3D) = v
   float eps = 1e-6f;
+  // text-encoder variants of EPI_QKV_ROPE (te.cu): grouped-query column ranges (0 = dmodel / 2 * dmodel), rotate-half pairing
+  // (element j with j + 64, MLXFast.RoPE traditional = false) instead of adjacent pairs; norm_q / norm_k may be null (no QK-norm)
+  int k_col0 = 0, v_col0 = 0;
+  int rope_half = 0;
   // EPI_QKV_ROPE under Ulysses sequence parallelism (sp_hp > 0): head h of q / k / v goes to rank h / sp_hp, i.e. the
   // epilogue stores straight into the all-to-all layout [dest rank][local token][q | k | v][sp_hp * 128]. sp_base[d] is
   // where rank d's slab for THIS rank's tokens starts (a local send buffer, or rank d's gather buffer mapped over

@@ -323,6 +323,87 @@ int finalize_dit(flux2b_ctx* c) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ text encoder
+// Keys are the module paths of Qwen3ForCausalLM / MistralForCausalLM (FluxTextEncoders/Model/Qwen3/Qwen3Model.swift:33-55,
+// Qwen3DecoderLayer.swift:14-18, Qwen3Attention.swift:54-62, Qwen3MLP.swift:19-21), i.e. the HF checkpoint names:
+//   model.embed_tokens.weight, model.layers.N.{input_layernorm,post_attention_layernorm}.weight,
+//   model.layers.N.self_attn.{q_proj,k_proj,v_proj,o_proj}.weight (+ .scales / .biases when MLX-quantized),
+//   model.layers.N.self_attn.{q_norm,k_norm}.weight (Qwen3), model.layers.N.mlp.{gate_proj,up_proj,down_proj}.weight, model.norm.weight
+// Only the layers up to the deepest extracted hidden state are ever run, so layers that are absent are simply not built
+// (the Klein extractor needs 27 of 36, the Mistral one 30 of 40); lm_head is never used by the embedding path.
+int finalize_te(flux2b_ctx* c) {
+  const flux2b_te_config& t = c->te;
+  const int Hd = t.hidden_size, I = t.intermediate_size, Nq = t.num_heads * 128, Nkv = t.num_kv_heads * 128;
+  {
+    int N, K;
+    F2B_TRY(dense16_from_key(c, "model.embed_tokens", &c->te_embed, &N, &K));
+    F2B_TRY(expect_shape("model.embed_tokens", N, K, t.vocab_size, Hd));
+  }
+  F2B_TRY(vector_f32_from_key(c, "model.norm.weight", &c->te_norm, Hd, false, 1.f));
+  F2B_TRY(vector_f32_from_key(c, "__te_ones__", &c->te_ones, Hd, false, 1.f));
+  c->te_layers.clear();
+  c->te_layers.resize(t.num_layers);
+  c->te_layers_built = 0;
+  for (int i = 0; i < t.num_layers; ++i) {
+    const std::string p = "model.layers." + std::to_string(i) + ".";
+    if (!find(c, p + "self_attn.q_proj.weight")) break;   // deeper layers were not handed over
+    TeLayerW& L = c->te_layers[i];
+    F2B_TRY(vector_f32_from_key(c, p + "input_layernorm.weight", &L.ln1, Hd, true, 1.f));
+    F2B_TRY(vector_f32_from_key(c, p + "post_attention_layernorm.weight", &L.ln2, Hd, true, 1.f));
+    if (t.qk_norm) {
+      F2B_TRY(vector_f32_from_key(c, p + "self_attn.q_norm.weight", &L.nq, 128, true, 1.f));
+      F2B_TRY(vector_f32_from_key(c, p + "self_attn.k_norm.weight", &L.nk, 128, true, 1.f));
+    }
+    if (find(c, p + "self_attn.q_proj.bias")) return fail(FLUX2B_ERR_WEIGHT_LOADING, "attention_bias = true is not supported: " + p);
+    {
+      const char* names[3] = {"self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj"};
+      const int rows[3] = {Nq, Nkv, Nkv};
+      F2B_CUDA(L.qkv.w.alloc((size_t)(Nq + 2 * Nkv) * Hd * 2));
+      int64_t r0 = 0;
+      for (int j = 0; j < 3; ++j) {
+        DevBuf tmp; int N, K;
+        F2B_TRY(dense16_from_key(c, p + names[j], &tmp, &N, &K));
+        F2B_TRY(expect_shape(p + names[j], N, K, rows[j], Hd));
+        F2B_TRY(copy_rows16(c, tmp.p, K, 0, L.qkv.w.p, K, r0, N, K, false, 0));
+        F2B_CUDA(cudaStreamSynchronize(c->stream));
+        r0 += N;
+      }
+      L.qkv.N = Nq + 2 * Nkv; L.qkv.K = Hd;
+    }
+    F2B_TRY(build_lin(c, p + "self_attn.o_proj", &L.o, Hd, Nq));
+    {
+      DevBuf both;
+      F2B_CUDA(both.alloc((size_t)2 * I * Hd * 2));
+      const char* names[2] = {"mlp.gate_proj", "mlp.up_proj"};
+      for (int j = 0; j < 2; ++j) {
+        DevBuf tmp; int N, K;
+        F2B_TRY(dense16_from_key(c, p + names[j], &tmp, &N, &K));
+        F2B_TRY(expect_shape(p + names[j], N, K, I, Hd));
+        F2B_TRY(copy_rows16(c, tmp.p, K, 0, both.p, K, (int64_t)j * I, N, K, false, 0));
+        F2B_CUDA(cudaStreamSynchronize(c->stream));
+      }
+      F2B_TRY(build_swiglu(c, both.p, Hd, 0, &L.gate_up, I, Hd, &L.mlp_tiled));
+      F2B_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    F2B_TRY(build_lin(c, p + "mlp.down_proj", &L.down, Hd, I));
+    F2B_CUDA(cudaStreamSynchronize(c->stream));
+    c->te_layers_built = i + 1;
+    if (!c->option("keep_raw_weights", 1)) {
+      // the dense working copies are all the forward needs; packed (MLX-quantized) tensors stay for get_tensor
+      for (auto it = c->tensors.begin(); it != c->tensors.end();) {
+        if (it->first.rfind(p, 0) == 0 && is_float_dtype(it->second.dtype) && it->second.shape.size() == 2) it = c->tensors.erase(it);
+        else ++it;
+      }
+    }
+  }
+  if (c->te_layers_built == 0) return fail(FLUX2B_ERR_WEIGHT_LOADING, "no text-encoder layers were loaded (model.layers.0.* missing)");
+  if (!c->option("keep_raw_weights", 1)) {
+    auto it = c->tensors.find("model.embed_tokens.weight");
+    if (it != c->tensors.end() && is_float_dtype(it->second.dtype)) c->tensors.erase(it);
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ VAE
 static int build_conv(flux2b_ctx* c, const std::string& base, ConvW* w, int cout, int cin, int k) {
   Tensor* t = find(c, base + ".weight");

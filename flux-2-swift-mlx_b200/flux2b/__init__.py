@@ -55,6 +55,13 @@ class VaeConfigC(ctypes.Structure):
                 ("decoder_channels", ctypes.c_int * 4), ("norm_eps", ctypes.c_float), ("encoder_channels", ctypes.c_int * 4)]
 
 
+class TeConfigC(ctypes.Structure):
+    _fields_ = [("vocab_size", ctypes.c_int), ("hidden_size", ctypes.c_int), ("intermediate_size", ctypes.c_int),
+                ("num_layers", ctypes.c_int), ("num_heads", ctypes.c_int), ("num_kv_heads", ctypes.c_int),
+                ("head_dim", ctypes.c_int), ("qk_norm", ctypes.c_int), ("rms_norm_eps", ctypes.c_float),
+                ("rope_theta", ctypes.c_float), ("max_position_embeddings", ctypes.c_int)]
+
+
 class StepContextC(ctypes.Structure):
     _fields_ = [("step_idx", ctypes.c_int), ("total_steps", ctypes.c_int), ("sigma", ctypes.c_float),
                 ("sigma_next", ctypes.c_float), ("height", ctypes.c_int), ("width", ctypes.c_int), ("is_i2i", ctypes.c_int)]
@@ -86,6 +93,7 @@ EXPORTS = [
     "flux2b_prof_enable", "flux2b_prof_reset", "flux2b_prof_get", "flux2b_launch_count", "flux2b_op_gemm", "flux2b_op_gemm_mx", "flux2b_op_gemm_mxfp8",
     "flux2b_op_attention", "flux2b_op_ln_modulate", "flux2b_op_qk_norm_rope", "flux2b_op_rope_table",
     "flux2b_op_timestep_embedding", "flux2b_op_conv2d", "flux2b_op_groupnorm_silu",
+    "flux2b_te_create", "flux2b_te_hidden_states", "flux2b_op_attention_causal",
 ]
 
 _lib = None
@@ -570,6 +578,12 @@ class Context:
         _ck(lib().flux2b_op_attention(self._h, _ptr(qkv16), B, S, H, _ptr(out), variant))
         return out
 
+    def op_attention_causal(self, qkv16, S, num_heads, num_kv_heads, key_lo=0, key_hi=0):
+        import torch
+        out = torch.empty((S, num_heads * 128), dtype=qkv16.dtype, device=qkv16.device)
+        _ck(lib().flux2b_op_attention_causal(self._h, _ptr(qkv16), S, num_heads, num_kv_heads, key_lo, key_hi, _ptr(out)))
+        return out
+
     def op_ln_modulate(self, x, shift, scale, out_dtype):
         import torch
         rows, D = x.shape
@@ -607,6 +621,56 @@ class Context:
         _ck(lib().flux2b_op_groupnorm_silu(self._h, _ptr(x16), _ptr(out), _ptr(gamma), _ptr(beta), B, H * W, C, G,
                                            ctypes.c_float(eps), int(silu)))
         return out
+
+
+class TextEncoder(Context):
+    """A text-encoder context (flux2b_te_create): Qwen3Model / MistralModel as the embedding extractors use them
+    (FluxTextEncoders/Model/Qwen3/Qwen3Model.swift:104-191). Weights go in under the HF / Swift module paths with the
+    inherited set_tensor / load_weights / load_safetensors / finalize."""
+
+    def __init__(self, cfg, quant: int = 0, device: int = 0, options: Optional[Dict[str, int]] = None):
+        L = lib()
+        self._h = ctypes.c_void_p()
+        self.te_cfg = cfg
+        self.dit_cfg = self.vae_cfg = None
+        tc = TeConfigC(cfg.vocab_size, cfg.hidden_size, cfg.intermediate_size, cfg.num_layers, cfg.num_heads, cfg.num_kv_heads,
+                       cfg.head_dim, int(cfg.qk_norm), cfg.rms_norm_eps, cfg.rope_theta, int(getattr(cfg, "max_position_embeddings", 0)))
+        _ck(L.flux2b_te_create(device, ctypes.byref(tc), quant, ctypes.byref(self._h)))
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
+        self._keep = []
+
+    def forward_with_hidden_states(self, input_ids, layer_indices: Sequence[int], attention_mask=None, out_dtype=F32):
+        """Qwen3Model.forwardWithHiddenStates(_:layerIndices:attentionMask:) followed by the concatenation along the hidden
+        axis (KleinEmbeddingExtractor.swift:98-121). input_ids / attention_mask: int32 [B, S] -> [B, S, n * hidden]."""
+        ids = np.ascontiguousarray(np.asarray(input_ids, dtype=np.int32))
+        assert ids.ndim == 2
+        B, S = ids.shape
+        m = None if attention_mask is None else np.ascontiguousarray(np.asarray(attention_mask, dtype=np.int32).reshape(B, S))
+        li = (ctypes.c_int * len(layer_indices))(*[int(i) for i in layer_indices])
+        np_dt = {F32: np.float32, F16: np.float16, BF16: np.uint16}[out_dtype]   # bf16 comes back as raw uint16 words
+        out = np.empty((B, S, len(layer_indices) * self.te_cfg.hidden_size), dtype=np_dt)
+        _ck(lib().flux2b_te_hidden_states(self._h, B, S, _ptr(ids), _ptr(m), li, len(layer_indices), _ptr(out), out_dtype))
+        return out
+
+
+class KleinEmbeddingExtractor:
+    """Device half of KleinEmbeddingExtractor.extractKleinEmbeddings (Embeddings/KleinEmbeddingExtractor.swift:46-133): takes
+    the token ids the Swift side produced (chat template + tokenizer stay on the host), truncates, RIGHT-pads with
+    <|endoftext|> (151643) to 512, builds the mask and returns the [1, 512, 3 * hidden] embeddings of layers 9 / 18 / 27."""
+    PAD_TOKEN_ID = 151643
+    HIDDEN_STATE_LAYERS = (9, 18, 27)     # Embeddings/KleinConfig.swift:28-31
+    MAX_SEQUENCE_LENGTH = 512             # Embeddings/KleinConfig.swift:120
+
+    def __init__(self, model: TextEncoder):
+        self.model = model
+
+    def extract(self, token_ids: Sequence[int], max_length: int = MAX_SEQUENCE_LENGTH, out_dtype=F32):
+        ids = list(token_ids)[:max_length]
+        n = len(ids)
+        ids = ids + [self.PAD_TOKEN_ID] * (max_length - n)
+        mask = [1] * n + [0] * (max_length - n)
+        return self.model.forward_with_hidden_states([ids], self.HIDDEN_STATE_LAYERS, [mask], out_dtype)
 
 
 def _empty_like_backend(x, shape):

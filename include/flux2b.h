@@ -197,6 +197,35 @@ int flux2b_vae_encode(flux2b_ctx* ctx, int B, int H, int W, const float* image_n
  * packPatchifiedToSequence. H, W multiples of 16. seq: [B, (H/16) * (W/16), 4 * latent_ch] f32. */
 int flux2b_encode_image_to_sequence(flux2b_ctx* ctx, int B, int H, int W, const float* image_nchw, const float* noise, float* seq);
 
+/* ------------------------------------------------------------------ text-embedding producer
+ * The step on the other side of the DiT boundary: one causal prefill of the text encoder and extraction of the hidden
+ * states that become `encoderHiddenStates`. Replaces Qwen3Model.forwardWithHiddenStates
+ * (FluxTextEncoders/Model/Qwen3/Qwen3Model.swift:104-191) as called by KleinEmbeddingExtractor.extractKleinEmbeddings
+ * (Embeddings/KleinEmbeddingExtractor.swift:46-133) and MistralModel.callAsFunction(outputHiddenStates:attentionMask:)
+ * (Model/MistralModel.swift:97-148) as called by EmbeddingExtractor.extractFluxEmbeddings (Embeddings/EmbeddingExtractor.swift:202-285).
+ * Tokenisation, chat template, truncation and padding stay in Swift; this library receives the padded ids and the 0/1 mask.
+ * == Qwen3TextConfig (Configuration/Qwen3Configuration.swift:16-130) / MistralTextConfig: head_dim must be 128 (true of
+ * Qwen3-4B / 8B checkpoints, whose config.json carries head_dim = 128, and of Mistral Small 3.2); attention_bias = false. */
+typedef struct {
+  int vocab_size, hidden_size, intermediate_size;
+  int num_layers, num_heads, num_kv_heads, head_dim;
+  int qk_norm;                   /* 1 = Qwen3 (q_norm / k_norm per head before RoPE, Qwen3Attention.swift:108-111), 0 = Mistral */
+  float rms_norm_eps, rope_theta;
+  int max_position_embeddings;   /* Mistral original_max_position_embeddings: longer inputs are refused (Llama-4 query scale != 1); 0 = no check */
+} flux2b_te_config;
+/* A text-encoder context: set_tensor / load_safetensors / set_option / finalize_weights / prof_* / destroy work as for a DiT
+ * context. Tensor keys are the HF / Swift module paths ("model.embed_tokens.weight", "model.layers.3.self_attn.q_proj.weight",
+ * ".scales" / ".biases" for MLX-quantized checkpoints, "model.layers.3.self_attn.q_norm.weight", "model.layers.3.mlp.gate_proj.weight",
+ * "model.norm.weight", ...). Layers beyond the deepest hidden state that will be requested need not be loaded. `quant` is
+ * the mode of packed tensors in the checkpoint (mlx-community 8-bit / 4-bit = FLUX2B_QINT8 / FLUX2B_INT4) or FLUX2B_BF16. */
+int flux2b_te_create(int device, const flux2b_te_config* cfg, int quant, flux2b_ctx** out);
+/* input_ids [B, S] int32; attention_mask [B, S] int32 0/1 with the ones in one contiguous run (right padding for Klein,
+ * left padding for Dev), or NULL = no padding. layer_indices as in the reference: 0 = embedding output, i = output of decoder
+ * layer i (1-based), num_layers = after the final norm. out: [B, S, n_layers * hidden] in out_dtype (f32 / f16 / bf16), the
+ * layers concatenated along the last axis in the order given (KleinEmbeddingExtractor.swift:111-121). Host or device pointers. */
+int flux2b_te_hidden_states(flux2b_ctx* ctx, int B, int S, const int32_t* input_ids, const int32_t* attention_mask,
+                            const int* layer_indices, int n_layers, void* out, int out_dtype);
+
 /* ------------------------------------------------------------------ denoise loop (Pipeline/Flux2Pipeline.swift:1933-2052)
  * Flux2StepHook (:64): called after the Euler update of every step with the output latents [1, seq, 128] in HOST
  * memory; whatever the hook leaves in `latents` replaces them (:1985-2001). Flux2StepContext (:42-57). */
@@ -281,6 +310,10 @@ int flux2b_op_gemm_mxfp8(flux2b_ctx* ctx, const void* a16, const uint32_t* w_pac
                          float* out, uint8_t* a8_out, uint8_t* sfa_out);
 int flux2b_op_attention(flux2b_ctx* ctx, const void* qkv16 /* [B*S, 3*H*128] */, int B, int S, int H, void* out16 /* [B*S, H*128] */,
                         int variant);
+/* causal grouped-query attention with the text encoders' additive padding mask (createCausalMask, Qwen3Model.swift:196-231):
+ * qkv16 [S, (Hq + 2 Hkv) * 128] = q | k | v, attention_mask == 1 on keys [key_lo, key_hi) (key_hi = 0: no padding) */
+int flux2b_op_attention_causal(flux2b_ctx* ctx, const void* qkv16, int S, int num_heads, int num_kv_heads, int key_lo, int key_hi,
+                               void* out16 /* [S, Hq * 128] */);
 int flux2b_op_ln_modulate(flux2b_ctx* ctx, const float* x, int rows, int D, const float* shift, const float* scale, void* out16);
 int flux2b_op_qk_norm_rope(flux2b_ctx* ctx, void* qkv16, int rows, int D, const float* norm_q, const float* norm_k,
                            const float* cos_t, const float* sin_t);

@@ -802,3 +802,187 @@ def lora_merge(weight: Tensor, A: Tensor, B: Tensor, scale: float, dtype: torch.
     s = torch.tensor(scale, dtype=torch.float32).to(dtype).to(torch.float32)
     delta = (s * ba).to(dtype).to(torch.float32)
     return (weight.to(dtype).to(torch.float32) + delta).to(dtype)
+
+
+# ----------------------------------------------------------------------------------------------- text encoder
+# Cites below are relative to /root/reference/Sources/FluxTextEncoders. PARITY STATUS: unpinned (the reference holds no numeric
+# vectors for its text encoders; RMSNorm / RoPE / SDPA arithmetic lives in mlx-swift). What the reference does fix — layer
+# indexing, padding side, mask values, pair layout of the rotation, GQA head mapping — is restated here and self-tested in
+# tests/test_oracle_pins.py.
+@dataclass
+class TEConfig:
+    """Qwen3TextConfig (Configuration/Qwen3Configuration.swift:16-130) / MistralTextConfig."""
+    vocab_size: int = 151_936
+    hidden_size: int = 2560
+    intermediate_size: int = 9216
+    num_layers: int = 36
+    num_heads: int = 32
+    num_kv_heads: int = 8
+    head_dim: int = 128
+    qk_norm: bool = True           # Qwen3: q_norm / k_norm (Qwen3Attention.swift:58-61); Mistral: none
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1_000_000.0
+    max_position_embeddings: int = 0
+
+
+def qwen3_4b() -> TEConfig:  # Qwen3Configuration.swift:74-90 (head_dim 128 is what the checkpoint's config.json carries)
+    return TEConfig()
+
+
+def qwen3_8b() -> TEConfig:  # Qwen3Configuration.swift:93-109
+    return TEConfig(hidden_size=4096, intermediate_size=12288)
+
+
+KLEIN_HIDDEN_STATE_LAYERS = (9, 18, 27)   # Embeddings/KleinConfig.swift:28-31
+FLUX_HIDDEN_STATE_LAYERS = (10, 20, 30)   # Embeddings/EmbeddingExtractor.swift (FluxConfig.hiddenStateLayers)
+
+
+def te_weight_shapes(cfg: TEConfig, layers: Optional[int] = None) -> Dict[str, Tuple[int, ...]]:
+    """Module paths of Qwen3ForCausalLM (Model/Qwen3/Qwen3Model.swift:33-55, Qwen3DecoderLayer.swift:14-18,
+    Qwen3Attention.swift:54-62, Qwen3MLP.swift:19-21) = the HF checkpoint keys."""
+    Hd, I = cfg.hidden_size, cfg.intermediate_size
+    s: Dict[str, Tuple[int, ...]] = {"model.embed_tokens.weight": (cfg.vocab_size, Hd), "model.norm.weight": (Hd,)}
+    for i in range(cfg.num_layers if layers is None else layers):
+        p = f"model.layers.{i}."
+        s[p + "self_attn.q_proj.weight"] = (cfg.num_heads * cfg.head_dim, Hd)
+        s[p + "self_attn.k_proj.weight"] = (cfg.num_kv_heads * cfg.head_dim, Hd)
+        s[p + "self_attn.v_proj.weight"] = (cfg.num_kv_heads * cfg.head_dim, Hd)
+        s[p + "self_attn.o_proj.weight"] = (Hd, cfg.num_heads * cfg.head_dim)
+        s[p + "mlp.gate_proj.weight"] = (I, Hd)
+        s[p + "mlp.up_proj.weight"] = (I, Hd)
+        s[p + "mlp.down_proj.weight"] = (Hd, I)
+        s[p + "input_layernorm.weight"] = (Hd,)
+        s[p + "post_attention_layernorm.weight"] = (Hd,)
+        if cfg.qk_norm:
+            s[p + "self_attn.q_norm.weight"] = (cfg.head_dim,)
+            s[p + "self_attn.k_norm.weight"] = (cfg.head_dim,)
+    return s
+
+
+def random_te_weights(cfg: TEConfig, seed: int = 2, layers: Optional[int] = None,
+                      round_to: Optional[torch.dtype] = torch.bfloat16) -> Dict[str, Tensor]:
+    """Random-init text encoder: Linear U(-1/sqrt(in), 1/sqrt(in)) (MLX default), Embedding N(0, 1) scaled to the residual
+    magnitude of a trained model's embedding (std 0.05), norm weights perturbed around one so that a wrong weight shows."""
+    gen = torch.Generator().manual_seed(seed)
+    W: Dict[str, Tensor] = {}
+    for k, shp in te_weight_shapes(cfg, layers).items():
+        if len(shp) == 1:
+            W[k] = (1.0 + 0.1 * torch.randn(shp[0], generator=gen)).to(torch.float32)
+        elif k == "model.embed_tokens.weight":
+            w = torch.randn(shp[0], shp[1], generator=gen) * 0.05
+            W[k] = w.to(round_to).to(torch.float32) if round_to is not None else w
+        else:
+            W[k] = _uniform_linear(gen, shp[0], shp[1], round_to)
+    return W
+
+
+def te_rope_half(x: Tensor, base: float, offset: int = 0) -> Tensor:
+    """MLXFast.RoPE(traditional: false, scale 1) as used by Qwen3RoPE / MistralRoPE (Model/Qwen3/Qwen3Attention.swift:29-35,
+    Model/MistralAttention.swift:336-357): x [B, H, S, hd]; element j < hd/2 pairs with j + hd/2, angle = pos * base^(-j/(hd/2))
+    (upstream kernel: inv_freq = exp2(-(j / (hd/2)) * log2(base)), fp32)."""
+    hd = x.shape[-1]
+    half = hd // 2
+    j = torch.arange(half, dtype=torch.float32)
+    inv_freq = torch.exp2(-(j / half) * math.log2(base)).to(torch.float32)
+    pos = torch.arange(offset, offset + x.shape[-2], dtype=torch.float32)
+    ang = pos[:, None] * inv_freq[None, :]
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    x1, x2 = x[..., :half], x[..., half:]
+    return torch.cat([x1 * cos - x2 * sin, x2 * cos + x1 * sin], dim=-1)
+
+
+def te_causal_mask(seq_len: int, attention_mask: Optional[Tensor]) -> Tensor:
+    """Qwen3Model.createCausalMask (Model/Qwen3/Qwen3Model.swift:196-231; MistralModel.swift:150-194): 0 where j <= i else
+    -inf, plus -1e9 on padded keys (attention_mask == 0), fp32, shape [1, 1, S, S]."""
+    i = torch.arange(seq_len, dtype=torch.float32)[:, None]
+    j = torch.arange(seq_len, dtype=torch.float32)[None, :]
+    mask = torch.where(j <= i, torch.tensor(0.0), torch.tensor(-float("inf")))
+    mask = mask.reshape(1, 1, seq_len, seq_len)
+    if attention_mask is not None:
+        pad = torch.where(attention_mask.reshape(1, -1) == 1, torch.tensor(0.0), torch.tensor(-1e9)).reshape(1, 1, 1, seq_len)
+        mask = mask + pad
+    return mask
+
+
+def _rnd(x: Tensor, dt: Optional[torch.dtype]) -> Tensor:
+    return x if dt is None else x.to(dt).to(torch.float32)
+
+
+def te_attention(W, p: str, cfg: TEConfig, x: Tensor, mask: Tensor, operand_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """Qwen3Attention.callAsFunction (Model/Qwen3/Qwen3Attention.swift:92-163); with qk_norm False it is
+    MistralAttention.callAsFunction (Model/MistralAttention.swift:393-474; its Llama-4 query scale is 1 for positions below
+    original_max_position_embeddings).
+
+    operand_dtype (checker-side model, not a reference behaviour): round to that 16-bit type exactly where the device path
+    stores tensor-core operands (q / k after RoPE, v, the unnormalised softmax numerator, the attention output). The
+    reference itself runs the whole encoder in the checkpoint's 16-bit dtype, i.e. it rounds at MORE points than this."""
+    B, S, _ = x.shape
+    Hq, Hkv, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+    q = linear(x, W[p + "q_proj.weight"]).reshape(B, S, Hq, hd)
+    k = linear(x, W[p + "k_proj.weight"]).reshape(B, S, Hkv, hd)
+    v = _rnd(linear(x, W[p + "v_proj.weight"]), operand_dtype).reshape(B, S, Hkv, hd)
+    if cfg.qk_norm:  # per head, BEFORE RoPE (:108-111)
+        q = rms_norm(q, W[p + "q_norm.weight"], cfg.rms_norm_eps)
+        k = rms_norm(k, W[p + "k_norm.weight"], cfg.rms_norm_eps)
+    q, k, v = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+    q = _rnd(te_rope_half(q, cfg.rope_theta), operand_dtype)
+    k = _rnd(te_rope_half(k, cfg.rope_theta), operand_dtype)
+    rep = Hq // Hkv  # query head h uses kv head h // rep (:133-145: expand axis 2, broadcast, reshape)
+    k = k[:, :, None].expand(B, Hkv, rep, S, hd).reshape(B, Hq, S, hd)
+    v = v[:, :, None].expand(B, Hkv, rep, S, hd).reshape(B, Hq, S, hd)
+    scores = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(hd)) + mask   # additive mask on the scaled scores, fp32
+    if operand_dtype is None:
+        o = torch.softmax(scores, dim=-1) @ v
+    else:
+        e = torch.exp(scores - scores.max(dim=-1, keepdim=True).values)
+        o = _rnd((_rnd(e, operand_dtype) @ v) / e.sum(dim=-1, keepdim=True), operand_dtype)
+    o = o.transpose(1, 2).reshape(B, S, Hq * hd)
+    return linear(o, W[p + "o_proj.weight"])
+
+
+def te_mlp(W, p: str, x: Tensor, operand_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """Qwen3MLP (Model/Qwen3/Qwen3MLP.swift:42-47): down(silu(gate(x)) * up(x))."""
+    a = F.silu(linear(x, W[p + "gate_proj.weight"])) * linear(x, W[p + "up_proj.weight"])
+    return linear(_rnd(a, operand_dtype), W[p + "down_proj.weight"])
+
+
+def te_decoder_layer(W, i: int, cfg: TEConfig, h: Tensor, mask: Tensor, operand_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """Qwen3DecoderLayer (Model/Qwen3/Qwen3DecoderLayer.swift:32-48)."""
+    p = f"model.layers.{i}."
+    x = _rnd(rms_norm(h, W[p + "input_layernorm.weight"], cfg.rms_norm_eps), operand_dtype)
+    h = h + te_attention(W, p + "self_attn.", cfg, x, mask, operand_dtype)
+    x = _rnd(rms_norm(h, W[p + "post_attention_layernorm.weight"], cfg.rms_norm_eps), operand_dtype)
+    return h + te_mlp(W, p + "mlp.", x, operand_dtype)
+
+
+def te_hidden_states(W, cfg: TEConfig, input_ids: Tensor, attention_mask: Optional[Tensor], layer_indices,
+                     operand_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """Qwen3Model.forwardWithHiddenStates (Model/Qwen3/Qwen3Model.swift:104-191) + the concatenation of
+    KleinEmbeddingExtractor.extractKleinEmbeddings (Embeddings/KleinEmbeddingExtractor.swift:98-121): index 0 = embedding
+    output, i = output of decoder layer i (1-based), num_layers = after the final norm. input_ids [1, S] -> [1, S, n * hidden]."""
+    h = W["model.embed_tokens.weight"][input_ids.long()]
+    mask = te_causal_mask(input_ids.shape[1], attention_mask)
+    want = set(int(x) for x in layer_indices)
+    got: Dict[int, Tensor] = {}
+    if 0 in want:
+        got[0] = h
+    for i in range(max(want)):
+        h = te_decoder_layer(W, i, cfg, h, mask, operand_dtype)
+        if (i + 1) in want and (i + 1) < cfg.num_layers:
+            got[i + 1] = h
+    if cfg.num_layers in want:
+        got[cfg.num_layers] = rms_norm(h, W["model.norm.weight"], cfg.rms_norm_eps)
+    return torch.cat([got[int(i)] for i in layer_indices], dim=-1)
+
+
+def te_pad_tokens(token_ids: List[int], max_length: int, pad_id: int, side: str) -> Tuple[Tensor, Tensor]:
+    """Truncate + pad + mask as the extractors do: Klein RIGHT-pads with <|endoftext|> 151643
+    (Embeddings/KleinEmbeddingExtractor.swift:69-95), Dev LEFT-pads (Embeddings/EmbeddingExtractor.swift:221-248)."""
+    ids = list(token_ids[:max_length])
+    n = len(ids)
+    pad = [pad_id] * (max_length - n)
+    if side == "right":
+        ids, m = ids + pad, [1] * n + [0] * len(pad)
+    else:
+        ids, m = pad + ids, [0] * len(pad) + [1] * n
+    return torch.tensor([ids], dtype=torch.int32), torch.tensor([m], dtype=torch.int32)

@@ -86,3 +86,12 @@ def test_quant_table(flux2b):
         assert (b, g, h) == (bits, group, has_b)
     with pytest.raises(flux2b.Flux2Error):
         flux2b.quant_params(0)
+
+
+def test_te_config_is_validated_before_the_device(flux2b):
+    """flux2b_te_create: configuration errors are Flux2Error.invalidConfiguration and are raised without a GPU."""
+    from oracle import flux2_oracle as O
+    for bad in (O.TEConfig(head_dim=80), O.TEConfig(num_heads=32, num_kv_heads=5), O.TEConfig(hidden_size=2561)):
+        with pytest.raises(flux2b.Flux2Error) as e:
+            flux2b.TextEncoder(bad)
+        assert e.value.case == "invalidConfiguration"

@@ -193,3 +193,72 @@ def test_fp4_dequantized_values_lie_on_the_scaled_grid():
         amax = np.abs(w.astype(np.float32)).reshape(16, -1, group).max(-1)
         dmax = np.abs(d).reshape(16, -1, group).max(-1)
         assert np.all(dmax <= 6.0 * sc.reshape(16, -1, group)[:, :, 0] + 1e-12) and np.all(dmax >= 0.5 * amax)
+
+
+# ------------------------------------------------------------------ text encoder: what the reference's source fixes
+def test_te_causal_mask_values_and_padding():
+    """createCausalMask (FluxTextEncoders/Model/Qwen3/Qwen3Model.swift:196-231): 0 on/below the diagonal, -inf above, -1e9 added on
+    padded keys; right padding for Klein (KleinEmbeddingExtractor.swift:78-95), left padding for Dev (EmbeddingExtractor.swift:227-248)."""
+    ids, m = O.te_pad_tokens([11, 12, 13], 6, 151643, "right")
+    assert ids.tolist() == [[11, 12, 13, 151643, 151643, 151643]] and m.tolist() == [[1, 1, 1, 0, 0, 0]]
+    ids, m = O.te_pad_tokens([11, 12, 13], 6, 11, "left")
+    assert ids.tolist() == [[11, 11, 11, 11, 12, 13]] and m.tolist() == [[0, 0, 0, 1, 1, 1]]
+    ids, m = O.te_pad_tokens(list(range(10)), 6, 0, "right")          # truncation keeps the prefix
+    assert ids.tolist() == [list(range(6))] and m.sum() == 6
+    mask = O.te_causal_mask(4, torch.tensor([[1, 1, 0, 0]]))[0, 0]
+    assert mask[0, 0] == 0 and mask[1, 0] == 0 and mask[1, 1] == 0
+    assert torch.isinf(mask[0, 1]) and mask[0, 1] < 0 and torch.isinf(mask[2, 3])
+    assert mask[2, 2] == -1e9 and mask[3, 2] == -1e9 and mask[3, 3] == -1e9 and mask[3, 1] == 0
+    assert O.te_causal_mask(3, None).shape == (1, 1, 3, 3)
+
+
+def test_te_left_padded_rows_attend_uniformly():
+    """-1e9 absorbs every realistic score in fp32 (ulp(1e9) = 64), so a padded query row that sees only padded keys gets a uniform
+    softmax — the behaviour the device kernel reproduces instead of treating the bias as -inf."""
+    s = torch.tensor([3.5, -7.25, 0.125]) + torch.tensor(-1e9)
+    assert torch.all(s == -1e9)
+    p = torch.softmax(s, dim=-1)
+    assert torch.allclose(p, torch.full((3,), 1 / 3))
+
+
+def test_te_rope_is_rotate_half_and_position_zero_is_identity():
+    """MLXFast.RoPE(traditional: false): pairs (j, j + hd/2), angle pos * base^(-j/(hd/2)) (Qwen3Attention.swift:29-35)."""
+    x = torch.randn(1, 2, 5, 128, generator=torch.Generator().manual_seed(0))
+    y = O.te_rope_half(x, 1e6)
+    assert torch.equal(y[:, :, 0], x[:, :, 0])                             # position 0: angle 0
+    # the norm of each (j, j + 64) pair is preserved
+    n0 = x[..., :64] ** 2 + x[..., 64:] ** 2
+    n1 = y[..., :64] ** 2 + y[..., 64:] ** 2
+    assert torch.allclose(n0, n1, rtol=1e-4, atol=1e-5)
+    j = 1
+    ang = 3 * 1e6 ** (-j / 64)
+    assert torch.allclose(y[0, 0, 3, j], x[0, 0, 3, j] * math.cos(ang) - x[0, 0, 3, j + 64] * math.sin(ang), atol=1e-5)
+    assert torch.allclose(y[0, 0, 3, j + 64], x[0, 0, 3, j + 64] * math.cos(ang) + x[0, 0, 3, j] * math.sin(ang), atol=1e-5)
+
+
+def test_te_hidden_state_indexing_and_gqa():
+    """forwardWithHiddenStates (Qwen3Model.swift:104-191): index 0 = embeddings, i = after layer i, num_layers = after the final norm;
+    Klein extracts 9/18/27, Dev 10/20/30; concatenation order = request order. GQA: query head h uses kv head h // rep."""
+    assert O.KLEIN_HIDDEN_STATE_LAYERS == (9, 18, 27) and O.FLUX_HIDDEN_STATE_LAYERS == (10, 20, 30)
+    assert 3 * O.qwen3_4b().hidden_size == 7680 and 3 * O.qwen3_8b().hidden_size == 12288     # == joint_attention_dim of Klein 4B / 9B
+    cfg = O.TEConfig(vocab_size=64, hidden_size=128, intermediate_size=128, num_layers=2, num_heads=2, num_kv_heads=1)
+    W = O.random_te_weights(cfg, seed=0)
+    ids = torch.tensor([[5, 9, 33, 2]], dtype=torch.int32)
+    h = O.te_hidden_states(W, cfg, ids, None, (0, 1, 2))
+    assert h.shape == (1, 4, 3 * 128)
+    assert torch.equal(h[..., :128], W["model.embed_tokens.weight"][ids.long()])
+    mask = O.te_causal_mask(4, None)
+    l1 = O.te_decoder_layer(W, 0, cfg, h[..., :128], mask)
+    assert torch.allclose(h[..., 128:256], l1, atol=1e-6)
+    l2 = O.rms_norm(O.te_decoder_layer(W, 1, cfg, l1, mask), W["model.norm.weight"], cfg.rms_norm_eps)
+    assert torch.allclose(h[..., 256:], l2, atol=1e-6)
+    swapped = O.te_hidden_states(W, cfg, ids, None, (2, 0))
+    assert torch.equal(swapped[..., :128], h[..., 256:]) and torch.equal(swapped[..., 128:], h[..., :128])
+    # causality: changing the last token leaves every earlier row untouched
+    ids2 = ids.clone(); ids2[0, 3] = 7
+    h2 = O.te_hidden_states(W, cfg, ids2, None, (1,))
+    assert torch.equal(h2[:, :3], h[:, :3, 128:256]) and not torch.equal(h2[:, 3], h[:, 3, 128:256])
+    # right padding never changes the real tokens' rows
+    idp, mp = O.te_pad_tokens([5, 9, 33, 2], 8, 63, "right")
+    hp = O.te_hidden_states(W, cfg, idp, mp, (1,))
+    assert torch.allclose(hp[:, :4], h[..., 128:256], atol=1e-6)

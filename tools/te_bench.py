@@ -1,0 +1,62 @@
+"""Times the text-embedding producer on one B200: Klein's Qwen3 encoders at their real shapes, 512 tokens,
+hidden states of layers 9 / 18 / 27 (only 27 layers are built and run). Random-init bf16 weights generated on the device.
+usage: python tools/te_bench.py [qwen3_4b qwen3_8b] -> one JSON line per model on stdout."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "flux-2-swift-mlx_b200")):
+    sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+import flux2b
+from oracle import flux2_oracle as O   # configs / weight shapes only (bench-side, never on the product path)
+
+
+def run(name, reps=10):
+    cfg = getattr(O, name)()
+    layers = O.KLEIN_HIDDEN_STATE_LAYERS
+    te = flux2b.TextEncoder(cfg, options={"keep_raw_weights": 0})
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for k, shp in O.te_weight_shapes(cfg, layers=max(layers)).items():
+        if len(shp) == 1:
+            t = torch.ones(shp, device="cuda")
+        elif k == "model.embed_tokens.weight":
+            t = (torch.randn(shp, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+        else:
+            t = ((torch.rand(shp, device="cuda", generator=g) * 2 - 1) / shp[1] ** 0.5).to(torch.bfloat16)
+        te.set_tensor(k, t)
+    te.finalize()
+    torch.cuda.empty_cache()
+    ex = flux2b.KleinEmbeddingExtractor(te)
+    toks = np.random.default_rng(0).integers(0, cfg.vocab_size, 77).tolist()
+    for _ in range(3):
+        out = ex.extract(toks)
+    te.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = ex.extract(toks)              # host ids in, host fp32 [1, 512, 3 * hidden] out: end to end
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    te.prof_enable(True); te.prof_reset()
+    l0 = te.launch_count()
+    ex.extract(toks)
+    prof = {n: te.prof_get(k) for k, n in enumerate(("gemm", "attn", "elem"))}
+    launches = te.launch_count() - l0
+    kern_ms = sum(p["ms"] for p in prof.values())
+    Hd, I, Nq, Nkv = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads * 128, cfg.num_kv_heads * 128
+    flops = max(layers) * 2.0 * 512 * (Hd * (Nq + 2 * Nkv) + Nq * Hd + 3 * Hd * I)
+    line = {"what": "text_embedding_producer", "model": name, "tokens": 512, "layers_run": max(layers), "hidden_state_layers": list(layers),
+            "e2e_ms": e2e_ms, "kernel_ms": kern_ms, "launches": launches, "gemm_tflops": prof["gemm"]["flops"] / prof["gemm"]["ms"] / 1e9,
+            "gemm_ms": prof["gemm"]["ms"], "attn_ms": prof["attn"]["ms"], "elem_ms": prof["elem"]["ms"],
+            "gemm_flops_check": flops / prof["gemm"]["flops"], "out_shape": list(out.shape), "finite": bool(np.isfinite(out).all())}
+    print(json.dumps(line), flush=True)
+    te.close()
+
+
+if __name__ == "__main__":
+    for n in (sys.argv[1:] or ["qwen3_4b", "qwen3_8b"]):
+        run(n)
