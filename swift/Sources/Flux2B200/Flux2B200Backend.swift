@@ -174,3 +174,56 @@ extension AutoencoderKLFlux2 {
         return MLXArray(seq, [B, (H / 16) * (W / 16), 128])
     }
 }
+
+// MARK: - Text-embedding producer (SURVEY §8 f-4). Lives in the FluxTextEncoders target in practice (it only needs CFlux2B).
+
+/// One flux2b text-encoder context == the decoder layers of Qwen3Model / MistralModel that the embedding extractors run.
+public final class Flux2B200TextEncoder: @unchecked Sendable {
+    let handle: OpaquePointer
+    public let hiddenSize: Int
+
+    /// `bits` / `groupSize` come from the checkpoint's config.json "quantization" block (Qwen3Model.swift:311-345): mlx-community
+    /// 8-bit / 4-bit (group 64, affine) map to FLUX2B_QINT8 / FLUX2B_INT4; an unquantized checkpoint is FLUX2B_BF16.
+    public init(device: Int32 = 0, config c: Qwen3TextConfig, quantBits: Int? = nil) throws {
+        var t = flux2b_te_config()
+        t.vocab_size = Int32(c.vocabSize); t.hidden_size = Int32(c.hiddenSize); t.intermediate_size = Int32(c.intermediateSize)
+        t.num_layers = Int32(c.numHiddenLayers); t.num_heads = Int32(c.numAttentionHeads); t.num_kv_heads = Int32(c.numKeyValueHeads)
+        t.head_dim = Int32(c.headDim); t.qk_norm = 1; t.rms_norm_eps = c.rmsNormEps; t.rope_theta = c.ropeTheta
+        t.max_position_embeddings = 0
+        let q: Int32 = quantBits == 8 ? 1 : (quantBits == 4 ? 2 : 0)
+        var h: OpaquePointer?
+        try withUnsafePointer(to: &t) { tp in try f2bCheck(flux2b_te_create(device, tp, q, &h)) }
+        handle = h!
+        hiddenSize = c.hiddenSize
+    }
+    deinit { flux2b_destroy(handle) }
+
+    /// Same keys as the checkpoint / Module paths ("model.layers.3.self_attn.q_proj.weight", ".scales", ".biases", ...).
+    /// Layers beyond the deepest extracted hidden state (27 for Klein) may be skipped.
+    public func setWeights(_ weights: [String: MLXArray]) throws {
+        for (key, w) in weights {
+            eval(w)
+            let code: Int32 = { switch w.dtype { case .float32: return 0; case .float16: return 1; case .bfloat16: return 2
+                                                   case .uint32: return 3; case .uint8: return 4; default: return 5 } }()
+            var shape = w.shape.map { Int64($0) }
+            let data = w.asData(access: .noCopyIfContiguous)
+            try data.data.withUnsafeBytes { raw in
+                try f2bCheck(flux2b_set_tensor(handle, key, raw.baseAddress, code, &shape, Int32(shape.count)))
+            }
+        }
+    }
+    public func finalize() throws { try f2bCheck(flux2b_finalize_weights(handle)) }
+
+    /// Drop-in body for Qwen3Model.forwardWithHiddenStates(_:layerIndices:attentionMask:) (Qwen3Model.swift:104-191) followed by
+    /// the concatenation of KleinEmbeddingExtractor.extractKleinEmbeddings step 9-10 (KleinEmbeddingExtractor.swift:111-121).
+    /// Tokenisation, chat template, truncation and RIGHT padding (steps 1-7) stay in the extractor.
+    public func hiddenStates(inputIds: MLXArray, layerIndices: [Int], attentionMask: MLXArray?) throws -> MLXArray {
+        let B = inputIds.dim(0), S = inputIds.dim(1)
+        let ids = inputIds.asType(.int32).asArray(Int32.self)
+        let mask = attentionMask?.asType(.int32).asArray(Int32.self)
+        let layers = layerIndices.map { Int32($0) }
+        var out = [Float](repeating: 0, count: B * S * layers.count * hiddenSize)
+        try f2bCheck(flux2b_te_hidden_states(handle, Int32(B), Int32(S), ids, mask, layers, Int32(layers.count), &out, 0))
+        return MLXArray(out, [B, S, layers.count * hiddenSize])
+    }
+}
