@@ -431,7 +431,7 @@ def main():
     ctx.prof_reset()
     ms = timed(one_image_device, args.steps)
     prof = {k: ctx.prof_get(i) for k, i in (("gemm", flux2b.PROF_GEMM), ("attn", flux2b.PROF_ATTN), ("elem", flux2b.PROF_ELEMWISE),
-                                            ("conv", flux2b.PROF_CONV), ("gemv", flux2b.PROF_GEMV))}
+                                            ("conv", flux2b.PROF_CONV), ("gemv", flux2b.PROF_GEMV), ("groupnorm", flux2b.PROF_GROUPNORM))}
     launches = ctx.launch_count()
     ctx.prof_enable(False)
     ctx.prof_reset()

@@ -63,6 +63,7 @@ struct AttnKParams {
   int kv_group;      // query head h reads K / V head h / kv_group
   int key_lo, key_hi;  // keys outside [key_lo, key_hi) get the additive padding mask pad_bias (key_hi == 0: no padding mask)
   float pad_raw;     // raw (pre-scale) score given to padded keys: -(2^k) with 2^k >= |pad_bias| / scale
+  int pingpong;      // variant 3: alternate the two warpgroups' exponential phases (default 1; FLUX2B_ATTN_PINGPONG=0 turns it off)
   int dbg;  // FLUX2B_ATTN_TIMELINE=1: CTA (0,0,0) prints its softmax / MMA time line (debug aid, off by default)
 };
 
@@ -78,6 +79,7 @@ struct ACfg {
   static constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;
   static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int THREADS = 352;   // 8 softmax warps, TMA producer, two MMA issuers
 };
 
 template <int BN, bool kPTmem>
@@ -364,6 +366,7 @@ struct A3 {
   static constexpr int OFF_V = OFF_K + KS * KV_BYTES;
   static constexpr int OFF_BAR = OFF_V + VS * KV_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int THREADS = 352;   // 8 softmax warps, TMA producer, two MMA issuers
 };
 
 // 2^x on the FMA / ALU pipes instead of the MUFU: round-to-nearest split x = n + f by the 1.5 * 2^23 trick, a degree-3
@@ -400,7 +403,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // (16 ex2 / clk / SM: 1024 clk per 128 x 128 tile) is as busy as the tensor pipe (QK^T + PV: 1024 clk), so moving a share of the
 // exponentials onto the otherwise idle FMA lanes is what lets the MMAs run closer to back to back.
 template <bool kF16, int kPoly, bool kMask = false>
-__global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__ AttnKParams p) {
+__global__ void __launch_bounds__(A3::THREADS, 1) attn_kernel_v3(const __grid_constant__ AttnKParams p) {
   using C = A3;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -448,8 +451,9 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
       mbar_init(&p_ready[i], 128);
       mbar_init(&o_done[i], 1);
     }
-    for (int i = 0; i < C::KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
-    for (int i = 0; i < C::VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    // a K / V stage is free once BOTH issuers' MMAs on it have completed (tcgen05.commit tracks the committing thread's own MMAs)
+    for (int i = 0; i < C::KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); }
+    for (int i = 0; i < C::VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2); }
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<1>(tmem_slot, 512);
@@ -511,21 +515,27 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
           printf("[attn timeline] producer: tile %d  K issued at %6d  V slot awaited from %6d, V issued at %6d\n", j, pk_t[j], pv_w[j], pv_t[j]);
     }
     __syncwarp();
-  } else if (warp == 9) {
-    // ============================================================ MMA issuer
+  } else if (warp == 9 || warp == 10) {
+    // ============================================================ MMA issuers: one warp per query tile / softmax warpgroup
+    // One issuing warp for both tiles was the kernel's limiter: per key tile it spent ~2 x 1030 clk blocked in the issue of
+    // its 32 MMAs (the tensor pipe's queue is only a few MMAs deep) plus ~1000 clk in four mbarrier waits during which the
+    // pipe ran dry (timeline: period 3100 clk against 2048 clk of MMA work). With one issuer per tile the waits of one warp
+    // overlap the issue of the other; the tensor pipe executes the two streams in arrival order, and they only share the K / V
+    // stages, whose release barriers therefore count two commits.
     // The whole warp walks the loop (warp-uniform control flow, barrier waits by all lanes) and one elected lane issues:
     // inside an `if (lane == 0)` region ptxas wraps every tcgen05.mma in an elect / broadcast loop and reloads its
     // operands from the stack (~25 instructions per MMA), which is slower than the 64 clk a 128x128x16 MMA takes.
     // The 512-column allocation starts at TMEM address 0 (checked below), so accumulator addresses are immediates, and
     // descriptors are (constant high word, 32-bit low word = address field + constants).
     if (tmem_base != 0) __trap();
+    const int w = warp - 9;
     const uint32_t idesc_s = make_idesc_f16(QT, BN, !kF16, false, false);
     const uint32_t idesc_o = make_idesc_f16(QT, HD, !kF16, false, true);
     const uint32_t smem_base = smem_u32(smem);
     // K-major operands (Q, K): LBO 16 B, SBO 1024 B; V (MN-major): LBO = panel stride, SBO 1024 B
     const uint64_t desc_kmajor = make_smem_desc(0, 16, 1024, SWZ_128B);
     const uint64_t desc_v = make_smem_desc(0, C::KV_PANEL, 1024, SWZ_128B);
-    auto issue_s = [&](int w, int ks) {
+    auto issue_s = [&](int ks) {
       const uint32_t qa = (smem_base + w * C::Q_BYTES) >> 4;
       const uint32_t ka = (smem_base + C::OFF_K + ks * C::KV_BYTES) >> 4;
 #pragma unroll
@@ -536,65 +546,55 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
       }
       umma_commit(&s_ready[w]);
     };
-    auto issue_pv = [&](int w, int vs, bool accumulate) {
+    auto issue_pv = [&](int vs, bool accumulate) {
       const uint32_t va = (smem_base + C::OFF_V + vs * C::KV_BYTES) >> 4;
 #pragma unroll
       for (int k = 0; k < BN / 16; ++k)
         umma_f16_ts(256 + w * 128, w * 128 + k * 8, desc_v + (va + k * (2048 >> 4)), idesc_o, (accumulate || k) ? 1u : 0u);
     };
-    mbar_wait(&q_full[0], 0, 20);
+    mbar_wait(&q_full[w], 0, 20);
     mbar_wait(&k_full[0], 0, 21);
     tc_fence_after();
-    if (elect_one()) issue_s(0, 0);
-    __syncwarp();
-    mbar_wait(&q_full[1], 0, 22);
-    tc_fence_after();
-    if (elect_one()) { issue_s(1, 0); umma_commit(&k_empty[0]); }
+    if (elect_one()) { issue_s(0); umma_commit(&k_empty[0]); }
     __syncwarp();
     const bool mdbg = dbg0;
     const long long mt0 = t0_shared;
-    int m_seen[2][8], m_kv[2][8], m_iss[2][8], m_v[8];
+    int m_seen[8], m_kv[8], m_iss[8], m_v[8];
     for (int j = 0; j < n_tiles; ++j) {
       const int vs = j % C::VS;
       const int ksn = (j + 1) % C::KS;
       const bool more = j + 1 < n_tiles;
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        if (w == 0) {
-          // operand barriers first: they completed long ago, but every mbarrier wait costs ~200 clk of latency, which
-          // must not sit between "P is ready" and the MMAs that consume it
-          mbar_wait(&v_full[vs], (j / C::VS) & 1, 24);
-          if (mdbg && j < 8) m_v[j] = (int)(clock64() - mt0);
-          if (more) mbar_wait(&k_full[ksn], ((j + 1) / C::KS) & 1, 25);
+      // operand barriers first: they completed long ago, but every mbarrier wait costs ~200 clk of latency, which
+      // must not sit between "P is ready" and the MMAs that consume it
+      mbar_wait(&v_full[vs], (j / C::VS) & 1, 24);
+      if (mdbg && j < 8) m_v[j] = (int)(clock64() - mt0);
+      if (more) mbar_wait(&k_full[ksn], ((j + 1) / C::KS) & 1, 25);
+      if (p.spin) mbar_spin(&p_ready[w], j & 1, 23); else mbar_wait(&p_ready[w], j & 1, 23);
+      if (mdbg && j < 8) m_seen[j] = (int)(clock64() - mt0);
+      if (mdbg && j < 8) m_kv[j] = (int)(clock64() - mt0);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_pv(vs, j > 0);
+        umma_commit(&v_empty[vs]);
+        if (more) {
+          issue_s(ksn);
+          umma_commit(&k_empty[ksn]);
+        } else {
+          umma_commit(&o_done[w]);
         }
-        if (p.spin) mbar_spin(&p_ready[w], j & 1, 23); else mbar_wait(&p_ready[w], j & 1, 23);
-        if (mdbg && j < 8) m_seen[w][j] = (int)(clock64() - mt0);
-        if (mdbg && j < 8) m_kv[w][j] = (int)(clock64() - mt0);
-        tc_fence_after();
-        if (elect_one()) {
-          issue_pv(w, vs, j > 0);
-          if (w == 1) umma_commit(&v_empty[vs]);
-          if (more) {
-            issue_s(w, ksn);
-            if (w == 1) umma_commit(&k_empty[ksn]);
-          } else {
-            umma_commit(&o_done[w]);
-          }
-        }
-        __syncwarp();
-        if (mdbg && j < 8) m_iss[w][j] = (int)(clock64() - mt0);
-        if (mdbg && more && getenv_dbg2(p)) {  // debug level 2: block until the S MMAs just issued have completed (perturbs the schedule)
-          mbar_wait(&s_ready[w], (j + 1) & 1, 26);
-          if (j < 8) m_kv[w][j] = (int)(clock64() - mt0);   // reuse the slot: completion time
-        }
+      }
+      __syncwarp();
+      if (mdbg && j < 8) m_iss[j] = (int)(clock64() - mt0);
+      if (mdbg && more && getenv_dbg2(p)) {  // debug level 2: block until the S MMAs just issued have completed (perturbs the schedule)
+        mbar_wait(&s_ready[w], (j + 1) & 1, 26);
+        if (j < 8) m_kv[j] = (int)(clock64() - mt0);   // reuse the slot: completion time
       }
     }
     if (mdbg && lane == 0)
       for (int j = 0; j < 8 && j < n_tiles; ++j)
-        for (int w = 0; w < 2; ++w)
-          printf("[attn timeline] mma warp: wg %d tile %d  P seen at %6d  V full at %6d  K/V ready at %6d  PV + next S issued at %6d\n",
-                 w, j, m_seen[w][j], w == 0 ? m_v[j] : 0, m_kv[w][j], m_iss[w][j]);
-  } else {
+        printf("[attn timeline] mma warp: wg %d tile %d  V full at %6d  P seen at %6d  K/V ready at %6d  PV + next S issued at %6d\n",
+               w, j, m_v[j], m_seen[j], m_kv[j], m_iss[j]);
+  } else if (warp < 8) {
     // ============================================================ softmax warpgroups
     const int w = warp >> 2;
     const int quarter = warp & 3;
@@ -612,6 +612,10 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
       const int tiles = (seg_len_of(s) + BN - 1) / BN;
       for (int t = 0; t < tiles; ++t, ++j) {
         const int nvalid = min(BN, seg_len_of(s) - t * BN);
+        // Named barriers (bar.sync / bar.arrive, 128 + 128 threads): a waiting warpgroup is descheduled by the hardware; polling an
+        // mbarrier with 128 threads for a whole exp phase slowed the working warpgroup down 2x. Taken at the top of the tile, where
+        // nothing but the running state is live (between the max and exp phases it cost 400 B of spills in the hot loop).
+        if (p.pingpong && (w == 1 || j > 0)) asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
         if (p.spin) mbar_spin(&s_ready[w], j & 1, 30); else mbar_wait(&s_ready[w], j & 1, 30);
         long long t_wake = dbg ? clock64() : 0;
         tc_fence_after();
@@ -662,6 +666,9 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
         const float m_use = move ? m_new : m_run;
         const float alpha = move ? fast_exp2(m_run - m_new) : 1.0f;
         const float neg_m = -m_use;
+        // Ping-pong: the exponential phases of the two warpgroups alternate strictly (warpgroup 0 first). Left alone they fall
+        // into lock-step — both in the MUFU-bound exp phase at once (each 1.6x slower), then both MMA batches at once — and the
+        // tensor pipe idles through every softmax; alternating, one warpgroup's exponentials run beside the other's MMAs.
         const long long t_max = dbg ? clock64() : 0;
         // packed fp32x2 arithmetic (FFMA2 / FADD2): the loop is bound by the issue rate of its single warp per scheduler
         // as much as by the MUFU, so two elements per instruction wherever the ISA has it
@@ -682,6 +689,8 @@ __global__ void __launch_bounds__(320, 1) attn_kernel_v3(const __grid_constant__
           }
         }
         const float rs[4] = {rs2[0].x + rs2[0].y, rs2[1].x + rs2[1].y, rs2[2].x + rs2[2].y, rs2[3].x + rs2[3].y};
+        // ping-pong: the other warpgroup may start its tile now (this one's exponentials are done)
+        if (p.pingpong && (w == 0 || j + 1 < n_tiles)) asm volatile("bar.arrive %0, 256;" ::"r"(2 - w) : "memory");
         const long long t_exp = dbg ? clock64() : 0;
         // P (16-bit) back into the first 64 columns of the S region
         tmem_st_32x32(t_s, *reinterpret_cast<const uint32_t(*)[32]>(&pk[0]));
@@ -803,11 +812,13 @@ static bool fill_params(const AttnProblem& a, int BN, AttnKParams& p) {
   p.dbg = timeline;
   static const int spin = getenv("FLUX2B_ATTN_SPIN") ? atoi(getenv("FLUX2B_ATTN_SPIN")) : 0;
   p.spin = spin;
+  static const int pingpong = getenv("FLUX2B_ATTN_PINGPONG") ? atoi(getenv("FLUX2B_ATTN_PINGPONG")) : 1;
+  p.pingpong = pingpong;
   return true;
 }
 
 #ifndef F2B_ATTN_POLY_DEFAULT
-#define F2B_ATTN_POLY_DEFAULT 4   // share of the exponentials on the FMA pipe when AttnProblem::poly == 0 (1 element in n; 0 = none)
+#define F2B_ATTN_POLY_DEFAULT 3   // share of the exponentials on the FMA pipe when AttnProblem::poly == 0 (1 element in n; 0 = none)
 #endif
 static cudaError_t launch_attn_v3(const AttnProblem& a, cudaStream_t stream) {
   AttnKParams p{};
@@ -829,13 +840,13 @@ static cudaError_t launch_attn_v3(const AttnProblem& a, cudaStream_t stream) {
   const int poly = a.poly < 0 ? 0 : (a.poly == 0 ? F2B_ATTN_POLY_DEFAULT : a.poly);
   if (a.causal || a.key_hi > 0 || a.kv_group > 1) {
     // text-encoder mode: two exponential variants are enough (all on the MUFU, or the default one-in-four polynomial)
-#define F2B_GO_M(F16_, POLY_) attn_kernel_v3<F16_, POLY_, true><<<grid, 320, A3::SMEM_BYTES, stream>>>(p)
+#define F2B_GO_M(F16_, POLY_) attn_kernel_v3<F16_, POLY_, true><<<grid, A3::THREADS, A3::SMEM_BYTES, stream>>>(p)
     if (a.f16) { if (poly == 0) F2B_GO_M(true, 0); else F2B_GO_M(true, 4); }
     else { if (poly == 0) F2B_GO_M(false, 0); else F2B_GO_M(false, 4); }
 #undef F2B_GO_M
     return cudaGetLastError();
   }
-#define F2B_GO(F16_, POLY_) attn_kernel_v3<F16_, POLY_><<<grid, 320, A3::SMEM_BYTES, stream>>>(p)
+#define F2B_GO(F16_, POLY_) attn_kernel_v3<F16_, POLY_><<<grid, A3::THREADS, A3::SMEM_BYTES, stream>>>(p)
   if (a.f16) { if (poly == 2) F2B_GO(true, 2); else if (poly == 3) F2B_GO(true, 3); else if (poly == 4) F2B_GO(true, 4); else F2B_GO(true, 0); }
   else { if (poly == 2) F2B_GO(false, 2); else if (poly == 3) F2B_GO(false, 3); else if (poly == 4) F2B_GO(false, 4); else F2B_GO(false, 0); }
 #undef F2B_GO

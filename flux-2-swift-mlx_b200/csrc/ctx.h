@@ -254,10 +254,10 @@ namespace f2b {
 struct ProfScope {
   flux2b_ctx* c; int kind; bool on;
   cudaEvent_t stop = nullptr;
-  ProfScope(flux2b_ctx* ctx, int k, double flops, double bytes) : c(ctx), kind(k), on(ctx->prof_on) {
-    c->launches++;
+  ProfScope(flux2b_ctx* ctx, int k, double flops, double bytes, int n_launches = 1) : c(ctx), kind(k), on(ctx->prof_on) {
+    c->launches += n_launches;
     ProfKind& pk = c->prof[kind];
-    pk.launches++; pk.flops += flops; pk.bytes += bytes;
+    pk.launches += n_launches; pk.flops += flops; pk.bytes += bytes;
     if (!on) return;
     if (pk.used == pk.ev.size()) {
       cudaEvent_t a, b;

@@ -618,8 +618,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
   float s[8], q[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
+  auto accumulate = [&](const uint4& v) {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -627,7 +626,18 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
       s[2 * k] += f.x; q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
       s[2 * k + 1] += f.y; q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
     }
+  };
+  // four independent 16 B loads in flight per thread (one load per thread leaves the SM ~16 KB short of the ~35 KB in flight
+  // that HBM latency x bandwidth needs); the accumulation order per thread is unchanged (ascending i)
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(xb + (i + j * stride) * 8));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) accumulate(v[j]);
   }
+  for (; i < nvec; i += stride) accumulate(__ldg(reinterpret_cast<const uint4*>(xb + i * 8)));
   float* acc = gsm;
 #pragma unroll
   for (int k = 0; k < 8; ++k) { acc[threadIdx.x * 16 + k] = s[k]; acc[threadIdx.x * 16 + 8 + k] = q[k]; }
@@ -660,22 +670,34 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
     dst[G + threadIdx.x] = gq;
   }
 }
-// grid (B), block 256 = `lanes` sub-lanes per statistic (2G statistics, G <= 128): sub-lane l sums partials l, l + lanes,
-// ... in index order, then thread g folds the sub-lanes of (sum_g, sumsq_g) in index order
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ partial, double* __restrict__ stats,
-                                                          int chunks, int G, double count, float eps) {
-  __shared__ double sm[256];
+// grid (B), block 1024 = `lanes` sub-lanes per statistic (2G statistics, G <= 128), statistic index fastest so that a warp reads
+// consecutive floats: sub-lane l sums partials l, l + lanes, ... in index order (eight loads in flight, folded in order), then
+// thread g folds the sub-lanes of (sum_g, sumsq_g) in index order
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ partial, double* __restrict__ stats,
+                                                           int chunks, int G, double count, float eps) {
+  __shared__ double sm[1024];
   const int b = blockIdx.x;
-  const int lanes = 256 / (2 * G);
-  const int j = threadIdx.x / lanes, l = threadIdx.x % lanes;  // statistic j in [0, 2G), sub-lane l
+  const int nstat = 2 * G;
+  const int lanes = 1024 / nstat;
+  const int j = threadIdx.x % nstat, l = threadIdx.x / nstat;  // statistic j in [0, 2G), sub-lane l
   double a = 0.0;
-  if (j < 2 * G)
-    for (int c = l; c < chunks; c += lanes) a += (double)partial[((int64_t)b * chunks + c) * 2 * G + j];
-  sm[threadIdx.x] = a;
+  if (l < lanes) {
+    const float* src = partial + (int64_t)b * chunks * nstat + j;
+    int c = l;
+    for (; c + 7 * lanes < chunks; c += 8 * lanes) {
+      float t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] = src[(int64_t)(c + k * lanes) * nstat];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += (double)t[k];
+    }
+    for (; c < chunks; c += lanes) a += (double)src[(int64_t)c * nstat];
+    sm[l * nstat + j] = a;
+  }
   __syncthreads();
   if (threadIdx.x < G) {
     double s = 0.0, q = 0.0;
-    for (int k = 0; k < lanes; ++k) { s += sm[threadIdx.x * lanes + k]; q += sm[(G + threadIdx.x) * lanes + k]; }
+    for (int k = 0; k < lanes; ++k) { s += sm[k * nstat + threadIdx.x]; q += sm[k * nstat + G + threadIdx.x]; }
     const double m = s / count;
     const double var = q / count - m * m;
     stats[((int64_t)b * G + threadIdx.x) * 2] = m;
@@ -707,8 +729,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
     sc[k] = rstd * ga;
     sh[k] = __ldg(beta + c) - m * rstd * ga;
   }
-  for (int64_t i = i0; i < nvec; i += stride) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + i * 8));
+  auto apply = [&](const uint4& v, int64_t i) {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
@@ -720,7 +741,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
       o[k] = pack2(z0, z1, f16);
     }
     *reinterpret_cast<uint4*>(yb + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  // Back to front: the statistics pass has just streamed the tensor in ascending order, so its tail is what the L2 still holds
+  // when the tensor is larger than the cache (the 1024^2 layers are 100 - 200 MB against 126 MB of L2). Four loads in flight.
+  const int64_t n_it = (nvec - i0 + stride - 1) / stride;   // iterations of this thread
+  int64_t k = n_it - 1;
+  for (; k >= 3; k -= 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(xb + (i0 + (k - j) * stride) * 8));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) apply(v[j], i0 + (k - j) * stride);
   }
+  for (; k >= 0; --k) apply(__ldg(reinterpret_cast<const uint4*>(xb + (i0 + k * stride) * 8)), i0 + k * stride);
 }
 size_t groupnorm_ws_bytes(int B, int G) {
   // [B, G] x (mean, rstd) doubles followed by the per-CTA partials [B, <= 592 chunks, 2G] floats
@@ -737,7 +770,7 @@ cudaError_t groupnorm_silu(const void* x16, void* y16, const float* gamma, const
   const int chunks = (int)std::min<int64_t>((nvec + threads - 1) / threads, 148 * 4);
   const size_t smem = std::max((size_t)threads * 16, (size_t)2 * C) * sizeof(float);
   gn_stats_kernel<<<dim3(chunks, B), threads, smem, s>>>(x16, partial, HW, C, G, f16);
-  gn_finalize_kernel<<<B, 256, 0, s>>>(partial, stats_ws, chunks, G, (double)HW * (C / G), eps);
+  gn_finalize_kernel<<<B, 1024, 0, s>>>(partial, stats_ws, chunks, G, (double)HW * (C / G), eps);
   const int chunks2 = (int)std::min<int64_t>((nvec + threads - 1) / threads, 148 * 8);
   gn_apply_kernel<<<dim3(chunks2, B), threads, 0, s>>>(x16, y16, gamma, beta, stats_ws, HW, C, G, silu, f16);
   return cudaGetLastError();

@@ -64,14 +64,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint (ns): without one the instruction returns after a very short system-dependent limit and a
+// waiting warp becomes a hot polling loop that competes for issue slots and the shared-memory pipe with the warps that do the
+// work on the same scheduler (measured in the attention kernel: a warp polling p_ready through a whole exp phase slowed the
+// softmax warps of its scheduler down ~2x). With the hint the warp sleeps in hardware until the phase completes.
+#ifndef F2B_MBAR_SUSPEND_NS
+#define F2B_MBAR_SUSPEND_NS 1000000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)F2B_MBAR_SUSPEND_NS)
       : "memory");
   return ok != 0;
 }
@@ -115,7 +122,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   while (true) {
     bool ok = kClusterAcquire ? mbar_try_wait_cluster_acq(bar, parity) : mbar_try_wait(bar, parity);
     if (ok) return;
-    if ((++spins & 0x3ff) == 0) {
+    if ((++spins & 0x3) == 0) {   // a failed try_wait has slept for up to F2B_MBAR_SUSPEND_NS: checking the clock is cheap by comparison
       uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > F2B_MBAR_TIMEOUT_NS) {

@@ -70,8 +70,7 @@ int te_forward_device(flux2b_ctx* c, int S, const int32_t* ids, int key_lo, int 
     for (int i = 0; i < n_layers; ++i)
       if (layers[i] == layer_idx) {
         ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)S * Hd * 8);
-        F2B_CUDA(cudaMemcpy2DAsync(out_f32 + (size_t)i * Hd, (size_t)ldo * 4, src, (size_t)Hd * 4, (size_t)Hd * 4, S,
-                                   cudaMemcpyDeviceToDevice, st));
+        F2B_CUDA(copy_f32_to_any(src, Hd, out_f32 + (size_t)i * Hd, ldo, S, Hd, 0, st));
       }
     return 0;
   };

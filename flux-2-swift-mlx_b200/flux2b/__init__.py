@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libflux2b.so")
 
 F32, F16, BF16, U32, U8, I32 = 0, 1, 2, 3, 4, 5
 QUANT = {"bf16": 0, "qint8": 1, "int4": 2, "mxfp8": 3, "mxfp4": 4, "nvfp4": 5}
-PROF_GEMM, PROF_ATTN, PROF_ELEMWISE, PROF_CONV, PROF_GEMV, PROF_COMM = range(6)
+PROF_GEMM, PROF_ATTN, PROF_ELEMWISE, PROF_CONV, PROF_GEMV, PROF_COMM, PROF_GROUPNORM = range(7)
 
 _STATUS = {-1: "modelNotLoaded", -2: "invalidConfiguration", -3: "insufficientMemory", -4: "weightLoadingFailed",
            -5: "imageProcessingFailed", -6: "generationFailed", -7: "generationCancelled", -8: "noDevice", -9: "cuda"}

@@ -283,7 +283,7 @@ int flux2b_sp_layout(int world, int rank, int S_txt, int S_img, int num_heads, f
 
 /* ------------------------------------------------------------------ profiling (CUDA events on the context stream) */
 enum { FLUX2B_PROF_GEMM = 0, FLUX2B_PROF_ATTN = 1, FLUX2B_PROF_ELEMWISE = 2, FLUX2B_PROF_CONV = 3, FLUX2B_PROF_GEMV = 4,
-       FLUX2B_PROF_COMM = 5, FLUX2B_PROF_KINDS = 6 };
+       FLUX2B_PROF_COMM = 5, FLUX2B_PROF_GROUPNORM = 6 /* VAE GroupNorm(+SiLU): statistics + finalize + apply */, FLUX2B_PROF_KINDS = 7 };
 int flux2b_prof_enable(flux2b_ctx* ctx, int on);
 int flux2b_prof_reset(flux2b_ctx* ctx);
 /* resolves pending events; ms = summed device time, launches, flops and algorithmic bytes of that kernel class */
