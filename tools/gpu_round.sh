@@ -23,6 +23,11 @@ for w in $WHAT; do
       timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 2000 --csv \
         --log-file gpurun_out/launches.csv python bench.py --profile-one > gpurun_out/ncu_launches.log 2>&1
       echo "ncu launches rc=$?"; wc -l gpurun_out/launches.csv ;;
+    te_ncu)
+      # launch list of ONE text-encoder prefill (Klein 4B's Qwen3-4B, 27 layers, 512 tokens)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv \
+        --log-file gpurun_out/te_launches.csv python tools/te_bench.py qwen3_4b --profile-one > gpurun_out/ncu_te.log 2>&1
+      echo "ncu te launches rc=$?"; wc -l gpurun_out/te_launches.csv ;;
     traffic)
       # DRAM bytes of EVERY launch of one image (cheap pass: two counters, no --set full)
       timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --profile-from-start off \

@@ -17,7 +17,7 @@ import flux2b
 from oracle import flux2_oracle as O   # configs / weight shapes only (bench-side, never on the product path)
 
 
-def run(name, reps=10):
+def run(name, reps=10, profile_one=False):
     cfg = getattr(O, name)()
     layers = O.KLEIN_HIDDEN_STATE_LAYERS
     te = flux2b.TextEncoder(cfg, options={"keep_raw_weights": 0})
@@ -37,6 +37,12 @@ def run(name, reps=10):
     for _ in range(3):
         out = ex.extract(toks)
     te.synchronize()
+    if profile_one:   # for `ncu --profile-from-start off`: one prefill between cudaProfilerStart / Stop, no bench line
+        torch.cuda.synchronize(); torch.cuda.profiler.start()
+        ex.extract(toks)
+        torch.cuda.synchronize(); torch.cuda.profiler.stop()
+        te.close()
+        return
     t0 = time.perf_counter()
     for _ in range(reps):
         out = ex.extract(toks)              # host ids in, host fp32 [1, 512, 3 * hidden] out: end to end
@@ -58,5 +64,6 @@ def run(name, reps=10):
 
 
 if __name__ == "__main__":
-    for n in (sys.argv[1:] or ["qwen3_4b", "qwen3_8b"]):
-        run(n)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    for n in (args or ["qwen3_4b", "qwen3_8b"]):
+        run(n, profile_one="--profile-one" in sys.argv)
