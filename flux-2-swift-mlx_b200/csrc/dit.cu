@@ -403,9 +403,60 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
 
   // ---- double-stream blocks (Flux2TransformerBlock.swift:80-168)
   QView q_img, q_txt, q_all, q_mlp;
+  // option group_streams (default 1): one launch per operation for both streams (16-bit operands, fused epilogues, single GPU)
+  bool group = P == 1 && !mxk && fuse_qk && S_txt > 0 && S_txt % 256 == 0 && S_im_all > 0 && c->option("group_streams", 1) != 0;
+  for (int i = 0; group && i < cfg.num_layers; ++i) group = c->dbl[i].ff_tiled && !c->dbl[i].qkv_img.mx;
   for (int i = 0; i < cfg.num_layers; ++i) {
     DoubleBlockW& b = c->dbl[i];
     uint16_t* XNi = XN + (size_t)S_txt * D;
+    if (group) {
+      // Both streams in one launch per operation (7 launches instead of 13): text rows [0, S_txt) and image rows behind them
+      // share X / XN / QKV / CAT and differ only in weights, modulation and QK-norm weights. A text-stream GEMM of its own
+      // (M = 512) fills a third of the SMs for ~35 us; as two extra M units of the image GEMM's tile schedule it costs ~1/9 more.
+      auto ln2 = [&](int set) -> int {
+        ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)S * D * 6);
+        F2B_CUDA(ln_modulate(X, D, XN, D, S, D, mod_img + (3 * set) * D, mod_img + (3 * set + 1) * D, 0, S, 1e-6f, f16, st, nullptr,
+                             S_txt, mod_txt + (3 * set) * D, mod_txt + (3 * set + 1) * D));
+        return 0;
+      };
+      auto gemm2 = [&](const void* A, int64_t lda, const Lin& Wimg, const Lin& Wtxt, Epilogue e) -> int {
+        GemmProblem g;
+        g.M = S; g.N = Wimg.N; g.K = Wimg.K;
+        g.A = A; g.lda = lda; g.B = Wimg.w.p; g.ldb = Wimg.K; g.B_lo = Wtxt.w.p; g.M_lo = S_txt;
+        e.f16 = f16 ? 1 : 0; e.split_row = S_txt;
+        g.epi = e;
+        g.force_cta_group = c->option("gemm_cta_group", 0);
+        ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * S * (double)g.N * g.K,
+                     2.0 * ((double)S * g.K + 2.0 * (double)g.N * g.K + (double)S * g.N));
+        F2B_CUDA(gemm_launch(g, st));
+        return 0;
+      };
+      F2B_TRY(ln2(0));
+      {
+        Epilogue e; e.mode = EPI_QKV_ROPE; e.out = QKV; e.ldo = 3 * D; e.cos = cosT; e.sin = sinT; e.dmodel = D; e.eps = 1e-6f;
+        e.norm_q = b.nq_img.as<float>(); e.norm_k = b.nk_img.as<float>();
+        e.norm_q_lo = b.nq_txt.as<float>(); e.norm_k_lo = b.nk_txt.as<float>();
+        F2B_TRY(gemm2(XN, D, b.qkv_img, b.qkv_txt, e));
+      }
+      F2B_TRY(full_attention(i, CAT, D));
+      {
+        Epilogue e; e.mode = EPI_GATE_RES; e.out = X; e.ldo = D; e.res = X; e.ldr = D;
+        e.gate = mod_img + 2 * D; e.gate_lo = mod_txt + 2 * D;
+        F2B_TRY(gemm2(CAT, D, b.out_img, b.out_txt, e));
+      }
+      F2B_TRY(ln2(1));
+      {
+        Epilogue e; e.mode = EPI_SWIGLU; e.out = CAT; e.ldo = Hm;
+        F2B_TRY(gemm2(XN, D, b.ff_in_img, b.ff_in_txt, e));
+      }
+      {
+        Epilogue e; e.mode = EPI_GATE_RES; e.out = X; e.ldo = D; e.res = X; e.ldr = D;
+        e.gate = mod_img + 5 * D; e.gate_lo = mod_txt + 5 * D;
+        F2B_TRY(gemm2(CAT, Hm, b.ff_out_img, b.ff_out_txt, e));
+      }
+      F2B_TRY(record_block(c, i, S));
+      continue;
+    }
     F2B_TRY(ln_mod(Ximg, S_im_all, mod_img + 0, mod_img + D, XNi, 1, &q_img));
     F2B_TRY(ln_mod(X, S_txt, mod_txt + 0, mod_txt + D, XN, 0, &q_txt));
     F2B_TRY(qkv_gemm(XNi, &q_img, b.qkv_img, S_im_all, S_txt, b.nq_img, b.nk_img));

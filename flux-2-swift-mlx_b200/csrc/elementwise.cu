@@ -55,7 +55,8 @@ template <int MAXV, int KIND>  // float4 vectors per thread
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, int64_t ldx, void* __restrict__ out,
                                                           int64_t ldo, int rows, int D, const float* __restrict__ shift,
                                                           const float* __restrict__ scale, int64_t mod_bs,
-                                                          int rows_per_batch, float eps, bool f16, MxOut mx) {
+                                                          int rows_per_batch, float eps, bool f16, MxOut mx, int split_row,
+                                                          const float* __restrict__ shift_lo, const float* __restrict__ scale_lo) {
   __shared__ float sm[8];
   constexpr int GROUP = KIND == 3 ? 16 : 32;
   constexpr int LPG = GROUP / 4;
@@ -89,8 +90,9 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
     }
   }
   const float rstd = rsqrtf(block_sum<256>(q, sm) / (float)D + eps);
-  const float* sh = shift + b * mod_bs;
-  const float* sc = scale + b * mod_bs;
+  // rows below split_row form a second stream with its own modulation (text rows of a double-stream block, one launch for both)
+  const float* sh = row < split_row ? shift_lo : shift + b * mod_bs;
+  const float* sc = row < split_row ? scale_lo : scale + b * mod_bs;
   uint16_t* orow = reinterpret_cast<uint16_t*>(out) + (int64_t)row * ldo;
   const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -236,8 +238,9 @@ cudaError_t copy_f32_to_any(const float* in, int64_t ldi, void* out, int64_t ldo
 
 template <int KIND>
 static void ln_launch(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int grid_rows, int D, const float* shift,
-                      const float* scale, int64_t mod_bs, int rows_per_batch, float eps, bool f16, const MxOut& mx, cudaStream_t s) {
-#define F2B_LN(V) ln_modulate_kernel<V, KIND><<<grid_rows, 256, 0, s>>>(x, ldx, out16, ldo, rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, mx)
+                      const float* scale, int64_t mod_bs, int rows_per_batch, float eps, bool f16, const MxOut& mx, cudaStream_t s,
+                      int split_row = 0, const float* shift_lo = nullptr, const float* scale_lo = nullptr) {
+#define F2B_LN(V) ln_modulate_kernel<V, KIND><<<grid_rows, 256, 0, s>>>(x, ldx, out16, ldo, rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, mx, split_row, shift_lo, scale_lo)
   if (D <= 1024) F2B_LN(1);
   else if (D <= 3072) F2B_LN(3);
   else if (D <= 4096) F2B_LN(4);
@@ -247,8 +250,9 @@ static void ln_launch(const float* x, int64_t ldx, void* out16, int64_t ldo, int
 }
 cudaError_t ln_modulate(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int D, const float* shift,
                         const float* scale, int64_t mod_bs, int rows_per_batch, float eps, bool f16, cudaStream_t s,
-                        const MxOut* mx) {
+                        const MxOut* mx, int split_row, const float* shift_lo, const float* scale_lo) {
   if (rows <= 0) return cudaSuccess;
+  if (split_row && (mx && mx->kind)) return cudaErrorInvalidValue;
   if (D % 4 || D > 8192 || ldx % 4 || ldo % 4) return cudaErrorInvalidValue;
   MxOut m;
   if (mx) m = *mx;
@@ -259,7 +263,7 @@ cudaError_t ln_modulate(const float* x, int64_t ldx, void* out16, int64_t ldo, i
     else if (m.kind == 2) ln_launch<2>(x, ldx, out16, ldo, rows, grid_rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, m, s);
     else ln_launch<3>(x, ldx, out16, ldo, rows, grid_rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, m, s);
   } else {
-    ln_launch<0>(x, ldx, out16, ldo, rows, rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, m, s);
+    ln_launch<0>(x, ldx, out16, ldo, rows, rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, m, s, split_row, shift_lo, scale_lo);
   }
   return cudaGetLastError();
 }

@@ -12,7 +12,10 @@ namespace f2b {
 // LayerNorm: biased variance, eps, no affine (Flux2TransformerBlock.swift:56-61; Flux2Modulation.swift:96-112).
 cudaError_t ln_modulate(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int D, const float* shift,
                         const float* scale, int64_t mod_batch_stride, int rows_per_batch, float eps, bool f16,
-                        cudaStream_t s, const MxOut* mx = nullptr);
+                        cudaStream_t s, const MxOut* mx = nullptr, int split_row = 0, const float* shift_lo = nullptr,
+                        const float* scale_lo = nullptr);
+// split_row > 0: rows [0, split_row) take (shift_lo, scale_lo) instead — the text rows of a double-stream block, so that both
+// streams are one launch (16-bit output only).
 // With mx->kind != 0 (native block-scaled path) out16 is not written: the 16-bit result is quantised in the same pass to
 // mxfp8 / mxfp4 / nvfp4 (bit-identical to mx_quantize_act applied to the 16-bit output); D % 128 == 0.
 

@@ -44,6 +44,7 @@ struct KParams {
   const uint8_t* sfa;
   const uint8_t* sfb;
   int sfa_ld, sfb_ld;
+  int split_units;  // two-problem launch: M units below this one read B through the second weight map (passed in the tmSFB slot)
   int dbg;  // FLUX2B_GEMM_TIMELINE=1: cluster 0 prints where its producer / issuer / epilogue warps waited (debug aid)
 };
 
@@ -190,7 +191,8 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
       if (hc >= p.N) break;
       const int kc0 = e.k_col0 ? e.k_col0 : e.dmodel, vc0 = e.v_col0 ? e.v_col0 : 2 * e.dmodel;
       const bool is_v = hc >= vc0;
-      const float* nw = (hc < kc0) ? e.norm_q : e.norm_k;
+      const bool lo = grow < e.split_row;   // uniform over the tile (split_row is a multiple of the M tile)
+      const float* nw = (hc < kc0) ? (lo ? e.norm_q_lo : e.norm_q) : (lo ? e.norm_k_lo : e.norm_k);
       float rstd = 1.0f;
       if (!is_v && nw) {
         float ss = 0.f;
@@ -303,11 +305,12 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
     if (e.mode == EPI_GATE_RES) {
       float* out = reinterpret_cast<float*>(e.out) + grow * e.ldo + col;
       const float* res = e.res + grow * e.ldr + col;
+      const float* gate = (grow < e.split_row) ? e.gate_lo : e.gate;
       if (full) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 r = *reinterpret_cast<const float4*>(res + 4 * j);
-          float4 g = __ldg(reinterpret_cast<const float4*>(e.gate + col + 4 * j));
+          float4 g = __ldg(reinterpret_cast<const float4*>(gate + col + 4 * j));
           float4 o;
           o.x = fmaf(g.x, a[4 * j + 0], r.x);
           o.y = fmaf(g.y, a[4 * j + 1], r.y);
@@ -316,7 +319,7 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
           *reinterpret_cast<float4*>(out + 4 * j) = o;
         }
       } else {
-        for (int j = 0; j < 32 && col + j < p.N; ++j) out[j] = fmaf(__ldg(e.gate + col + j), a[j], res[j]);
+        for (int j = 0; j < 32 && col + j < p.N; ++j) out[j] = fmaf(__ldg(gate + col + j), a[j], res[j]);
       }
     } else if (e.mode == EPI_F32) {
       float* out = reinterpret_cast<float*>(e.out) + grow * e.ldo + col;
@@ -391,6 +394,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (MXK == 0 && !CONV && p.split_units > 0) tma_prefetch_desc(&tmSFB);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -421,6 +425,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int n_blk = t / p.num_m_units;
         const int m_blk = m_unit * CG + (int)cta_rank;
         const int nrow0 = n_blk * BN + (int)cta_rank * C::B_ROWS;
+        const CUtensorMap* tmBsel = (MXK == 0 && !CONV && m_unit < p.split_units) ? &tmSFB : &tmB;
         int img = 0, y0 = 0, x0 = 0;
         if (CONV) {
           const int per_img = p.tiles_x * p.tiles_y;
@@ -447,7 +452,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             } else {
               // (tensor-map coordinates are in elements: 64 bf16, or 128 bytes of fp8 / packed fp4, per 128 B row)
               tma_load_2d(a_dst, &tmA, &full[stage], kb * (MXK ? 2 * BK : BK), m_blk * BM);
-              tma_load_2d(b_dst, &tmB, &full[stage], kb * (MXK ? 2 * BK : BK), nrow0);
+              tma_load_2d(b_dst, tmBsel, &full[stage], kb * (MXK ? 2 * BK : BK), nrow0);
               if (MXK) {
                 uint8_t* sf = smSF + stage * C::SF_BYTES;
                 bulk_load(sf, p.sfa + ((size_t)m_blk * p.sfa_ld + kb * C::SFPK) * 512, C::SFA_BYTES, &full[stage]);
@@ -470,7 +475,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_4d_cg2(b_dst, &tmB, lbar, c0, tap, nrow0, 0);
             } else {
               tma_load_2d_cg2(a_dst, &tmA, lbar, kb * (MXK ? 2 * BK : BK), m_blk * BM);
-              tma_load_2d_cg2(b_dst, &tmB, lbar, kb * (MXK ? 2 * BK : BK), nrow0);
+              tma_load_2d_cg2(b_dst, tmBsel, lbar, kb * (MXK ? 2 * BK : BK), nrow0);
               if (MXK) {
                 // scale factors through tensor maps ([blocks][128 x u32]): a plain bulk copy cannot signal the leader's barrier.
                 // Each CTA stages the scales of its own 128 A rows and of ALL BN weight rows of the tile.
@@ -727,6 +732,10 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     uint64_t bs[1] = {(uint64_t)g.ldb * 2};
     uint32_t bb[2] = {BK, (uint32_t)C::B_ROWS};
     if (!make_tmap_bf16(&tmB, g.B, 2, bd, bs, bb)) return cudaErrorInvalidValue;
+    if (g.B_lo) {
+      if (!make_tmap_bf16(&tmSFB, g.B_lo, 2, bd, bs, bb)) return cudaErrorInvalidValue;
+      p.split_units = g.M_lo / (BM * CG);
+    }
   }
   p.num_m_units = (num_m_blks + CG - 1) / CG;
   p.num_n_blks = (g.N + BN - 1) / BN;
@@ -753,7 +762,7 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  if (!(MXK && CG == 2)) { tmSFA = tmA; tmSFB = tmA; }  // unused by those instantiations
+  if (!(MXK && CG == 2)) { tmSFA = tmA; if (!(MXK == 0 && !CONV && g.B_lo)) tmSFB = tmA; }  // unused by those instantiations
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmSFA, tmSFB, p);
 }
 
@@ -808,6 +817,10 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
     }
   }
   if (!conv && (g.lda % 8 || g.ldb % 8)) { g_err = "lda/ldb must be multiples of 8 elements (TMA 16 B stride)"; return cudaErrorInvalidValue; }
+  if (g.B_lo && (conv || g.M_lo <= 0 || g.M_lo >= g.M || g.M_lo % (2 * BM) || (reinterpret_cast<uintptr_t>(g.B_lo) & 15) || g.epi.split_row != g.M_lo)) {
+    g_err = "two-problem GEMM: plain GEMM only, 0 < M_lo < M, M_lo a multiple of 256, epilogue split_row == M_lo";
+    return cudaErrorInvalidValue;
+  }
   if (conv && (g.Cin % 8 || g.lda % 8)) { g_err = "conv Cin / pixel stride must be multiples of 8"; return cudaErrorInvalidValue; }
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) { g_err = "A/B must be 16 B aligned"; return cudaErrorInvalidValue; }
   int bn = g.force_bn;

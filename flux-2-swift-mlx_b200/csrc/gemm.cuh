@@ -37,6 +37,12 @@ struct Epilogue {
   // (element j with j + 64, MLXFast.RoPE traditional = false) instead of adjacent pairs; norm_q / norm_k may be null (no QK-norm)
   int k_col0 = 0, v_col0 = 0;
   int rope_half = 0;
+  // two-problem launch (GemmProblem::B_lo): rows below split_row belong to the second problem and take these instead of
+  // gate / norm_q / norm_k (the double-stream blocks' text rows: own modulation gate, own QK-norm weights)
+  int split_row = 0;
+  const float* gate_lo = nullptr;
+  const float* norm_q_lo = nullptr;
+  const float* norm_k_lo = nullptr;
   // EPI_QKV_ROPE under Ulysses sequence parallelism (sp_hp > 0): head h of q / k / v goes to rank h / sp_hp, i.e. the
   // epilogue stores straight into the all-to-all layout [dest rank][local token][q | k | v][sp_hp * 128]. sp_base[d] is
   // where rank d's slab for THIS rank's tokens starts (a local send buffer, or rank d's gather buffer mapped over
@@ -56,6 +62,12 @@ struct GemmProblem {
   const void* B = nullptr;
   int64_t ldb = 0;
   int M = 0, N = 0, K = 0;
+  // Two problems in one launch (plain 16-bit GEMM only): rows [0, M_lo) of A are multiplied by B_lo (same [N, K] shape and ldb),
+  // rows [M_lo, M) by B. The double-stream blocks use it for their text (512 rows) and image streams, which share the A / output
+  // buffers but not the weights: the text tiles ride in the image GEMM's tile schedule instead of a launch of their own that
+  // occupies a third of the SMs. M_lo must be a multiple of 256.
+  const void* B_lo = nullptr;
+  int M_lo = 0;
   // implicit-GEMM 3x3 / 1x1 convolution (NHWC activations, OHWI weights): M = batch*H*W, K = taps*Cin
   int conv_taps = 0;  // 0 = plain GEMM, 1 = 1x1, 9 = 3x3 (stride 1: pad 1; stride 2: pad 0 top / left, 1 bottom / right)
   int batch = 1, H = 0, W = 0, Cin = 0;  // H, W = OUTPUT extent

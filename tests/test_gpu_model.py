@@ -87,6 +87,32 @@ def test_dit_forward_tiny_vs_oracle(flux2b, opts):
     run_and_compare(flux2b, O, cfg, O.random_dit_weights(cfg, seed=0), opts)
 
 
+@pytest.mark.parametrize("S_img,S_txt,quant", [(100, 256, "bf16"), (256, 512, "bf16"), (81, 256, "qint8")])
+def test_dit_forward_grouped_streams(flux2b, S_img, S_txt, quant):
+    """Double-stream blocks with text and image rows in one launch per operation (option group_streams, taken when S_txt is a
+    multiple of 256): same bits as the per-stream launches, and the oracle's tolerance."""
+    from oracle import flux2_oracle as O
+    cfg = tiny_cfg(O, layers=(2, 1))
+    W = O.random_dit_weights(cfg, seed=5, round_to=torch.float16 if quant != "bf16" else torch.bfloat16)
+    hidden, enc, t, gd, img_ids, txt_ids = dit_inputs(O, cfg, S_img, S_txt)
+    img_ids = O.image_position_ids(16, 16 * S_img) if int(math.isqrt(S_img)) ** 2 != S_img else img_ids
+    outs, launches = [], []
+    for g in (1, 0):
+        ctx = make_ctx(flux2b, cfg, W, quant=flux2b.QUANT[quant], opts={"group_streams": g},
+                       dtype=torch.float16 if quant != "bf16" else torch.bfloat16)
+        l0 = ctx.launch_count()
+        outs.append(ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), gd.numpy(), img_ids.numpy(), txt_ids.numpy()))
+        launches.append(ctx.launch_count() - l0)
+        if g == 1 and quant == "bf16":
+            rec = []
+            ref = O.dit_forward(W, cfg, hidden, enc, t, gd, img_ids, txt_ids, record=rec)
+            errs = [rel_l2(ctx.block_output(i, S_txt + S_img, cfg.inner_dim), r) for i, r in enumerate(rec)]
+            assert max(errs) < TOL_BLOCK and rel_l2(outs[0], ref) < TOL_OUT
+        ctx.close()
+    assert launches[0] == launches[1] - 6 * cfg.num_layers     # 7 instead of 13 launches per double block
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_dit_forward_f16_compute(flux2b):
     from oracle import flux2_oracle as O
     cfg = tiny_cfg(O, guidance=False)
