@@ -26,6 +26,10 @@ import subprocess
 import sys
 import time
 
+# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when the box exports NCCL_DEBUG=VERSION)
+# goes to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "flux-2-swift-mlx_b200")):
     if p not in sys.path:
