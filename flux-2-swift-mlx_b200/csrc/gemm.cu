@@ -777,6 +777,10 @@ static cudaError_t dispatch(const GemmProblem& g, cudaStream_t s, int bn, int cg
   F2B_CASE(128)
   F2B_CASE(64)
   F2B_CASE(32)
+  if constexpr (CONV) {   // VAE channel counts (96, 192, 384) are multiples of 96, not of 128
+    F2B_CASE(192)
+    F2B_CASE(96)
+  }
 #undef F2B_CASE
   g_err = "unsupported BN";
   return cudaErrorInvalidValue;
@@ -825,6 +829,15 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) { g_err = "A/B must be 16 B aligned"; return cudaErrorInvalidValue; }
   int bn = g.force_bn;
   if (!bn) bn = g.N > 128 ? 256 : g.N > 64 ? 128 : g.N > 32 ? 64 : 32;
+  if (conv && !g.force_bn) {
+    // N tile with the least padding (ties -> the wider tile): Cout = 384 -> 2 x 192 (256-wide tiles would compute 512 columns),
+    // 192 -> 192, 96 -> 96. The small decoder's 96 / 192 / 384-channel layers lose a quarter of the tensor pipe otherwise.
+    int best_pad = 1 << 30;
+    for (int cand : {256, 192, 128, 96, 64, 32}) {
+      const int pad = (g.N + cand - 1) / cand * cand;
+      if (pad < best_pad) { best_pad = pad; bn = cand; }
+    }
+  }
   if (g.epi.mode == EPI_SWIGLU) bn = 256;
   if (g.epi.mode == EPI_QKV_ROPE && bn < 128) bn = 128;
   // CTA pairs (cta_group::2, 256 x BN tiles) by default: each CTA stages only half of B, which buys two more pipeline

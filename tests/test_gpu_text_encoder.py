@@ -263,3 +263,44 @@ def test_te_qwen3_4b_shapes_klein_extractor(flux2b):
     print(f"te qwen3-4b shapes, layers 3/6/9: f16 rel-L2 vs fp32 {['%.2e' % e for e in errsf]}")
     assert max(errsf) < TOL_F16
     tf.close()
+
+
+def test_prompt_tokens_to_dit_forward(flux2b):
+    """Both sides of the boundary together, as the pipeline wires them (Flux2Pipeline: textEmbeddings = extractor output ->
+    Flux2Transformer2DModel(encoderHiddenStates:)): token ids -> text-encoder hidden states (bf16, the dtype an MLX bf16 checkpoint
+    produces, KleinEmbeddingExtractor.swift:122-133) -> DiT forward with enc_dtype = bf16, against the oracle's composition."""
+    from oracle import flux2_oracle as O
+    tcfg = O.TEConfig(vocab_size=512, hidden_size=256, intermediate_size=512, num_layers=3, num_heads=2, num_kv_heads=1)
+    dcfg = O.DiTConfig(num_layers=1, num_single_layers=1, num_attention_heads=2, joint_attention_dim=3 * tcfg.hidden_size,
+                       guidance_embeds=False)
+    TW, DW = O.random_te_weights(tcfg, seed=8), O.random_dit_weights(dcfg, seed=9)
+    te = flux2b.TextEncoder(tcfg)
+    te.load_weights(TW, dtype=torch.bfloat16)
+    te.finalize()
+    ex = flux2b.KleinEmbeddingExtractor(te)
+    ex.HIDDEN_STATE_LAYERS, ex.PAD_TOKEN_ID = (1, 2, 3), 3
+    toks = list(range(10, 90))
+    S_txt, S_img = 256, 64
+    emb16 = ex.extract(toks, max_length=S_txt, out_dtype=flux2b.BF16)                       # uint16 words
+    emb_bf16 = torch.from_numpy((emb16.astype(np.uint32) << 16).view(np.float32))            # exact widening of the bf16 bits
+    ctx = flux2b.Context(dit=dcfg)
+    ctx.load_weights(DW, dtype=torch.bfloat16)
+    ctx.finalize()
+    hidden = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(4))
+    t = torch.tensor([0.5])
+    img_ids, txt_ids = O.image_position_ids(128, 128), O.text_position_ids(S_txt)
+    enc_dev = torch.from_numpy(emb16.view(np.int16)).view(torch.bfloat16).cuda()
+    out = ctx.dit_forward(hidden.cuda(), enc_dev, t.cuda(), None, img_ids.cuda(), txt_ids.cuda())
+    ctx.synchronize()
+    # (a) DiT on the device's own embeddings vs the oracle DiT on the same embeddings: the DiT tolerance
+    ref_same = O.dit_forward(DW, dcfg, hidden, emb_bf16, t, None, img_ids, txt_ids)
+    assert rel_l2(out, ref_same) < 4e-3
+    # (b) the whole chain vs the oracle chain (fp32 text encoder): text-encoder operand rounding propagates through contextEmbedder
+    ids, mask = O.te_pad_tokens(toks, S_txt, 3, "right")
+    ref_emb = O.te_hidden_states(TW, tcfg, ids, mask, (1, 2, 3))
+    assert rel_l2(emb_bf16, ref_emb) < 8e-3
+    ref_chain = O.dit_forward(DW, dcfg, hidden, ref_emb, t, None, img_ids, txt_ids)
+    e = rel_l2(out, ref_chain)
+    print(f"tokens -> embeddings -> DiT: rel-L2 vs oracle chain {e:.2e}, vs oracle DiT on the device embeddings {rel_l2(out, ref_same):.2e}")
+    assert e < 8e-3
+    te.close(); ctx.close()

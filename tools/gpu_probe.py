@@ -236,6 +236,15 @@ PROBES = {
     "gemm_bn128_cg1": lambda: probe_gemm(512, 128, 3072, 1, 1),
     "gemm_small_cg2": lambda: probe_gemm(256, 256, 128, 1, 2),
     "gemm_tail_cg2": lambda: probe_gemm(300, 200, 192, 1, 2),
+    "gemm_m512_out": lambda: probe_gemm(512, 3072, 3072, 2, 0),
+    "gemm_m512_out_bn256": lambda: probe_gemm(512, 3072, 3072, 2, 2, bn=256),
+    "gemm_m512_out_bn64": lambda: probe_gemm(512, 3072, 3072, 2, 2, bn=64),
+    "gemm_m512_out_cg1_bn128": lambda: probe_gemm(512, 3072, 3072, 2, 1, bn=128),
+    "gemm_m512_down": lambda: probe_gemm(512, 2560, 9216, 2, 0),
+    "gemm_m512_down_bn64": lambda: probe_gemm(512, 2560, 9216, 2, 2, bn=64),
+    "gemm_m512_down_cg1_bn64": lambda: probe_gemm(512, 2560, 9216, 2, 1, bn=64),
+    "gemm_m512_qkv": lambda: probe_gemm(512, 6144, 2560, 0, 0),
+    "gemm_m512_qkv_bn128": lambda: probe_gemm(512, 6144, 2560, 0, 2, bn=128),
     "gemm_big_cg1": lambda: probe_gemm(4608, 3072, 3072, 0, 1),
     "gemm_big_cg2": lambda: probe_gemm(4608, 3072, 3072, 0, 2),
     "gemm_ffin_cg1": lambda: probe_gemm(4608, 18432, 3072, 3, 1),
