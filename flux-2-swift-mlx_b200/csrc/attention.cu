@@ -62,6 +62,7 @@ struct AttnKParams {
   int causal;        // key j is visible to query i iff j <= i (query index == key index, one segment)
   int kv_group;      // query head h reads K / V head h / kv_group
   int key_lo, key_hi;  // keys outside [key_lo, key_hi) get the additive padding mask pad_bias (key_hi == 0: no padding mask)
+  const int* mask_dev; // if set: {key_lo, key_hi} are read from device memory (a captured CUDA graph is replayed for every prompt length)
   float pad_raw;     // raw (pre-scale) score given to padded keys: -(2^k) with 2^k >= |pad_bias| / scale
   int pingpong;      // variant 3: alternate the two warpgroups' exponential phases (default 1; FLUX2B_ATTN_PINGPONG=0 turns it off)
   int dbg;  // FLUX2B_ATTN_TIMELINE=1: CTA (0,0,0) prints its softmax / MMA time line (debug aid, off by default)
@@ -428,11 +429,16 @@ __global__ void __launch_bounds__(A3::THREADS, 1) attn_kernel_v3(const __grid_co
   // causal: this CTA's 256 query rows see keys [0, q_blk0 + 256) at most (tiles above the diagonal are never loaded)
   // right padding (key_lo == 0): keys >= key_hi carry exactly zero weight for every row (key 0 is always visible), so they are not loaded either
   // (kMask: the causal / padded / grouped-query mode is a separate instantiation; the DiT kernel carries none of it)
+  int key_lo = 0, key_hi = 0;
+  if constexpr (kMask) {
+    key_lo = p.key_lo; key_hi = p.key_hi;
+    if (p.mask_dev) { key_lo = __ldg(p.mask_dev); key_hi = __ldg(p.mask_dev + 1); }
+  }
   auto seg_len_of = [&](int s) {
     int n = p.seg_len[s];
     if constexpr (kMask) {
       if (p.causal && s == 0) n = min(n, q_blk0 + 2 * QT);
-      if (p.key_hi > 0 && p.key_lo == 0 && s == 0) n = min(n, p.key_hi);
+      if (key_hi > 0 && key_lo == 0 && s == 0) n = min(n, key_hi);
     }
     return n;
   };
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__(A3::THREADS, 1) attn_kernel_v3(const __grid_co
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= nvalid) v[c][i] = 0xff800000u;  // -inf: ignored by the max, exp2 -> 0
         }
-        if (kMask && p.key_hi > 0 && (t * BN < p.key_lo || t * BN + BN > p.key_hi)) {
+        if (kMask && key_hi > 0 && (t * BN < key_lo || t * BN + BN > key_hi)) {
           // additive padding mask of the reference (createCausalMask: -1e9 on padded keys, added to the scaled score in fp32).
           // ulp(1e9) = 64, so the score is absorbed: every padded key ends up with the SAME value, a row that sees real keys
           // gives them weight exp(-1e9) = 0, and a row that sees nothing but padding (left padding) attends uniformly. That is
@@ -644,7 +650,7 @@ __global__ void __launch_bounds__(A3::THREADS, 1) attn_kernel_v3(const __grid_co
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int kj = t * BN + c * 32 + i;
-              if (kj < p.key_lo || kj >= p.key_hi) v[c][i] = __float_as_uint(p.pad_raw);
+              if (kj < key_lo || kj >= key_hi) v[c][i] = __float_as_uint(p.pad_raw);
             }
         }
         if (kMask && p.causal && t * BN + BN - 1 > q_blk0 + w * QT + quarter * 32) {
@@ -793,7 +799,7 @@ static bool fill_params(const AttnProblem& a, int BN, AttnKParams& p) {
   p.nseg = a.num_segments;
   p.causal = a.causal;
   p.kv_group = a.kv_group > 0 ? a.kv_group : 1;
-  p.key_lo = a.key_lo; p.key_hi = a.key_hi;
+  p.key_lo = a.key_lo; p.key_hi = a.key_hi; p.mask_dev = a.mask_dev;
   p.pad_raw = -exp2f(ceilf(log2f(fabsf(a.pad_bias) / a.scale)));
   p.sq = a.sq;
   p.num_heads = a.num_heads;
@@ -838,7 +844,7 @@ static cudaError_t launch_attn_v3(const AttnProblem& a, cudaStream_t stream) {
   }
   dim3 grid((a.sq + 2 * QT - 1) / (2 * QT), a.num_heads, a.batch);
   const int poly = a.poly < 0 ? 0 : (a.poly == 0 ? F2B_ATTN_POLY_DEFAULT : a.poly);
-  if (a.causal || a.key_hi > 0 || a.kv_group > 1) {
+  if (a.causal || a.key_hi > 0 || a.kv_group > 1 || a.mask_dev) {
     // text-encoder mode: two exponential variants are enough (all on the MUFU, or the default one-in-four polynomial)
 #define F2B_GO_M(F16_, POLY_) attn_kernel_v3<F16_, POLY_, true><<<grid, A3::THREADS, A3::SMEM_BYTES, stream>>>(p)
     if (a.f16) { if (poly == 0) F2B_GO_M(true, 0); else F2B_GO_M(true, 4); }
@@ -881,7 +887,7 @@ cudaError_t attention_launch(const AttnProblem& a, cudaStream_t stream) {
     if (a.seg[i].len <= 0) return cudaErrorInvalidValue;
   const int variant = a.variant ? a.variant : 3;
   if (a.o_rows_per_peer > 0 && variant != 3) return cudaErrorInvalidValue;
-  if ((a.causal || a.key_hi > 0 || a.kv_group > 1) && (variant != 3 || a.num_segments != 1 || a.seg[0].len != a.sq)) return cudaErrorInvalidValue;
+  if ((a.causal || a.key_hi > 0 || a.kv_group > 1 || a.mask_dev) && (variant != 3 || a.num_segments != 1 || a.seg[0].len != a.sq)) return cudaErrorInvalidValue;
   if (variant == 3) return launch_attn_v3(a, stream);
   if (variant == 2) return launch_attn<128, true>(a, stream);
   return launch_attn<64, false>(a, stream);

@@ -44,6 +44,7 @@ struct AttnProblem {
   int kv_group = 1;      // grouped-query attention: query head h uses K / V head h / kv_group (Qwen3Attention.swift:133-145)
   int key_lo = 0, key_hi = 0;  // attention_mask == 1 exactly on keys [key_lo, key_hi); the others get `pad_bias` added (0, 0 = no mask)
   float pad_bias = -1e9f;
+  const int* mask_dev = nullptr;   // device int[2] = {key_lo, key_hi}, read by the kernel instead of the two fields above (graph replay)
   int f16 = 0;      // 16-bit storage type: 0 = bf16, 1 = f16
   int variant = 0;  // 0 = auto, 1 = P through shared memory (64-key tiles), 2 = P kept in TMEM (128-key tiles)
   int poly = 0;     // variant 3: 0 = default, -1 = all exponentials on the MUFU, n in {2, 3, 4} = one element in n by polynomial on the FMA pipe

@@ -148,6 +148,14 @@ struct TeLayerW {
   bool mlp_tiled = false;
 };
 
+struct TeGraph {
+  int S = 0;
+  std::vector<int> layers;
+  void* exec = nullptr;        // cudaGraphExec_t
+  DevBuf ids, mask, out32;     // stable device addresses baked into the graph: token ids [S], {key_lo, key_hi}, fp32 [S, n * hidden]
+  int64_t launches = 0;        // kernels per replay
+};
+
 // Ulysses sequence-parallel state (sp.cu). world == 1: off.
 struct SpState {
   int world = 1, rank = 0;
@@ -202,6 +210,8 @@ struct flux2b_ctx {
   f2b::DevBuf te_norm;    // final norm weight fp32 [hidden]
   f2b::DevBuf te_ones;    // fp32 ones [hidden]: "gate" of the residual-add GEMM epilogue
   int te_layers_built = 0;
+  // the prefill captured as a CUDA graph per (tokens, layer set): ~190 launches of 5 - 40 us each are host-bound otherwise
+  std::vector<f2b::TeGraph> te_graphs;
 
   // ---- workspaces (grown on demand)
   f2b::DevBuf ws_x, ws_xn, ws_qkv, ws_cat, ws_cos, ws_sin, ws_ids, ws_small, ws_hid16, ws_enc16, ws_out;
@@ -286,7 +296,8 @@ int finalize_te(flux2b_ctx* c);
 // text-encoder prefill (te.cu): ids [S] int32 on the device; attention_mask == 1 exactly on [key_lo, key_hi) (key_hi == 0: no mask);
 // hidden states after layers `layers[i]` (0 = embeddings, num_layers = after the final norm) -> out_f32[:, i * hidden ...], row stride ldo
 int te_forward_device(flux2b_ctx* c, int S, const int32_t* ids, int key_lo, int key_hi, const int* layers, int n_layers,
-                      float* out_f32, int64_t ldo);
+                      float* out_f32, int64_t ldo, const int* mask_dev = nullptr);
+void te_destroy_graphs(flux2b_ctx* c);
 
 // forward passes
 struct DitIO {

@@ -36,7 +36,7 @@ static int te_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int 
 }
 
 int te_forward_device(flux2b_ctx* c, int S, const int32_t* ids, int key_lo, int key_hi, const int* layers, int n_layers,
-                      float* out_f32, int64_t ldo) {
+                      float* out_f32, int64_t ldo, const int* mask_dev) {
   const flux2b_te_config& t = c->te;
   const int Hd = t.hidden_size, I = t.intermediate_size, Hq = t.num_heads, Hkv = t.num_kv_heads;
   const int Nq = Hq * 128, Nkv = Hkv * 128, Nqkv = Nq + 2 * Nkv;
@@ -109,7 +109,7 @@ int te_forward_device(flux2b_ctx* c, int S, const int32_t* ids, int key_lo, int 
       a.num_segments = 1;
       a.seg[0].k = QKV + Nq; a.seg[0].v = QKV + Nq + Nkv; a.seg[0].ldk = a.seg[0].ldv = Nqkv;
       a.seg[0].rows_total = S; a.seg[0].row0 = 0; a.seg[0].len = S;
-      a.causal = 1; a.kv_group = Hq / Hkv; a.key_lo = key_lo; a.key_hi = key_hi; a.pad_bias = -1e9f;
+      a.causal = 1; a.kv_group = Hq / Hkv; a.key_lo = key_lo; a.key_hi = key_hi; a.pad_bias = -1e9f; a.mask_dev = mask_dev;
       a.f16 = f16 ? 1 : 0; a.variant = 3; a.poly = c->option("attn_poly", 0);
       ProfScope ps(c, FLUX2B_PROF_ATTN, 2.0 * S * (double)S * Nq, 2.0 * S * (2.0 * Nq + 2.0 * Nkv));   // causal: half of 4 S^2 D
       F2B_CUDA(attention_launch(a, st));
@@ -145,6 +145,59 @@ int te_forward_device(flux2b_ctx* c, int S, const int32_t* ids, int key_lo, int 
         F2B_CUDA(rms_norm_rows(X, Hd, c->te_norm.as<float>(), out_f32 + (size_t)i * Hd, ldo, S, Hd, t.rms_norm_eps, true, f16, st));
       }
   }
+  return 0;
+}
+
+void te_destroy_graphs(flux2b_ctx* c) {
+  for (TeGraph& g : c->te_graphs)
+    if (g.exec) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(g.exec));
+  c->te_graphs.clear();
+}
+
+// The prefill as a CUDA graph (option te_graph, default 1): the ~190 kernels of a 27-layer prefill run 5 - 40 us each, less than
+// the host needs to encode their tensor maps and launch them, so the un-captured forward is host-bound. One graph per
+// (token count, layer set); token ids, the padding bounds and the fp32 result live at fixed device addresses owned by the graph
+// entry, the bounds are read by the attention kernel from device memory, so one graph serves every prompt length.
+static int te_graph_for(flux2b_ctx* c, int S, const int* layers, int n_layers, TeGraph** out) {
+  for (TeGraph& g : c->te_graphs)
+    if (g.S == S && (int)g.layers.size() == n_layers && std::equal(g.layers.begin(), g.layers.end(), layers)) { *out = &g; return 0; }
+  if (c->te_graphs.size() >= 8) te_destroy_graphs(c);   // bounded cache (a pipeline uses one or two shapes)
+  c->te_graphs.emplace_back();
+  TeGraph& g = c->te_graphs.back();
+  g.S = S; g.layers.assign(layers, layers + n_layers);
+  const int64_t ldo = (int64_t)n_layers * c->te.hidden_size;
+  auto drop = [&](int rc) { c->te_graphs.pop_back(); return rc; };
+  if (g.ids.alloc((size_t)S * 4) != cudaSuccess || g.mask.alloc(8) != cudaSuccess || g.out32.alloc((size_t)S * ldo * 4) != cudaSuccess) {
+    cudaGetLastError();
+    return drop(fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "text-encoder graph buffers"));
+  }
+  cudaError_t e = cudaMemsetAsync(g.ids.p, 0, (size_t)S * 4, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g.mask.p, 0, 8, c->stream);
+  if (e != cudaSuccess) return drop(fail(FLUX2B_ERR_CUDA, cudaGetErrorString(e)));
+  // un-captured warm-up: grows the workspaces and sets the kernels' attributes, so that the capture allocates nothing
+  const int64_t l0 = c->launches;
+  int rc = te_forward_device(c, S, g.ids.as<int32_t>(), 0, 0, layers, n_layers, g.out32.as<float>(), ldo, g.mask.as<int>());
+  if (rc) return drop(rc);
+  g.launches = c->launches - l0;
+  e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return drop(fail(FLUX2B_ERR_CUDA, cudaGetErrorString(e)));
+  e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) return drop(fail(FLUX2B_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e)));
+  rc = te_forward_device(c, S, g.ids.as<int32_t>(), 0, 0, layers, n_layers, g.out32.as<float>(), ldo, g.mask.as<int>());
+  c->launches -= g.launches;   // the capture enqueued nothing
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(c->stream, &graph);
+  if (rc || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return drop(rc ? rc : fail(FLUX2B_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)));
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return drop(fail(FLUX2B_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)));
+  g.exec = exec;
+  *out = &g;
   return 0;
 }
 
@@ -203,10 +256,24 @@ int flux2b_te_hidden_states(flux2b_ctx* c, int B, int S, const int32_t* input_id
     acc = reinterpret_cast<float*>(c->scratch_buf("te_out_f32", (size_t)S * ldo * 4));
     if (!acc) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "te output scratch allocation failed"); }
   }
+  const bool use_graph = c->option("te_graph", 1) != 0 && !c->prof_on;
+  TeGraph* tg = nullptr;
+  if (use_graph) F2B_TRY(te_graph_for(c, S, layer_indices, n_layers, &tg));
   for (int b = 0; b < B; ++b) {
     float* dst32 = out_dtype == FLUX2B_F32 ? acc + (size_t)b * S * ldo : acc;
-    F2B_TRY(te_forward_device(c, S, reinterpret_cast<const int32_t*>(d_ids) + (size_t)b * S, lo[b], hi[b], layer_indices, n_layers,
-                              dst32, ldo));
+    const int32_t* ids_b = reinterpret_cast<const int32_t*>(d_ids) + (size_t)b * S;
+    if (tg) {
+      const int bounds[2] = {lo[b], hi[b]};
+      F2B_CUDA(cudaMemcpyAsync(tg->ids.p, ids_b, (size_t)S * 4, cudaMemcpyDeviceToDevice, c->stream));
+      F2B_CUDA(cudaMemcpyAsync(tg->mask.p, bounds, 8, cudaMemcpyHostToDevice, c->stream));   // pageable source: staged before return
+      F2B_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(tg->exec), c->stream));
+      c->launches += tg->launches;
+      c->prof[FLUX2B_PROF_ELEMWISE].launches++; c->launches++;
+      F2B_CUDA(copy_f32_to_any(tg->out32.as<float>(), ldo, reinterpret_cast<uint8_t*>(dout) + (size_t)b * S * ldo * esz, ldo, S, (int)ldo,
+                               out_dtype == FLUX2B_F32 ? 0 : out_dtype == FLUX2B_F16 ? 1 : 2, c->stream));
+      continue;
+    }
+    F2B_TRY(te_forward_device(c, S, ids_b, lo[b], hi[b], layer_indices, n_layers, dst32, ldo));
     if (out_dtype != FLUX2B_F32) {
       ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)S * ldo * 6);
       F2B_CUDA(copy_f32_to_any(acc, ldo, reinterpret_cast<uint8_t*>(dout) + (size_t)b * S * ldo * esz, ldo, S, (int)ldo,

@@ -332,6 +332,7 @@ int finalize_dit(flux2b_ctx* c) {
 // Only the layers up to the deepest extracted hidden state are ever run, so layers that are absent are simply not built
 // (the Klein extractor needs 27 of 36, the Mistral one 30 of 40); lm_head is never used by the embedding path.
 int finalize_te(flux2b_ctx* c) {
+  te_destroy_graphs(c);   // captured prefills hold the old working weights' addresses
   const flux2b_te_config& t = c->te;
   const int Hd = t.hidden_size, I = t.intermediate_size, Nq = t.num_heads * 128, Nkv = t.num_kv_heads * 128;
   {

@@ -167,6 +167,16 @@ def test_te_batch_dtypes_and_errors(flux2b):
     assert np.array_equal(obf, torch.from_numpy(out).to(torch.bfloat16).view(torch.uint16).numpy())
     # deterministic
     assert np.array_equal(out, te.forward_with_hidden_states(ids.numpy(), (1, 2), mask.numpy()))
+    # the CUDA-graph replay (default; one graph for both rows although their padding differs: the bounds live in device memory)
+    # and the plain launch sequence give the same bits
+    te.set_option("te_graph", 0)
+    assert np.array_equal(out, te.forward_with_hidden_states(ids.numpy(), (1, 2), mask.numpy()))
+    te.set_option("te_graph", 1)
+    left_ids, left_mask = O.te_pad_tokens(list(range(7, 60)), 64, 3, "left")
+    o_g = te.forward_with_hidden_states(left_ids.numpy(), (1, 2), left_mask.numpy())
+    te.set_option("te_graph", 0)
+    assert np.array_equal(o_g, te.forward_with_hidden_states(left_ids.numpy(), (1, 2), left_mask.numpy()))
+    te.set_option("te_graph", 1)
     # errors mirror the reference's throws (KleinEmbeddingError.invalidLayerIndex -> invalidConfiguration; missing layers -> modelNotLoaded)
     with pytest.raises(flux2b.Flux2Error) as e:
         te.forward_with_hidden_states(ids.numpy(), (1, 7), mask.numpy())

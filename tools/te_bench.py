@@ -47,6 +47,32 @@ def run(name, reps=10, profile_one=False):
     for _ in range(reps):
         out = ex.extract(toks)              # host ids in, host fp32 [1, 512, 3 * hidden] out: end to end
     e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    # the same with the result left on the device in bf16 (what a pipeline that feeds the DiT directly does): no 15 - 25 MB D2H
+    ids_np = np.asarray([toks + [ex.PAD_TOKEN_ID] * (512 - len(toks))], dtype=np.int32)
+    mask_np = np.asarray([[1] * len(toks) + [0] * (512 - len(toks))], dtype=np.int32)
+    out_dev = torch.empty((1, 512, 3 * cfg.hidden_size), dtype=torch.bfloat16, device="cuda")
+    li = (flux2b.ctypes.c_int * 3)(*layers)
+    def dev_call():
+        flux2b._ck(flux2b.lib().flux2b_te_hidden_states(te._h, 1, 512, flux2b._ptr(ids_np), flux2b._ptr(mask_np), li, 3,
+                                                        flux2b._ptr(out_dev), flux2b.BF16))
+    for _ in range(3):
+        dev_call()
+    te.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dev_call()
+    te.synchronize()
+    dev_ms = (time.perf_counter() - t0) / reps * 1e3
+    te.set_option("te_graph", 0)
+    for _ in range(2):
+        dev_call()
+    te.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dev_call()
+    te.synchronize()
+    dev_nograph_ms = (time.perf_counter() - t0) / reps * 1e3
+    te.set_option("te_graph", 1)
     te.prof_enable(True); te.prof_reset()
     l0 = te.launch_count()
     ex.extract(toks)
@@ -56,7 +82,7 @@ def run(name, reps=10, profile_one=False):
     Hd, I, Nq, Nkv = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads * 128, cfg.num_kv_heads * 128
     flops = max(layers) * 2.0 * 512 * (Hd * (Nq + 2 * Nkv) + Nq * Hd + 3 * Hd * I)
     line = {"what": "text_embedding_producer", "model": name, "tokens": 512, "layers_run": max(layers), "hidden_state_layers": list(layers),
-            "e2e_ms": e2e_ms, "kernel_ms": kern_ms, "launches": launches, "gemm_tflops": prof["gemm"]["flops"] / prof["gemm"]["ms"] / 1e9,
+            "e2e_ms": e2e_ms, "device_out_bf16_ms": dev_ms, "device_out_bf16_no_graph_ms": dev_nograph_ms, "kernel_ms": kern_ms, "launches": launches, "gemm_tflops": prof["gemm"]["flops"] / prof["gemm"]["ms"] / 1e9,
             "gemm_ms": prof["gemm"]["ms"], "attn_ms": prof["attn"]["ms"], "elem_ms": prof["elem"]["ms"],
             "gemm_flops_check": flops / prof["gemm"]["flops"], "out_shape": list(out.shape), "finite": bool(np.isfinite(out).all())}
     print(json.dumps(line), flush=True)
