@@ -18,6 +18,7 @@
 // kPTmem=true writes P back into the S columns of TMEM and issues the PV MMA with A from TMEM (128-key tiles).
 #include "attention.cuh"
 #include "ptx.cuh"
+#include "gemm.cuh"
 
 #include <cstdlib>
 #include <string>
@@ -470,6 +471,8 @@ __global__ void __launch_bounds__(A3::THREADS, 1) attn_kernel_v3(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool dbg0 = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  pdl_trigger();   // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  pdl_wait();
 
   if (warp == 8) {
     // ============================================================ TMA producer
@@ -844,15 +847,21 @@ static cudaError_t launch_attn_v3(const AttnProblem& a, cudaStream_t stream) {
   }
   dim3 grid((a.sq + 2 * QT - 1) / (2 * QT), a.num_heads, a.batch);
   const int poly = a.poly < 0 ? 0 : (a.poly == 0 ? F2B_ATTN_POLY_DEFAULT : a.poly);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(A3::THREADS); cfg.dynamicSmemBytes = A3::SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs; cfg.numAttrs = pdl_enabled() ? 1 : 0;
   if (a.causal || a.key_hi > 0 || a.kv_group > 1 || a.mask_dev) {
     // text-encoder mode: two exponential variants are enough (all on the MUFU, or the default one-in-four polynomial)
-#define F2B_GO_M(F16_, POLY_) attn_kernel_v3<F16_, POLY_, true><<<grid, A3::THREADS, A3::SMEM_BYTES, stream>>>(p)
+#define F2B_GO_M(F16_, POLY_) cudaLaunchKernelEx(&cfg, attn_kernel_v3<F16_, POLY_, true>, p)
     if (a.f16) { if (poly == 0) F2B_GO_M(true, 0); else F2B_GO_M(true, 4); }
     else { if (poly == 0) F2B_GO_M(false, 0); else F2B_GO_M(false, 4); }
 #undef F2B_GO_M
     return cudaGetLastError();
   }
-#define F2B_GO(F16_, POLY_) attn_kernel_v3<F16_, POLY_><<<grid, A3::THREADS, A3::SMEM_BYTES, stream>>>(p)
+#define F2B_GO(F16_, POLY_) cudaLaunchKernelEx(&cfg, attn_kernel_v3<F16_, POLY_>, p)
   if (a.f16) { if (poly == 2) F2B_GO(true, 2); else if (poly == 3) F2B_GO(true, 3); else if (poly == 4) F2B_GO(true, 4); else F2B_GO(true, 0); }
   else { if (poly == 2) F2B_GO(false, 2); else if (poly == 3) F2B_GO(false, 3); else if (poly == 4) F2B_GO(false, 4); else F2B_GO(false, 0); }
 #undef F2B_GO

@@ -3,6 +3,7 @@
 // oversubscribe the 148 SMs).
 #include "elementwise.cuh"
 #include "ptx.cuh"
+#include "gemm.cuh"
 #include "quant_dev.cuh"
 #include <algorithm>
 
@@ -60,6 +61,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
   __shared__ float sm[8];
   constexpr int GROUP = KIND == 3 ? 16 : 32;
   constexpr int LPG = GROUP / 4;
+  pdl_trigger();   // programmatic dependent launch (ptx.cuh): the GEMM behind this kernel may set itself up meanwhile
+  pdl_wait();
   const int row = blockIdx.x;
   if (KIND != 0 && row >= rows) {
     for (int g = threadIdx.x; g < D / GROUP; g += 256) mx.sf[sf_offset(row, mx.g0 + g, mx.sf_ld)] = mx_scale_one(KIND);
@@ -240,7 +243,13 @@ template <int KIND>
 static void ln_launch(const float* x, int64_t ldx, void* out16, int64_t ldo, int rows, int grid_rows, int D, const float* shift,
                       const float* scale, int64_t mod_bs, int rows_per_batch, float eps, bool f16, const MxOut& mx, cudaStream_t s,
                       int split_row = 0, const float* shift_lo = nullptr, const float* scale_lo = nullptr) {
-#define F2B_LN(V) ln_modulate_kernel<V, KIND><<<grid_rows, 256, 0, s>>>(x, ldx, out16, ldo, rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, mx, split_row, shift_lo, scale_lo)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid_rows); cfg.blockDim = dim3(256); cfg.stream = s;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+#define F2B_LN(V) cudaLaunchKernelEx(&cfg, ln_modulate_kernel<V, KIND>, x, ldx, out16, ldo, rows, D, shift, scale, mod_bs, rows_per_batch, eps, f16, mx, split_row, shift_lo, scale_lo)
   if (D <= 1024) F2B_LN(1);
   else if (D <= 3072) F2B_LN(3);
   else if (D <= 4096) F2B_LN(4);

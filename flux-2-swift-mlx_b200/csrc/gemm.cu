@@ -412,6 +412,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above ran beside the tail of the previous kernel (programmatic dependent launch); global memory from here on
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -620,6 +623,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 static int g_num_sms = 0;
+bool pdl_enabled() {
+  static const bool on = !(getenv("FLUX2B_PDL") && atoi(getenv("FLUX2B_PDL")) == 0);
+  return on;
+}
 static thread_local std::string g_err;
 const char* gemm_last_error() { return g_err.c_str(); }
 
@@ -755,13 +762,15 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   cfg.blockDim = dim3(192);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = CG;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (!(MXK && CG == 2)) { tmSFA = tmA; if (!(MXK == 0 && !CONV && g.B_lo)) tmSFB = tmA; }  // unused by those instantiations
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmSFA, tmSFB, p);
 }

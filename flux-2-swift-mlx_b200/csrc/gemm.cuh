@@ -94,5 +94,7 @@ cudaError_t gemm_launch(const GemmProblem& p, cudaStream_t stream);
 // One-time driver entry point lookup; returns false if cuTensorMapEncodeTiled cannot be resolved.
 bool gemm_init();
 const char* gemm_last_error();
+// programmatic dependent launch for the GEMM / attention / LayerNorm kernels (default on; FLUX2B_PDL=0 turns it off)
+bool pdl_enabled();
 
 }  // namespace f2b

@@ -151,6 +151,14 @@ __device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may begin (CTA scheduling, its prologue: barrier
+// init, TMEM allocation, descriptor prefetch) while its predecessor in the stream is still draining; pdl_wait() returns once the
+// predecessor grid has completed and its memory is visible — every global access of the kernel comes after it. pdl_trigger()
+// lets the successor's CTAs be scheduled as SMs free up. Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -181,21 +181,29 @@ static int te_graph_for(flux2b_ctx* c, int S, const int* layers, int n_layers, T
   g.launches = c->launches - l0;
   e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) return drop(fail(FLUX2B_ERR_CUDA, cudaGetErrorString(e)));
+  // Capture problems are not errors of the call: the plain launch sequence is always available (option te_graph is switched off).
+  auto no_graph = [&](const std::string& why) {
+    cudaGetLastError();
+    set_error("text-encoder CUDA graph disabled: " + why);
+    c->opt["te_graph"] = 0;
+    c->te_graphs.pop_back();
+    *out = nullptr;
+    return 0;
+  };
   e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
-  if (e != cudaSuccess) return drop(fail(FLUX2B_ERR_CUDA, std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e)));
+  if (e != cudaSuccess) return no_graph(std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
   rc = te_forward_device(c, S, g.ids.as<int32_t>(), 0, 0, layers, n_layers, g.out32.as<float>(), ldo, g.mask.as<int>());
   c->launches -= g.launches;   // the capture enqueued nothing
   cudaGraph_t graph = nullptr;
   e = cudaStreamEndCapture(c->stream, &graph);
   if (rc || e != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
-    cudaGetLastError();
-    return drop(rc ? rc : fail(FLUX2B_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)));
+    return no_graph(rc ? std::string("launch failed during capture") : std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
   }
   cudaGraphExec_t exec = nullptr;
   e = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
-  if (e != cudaSuccess) return drop(fail(FLUX2B_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)));
+  if (e != cudaSuccess) return no_graph(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
   g.exec = exec;
   *out = &g;
   return 0;
