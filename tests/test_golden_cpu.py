@@ -70,3 +70,12 @@ def test_vae_encoder_fixture():
             patch = xp[0, 2 * oy:2 * oy + 3, 2 * ox:2 * ox + 3]          # [3, 3, 4]
             ref[0, oy, ox] = (W["d.conv.weight"] * patch[None]).sum(dim=(1, 2, 3)) + W["d.conv.bias"]
     np.testing.assert_allclose(y.numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_text_encoder_fixture():
+    g = dict(np.load(MG.GOLDEN_TE))
+    for name, (cfg, seed, side, layers, toks) in MG.te_configs().items():
+        W = O.random_te_weights(cfg, seed=seed)
+        ids, mask = O.te_pad_tokens(toks, 32, 3, side)
+        assert np.array_equal(ids.numpy(), g[f"{name}_ids"]) and np.array_equal(mask.numpy(), g[f"{name}_mask"])
+        np.testing.assert_allclose(O.te_hidden_states(W, cfg, ids, mask, layers).numpy(), g[f"{name}_hidden"], rtol=1e-4, atol=1e-5)

@@ -314,3 +314,26 @@ def test_prompt_tokens_to_dit_forward(flux2b):
     print(f"tokens -> embeddings -> DiT: rel-L2 vs oracle chain {e:.2e}, vs oracle DiT on the device embeddings {rel_l2(out, ref_same):.2e}")
     assert e < 8e-3
     te.close(); ctx.close()
+
+
+def test_te_golden_fixture(flux2b):
+    """Device vs the committed fixture (tests/golden/golden_text_encoder.npz, tools/make_golden.py text_encoder): needs nothing but
+    the file and the weight generator; f16 operands for the tight bound, bf16 for the default."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import make_golden as MG
+    from oracle import flux2_oracle as O
+    g = dict(np.load(MG.GOLDEN_TE))
+    for name, (cfg, seed, side, layers, toks) in MG.te_configs().items():
+        W = O.random_te_weights(cfg, seed=seed)
+        for f16, tol in ((0, TOL_BF16), (1, TOL_F16)):
+            te = flux2b.TextEncoder(cfg, options={"compute_f16": f16})
+            te.load_weights(W, dtype=torch.float16 if f16 else torch.bfloat16)
+            te.finalize()
+            out = te.forward_with_hidden_states(g[f"{name}_ids"], layers, g[f"{name}_mask"])
+            err = rel_l2(out, g[f"{name}_hidden"])
+            print(f"te golden {name} compute_f16={f16}: rel-L2 {err:.2e}")
+            assert err < tol
+            te.close()

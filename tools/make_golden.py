@@ -23,6 +23,7 @@ from oracle import quant_oracle as Q  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden", "golden.npz")
 GOLDEN_ENC = os.path.join(ROOT, "tests", "golden", "golden_vae_encoder.npz")   # added later: kept apart so golden.npz never changes
+GOLDEN_TE = os.path.join(ROOT, "tests", "golden", "golden_text_encoder.npz")    # likewise
 
 TINY = dict(num_layers=1, num_single_layers=2, num_attention_heads=2, joint_attention_dim=256, guidance_embeds=True)
 S_IMG, S_TXT, HW = 64, 64, 128  # 128x128 pixels -> 8x8 tokens
@@ -95,8 +96,32 @@ def encoder_fixture():
     print(f"wrote {GOLDEN_ENC}: {os.path.getsize(GOLDEN_ENC) / 1024:.0f} KiB")
 
 
+def te_configs():
+    """Qwen3-style (QK-norm, right padding, final-norm layer included) and Mistral-style (no QK-norm, left padding) tiny encoders."""
+    q = O.TEConfig(vocab_size=300, hidden_size=128, intermediate_size=256, num_layers=3, num_heads=2, num_kv_heads=1)
+    m = O.TEConfig(vocab_size=300, hidden_size=128, intermediate_size=256, num_layers=3, num_heads=2, num_kv_heads=2, qk_norm=False,
+                   rope_theta=1e9)
+    toks = [7, 250, 31, 4, 199, 42, 42, 8, 120, 77, 5]
+    return {"qwen3": (q, 4, "right", (1, 2, 3), toks), "mistral": (m, 5, "left", (0, 2), toks)}
+
+
+def text_encoder_fixture():
+    """Text-embedding producer: token ids -> concatenated hidden states, 32 positions."""
+    torch.set_num_threads(1)
+    out = {}
+    for name, (cfg, seed, side, layers, toks) in te_configs().items():
+        W = O.random_te_weights(cfg, seed=seed)
+        ids, mask = O.te_pad_tokens(toks, 32, 3, side)
+        out[f"{name}_ids"], out[f"{name}_mask"] = ids.numpy(), mask.numpy()
+        out[f"{name}_hidden"] = O.te_hidden_states(W, cfg, ids, mask, layers).numpy()
+    np.savez_compressed(GOLDEN_TE, **out)
+    print(f"wrote {GOLDEN_TE}: {os.path.getsize(GOLDEN_TE) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "encoder":
         encoder_fixture()      # golden.npz untouched
+    elif len(sys.argv) > 1 and sys.argv[1] == "text_encoder":
+        text_encoder_fixture()
     else:
         main()
