@@ -385,6 +385,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint64_t t_entry = p.dbg ? globaltimer_ns() : 0;   // debug timeline: ns since this thread entered the kernel
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = (cta_rank == 0);
   const int unit_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
@@ -415,6 +416,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // everything above ran beside the tail of the previous kernel (programmatic dependent launch); global memory from here on
   pdl_trigger();
   pdl_wait();
+  const uint64_t t_prologue = p.dbg ? globaltimer_ns() - t_entry : 0;   // printed at the end: a printf here would stall the producer thread
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -494,8 +496,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (dbg) printf("[gemm timeline] cta %d producer: total %lld clk, waited on empty slots %lld clk\n", (int)cta_rank,
-                      clock64() - t_begin, w_empty);
+      if (dbg) printf("[gemm timeline] cta %d producer: total %lld clk, waited on empty slots %lld clk; last load issued at %llu ns\n", (int)cta_rank,
+                      clock64() - t_begin, w_empty, (unsigned long long)(globaltimer_ns() - t_entry));
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -572,8 +574,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
       if (dbg && lane == 0)
-        printf("[gemm timeline] issuer: total %lld clk, waited on operands %lld clk, on accumulator drain %lld clk (%d k-blocks / tile)\n",
-               clock64() - t_begin, w_full, w_tempty, p.num_kb);
+        printf("[gemm timeline] issuer: total %lld clk, waited on operands %lld clk, on accumulator drain %lld clk (%d k-blocks / tile); last MMA issued at %llu ns\n",
+               clock64() - t_begin, w_full, w_tempty, p.num_kb, (unsigned long long)(globaltimer_ns() - t_entry));
     }
   } else {
     // ===================================================== epilogue warps (2..5): TMEM lane quarter = warp % 4
@@ -601,9 +603,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       mbar_wait<CG == 2>(&tfull[acc], acc_phase, 4);
       tc_fence_after();
+      const uint64_t t_e0 = p.dbg ? globaltimer_ns() : 0;
       epilogue_tile<BN>(p, tmem_base + acc * BN, quarter, lane, row_ok, grow, n_blk * BN);
       tc_fence_before();
       __syncwarp();
+      if (p.dbg && unit_id == 0 && warp == 2 && lane == 0 && t < 2 * num_units)
+        printf("[gemm timeline] cta %d epilogue of tile %d: accumulator ready at %llu ns, stored at %llu ns\n", (int)cta_rank, t,
+               (unsigned long long)(t_e0 - t_entry), (unsigned long long)(globaltimer_ns() - t_entry));
       if (lane == 0) {
         if (CG == 1) mbar_arrive(&tempty[acc]);
         else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
@@ -615,6 +621,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
+  if (p.dbg && unit_id == 0 && threadIdx.x == 0)
+    printf("[gemm timeline] cta %d: prologue (barriers, TMEM alloc, cluster sync, dependency wait) done at %llu ns, kernel end at %llu ns\n",
+           (int)cta_rank, (unsigned long long)t_prologue, (unsigned long long)(globaltimer_ns() - t_entry));
 }
 
 // ------------------------------------------------------------------------------------------------ host side
