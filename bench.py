@@ -26,9 +26,17 @@ import subprocess
 import sys
 import time
 
-# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when the box exports NCCL_DEBUG=VERSION)
-# goes to stderr instead
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line. Libraries that write to file descriptor 1 on their own (NCCL prints "NCCL version ..." when
+# the box exports NCCL_DEBUG=VERSION) are sent to stderr: fd 1 is re-pointed at fd 2 and the result line goes to a saved copy.
+sys.stdout.flush()
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: str) -> None:
+    _RESULT_OUT.write(line + "\n")
+    _RESULT_OUT.flush()
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "flux-2-swift-mlx_b200")):
@@ -172,7 +180,7 @@ def run_reference(args, rank):
     vals = [cpu_sample(threads) for _ in range(max(1, min(args.steps, 3)))]
     best = min(vals, key=lambda v: v["step_s"])
     v = 1.0 / best["step_s"]
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": best["step_s"] * 1e3 * NUM_STEPS, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -281,7 +289,7 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
         pk = peaks(rate_mult(args))
         gp = prof["gemm"]
         achieved = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] > 0 else 0.0
-        print(json.dumps({
+        emit(json.dumps({
             "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": dtype_name(args), "data": "synthetic",
@@ -520,7 +528,7 @@ def main():
         c = cpu_sample(os.cpu_count() or 1)
         out["cpu_baseline"] = {"value": 1.0 / c["step_s"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                "sample": c["sample"], "cpu_tflops": c["tflops"]}
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
 
