@@ -516,10 +516,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t acc_phase = 0;
       const bool dbg = p.dbg && unit_id == 0;
       long long w_full = 0, w_tempty = 0, t_begin = dbg ? clock64() : 0;
+      int tl_n = 0;
+      unsigned tl_start[8], tl_drain[8], tl_oper[8];
       for (int t = unit_id; t < total_tiles; t += num_units) {
         long long t0 = dbg ? clock64() : 0;
+        const long long w_full_before = w_full;
         mbar_wait<CG == 2>(&tempty[acc], acc_phase ^ 1, 2);
         if (dbg) w_tempty += clock64() - t0;
+        if (dbg && tl_n < 8) { tl_start[tl_n] = (unsigned)(globaltimer_ns() - t_entry); tl_drain[tl_n] = (unsigned)(clock64() - t0); }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -571,8 +575,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        if (dbg && tl_n < 8) { tl_oper[tl_n] = (unsigned)(w_full - w_full_before); ++tl_n; }
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
+      if (dbg && lane == 0)
+        for (int i = 0; i < tl_n; ++i)
+          printf("[gemm timeline] issuer tile %d: started at %u ns after waiting %u clk for its accumulator stage, then %u clk for operands\n",
+                 i, tl_start[i], tl_drain[i], tl_oper[i]);
       if (dbg && lane == 0)
         printf("[gemm timeline] issuer: total %lld clk, waited on operands %lld clk, on accumulator drain %lld clk (%d k-blocks / tile); last MMA issued at %llu ns\n",
                clock64() - t_begin, w_full, w_tempty, p.num_kb, (unsigned long long)(globaltimer_ns() - t_entry));
@@ -607,13 +616,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       epilogue_tile<BN>(p, tmem_base + acc * BN, quarter, lane, row_ok, grow, n_blk * BN);
       tc_fence_before();
       __syncwarp();
-      if (p.dbg && unit_id == 0 && warp == 2 && lane == 0 && t < 2 * num_units)
-        printf("[gemm timeline] cta %d epilogue of tile %d: accumulator ready at %llu ns, stored at %llu ns\n", (int)cta_rank, t,
-               (unsigned long long)(t_e0 - t_entry), (unsigned long long)(globaltimer_ns() - t_entry));
+      const uint64_t t_e1 = p.dbg ? globaltimer_ns() : 0;
       if (lane == 0) {
         if (CG == 1) mbar_arrive(&tempty[acc]);
         else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
       }
+      // (debug print AFTER the accumulator stage has been handed back: a printf takes tens of microseconds)
+      if (p.dbg && unit_id == 0 && warp == 2 && lane == 0 && t < 2 * num_units)
+        printf("[gemm timeline] cta %d epilogue of tile %d: accumulator ready at %llu ns, stored at %llu ns\n", (int)cta_rank, t,
+               (unsigned long long)(t_e0 - t_entry), (unsigned long long)(t_e1 - t_entry));
       if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
