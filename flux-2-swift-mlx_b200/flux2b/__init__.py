@@ -673,6 +673,26 @@ class KleinEmbeddingExtractor:
         return self.model.forward_with_hidden_states([ids], self.HIDDEN_STATE_LAYERS, [mask], out_dtype)
 
 
+class FluxEmbeddingExtractor:
+    """Device half of EmbeddingExtractor.extractFluxEmbeddings (Embeddings/EmbeddingExtractor.swift:202-285; Flux.2 Dev, Mistral Small
+    3.2): token ids of the chat-templated prompt (system message + user prompt, TekkenTokenizer on the Swift side) are truncated,
+    LEFT-padded with the tokenizer's pad token to 512, masked, and the hidden states of layers 10 / 20 / 30 (hidden_states index i =
+    output of decoder layer i, 0 = embeddings) are concatenated to [1, 512, 3 * 5120 = 15360]."""
+    HIDDEN_STATE_LAYERS = (10, 20, 30)    # FluxConfig.hiddenStateLayers
+    MAX_SEQUENCE_LENGTH = 512             # FluxConfig.maxSequenceLength
+
+    def __init__(self, model: "TextEncoder", pad_token_id: int):
+        self.model = model
+        self.pad_token_id = int(pad_token_id)
+
+    def extract(self, token_ids: Sequence[int], max_length: int = MAX_SEQUENCE_LENGTH, out_dtype=F32):
+        ids = list(token_ids)[:max_length]
+        n = len(ids)
+        ids = [self.pad_token_id] * (max_length - n) + ids
+        mask = [0] * (max_length - n) + [1] * n
+        return self.model.forward_with_hidden_states([ids], self.HIDDEN_STATE_LAYERS, [mask], out_dtype)
+
+
 def _empty_like_backend(x, shape):
     if _is_torch(x):
         import torch

@@ -337,3 +337,35 @@ def test_te_golden_fixture(flux2b):
             print(f"te golden {name} compute_f16={f16}: rel-L2 {err:.2e}")
             assert err < tol
             te.close()
+
+
+def test_flux_dev_extractor_left_padding(flux2b):
+    """EmbeddingExtractor.extractFluxEmbeddings mirror (Mistral-style: no QK-norm, LEFT padding, layers as requested)."""
+    from oracle import flux2_oracle as O
+    cfg = O.TEConfig(vocab_size=400, hidden_size=256, intermediate_size=512, num_layers=4, num_heads=4, num_kv_heads=2, qk_norm=False,
+                     rope_theta=1e9, max_position_embeddings=4096)
+    W = O.random_te_weights(cfg, seed=12)
+    te = flux2b.TextEncoder(cfg, options={"compute_f16": 1})
+    te.load_weights(W, dtype=torch.float16)
+    te.finalize()
+    ex = flux2b.FluxEmbeddingExtractor(te, pad_token_id=11)
+    ex.HIDDEN_STATE_LAYERS = (1, 2, 3)
+    toks = list(range(20, 150))
+    out = ex.extract(toks, max_length=192)
+    ids, mask = O.te_pad_tokens(toks, 192, 11, "left")
+    assert ids[0, :62].eq(11).all() and mask[0, :62].eq(0).all() and mask[0, 62:].eq(1).all()
+    Wf = {k: (w.half().float() if w.dim() == 2 else w) for k, w in W.items()}
+    ref = O.te_hidden_states(Wf, cfg, ids, mask, (1, 2, 3))
+    assert out.shape == (1, 192, 3 * 256)
+    # real tokens and the padded prefix (uniform attention over the visible padding) separately
+    assert rel_l2(out[:, 62:], ref[:, 62:]) < TOL_F16 and rel_l2(out[:, :62], ref[:, :62]) < TOL_F16
+    # longer than original_max_position_embeddings: refused (the Llama-4 query scale would no longer be 1)
+    cfg2 = O.TEConfig(vocab_size=400, hidden_size=256, intermediate_size=512, num_layers=1, num_heads=2, num_kv_heads=1, qk_norm=False,
+                      max_position_embeddings=64)
+    te2 = flux2b.TextEncoder(cfg2)
+    te2.load_weights(O.random_te_weights(cfg2, seed=1), dtype=torch.bfloat16)
+    te2.finalize()
+    with pytest.raises(flux2b.Flux2Error) as e:
+        te2.forward_with_hidden_states(np.zeros((1, 128), dtype=np.int32), (1,))
+    assert e.value.case == "invalidConfiguration"
+    te.close(); te2.close()
