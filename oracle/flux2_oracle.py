@@ -975,6 +975,14 @@ def te_hidden_states(W, cfg: TEConfig, input_ids: Tensor, attention_mask: Option
     return torch.cat([got[int(i)] for i in layer_indices], dim=-1)
 
 
+def llama4_attention_scale(start: int, stop: int, beta: float, max_position_embeddings: int) -> Tensor:
+    """getLlama4AttentionScale (Model/MistralAttention.swift:15-32): 1 + beta * log(1 + floor(pos / max_pos)), applied to the rotated
+    queries (:422-432). It is exactly 1 for every position below original_max_position_embeddings, which is why the device path
+    refuses longer inputs instead of computing it (512-token prompts never get there)."""
+    pos = torch.arange(start, stop, dtype=torch.float32)
+    return 1.0 + beta * torch.log(1.0 + torch.floor(pos / float(max_position_embeddings)))
+
+
 def te_pad_tokens(token_ids: List[int], max_length: int, pad_id: int, side: str) -> Tuple[Tensor, Tensor]:
     """Truncate + pad + mask as the extractors do: Klein RIGHT-pads with <|endoftext|> 151643
     (Embeddings/KleinEmbeddingExtractor.swift:69-95), Dev LEFT-pads (Embeddings/EmbeddingExtractor.swift:221-248)."""

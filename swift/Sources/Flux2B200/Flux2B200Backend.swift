@@ -196,6 +196,21 @@ public final class Flux2B200TextEncoder: @unchecked Sendable {
         handle = h!
         hiddenSize = c.hiddenSize
     }
+    /// Flux.2 Dev: Mistral Small 3.2 as EmbeddingExtractor.extractFluxEmbeddings uses it (EmbeddingExtractor.swift:202-285; LEFT
+    /// padding, hidden states 10 / 20 / 30). No QK-norm; the Llama-4 query scale (MistralAttention.swift:15-32) is 1 below
+    /// originalMaxPositionEmbeddings, which the library checks instead of computing.
+    public init(device: Int32 = 0, mistral c: MistralTextConfig, quantBits: Int? = nil) throws {
+        var t = flux2b_te_config()
+        t.vocab_size = Int32(c.vocabSize); t.hidden_size = Int32(c.hiddenSize); t.intermediate_size = Int32(c.intermediateSize)
+        t.num_layers = Int32(c.numHiddenLayers); t.num_heads = Int32(c.numAttentionHeads); t.num_kv_heads = Int32(c.numKeyValueHeads)
+        t.head_dim = Int32(c.headDim); t.qk_norm = 0; t.rms_norm_eps = c.rmsNormEps; t.rope_theta = c.ropeTheta
+        t.max_position_embeddings = Int32(c.originalMaxPositionEmbeddings)
+        let q: Int32 = quantBits == 8 ? 1 : (quantBits == 4 ? 2 : 0)
+        var h: OpaquePointer?
+        try withUnsafePointer(to: &t) { tp in try f2bCheck(flux2b_te_create(device, tp, q, &h)) }
+        handle = h!
+        hiddenSize = c.hiddenSize
+    }
     deinit { flux2b_destroy(handle) }
 
     /// Same keys as the checkpoint / Module paths ("model.layers.3.self_attn.q_proj.weight", ".scales", ".biases", ...).

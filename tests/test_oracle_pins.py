@@ -262,3 +262,11 @@ def test_te_hidden_state_indexing_and_gqa():
     idp, mp = O.te_pad_tokens([5, 9, 33, 2], 8, 63, "right")
     hp = O.te_hidden_states(W, cfg, idp, mp, (1,))
     assert torch.allclose(hp[:, :4], h[..., 128:256], atol=1e-6)
+
+
+def test_llama4_query_scale_is_one_below_the_original_context():
+    """MistralAttention.swift:15-32,422-432: the query scale only departs from 1 at positions >= original_max_position_embeddings."""
+    s = O.llama4_attention_scale(0, 512, beta=0.1, max_position_embeddings=8192)
+    assert torch.all(s == 1.0)
+    s = O.llama4_attention_scale(8190, 8194, beta=0.1, max_position_embeddings=8192)
+    assert s[0] == 1.0 and s[1] == 1.0 and torch.allclose(s[2:], torch.tensor(1.0 + 0.1 * math.log(2.0)))
