@@ -621,6 +621,9 @@ __global__ void __launch_bounds__(A3::THREADS, 1) attn_kernel_v3(const __grid_co
       const int tiles = (seg_len_of(s) + BN - 1) / BN;
       for (int t = 0; t < tiles; ++t, ++j) {
         const int nvalid = min(BN, seg_len_of(s) - t * BN);
+        // Ping-pong: the tiles of the two warpgroups alternate strictly (warpgroup 0 first). Left alone — with an issuer warp each —
+        // they fall into lock-step: both in the MUFU-bound exponential phase at once (each 1.6x slower), then both MMA batches at
+        // once, and the tensor pipe idles through every softmax; alternating, one warpgroup's softmax runs beside the other's MMAs.
         // Named barriers (bar.sync / bar.arrive, 128 + 128 threads): a waiting warpgroup is descheduled by the hardware; polling an
         // mbarrier with 128 threads for a whole exp phase slowed the working warpgroup down 2x. Taken at the top of the tile, where
         // nothing but the running state is live (between the max and exp phases it cost 400 B of spills in the hot loop).
@@ -675,9 +678,6 @@ __global__ void __launch_bounds__(A3::THREADS, 1) attn_kernel_v3(const __grid_co
         const float m_use = move ? m_new : m_run;
         const float alpha = move ? fast_exp2(m_run - m_new) : 1.0f;
         const float neg_m = -m_use;
-        // Ping-pong: the exponential phases of the two warpgroups alternate strictly (warpgroup 0 first). Left alone they fall
-        // into lock-step — both in the MUFU-bound exp phase at once (each 1.6x slower), then both MMA batches at once — and the
-        // tensor pipe idles through every softmax; alternating, one warpgroup's exponentials run beside the other's MMAs.
         const long long t_max = dbg ? clock64() : 0;
         // packed fp32x2 arithmetic (FFMA2 / FADD2): the loop is bound by the issue rate of its single warp per scheduler
         // as much as by the MUFU, so two elements per instruction wherever the ISA has it
