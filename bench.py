@@ -63,27 +63,36 @@ def peaks(rate_mult: int = 1):
     return {"tflops": rate_mult * 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md sustained figure)" + mult}
 
 
+def csrc_sha() -> str:
+    """sha256 over the kernel sources (csrc/*.cu, *.cuh, ctx.h): what a profile is valid for. The GPU box has no .git, so
+    profiles are stamped with this instead of a commit id."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "flux-2-swift-mlx_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic(kernel_class: str):
-    """DRAM bytes per launch of a kernel class from the committed ncu pass (profiles/r01_traffic.json, written by
-    tools/summarize_ncu.py traffic from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`), else None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of a kernel class from the ncu pass of THIS tree (tools/gpu_round.sh traffic ->
+    tools/summarize_ncu.py traffic -> profiles/r02_traffic.json, stamped with csrc_sha). A file measured on other kernel
+    sources is not served: (None, why)."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
-        return json.load(open(path)).get(kernel_class)
+        d = json.load(open(path))
     except Exception:
-        return None
+        return None, "no ncu traffic pass committed for this round"
+    if d.get("csrc_sha") != csrc_sha():
+        return None, f"profiles/r02_traffic.json was measured on kernel sources {d.get('csrc_sha')}, this tree is {csrc_sha()}"
+    return d.get(kernel_class), f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, csrc_sha {d.get('csrc_sha')}"
 
 
 def dit_flops(cfg, S_img, S_txt=512):
-    """Algorithmic FLOPs of one DiT forward (BASELINE.md §3 accounting)."""
-    D, Hm = cfg.inner_dim, cfg.mlp_hidden
-    S = S_img + S_txt
-    g = lambda M, N, K: 2 * M * N * K
-    gemm = g(S_img, D, cfg.in_channels) + g(S_txt, D, cfg.joint_attention_dim) + g(S_img, cfg.out_channels, D)
-    for s in (S_img, S_txt):
-        gemm += cfg.num_layers * (4 * g(s, D, D) + g(s, 2 * Hm, D) + g(s, D, Hm))
-    gemm += cfg.num_single_layers * (g(S, 3 * D + 2 * Hm, D) + g(S, D, D + Hm))
-    attn = (cfg.num_layers + cfg.num_single_layers) * 4 * S * S * D
-    return gemm, attn
+    """Algorithmic FLOPs of one DiT forward (BASELINE.md §3 accounting) — flux2b.configs.dit_flops."""
+    from flux2b import configs
+    return configs.dit_flops(cfg, S_img, S_txt)
 
 
 class ClockSampler:
@@ -166,63 +175,51 @@ def cpu_sample(threads: int):
         t_single = (time.perf_counter() - t0) / 2
     step_s = cfg.num_layers * t_double + cfg.num_single_layers * t_single
     gemm, attn = dit_flops(cfg, S_img)
-    return {"step_s": step_s, "t_double": t_double, "t_single": t_single, "tflops": (gemm + attn) / step_s / 1e12,
+    return {"step_s": step_s, "t_double": t_double, "t_single": t_single, "tflops": (gemm + attn) / step_s / 1e12, "flops": (gemm + attn, 0),
             "sample": "1 double-stream + 2 single-stream Klein-4B blocks at S=4608 (1024x1024), PyTorch-CPU fp32 restatement "
                       "of the reference path (oracle); scaled to one DiT step by block counts (5 double + 20 single)"}
 
 
 def run_reference(args, rank):
+    """--impl reference: the restated reference CPU path on all host threads. One "step" = one bounded sample (3 real Klein-4B
+    blocks at S = 4608, scaled to a DiT step by block counts): W warm-up samples, then EXACTLY K timed samples; the line says
+    "extrapolated": true. A real full step (25 blocks, 15.5 GB of fp32 weights) takes ~17 s on 16 cores, K of them do not fit the
+    few-minute budget of a bench run."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(max(1, min(args.warmup, 2))):
         cpu_sample(threads)
-    vals = [cpu_sample(threads) for _ in range(max(1, min(args.steps, 3)))]
-    best = min(vals, key=lambda v: v["step_s"])
-    v = 1.0 / best["step_s"]
+    vals = [cpu_sample(threads) for _ in range(max(1, args.steps))]
+    step_s = sum(v["step_s"] for v in vals) / len(vals)
+    v = 1.0 / step_s
+    gemm, attn = vals[0]["flops"]   # (total FLOPs of one DiT step, 0)
     emit(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": best["step_s"] * 1e3 * NUM_STEPS, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": step_s * 1e3 * NUM_STEPS, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "extrapolated": True,
         "config": {"workload": "Klein 4B t2i 1024x1024 (4096 img + 512 txt tokens), DiT step; CPU arm = restated reference path "
-                               "(MLX CPU backend not runnable here: no swift / mlx)", "l2": "n/a (host)"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": best["sample"],
-                         "cpu_tflops": best["tflops"]},
+                               "(MLX CPU backend not runnable here: no swift / mlx); each timed step is a bounded sample (1 double + 2 "
+                               "single blocks, really computed) scaled to 5 + 20 blocks; ms_per_step = 4 DiT steps, no VAE decode",
+                   "l2": "n/a (host)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": vals[0]["sample"],
+                         "cpu_tflops": (gemm + attn) / step_s / 1e12},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def make_weights_on_gpu(ctx, cfg, vcfg, device):
+def load_synthetic_dit(ctx, cfg, device, lora=False, seed=0):
+    """random-init DiT weights U(-1/sqrt(in), 1/sqrt(in)) (MLX Linear default) generated on the GPU, keys / shapes from the
+    product's own manifest (flux2b.configs.dit_weight_manifest). Same seed on every rank: replicated weights."""
     import torch
-    from oracle import flux2_oracle as O  # shapes / synthetic VAE weights only (input generation, not compute)
-    g = torch.Generator(device=device).manual_seed(0)
-    for k, (o, i) in O.dit_weight_shapes(cfg).items():
-        b = 1.0 / math.sqrt(i)
-        w = torch.empty(o, i, device=device, dtype=torch.float32).uniform_(-b, b, generator=g).to(torch.bfloat16)
-        ctx.set_tensor(k, w)
-        del w
-    ctx.load_weights(O.random_vae_weights(vcfg, seed=1))
-
-
-def run_sp(args, cfg, rank, local_rank, world, device, dist):
-    """BASELINE.json configs[3]: one denoising step of a large joint sequence, Ulysses sequence-parallel over all ranks.
-    Strong scaling: total work fixed, value = DiT steps/s of the whole job."""
-    import torch
-    import flux2b
-    H = W = args.res
-    S_img = (H // 16) * (W // 16)
-    ctx = flux2b.Context(dit=cfg, device=local_rank, quant=flux2b.QUANT[args.quant],
-                         options={"keep_raw_weights": 0, "sp_mode": args.sp_mode, "native_mx": args.native_mx, "mx_bn": args.mx_bn,
-                                  "gemm_cta_group": args.cta_group})
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    from oracle import flux2_oracle as O
-    g = torch.Generator(device=device).manual_seed(0)   # same seed on every rank: replicated weights
+    from flux2b import configs
+    g = torch.Generator(device=device).manual_seed(seed)
     n_lora = 0
-    for k, (o, i) in O.dit_weight_shapes(cfg).items():
+    for k, (o, i) in configs.dit_weight_manifest(cfg).items():
         b = 1.0 / math.sqrt(i)
         w = torch.empty(o, i, device=device, dtype=torch.float32).uniform_(-b, b, generator=g)
-        if args.lora and (".attn." in k or ".ff" in k):
+        if lora and (".attn." in k or ".ff" in k):
             # BASELINE.json configs[4]: a rank-16 LoRA (A, B ~ N(0, 0.02), scale 1) merged into every attention / FF linear at load
             # time (W += B · A before the packer runs; the on-device dequant -> add -> requant merge is covered by the tests)
             A = torch.randn(16, i, device=device, generator=g) * 0.02
@@ -231,12 +228,52 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
             n_lora += 1
         ctx.set_tensor(k, w.to(torch.bfloat16))
         del w
+    return n_lora
+
+
+def load_synthetic_vae(ctx, vcfg, device, seed=1):
+    """synthetic VAE decoder weights: fan-in-scaled uniform convs / linears, GroupNorm gamma ~ 1, beta ~ 0, BN mean ~ 0, var ~ 1"""
+    import torch
+    from flux2b import configs
+    g = torch.Generator(device=device).manual_seed(seed)
+    for k, shape in configs.vae_weight_manifest(vcfg).items():
+        if k.startswith("latentBatchNorm"):
+            t = 0.1 * torch.randn(shape, device=device, generator=g) if k.endswith("Mean") else 1.0 + 0.1 * torch.rand(shape, device=device, generator=g)
+        elif ".norm" in k or "groupNorm" in k or "convNormOut" in k:
+            t = (1.0 if k.endswith(".weight") else 0.0) + 0.1 * torch.randn(shape, device=device, generator=g)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            if k.endswith(".bias"):   # bias bound follows the layer's fan-in: look at the weight's shape
+                wshape = configs.vae_weight_manifest(vcfg)[k[:-len(".bias")] + ".weight"]
+                fan_in = 1
+                for d in wshape[1:]:
+                    fan_in *= d
+            bnd = 1.0 / math.sqrt(fan_in)
+            t = torch.empty(shape, device=device, dtype=torch.float32).uniform_(-bnd, bnd, generator=g)
+            if k.endswith(".weight"):
+                t = t.half().float()
+        ctx.set_tensor(k, t.contiguous())
+
+
+def sp_measure(args, cfg, rank, local_rank, world, device, dist, res, refs, modes, steps, lora=False, model_name="dev"):
+    """One denoising step of a large joint sequence, Ulysses sequence-parallel over all ranks of the job (BASELINE.json
+    configs[3] / [4]); strong scaling: the work is fixed, value = DiT steps/s of the whole job. At world == 1 the same step runs
+    on one GPU (the point scaling efficiency is computed against). Returns a dict per transport mode:
+      value, ms_per_step (CUDA events, max over ranks), kernels_ms (rank 0: sum of the compute kernels' own durations from a second
+      pass with an event pair per launch), exposed_comm_ms = ms_per_step - kernels_ms, parity_vs_single_gpu (rel-L2 of the sharded
+      forward against the same context running the whole forward alone, option sp_disable)."""
+    import torch
+    import flux2b
+    H = W = res
+    S_img = (H // 16) * (W // 16)
+    ctx = flux2b.Context(dit=cfg, device=local_rank, quant=flux2b.QUANT[args.quant],
+                         options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn, "gemm_cta_group": args.cta_group})
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    n_lora = load_synthetic_dit(ctx, cfg, device, lora=lora)
     ctx.finalize()
     torch.cuda.empty_cache()
-    if world > 1:
-        ids = [flux2b.sp_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0, device=device)
-        ctx.sp_init(ids[0], rank, world)
     sched = flux2b.FlowMatchEulerScheduler()
     sched.set_timesteps(28, S_img)
     sig = sched.sigmas[:2]
@@ -245,65 +282,110 @@ def run_sp(args, cfg, rank, local_rank, world, device, dist):
     guidance = 4.0 if cfg.guidance_embeds else None
     ref_lat = ref_ids = None
     S_ref = 0
-    if args.refs > 0:
+    if refs > 0:
         # image-to-image conditioning: `refs` reference images at the output resolution, T coordinates 10, 20, 30 ...
         # (LatentUtils.swift:324-346), token order [output | refs] (Flux2Pipeline.swift:1703)
-        S_ref = args.refs * S_img
+        S_ref = refs * S_img
         ref_lat = torch.randn(1, S_ref, 128, generator=torch.Generator().manual_seed(44)).to(device)
-        ref_ids = O.reference_position_ids([H // 16] * args.refs, [W // 16] * args.refs).to(torch.int32).to(device)
+        ref_ids = torch.from_numpy(flux2b.reference_position_ids([H // 16] * refs, [W // 16] * refs)).to(torch.int32).to(device)
 
-    def step():
-        x = lat.clone()
+    def step(x=None):
+        x = lat.clone() if x is None else x
         ctx.denoise(x, enc, sig, H, W, guidance=guidance, ref_latents=ref_lat, ref_ids=ref_ids)
+        return x
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    gemm_f, attn_f = dit_flops(cfg, S_img + S_ref)
+    out = {"workload": f"{model_name} one denoising step at {H}x{W} ({S_img} img + {S_ref} reference + {S_TXT} txt tokens), {dtype_name(args)}"
+                       f"{', rank-16 LoRA merged into ' + str(n_lora) + ' linears' if n_lora else ''}, Ulysses sequence-parallel over {world} rank(s)",
+           "scaling": "strong", "tflop_per_step": (gemm_f + attn_f) / 1e12, "steps": steps, "n_gpus": world, "modes": {}}
+    single = None
+    for mode in (modes if world > 1 else [None]):
+        if world > 1:
+            ctx.set_option("sp_mode", mode)
+            ids = [flux2b.sp_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0, device=device)
+            ctx.sp_init(ids[0], rank, world)
+        for _ in range(3):
+            step()
+        ctx.prof_enable(False); ctx.prof_reset()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        launches = ctx.launch_count()
+        # second pass: an event pair around every launch -> the compute kernels' own time on rank 0
+        ctx.prof_enable(True); ctx.prof_reset()
+        barrier()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        prof = {k: ctx.prof_get(i) for k, i in (("gemm", flux2b.PROF_GEMM), ("attn", flux2b.PROF_ATTN), ("elem", flux2b.PROF_ELEMWISE),
+                                                ("gemv", flux2b.PROF_GEMV), ("comm", flux2b.PROF_COMM))}
+        ctx.prof_enable(False); ctx.prof_reset()
+        kernels_ms = sum(prof[k]["ms"] for k in ("gemm", "attn", "elem", "gemv")) / steps
+        parity = None
+        if world > 1:
+            # the sharded step against the same context running the whole step alone (each rank computes it redundantly)
+            x_sp = step().float().cpu()
+            ctx.set_option("sp_disable", 1)
+            if single is None:
+                single = step().float().cpu()
+            ctx.set_option("sp_disable", 0)
+            parity = float((x_sp.double() - single.double()).norm() / single.double().norm())
+        barrier()
+        ms_step = ms / steps
+        gp = prof["gemm"]
+        out["modes"]["single_gpu" if mode is None else ("nccl_all_to_all" if mode == 0 else "peer_memory_fused")] = {
+            "value": 1e3 / ms_step, "unit": UNIT, "ms_per_step": ms_step, "kernels_ms": kernels_ms,
+            "exposed_comm_ms": max(0.0, ms_step - kernels_ms), "exposed_comm_frac": max(0.0, ms_step - kernels_ms) / ms_step,
+            "parity_vs_single_gpu": parity, "tflops_total": (gemm_f + attn_f) / (ms_step * 1e-3) / 1e12,
+            "gemm_tflops_rank0": gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] > 0 else None,
+            "gpu_launches": int(launches),
+            "kernel_classes_rank0": {k: {"ms_per_step": p["ms"] / steps, "launches_per_step": p["launches"] / steps} for k, p in prof.items()}}
+    best = max(out["modes"].values(), key=lambda m: m["value"])
+    out.update({"value": best["value"], "unit": UNIT, "ms_per_step": best["ms_per_step"], "kernels_ms": best["kernels_ms"],
+                "exposed_comm_ms": best["exposed_comm_ms"], "parity_vs_single_gpu": best["parity_vs_single_gpu"]})
+    ctx.close()
+    del ctx
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_sp(args, cfg, rank, local_rank, world, device, dist):
+    """--sp: the sequence-parallel measurement as the bench line itself (BASELINE.json configs[3] / [4])."""
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ctx.prof_enable(True); ctx.prof_reset()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    prof = {k: ctx.prof_get(i) for k, i in (("gemm", flux2b.PROF_GEMM), ("attn", flux2b.PROF_ATTN), ("elem", flux2b.PROF_ELEMWISE),
-                                            ("gemv", flux2b.PROF_GEMV), ("comm", flux2b.PROF_COMM))}
-    launches = ctx.launch_count()
+    r = sp_measure(args, cfg, rank, local_rank, world, device, dist, args.res, args.refs, [args.sp_mode], max(args.steps, 1),
+                   lora=args.lora, model_name=args.model)
     clocks = sampler.stop() if rank == 0 else {}
-    barrier()
     if rank == 0:
-        gemm_f, attn_f = dit_flops(cfg, S_img + S_ref)
+        m = list(r["modes"].values())[0]
         pk = peaks(rate_mult(args))
-        gp = prof["gemm"]
-        achieved = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] > 0 else 0.0
+        achieved = m["gemm_tflops_rank0"] or 0.0
         emit(json.dumps({
-            "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": dtype_name(args), "data": "synthetic",
-            "config": {"workload": f"{args.model} one denoising step at {H}x{W} ({S_img} img + {S_ref} reference + {S_TXT} txt tokens), "
-                                   f"{dtype_name(args)}{', rank-16 LoRA merged into ' + str(n_lora) + ' linears' if n_lora else ''}, Ulysses "
-                                   f"sequence-parallel over {world} rank(s), transport mode {args.sp_mode}",
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": r["steps"], "warmup": 3,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": dtype_name(args), "data": "synthetic",
+            "config": {"workload": r["workload"] + f", transport mode {args.sp_mode}",
                        "l2": "inputs larger than L2 (weights stream from HBM every step)"},
-            "tflops_total": (gemm_f + attn_f) * args.steps / (ms * 1e-3) / 1e12,
-            "gpu_launches": int(launches),
+            "tflops_total": m["tflops_total"], "gpu_launches": m["gpu_launches"], "sp": r,
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"]},
-            "kernel_classes_rank0": {k: {"ms_per_step": p["ms"] / args.steps, "launches_per_step": p["launches"] / args.steps}
-                                     for k, p in prof.items()},
-            "clocks": clocks}))
+            "kernel_classes_rank0": m["kernel_classes_rank0"], "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -345,6 +427,11 @@ def main():
     ap.add_argument("--res", type=int, default=1024, help="square resolution in pixels (--sp mode)")
     ap.add_argument("--refs", type=int, default=0, help="number of reference images (image-to-image conditioning tokens); without --sp also times the KV-cached loop")
     ap.add_argument("--lora", action="store_true", help="--sp mode: merge a rank-16 LoRA into every attention / FF linear at load time")
+    ap.add_argument("--no-sp-extra", dest="sp_extra", action="store_false",
+                    help="skip the extra Ulysses measurement (key `sp`) that follows the image-parallel headline")
+    ap.add_argument("--sp-model", default="dev", choices=["dev", "klein9b", "klein4b"])
+    ap.add_argument("--sp-res", type=int, default=2048)
+    ap.add_argument("--sp-steps", type=int, default=10)
     ap.add_argument("--profile-one", action="store_true",
                     help="bracket ONE image with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`); prints no bench line")
     args = ap.parse_args()
@@ -359,7 +446,7 @@ def main():
     import numpy as np
     import torch
     import flux2b
-    from oracle import flux2_oracle as O  # configs + FLOP accounting inputs + cpu_baseline checker leg
+    from flux2b import configs   # the product's own presets / manifests; the oracle is imported by the cpu_baseline leg only
 
     if flux2b.device_count() < 1:
         raise SystemExit("bench.py needs an sm_100 GPU: flux2b has no CPU fallback")
@@ -370,8 +457,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
 
-    cfg = {"klein4b": O.klein_4b, "klein9b": O.klein_9b, "dev": O.flux2_dev}[args.model]()
-    vcfg = O.vae_small_decoder()
+    cfg = configs.PRESETS[args.model]()
+    vcfg = configs.vae_small_decoder()
     if args.sp:
         run_sp(args, cfg, rank, local_rank, world, device, dist)
         return
@@ -379,7 +466,8 @@ def main():
                          options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn,
                                   "gemm_cta_group": args.cta_group})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    make_weights_on_gpu(ctx, cfg, vcfg, device)
+    load_synthetic_dit(ctx, cfg, device)
+    load_synthetic_vae(ctx, vcfg, device)
     ctx.finalize()
     torch.cuda.empty_cache()
 
@@ -427,6 +515,8 @@ def main():
         return ms
 
     if args.profile_one:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        open(os.path.join(ROOT, "gpurun_out", "csrc_sha.txt"), "w").write(csrc_sha())   # what the profile is valid for
         one_image_device()
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -464,7 +554,7 @@ def main():
         # every step ([output | refs], Flux2Pipeline.swift:1696-1767); the klein-9b-kv loop extracts their K / V once (:1565-1644)
         S_ref = args.refs * S_img
         ref_lat = torch.randn(1, S_ref, 128, generator=torch.Generator().manual_seed(44)).to(device)
-        ref_ids = O.reference_position_ids([HEIGHT // 16] * args.refs, [WIDTH // 16] * args.refs).to(torch.int32).to(device)
+        ref_ids = torch.from_numpy(flux2b.reference_position_ids([HEIGHT // 16] * args.refs, [WIDTH // 16] * args.refs)).to(torch.int32).to(device)
         res = {}
         for name, kv in (("standard", False), ("kv_cached", True)):
             def run():
@@ -478,6 +568,22 @@ def main():
         one_image_host()
     ms_e2e = timed(one_image_host, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
+
+    # Ulysses sequence parallelism in front of the driver (north_star's second split, BASELINE.json configs[3]): after the
+    # image-parallel headline every run — N = 1 included, so that strong-scaling efficiency has its denominator — times one
+    # Dev 32B bf16 denoising step at 2048^2 over all ranks of the job, both transports, with parity against the single-GPU step.
+    sp = None
+    if args.sp_extra and args.model == "klein4b" and args.quant == "bf16":
+        ctx.close()
+        del ctx
+        torch.cuda.empty_cache()
+        sp_args = argparse.Namespace(**vars(args))
+        sp_args.quant, sp_args.native_mx = "bf16", 0
+        try:
+            sp = sp_measure(sp_args, configs.PRESETS[args.sp_model](), rank, local_rank, world, device, dist, args.sp_res, 0, [0, 1],
+                            args.sp_steps, model_name=args.sp_model)
+        except Exception as e:   # the headline must survive a failure of the extra measurement
+            sp = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if dist is not None:
@@ -493,6 +599,7 @@ def main():
     achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     gemm_f, attn_f = dit_flops(cfg, S_img)
     total_kernel_ms = sum(p["ms"] for p in prof.values())
+    traffic, traffic_src = measured_traffic("gemm") if args.quant == "bf16" and args.model == "klein4b" else (None, "not measured for this configuration")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_image, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -512,7 +619,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 GEMM, all DiT linears)", "achieved": achieved,
                      "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"] if pk["tflops"] else None,
-                     "traffic": measured_traffic("gemm") if args.quant == "bf16" and args.model == "klein4b" else None,
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": g["bytes"] / g["launches"] if g["launches"] else None,
                      "peak_source": pk["src"], "launches": g["launches"],
                      "share_of_kernel_time": g["ms"] / total_kernel_ms if total_kernel_ms else None},
@@ -524,6 +631,8 @@ def main():
     }
     if i2i is not None:
         out["i2i"] = i2i
+    if sp is not None:
+        out["sp"] = sp
     if world == 1 and not args.no_cpu_baseline:
         c = cpu_sample(os.cpu_count() or 1)
         out["cpu_baseline"] = {"value": 1.0 / c["step_s"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",

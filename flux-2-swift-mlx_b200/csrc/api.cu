@@ -171,7 +171,7 @@ int flux2b_synchronize(flux2b_ctx* c) {
 int flux2b_set_option(flux2b_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "null argument");
   static const char* known[] = {"compute_f16", "fuse_qk_rope", "fuse_swiglu", "attn_variant", "gemm_cta_group",
-                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant", "attn_poly", "group_streams", "te_graph"};
+                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant", "attn_poly", "group_streams", "te_graph", "sp_disable", "vae_attn_chunk"};
   bool ok = false;
   for (const char* k : known) ok = ok || !strcmp(k, name);
   if (!ok) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string("unknown option: ") + name);
@@ -216,7 +216,7 @@ int64_t flux2b_get_tensor(flux2b_ctx* c, const char* key, void* dst, size_t capa
 int flux2b_finalize_weights(flux2b_ctx* c) {
   F2B_TRY(check_ctx(c));
   if (c->has_te) F2B_TRY(finalize_te(c));
-  if (c->has_dit) F2B_TRY(finalize_dit(c));
+  if (c->has_dit) { F2B_TRY(finalize_dit(c)); c->dit_dirty = false; }
   if (c->has_vae && c->tensors.count("decoder.convIn.weight")) F2B_TRY(finalize_vae(c));
   c->finalized = true;
   return 0;

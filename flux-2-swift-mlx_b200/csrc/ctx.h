@@ -154,6 +154,7 @@ struct TeGraph {
   void* exec = nullptr;        // cudaGraphExec_t
   DevBuf ids, mask, out32;     // stable device addresses baked into the graph: token ids [S], {key_lo, key_hi}, fp32 [S, n * hidden]
   int64_t launches = 0;        // kernels per replay
+  uint64_t ws_gen = 0;         // flux2b_ctx::te_ws_gen at capture time: the graph holds the workspaces' addresses of that generation
 };
 
 // Ulysses sequence-parallel state (sp.cu). world == 1: off.
@@ -172,6 +173,16 @@ struct SpState {
   void* cat_exported = nullptr;
   void* flag_exported = nullptr;
   uint32_t epoch = 0;
+};
+
+// state that survives between flux2b_denoise calls: position ids per (height, width, S_txt) and the schedule + guidance scalar live on
+// the device and are re-uploaded only when they change (host copies are context-owned: an asynchronous upload never reads a
+// caller's or a local buffer after the call returned)
+struct DenoiseCache {
+  int height = 0, width = 0, S_txt = 0, S_txt_u = 0;
+  std::vector<int32_t> ids_img, ids_txt, ids_txt_u;
+  const void *ids_img_dev = nullptr, *ids_txt_dev = nullptr, *ids_txt_u_dev = nullptr, *sigmas_dev = nullptr;
+  std::vector<float> sigmas;   // [sigmas ..., guidance]
 };
 
 struct ProfKind {
@@ -194,6 +205,7 @@ struct flux2b_ctx {
   std::map<std::string, int> opt;
   std::unordered_map<std::string, f2b::Tensor> tensors;
   bool finalized = false;
+  bool dit_dirty = false;   // tensors changed under a finalized context (flux2b_merge_lora): working copies are rebuilt before the next forward
 
   // ---- DiT working weights
   int D = 0, H = 0, Hm = 0;
@@ -212,6 +224,7 @@ struct flux2b_ctx {
   int te_layers_built = 0;
   // the prefill captured as a CUDA graph per (tokens, layer set): ~190 launches of 5 - 40 us each are host-bound otherwise
   std::vector<f2b::TeGraph> te_graphs;
+  uint64_t te_ws_gen = 0;   // bumped whenever a text-encoder workspace buffer is reallocated (captured graphs of older generations are stale)
 
   // ---- workspaces (grown on demand)
   f2b::DevBuf ws_x, ws_xn, ws_qkv, ws_cat, ws_cos, ws_sin, ws_ids, ws_small, ws_hid16, ws_enc16, ws_out;
@@ -244,6 +257,8 @@ struct flux2b_ctx {
     f2b::DevBuf& b = scratch[name];
     return b.ensure(bytes) == cudaSuccess ? b.p : nullptr;
   }
+
+  f2b::DenoiseCache dn_cache;
 
   // ---- sequence parallelism
   f2b::SpState sp;
@@ -289,6 +304,8 @@ int end_call(flux2b_ctx* c, bool sync);
 bool is_device_ptr(const void* p);
 
 // weights (weights.cu)
+struct PackedMeta { int bits = 0, group = 0, has_b = 0, sb_dtype = FLUX2B_F16; int64_t rows = 0, cols = 0; Tensor* w = nullptr; Tensor* s = nullptr; Tensor* b = nullptr; };
+int packed_meta(flux2b_ctx* c, const std::string& base, PackedMeta* m);   // validates a packed Linear's scales / biases (shape, dtype)
 int dense16_from_key(flux2b_ctx* c, const std::string& base, DevBuf* out, int* N, int* K);
 int finalize_dit(flux2b_ctx* c);
 int finalize_vae(flux2b_ctx* c);

@@ -170,7 +170,9 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
   const int D = c->D, Hm = c->Hm;
   const bool f16 = c->f16();
   cudaStream_t st = c->stream;
-  const int P = c->sp.world;
+  // option sp_disable: a sequence-parallel context runs this forward on its own GPU alone (the single-GPU reference the
+  // parity of the sharded forward is measured against, same weights, same process)
+  const int P = c->option("sp_disable", 0) ? 1 : c->sp.world;
   float* out_full = out;
   const int S_img_full = S_img;
   if (P > 1) {
@@ -554,6 +556,10 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
 
 int dit_forward_device(flux2b_ctx* c, const DitIO& io) {
   if (!c->has_dit || !c->finalized) return fail(FLUX2B_ERR_MODEL_NOT_LOADED, "transformer weights not finalized");
+  if (c->dit_dirty) {   // LoRA merges since the last forward: one rebuild of the working copies for all of them
+    F2B_TRY(finalize_dit(c));
+    c->dit_dirty = false;
+  }
   const flux2b_dit_config& cfg = c->dit;
   if (io.B < 1 || io.S_img < 1 || io.S_txt < 1) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "empty batch / sequence");
   if (io.kv_mode) {

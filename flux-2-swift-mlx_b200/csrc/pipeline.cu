@@ -231,21 +231,34 @@ int flux2b_merge_lora(flux2b_ctx* c, const char* layer_path, const void* A, cons
   F2B_TRY(stage_rounded(A, (size_t)rank * in_dim, &A32));
   F2B_TRY(stage_rounded(B, (size_t)out_dim * rank, &B32));
   if (quantized) {
-    Tensor& s = c->tensors[base + ".scales"];
-    Tensor* b = has_b ? &c->tensors[base + ".biases"] : nullptr;
+    // find(), not operator[]: a missing scales / biases tensor is an error, not an empty tensor to dereference on the device
+    PackedMeta m;
+    F2B_TRY(packed_meta(c, base, &m));
     DevBuf dense;
     F2B_CUDA(dense.alloc((size_t)out_dim * in_dim * 2));
-    F2B_CUDA(dequantize_matrix(c->quant, w.buf.as<uint32_t>(), s.buf.p, b ? b->buf.p : nullptr, out_dim, in_dim, dense.p, FLUX2B_F16, c->stream));
+    F2B_CUDA(dequantize_matrix(c->quant, w.buf.as<uint32_t>(), m.s->buf.p, m.b ? m.b->buf.p : nullptr, out_dim, in_dim, dense.p, FLUX2B_F16, c->stream, m.sb_dtype));
     F2B_CUDA(lora_add(dense.p, FLUX2B_F16, A32.as<float>(), B32.as<float>(), out_dim, in_dim, rank, scale, c->stream));
-    F2B_CUDA(quantize_matrix(c->quant, dense.p, FLUX2B_F16, out_dim, in_dim, w.buf.as<uint32_t>(), s.buf.p, b ? b->buf.p : nullptr, c->stream));
+    if (m.has_b && m.sb_dtype != FLUX2B_F16) {
+      // the re-quantization of the f16 merged weight produces f16 scales / biases (quantized(...) of a .float16 array)
+      const size_t groups = (size_t)m.s->numel();
+      if (m.sb_dtype == FLUX2B_F32) {
+        F2B_CUDA(cudaStreamSynchronize(c->stream));
+        F2B_CUDA(m.s->buf.alloc(groups * 2));
+        F2B_CUDA(m.b->buf.alloc(groups * 2));
+      }
+      m.s->dtype = FLUX2B_F16; m.b->dtype = FLUX2B_F16;
+    }
+    F2B_CUDA(quantize_matrix(c->quant, dense.p, FLUX2B_F16, out_dim, in_dim, w.buf.as<uint32_t>(), m.s->buf.p, m.b ? m.b->buf.p : nullptr, c->stream));
     F2B_CUDA(cudaStreamSynchronize(c->stream));
   } else {
     F2B_CUDA(lora_add(w.buf.p, w.dtype, A32.as<float>(), B32.as<float>(), out_dim, in_dim, rank, scale, c->stream));
     F2B_CUDA(cudaStreamSynchronize(c->stream));
   }
   c->staging_used = 0;
-  // working copies are rebuilt from the updated tensors
-  if (c->finalized && c->has_dit) { c->finalized = false; F2B_TRY(finalize_dit(c)); c->finalized = true; }
+  // The fused / re-tiled working copies are stale now. They are rebuilt ONCE, lazily, before the next forward (or by an explicit
+  // flux2b_finalize_weights): the reference merges a LoRA as a loop over ~200 layers (WeightLoader.swift:736-856), and a
+  // rebuild of the whole model per merged layer would make that loop quadratic.
+  if (c->finalized && c->has_dit) c->dit_dirty = true;
   return 0;
 }
 
@@ -255,46 +268,76 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
   if (!p || !latents || !p->sigmas || p->num_sigmas < 2 || !p->enc) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "bad denoise parameters");
   if (!c->has_dit || !c->finalized) return fail(FLUX2B_ERR_MODEL_NOT_LOADED, "transformer not loaded");
   const flux2b_dit_config& g = c->dit;
+  if (p->height < 16 || p->width < 16 || p->height % 16 || p->width % 16 || p->S_txt < 1)
+    return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "height / width must be positive multiples of 16, S_txt >= 1");
   const int h = p->height / 16, w = p->width / 16;
   const int S_img = h * w, S_ref = p->ref_latents ? p->S_ref : 0, S_all = S_img + S_ref;
+  // the negative prompt has its own length and position ids (uncondTextIds, Flux2Pipeline.swift:1690,1960-1975); 0 = same as S_txt
+  const int S_txt_u = (p->enc_uncond && p->S_txt_uncond > 0) ? p->S_txt_uncond : p->S_txt;
   const size_t n_lat = (size_t)S_img * g.in_channels;
-  // device-resident state for the whole loop
-  // persistent (context-owned) buffers: a steady-state call allocates nothing
+  const int n_sig = p->num_sigmas;
+  // device-resident state for the whole loop; persistent (context-owned) buffers: a steady-state call allocates nothing
   Buf x{c->scratch_buf("dn.x", n_lat * 4)}, hid{c->scratch_buf("dn.hid", (size_t)S_all * g.in_channels * 4)},
       pred{c->scratch_buf("dn.pred", (size_t)S_all * g.out_channels * 4)},
       pred_u{p->enc_uncond ? c->scratch_buf("dn.pred_u", (size_t)S_all * g.out_channels * 4) : nullptr},
       ids_img{c->scratch_buf("dn.ids_img", (size_t)S_all * 16)}, ids_txt{c->scratch_buf("dn.ids_txt", (size_t)p->S_txt * 16)},
-      tbuf{c->scratch_buf("dn.sigmas", (size_t)p->num_sigmas * 4)};
-  if (!x.p || !hid.p || !pred.p || (p->enc_uncond && !pred_u.p) || !ids_img.p || !ids_txt.p || !tbuf.p) {
+      ids_txt_u{c->scratch_buf("dn.ids_txt_u", (size_t)S_txt_u * 16)},
+      tbuf{c->scratch_buf("dn.sigmas", (size_t)(n_sig + 1) * 4)};
+  if (!x.p || !hid.p || !pred.p || (p->enc_uncond && !pred_u.p) || !ids_img.p || !ids_txt.p || !ids_txt_u.p || !tbuf.p) {
     cudaGetLastError();
     return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "denoise state allocation failed");
   }
   const bool lat_host = !is_device_ptr(latents);
   F2B_CUDA(cudaMemcpyAsync(x.p, latents, n_lat * 4, lat_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
+  // Position ids depend on (height, width, S_txt) only and the schedule + guidance scalar are a few floats: both live on the device
+  // across calls and are uploaded only when they change, from context-owned host storage, so a call with device pointers
+  // enqueues and returns without a single stream synchronisation (include/flux2b.h: "synchronise only when the destination is host
+  // memory"; the reference forces completion once per step only because its hook / progress consumers need it, Flux2Pipeline.swift:1983).
   {
-    std::vector<int32_t> ii((size_t)S_img * 4), ti((size_t)p->S_txt * 4);
-    flux2b_image_position_ids(p->height, p->width, ii.data());
-    flux2b_text_position_ids(p->S_txt, ti.data());
-    F2B_CUDA(cudaMemcpyAsync(ids_img.p, ii.data(), ii.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    F2B_CUDA(cudaMemcpyAsync(ids_txt.p, ti.data(), ti.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    if (S_ref) {
-      if (!p->ref_ids) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "ref_ids required with ref_latents");
-      F2B_CUDA(cudaMemcpyAsync(ids_img.as<int32_t>() + (size_t)S_img * 4, p->ref_ids, (size_t)S_ref * 16,
-                               is_device_ptr(p->ref_ids) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-      // [output | refs] (Flux2Pipeline.swift:1703); reference tokens do not change across steps
-      F2B_CUDA(cudaMemcpyAsync(hid.as<float>() + n_lat, p->ref_latents, (size_t)S_ref * g.in_channels * 4,
-                               is_device_ptr(p->ref_latents) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    DenoiseCache& dc = c->dn_cache;
+    if (dc.height != p->height || dc.width != p->width || dc.S_txt != p->S_txt || dc.S_txt_u != S_txt_u ||
+        dc.ids_img_dev != ids_img.p || dc.ids_txt_dev != ids_txt.p || dc.ids_txt_u_dev != ids_txt_u.p) {
+      F2B_CUDA(cudaStreamSynchronize(c->stream));   // an earlier upload may still be reading the host vectors (shape change: rare)
+      dc.ids_img.resize((size_t)S_img * 4); dc.ids_txt.resize((size_t)p->S_txt * 4); dc.ids_txt_u.resize((size_t)S_txt_u * 4);
+      flux2b_image_position_ids(p->height, p->width, dc.ids_img.data());
+      flux2b_text_position_ids(p->S_txt, dc.ids_txt.data());
+      flux2b_text_position_ids(S_txt_u, dc.ids_txt_u.data());
+      F2B_CUDA(cudaMemcpyAsync(ids_img.p, dc.ids_img.data(), dc.ids_img.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      F2B_CUDA(cudaMemcpyAsync(ids_txt.p, dc.ids_txt.data(), dc.ids_txt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      F2B_CUDA(cudaMemcpyAsync(ids_txt_u.p, dc.ids_txt_u.data(), dc.ids_txt_u.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      dc.height = p->height; dc.width = p->width; dc.S_txt = p->S_txt; dc.S_txt_u = S_txt_u;
+      dc.ids_img_dev = ids_img.p; dc.ids_txt_dev = ids_txt.p; dc.ids_txt_u_dev = ids_txt_u.p;
     }
-    F2B_CUDA(cudaMemcpyAsync(tbuf.p, p->sigmas, (size_t)p->num_sigmas * 4, cudaMemcpyHostToDevice, c->stream));
-    F2B_CUDA(cudaStreamSynchronize(c->stream));  // ii / ti are locals
+    // [sigmas ..., guidance]: the guidance scalar is read on the host when it is host memory (one float, as the reference's
+    // MLXArray([guidance]), Flux2Pipeline.swift:1916), so it never occupies a staging slot
+    std::vector<float> sg(p->sigmas, p->sigmas + n_sig);
+    const bool guid_dev = p->guidance && is_device_ptr(p->guidance);
+    sg.push_back(p->guidance && !guid_dev ? *p->guidance : 0.f);
+    if (dc.sigmas_dev != tbuf.p || dc.sigmas != sg) {
+      F2B_CUDA(cudaStreamSynchronize(c->stream));
+      dc.sigmas = sg;
+      F2B_CUDA(cudaMemcpyAsync(tbuf.p, dc.sigmas.data(), dc.sigmas.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      dc.sigmas_dev = tbuf.p;
+    }
   }
-  const void *enc_d, *encu_d, *guid_d;
+  if (S_ref) {
+    if (!p->ref_ids) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "ref_ids required with ref_latents");
+    const void *rid, *rlat;
+    F2B_TRY(dev_in(c, p->ref_ids, (size_t)S_ref * 16, &rid));
+    F2B_TRY(dev_in(c, p->ref_latents, (size_t)S_ref * g.in_channels * 4, &rlat));
+    F2B_CUDA(cudaMemcpyAsync(ids_img.as<int32_t>() + (size_t)S_img * 4, rid, (size_t)S_ref * 16, cudaMemcpyDeviceToDevice, c->stream));
+    // [output | refs] (Flux2Pipeline.swift:1703); reference tokens do not change across steps
+    F2B_CUDA(cudaMemcpyAsync(hid.as<float>() + n_lat, rlat, (size_t)S_ref * g.in_channels * 4, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  const void *enc_d, *encu_d;
   const size_t enc_bytes = (size_t)p->S_txt * g.joint_attention_dim * dtype_size(p->enc_dtype);
+  const size_t encu_bytes = (size_t)S_txt_u * g.joint_attention_dim * dtype_size(p->enc_dtype);
   F2B_TRY(dev_in(c, p->enc, enc_bytes, &enc_d));
-  F2B_TRY(dev_in(c, p->enc_uncond, enc_bytes, &encu_d));
-  F2B_TRY(dev_in(c, p->guidance, 4, &guid_d));
+  F2B_TRY(dev_in(c, p->enc_uncond, encu_bytes, &encu_d));
+  const float* guid_d = nullptr;
+  if (p->guidance) guid_d = is_device_ptr(p->guidance) ? p->guidance : tbuf.as<float>() + n_sig;
   std::vector<float> host_lat;
-  const int steps = p->num_sigmas - 1;
+  const int steps = n_sig - 1;
   const bool kv = p->kv_cache != 0 && S_ref > 0;
   if (kv && p->enc_uncond) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "the KV-cached loop has no classical-CFG branch (as the reference)");
   for (int i = 0; i < steps; ++i) {
@@ -302,7 +345,7 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
     F2B_CUDA(cudaMemcpyAsync(hid.p, x.p, n_lat * 4, cudaMemcpyDeviceToDevice, c->stream));
     DitIO io{};
     io.B = 1; io.S_img = S_all; io.S_txt = p->S_txt; io.hidden = hid.as<float>(); io.enc = enc_d; io.enc_dtype = p->enc_dtype;
-    io.timestep = tbuf.as<float>() + i; io.guidance = (const float*)guid_d;
+    io.timestep = tbuf.as<float>() + i; io.guidance = guid_d;
     io.img_ids = ids_img.as<int32_t>(); io.txt_ids = ids_txt.as<int32_t>(); io.out = pred.as<float>();
     if (kv) {
       // klein-9b-kv (Flux2Pipeline.swift:1565-1644): the reference tokens enter the transformer once, at step 0
@@ -316,12 +359,12 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
     }
     F2B_TRY(dit_forward_device(c, io));
     if (p->enc_uncond) {
-      io.enc = encu_d; io.out = pred_u.as<float>();
+      io.enc = encu_d; io.S_txt = S_txt_u; io.txt_ids = ids_txt_u.as<int32_t>(); io.out = pred_u.as<float>();
       F2B_TRY(dit_forward_device(c, io));
     }
     {
       // only the first S_img predictions feed the Euler step (:1743)
-      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 12.0 * n_lat);
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (p->enc_uncond ? 16.0 : 12.0) * n_lat);
       F2B_CUDA(euler_step(x.as<float>(), pred.as<float>(), p->enc_uncond ? pred_u.as<float>() : nullptr, p->cfg_scale,
                           sigma_next - sigma, (int64_t)n_lat, c->stream));
     }
@@ -339,7 +382,8 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
     }
   }
   F2B_CUDA(cudaMemcpyAsync(latents, x.p, n_lat * 4, lat_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
-  return end_call(c, true);
+  // host latents: the copy must have landed when the call returns; device pointers: stream-ordered, no synchronisation
+  return end_call(c, lat_host);
 }
 
 int flux2b_generate(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents, uint8_t* rgb) {
@@ -354,7 +398,7 @@ int flux2b_generate(flux2b_ctx* c, const flux2b_denoise_params* p, float* latent
   if (!xdev.p || !z.p) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "generate state allocation failed"); }
   const bool lat_host = !is_device_ptr(latents);
   F2B_CUDA(cudaMemcpyAsync(xdev.p, latents, n_lat * 4, lat_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, c->stream));
-  F2B_TRY(flux2b_denoise(c, p, xdev.as<float>()));
+  F2B_TRY(flux2b_denoise(c, p, xdev.as<float>()));   // device latents: synchronises only if p->enc / refs were staged from host memory
   F2B_CUDA(cudaMemcpyAsync(latents, xdev.p, n_lat * 4, lat_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
   // unpack -> BN denorm (eps 1e-4) -> unpatchify -> NHWC 16-bit, one fused gather (Flux2Pipeline.swift:2059-2079)
   const bool vf16 = c->option("vae_f16", 1) != 0;
@@ -372,7 +416,7 @@ int flux2b_generate(flux2b_ctx* c, const flux2b_denoise_params* p, float* latent
     F2B_CUDA(postprocess_u8(img16, ld, (uint8_t*)dout, npix, vf16, c->stream));
   }
   F2B_TRY(finish_out(c, rgb, dout, (size_t)npix * 3, ho));
-  return end_call(c, true);
+  return end_call(c, lat_host || ho);   // all-device call: stream-ordered, returns without synchronising
 }
 
 // ------------------------------------------------------------------ VAE entry points

@@ -113,7 +113,7 @@ __global__ void quantize_kernel(int quant, const void* __restrict__ w, int w_dty
 }
 
 __global__ void dequantize_kernel(int quant, const uint32_t* __restrict__ packed, const void* __restrict__ scales,
-                                  const void* __restrict__ biases, int64_t rows, int64_t cols, void* __restrict__ out,
+                                  const void* __restrict__ biases, int sb_dtype, int64_t rows, int64_t cols, void* __restrict__ out,
                                   int out_dtype) {
   const QSpec q = qspec(quant);
   const int per_word = 32 / q.bits;
@@ -126,8 +126,9 @@ __global__ void dequantize_kernel(int quant, const uint32_t* __restrict__ packed
   const uint32_t word = packed[wid];
   const uint32_t mask = (1u << q.bits) - 1u;
   if (q.mode == 0) {
-    const float s = __half2float(reinterpret_cast<const __half*>(scales)[gid]);
-    const float b = __half2float(reinterpret_cast<const __half*>(biases)[gid]);
+    // scales / biases in the checkpoint's own float type (f16 from this packer; MLX-quantized bf16 models store bf16)
+    const float s = load_w(scales, sb_dtype, gid);
+    const float b = load_w(biases, sb_dtype, gid);
     for (int j = 0; j < per_word; ++j) {
       const float qv = (float)((word >> (j * q.bits)) & mask);
       store_o(out, out_dtype, e0 + j, __fadd_rn(__fmul_rn(qv, s), b));
@@ -153,12 +154,12 @@ cudaError_t quantize_matrix(int quant, const void* w, int w_dtype, int64_t rows,
   return cudaGetLastError();
 }
 cudaError_t dequantize_matrix(int quant, const uint32_t* packed, const void* scales, const void* biases, int64_t rows,
-                              int64_t cols, void* out, int out_dtype, cudaStream_t s) {
+                              int64_t cols, void* out, int out_dtype, cudaStream_t s, int sb_dtype) {
   const QSpec q = qspec(quant);
-  if (q.mode < 0 || cols % q.group) return cudaErrorInvalidValue;
+  if (q.mode < 0 || cols % q.group || sb_dtype < 0 || sb_dtype > 2) return cudaErrorInvalidValue;
   const int64_t n = rows * cols / (32 / q.bits);
   if (n <= 0) return cudaSuccess;
-  dequantize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(quant, packed, scales, biases, rows, cols, out, out_dtype);
+  dequantize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(quant, packed, scales, biases, sb_dtype, rows, cols, out, out_dtype);
   return cudaGetLastError();
 }
 

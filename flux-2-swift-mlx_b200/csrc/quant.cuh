@@ -8,8 +8,9 @@ namespace f2b {
 bool quant_params(int quant, int* bits, int* group, int* has_biases, int* scale_dtype);
 cudaError_t quantize_matrix(int quant, const void* w, int w_dtype, int64_t rows, int64_t cols, uint32_t* packed,
                             void* scales, void* biases, cudaStream_t s);
+// sb_dtype: float type of the affine modes' scales / biases (0 f32, 1 f16, 2 bf16); the mx modes' scales are always one byte
 cudaError_t dequantize_matrix(int quant, const uint32_t* packed, const void* scales, const void* biases, int64_t rows,
-                              int64_t cols, void* out, int out_dtype, cudaStream_t s);
+                              int64_t cols, void* out, int out_dtype, cudaStream_t s, int sb_dtype = 1);
 cudaError_t lora_add(void* W, int w_dtype, const float* A, const float* B, int64_t out_dim, int64_t in_dim, int rank,
                      float scale, cudaStream_t s);
 

@@ -51,12 +51,21 @@ int te_forward_device(flux2b_ctx* c, int S, const int32_t* ids, int key_lo, int 
   if (deepest > c->te_layers_built)
     return fail(FLUX2B_ERR_MODEL_NOT_LOADED, "hidden state of layer " + std::to_string(deepest) + " requested but only " +
                                                  std::to_string(c->te_layers_built) + " layers are loaded");
-  F2B_CUDA(c->ws_x.ensure((size_t)S * Hd * 4));
-  F2B_CUDA(c->ws_xn.ensure((size_t)S * Hd * 2));
-  F2B_CUDA(c->ws_qkv.ensure((size_t)S * Nqkv * 2));
-  F2B_CUDA(c->ws_cat.ensure((size_t)S * ((size_t)Nq + 3 * (size_t)I) * 2));   // ATT | ACT (+ the unfused [gate | up] fallback)
-  F2B_CUDA(c->ws_cos.ensure((size_t)S * 128 * 4));
-  F2B_CUDA(c->ws_sin.ensure((size_t)S * 128 * 4));
+  {
+    // A captured prefill graph bakes in these buffers' addresses. DevBuf::ensure frees and reallocates when a longer sequence
+    // needs more room, so any growth starts a new workspace generation and graphs of older generations are never replayed
+    // (te_graph_for drops them): S = 128, then 512, then 128 again must not run the first graph against freed memory.
+    const void* before[6] = {c->ws_x.p, c->ws_xn.p, c->ws_qkv.p, c->ws_cat.p, c->ws_cos.p, c->ws_sin.p};
+    F2B_CUDA(c->ws_x.ensure((size_t)S * Hd * 4));
+    F2B_CUDA(c->ws_xn.ensure((size_t)S * Hd * 2));
+    F2B_CUDA(c->ws_qkv.ensure((size_t)S * Nqkv * 2));
+    F2B_CUDA(c->ws_cat.ensure((size_t)S * ((size_t)Nq + 3 * (size_t)I) * 2));   // ATT | ACT (+ the unfused [gate | up] fallback)
+    F2B_CUDA(c->ws_cos.ensure((size_t)S * 128 * 4));
+    F2B_CUDA(c->ws_sin.ensure((size_t)S * 128 * 4));
+    const void* after[6] = {c->ws_x.p, c->ws_xn.p, c->ws_qkv.p, c->ws_cat.p, c->ws_cos.p, c->ws_sin.p};
+    for (int i = 0; i < 6; ++i)
+      if (before[i] != after[i]) { ++c->te_ws_gen; break; }
+  }
   float* X = c->ws_x.as<float>();
   uint16_t* XN = c->ws_xn.as<uint16_t>();
   uint16_t* QKV = c->ws_qkv.as<uint16_t>();
@@ -159,6 +168,14 @@ void te_destroy_graphs(flux2b_ctx* c) {
 // (token count, layer set); token ids, the padding bounds and the fp32 result live at fixed device addresses owned by the graph
 // entry, the bounds are read by the attention kernel from device memory, so one graph serves every prompt length.
 static int te_graph_for(flux2b_ctx* c, int S, const int* layers, int n_layers, TeGraph** out) {
+  // graphs captured against an older workspace generation point at freed buffers: drop them before looking anything up
+  for (size_t i = 0; i < c->te_graphs.size();) {
+    TeGraph& g = c->te_graphs[i];
+    if (g.ws_gen != c->te_ws_gen) {
+      if (g.exec) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(g.exec));
+      c->te_graphs.erase(c->te_graphs.begin() + (long)i);
+    } else ++i;
+  }
   for (TeGraph& g : c->te_graphs)
     if (g.S == S && (int)g.layers.size() == n_layers && std::equal(g.layers.begin(), g.layers.end(), layers)) { *out = &g; return 0; }
   if (c->te_graphs.size() >= 8) te_destroy_graphs(c);   // bounded cache (a pipeline uses one or two shapes)
@@ -205,6 +222,7 @@ static int te_graph_for(flux2b_ctx* c, int S, const int* layers, int n_layers, T
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) return no_graph(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
   g.exec = exec;
+  g.ws_gen = c->te_ws_gen;   // the warm-up above grew the workspaces if needed; the capture saw their final addresses
   *out = &g;
   return 0;
 }

@@ -72,7 +72,8 @@ static int mid_attention(VaeRun& r, const VaeAttnRef& v, void*& x, int H, int W)
   F2B_TRY(gn(c, f16, v.attn_norm, x, hn, r.B, N, false));
   void* y = r.pick(x, hn);
   // scratch sized for one batch item
-  const int chunk = std::max(128, std::min(N, (int)(((size_t)1 << 28) / (size_t)N) / 128 * 128));  // <= 1 GiB of fp32 scores
+  int chunk = std::max(128, std::min(N, (int)(((size_t)1 << 28) / (size_t)N) / 128 * 128));  // <= 1 GiB of fp32 scores
+  if (c->option("vae_attn_chunk", 0) > 0) chunk = std::min(N, std::max(128, c->option("vae_attn_chunk", 0) / 128 * 128));  // tests: chunk < N at small N
   const int ldn = (N + 7) & ~7;  // TMA needs 16 B row strides; columns [N, ldn) are never read (tensor-map extent is N)
   // context-owned scratch: allocated once per resolution, so a steady-state decode performs no cudaMalloc / cudaFree
   Buf qkv{c->scratch_buf("vae.attn.qkv", (size_t)N * 3 * C * 2)}, vt{c->scratch_buf("vae.attn.vt", (size_t)C * ldn * 2)},

@@ -6,6 +6,8 @@
 //     tile as [128 gate | 128 value] so the GEMM epilogue can apply silu(gate)*value in registers,
 //   * quantized layers are quantized exactly like quantize(model:) (Flux2Pipeline.swift:567-578) and kept in MLX's
 //     packed form; the dense working copy is their dequantization (W-only path: x · dequant(W)^T).
+#include <cstring>
+
 #include "ctx.h"
 #include "ptx.cuh"
 
@@ -62,6 +64,10 @@ static Tensor* find(flux2b_ctx* c, const std::string& key) {
   return it == c->tensors.end() ? nullptr : &it->second;
 }
 static bool is_float_dtype(int dt) { return dt == FLUX2B_F32 || dt == FLUX2B_F16 || dt == FLUX2B_BF16_T; }
+static bool ends_with(const std::string& s, const char* suffix) {
+  const size_t n = strlen(suffix);
+  return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
 
 int vector_f32_from_key(flux2b_ctx* c, const std::string& key, DevBuf* out, int64_t expect, bool required, float fill) {
   Tensor* t = find(c, key);
@@ -78,6 +84,36 @@ int vector_f32_from_key(flux2b_ctx* c, const std::string& key, DevBuf* out, int6
   F2B_CUDA(out->alloc(sizeof(float) * expect));
   to_f32_kernel<<<(unsigned)((expect + 255) / 256), 256, 0, c->stream>>>(t->buf.p, t->dtype, out->as<float>(), expect);
   F2B_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// A packed Linear and its scale / bias tensors, validated against the context's quantization mode. The loader accepts the
+// float-category tensors in any float type (PrequantizedCheckpoint.swift:41-59; MLX-quantized bf16 models store bf16 scales),
+// so the type is part of the metadata and every consumer dequantizes with it — a bf16 scale read as f16 is garbage.
+int packed_meta(flux2b_ctx* c, const std::string& base, PackedMeta* m) {
+  Tensor* w = find(c, base + ".weight");
+  if (!w) return fail(FLUX2B_ERR_WEIGHT_LOADING, "missing tensor: " + base + ".weight");
+  int sdt;
+  if (!quant_params(c->quant, &m->bits, &m->group, &m->has_b, &sdt))
+    return fail(FLUX2B_ERR_WEIGHT_LOADING, "packed weight for " + base + " but context quantization is bf16");
+  if (w->dtype != FLUX2B_U32 || w->shape.size() != 2) return fail(FLUX2B_ERR_WEIGHT_LOADING, "packed weight must be 2-D uint32: " + base);
+  m->rows = w->shape[0]; m->cols = w->shape[1] * 32 / m->bits;
+  if (m->cols % m->group) return fail(FLUX2B_ERR_WEIGHT_LOADING, "input dim not divisible by group size: " + base);
+  Tensor* s = find(c, base + ".scales");
+  Tensor* b = find(c, base + ".biases");
+  if (!s || (m->has_b && !b)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "missing scales / biases for " + base);
+  if (!m->has_b && b) return fail(FLUX2B_ERR_WEIGHT_LOADING, "unexpected biases for non-affine mode: " + base);
+  const int64_t groups = m->rows * (m->cols / m->group);
+  if (s->numel() != groups || (b && b->numel() != groups)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "scales / biases shape mismatch: " + base);
+  if (m->has_b) {
+    if (!is_float_dtype(s->dtype) || b->dtype != s->dtype)
+      return fail(FLUX2B_ERR_WEIGHT_LOADING, "affine scales / biases must share one float type (f16, bf16 or f32): " + base);
+    m->sb_dtype = s->dtype;
+  } else {
+    if (s->dtype != FLUX2B_U8) return fail(FLUX2B_ERR_WEIGHT_LOADING, "block-scaled modes store one uint8 scale per group: " + base);
+    m->sb_dtype = FLUX2B_F16;  // unused
+  }
+  m->w = w; m->s = s; m->b = b;
   return 0;
 }
 
@@ -116,20 +152,12 @@ int dense16_from_key_ex(flux2b_ctx* c, const std::string& base, DevBuf* out, int
   if (!w) return fail(FLUX2B_ERR_WEIGHT_LOADING, "missing tensor: " + base + ".weight");
   const bool f16 = c->f16();
   if (w->dtype == FLUX2B_U32) {
-    int bits, group, has_b, sdt;
-    if (!quant_params(c->quant, &bits, &group, &has_b, &sdt))
-      return fail(FLUX2B_ERR_WEIGHT_LOADING, "packed weight for " + base + " but context quantization is bf16");
-    if (w->shape.size() != 2) return fail(FLUX2B_ERR_WEIGHT_LOADING, "packed weight must be 2-D: " + base);
-    const int64_t rows = w->shape[0], cols = w->shape[1] * 32 / bits;
-    Tensor* s = find(c, base + ".scales");
-    Tensor* b = find(c, base + ".biases");
-    if (!s || (has_b && !b)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "missing scales / biases for " + base);
-    if (!has_b && b) return fail(FLUX2B_ERR_WEIGHT_LOADING, "unexpected biases for non-affine mode: " + base);
-    if (s->numel() != rows * (cols / group)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "scales shape mismatch: " + base);
-    F2B_CUDA(out->alloc((size_t)rows * cols * 2));
-    F2B_CUDA(dequantize_matrix(c->quant, w->buf.as<uint32_t>(), s->buf.p, has_b ? b->buf.p : nullptr, rows, cols, out->p,
-                               f16 ? FLUX2B_F16 : FLUX2B_BF16_T, c->stream));
-    *N = (int)rows; *K = (int)cols;
+    PackedMeta m;
+    F2B_TRY(packed_meta(c, base, &m));
+    F2B_CUDA(out->alloc((size_t)m.rows * m.cols * 2));
+    F2B_CUDA(dequantize_matrix(c->quant, m.w->buf.as<uint32_t>(), m.s->buf.p, m.has_b ? m.b->buf.p : nullptr, m.rows, m.cols, out->p,
+                               f16 ? FLUX2B_F16 : FLUX2B_BF16_T, c->stream, m.sb_dtype));
+    *N = (int)m.rows; *K = (int)m.cols;
     return 0;
   }
   if (!is_float_dtype(w->dtype)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "unsupported weight dtype for " + base);
@@ -196,13 +224,11 @@ static int mx_rows(flux2b_ctx* c, const std::string& base, int eN, int eK, int64
   // N tile of the block-scaled GEMM: 128 keeps two accumulator stages next to the scale-factor columns in TMEM
   const int bn = (c->option("mx_bn", 0) == 256 && N_total % 256 == 0) ? 256 : 128;
   F2B_TRY(ensure_packed(c, base));
-  Tensor* w = find(c, base + ".weight");
-  Tensor* s = find(c, base + ".scales");
-  int bits, group, has_b, sdt;
-  quant_params(c->quant, &bits, &group, &has_b, &sdt);
-  if (!w || !s || w->dtype != FLUX2B_U32 || w->shape.size() != 2) return fail(FLUX2B_ERR_WEIGHT_LOADING, "packed weight / scales expected for " + base);
-  F2B_TRY(expect_shape(base, (int)w->shape[0], (int)(w->shape[1] * 32 / bits), eN, eK));
-  if (s->numel() != (int64_t)eN * (eK / group)) return fail(FLUX2B_ERR_WEIGHT_LOADING, "scales shape mismatch: " + base);
+  PackedMeta pm;
+  F2B_TRY(packed_meta(c, base, &pm));
+  Tensor* w = pm.w; Tensor* s = pm.s;
+  const int bits = pm.bits;
+  F2B_TRY(expect_shape(base, (int)pm.rows, (int)pm.cols, eN, eK));
   if (eK % (kind == 1 ? 128 : 256) || N_total % 128)
     return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "native_mx needs in-features % 128 (fp8) / 256 (fp4) == 0 and out-features % 128 == 0: " + base);
   if (!L->wq.p || L->N != N_total || L->K != eK || L->mx != kind || L->bn != bn) {
@@ -316,7 +342,9 @@ int finalize_dit(flux2b_ctx* c) {
       const bool dit_key = it->first.rfind("decoder.", 0) != 0 && it->first.rfind("encoder.", 0) != 0 &&
                            it->first.rfind("postQuantConv", 0) != 0 && it->first.rfind("quantConv", 0) != 0 &&
                            it->first.rfind("latentBatchNorm", 0) != 0;
-      if (dit_key && is_float_dtype(it->second.dtype) && it->second.shape.size() == 2) it = c->tensors.erase(it);
+      // only dense `.weight` matrices: the f16 `.scales` / `.biases` of packed layers are [rows, groups] floats too and must stay
+      // (get_tensor, save_prequantized and merge_lora need them)
+      if (dit_key && is_float_dtype(it->second.dtype) && it->second.shape.size() == 2 && ends_with(it->first, ".weight")) it = c->tensors.erase(it);
       else ++it;
     }
   }
@@ -392,7 +420,7 @@ int finalize_te(flux2b_ctx* c) {
     if (!c->option("keep_raw_weights", 1)) {
       // the dense working copies are all the forward needs; packed (MLX-quantized) tensors stay for get_tensor
       for (auto it = c->tensors.begin(); it != c->tensors.end();) {
-        if (it->first.rfind(p, 0) == 0 && is_float_dtype(it->second.dtype) && it->second.shape.size() == 2) it = c->tensors.erase(it);
+        if (it->first.rfind(p, 0) == 0 && is_float_dtype(it->second.dtype) && it->second.shape.size() == 2 && ends_with(it->first, ".weight")) it = c->tensors.erase(it);
         else ++it;
       }
     }

@@ -76,7 +76,8 @@ class DenoiseParamsC(ctypes.Structure):
                 ("sigmas", ctypes.POINTER(ctypes.c_float)), ("guidance", ctypes.c_void_p), ("cfg_scale", ctypes.c_float),
                 ("enc", ctypes.c_void_p), ("enc_uncond", ctypes.c_void_p), ("enc_dtype", ctypes.c_int),
                 ("S_txt", ctypes.c_int), ("ref_latents", ctypes.c_void_p), ("ref_ids", ctypes.c_void_p),
-                ("S_ref", ctypes.c_int), ("hook", HOOK_T), ("hook_user", ctypes.c_void_p), ("kv_cache", ctypes.c_int)]
+                ("S_ref", ctypes.c_int), ("hook", HOOK_T), ("hook_user", ctypes.c_void_p), ("kv_cache", ctypes.c_int),
+                ("S_txt_uncond", ctypes.c_int)]
 
 
 EXPORTS = [
@@ -491,6 +492,7 @@ class Context:
         p.guidance = _ptr(g)
         p.cfg_scale = cfg_scale
         p.enc, p.enc_uncond, p.enc_dtype, p.S_txt = _ptr(enc), _ptr(enc_uncond), _dtype_code(enc), enc.shape[-2]
+        p.S_txt_uncond = int(enc_uncond.shape[-2]) if enc_uncond is not None else 0   # the negative prompt has its own length
         p.ref_latents, p.ref_ids = _ptr(ref_latents), _ptr(ref_ids)
         p.S_ref = int(ref_latents.shape[-2]) if ref_latents is not None else 0
         cb = None

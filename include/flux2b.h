@@ -255,6 +255,8 @@ typedef struct {
   int kv_cache;                  /* with ref_latents: 1 = the klein-9b-kv loop (Flux2Pipeline.swift:1555-1683): step 0 is
                                   * forwardKVExtract over [txt | refs | output], later steps forwardKVCached over [txt | output]
                                   * against the cached reference K / V; 0 = the standard I2I loop ([output | refs] every step) */
+  int S_txt_uncond;              /* token count of enc_uncond [1, S_txt_uncond, joint]; 0 = S_txt. The negative prompt's position
+                                  * ids are built from its own length (uncondTextIds, Flux2Pipeline.swift:1690,1960-1975) */
 } flux2b_denoise_params;
 /* latents [1, S_img, 128] f32 in/out (packed sequence). */
 int flux2b_denoise(flux2b_ctx* ctx, const flux2b_denoise_params* p, float* latents_inout);

@@ -776,7 +776,9 @@ def denoise(W, cfg: DiTConfig, latents: Tensor, enc: Tensor, sigmas: List[float]
             hid, ids = x, img_ids
         pred = dit_forward(W, cfg, hid, enc, t, g, ids, txt_ids)[:, :S_img]   # (:1743)
         if enc_uncond is not None:
-            un = dit_forward(W, cfg, hid, enc_uncond, t, g, ids, txt_ids)[:, :S_img]
+            # the negative prompt's ids follow its own length (uncondTextIds, Flux2Pipeline.swift:1687-1694, 1919-1925)
+            un_ids = text_position_ids(enc_uncond.shape[1])
+            un = dit_forward(W, cfg, hid, enc_uncond, t, g, ids, un_ids)[:, :S_img]
             pred = un + cfg_scale * (pred - un)                      # (:1970)
         dt = _f32(sigmas[i + 1]) - _f32(sigmas[i])
         x = x + torch.tensor(dt, dtype=torch.float32) * pred         # FlowMatchEulerScheduler.swift:150-151

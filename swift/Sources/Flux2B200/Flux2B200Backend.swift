@@ -126,6 +126,7 @@ extension Flux2Pipeline {
             p.cfg_scale = cfgScale; p.enc_dtype = 0; p.S_txt = Int32(textEmbeddings.dim(1)); p.S_ref = Int32(refLatents?.dim(1) ?? 0)
             p.hook = cHook
             p.kv_cache = kvCache ? 1 : 0
+            p.S_txt_uncond = Int32(negativeEmbeddings?.dim(1) ?? 0)   // uncondTextIds follow the negative prompt's own length (:1690)
             p.hook_user = box.map { UnsafeMutableRawPointer(Unmanaged.passUnretained($0).toOpaque()) }
             try enc.withUnsafeBytes { e in
                 p.enc = e.baseAddress

@@ -1,0 +1,205 @@
+"""GPU regression tests for the defects found in review of round 1, all through the C ABI:
+
+  * affine scales / biases in bf16 (MLX-quantized bf16 checkpoints) are dequantized with their own type, not read as f16;
+  * a text-encoder context that sees S = 128, then 512, then 128 again does not replay a CUDA graph against freed workspaces;
+  * keep_raw_weights = 0 keeps the `.scales` / `.biases` of packed layers (get_tensor, merge_lora, save_prequantized);
+  * merge_lora on a missing scales tensor fails cleanly; a loop of merges rebuilds the working copies once, lazily;
+  * classical CFG with a negative prompt of a different length (its own position ids, Flux2Pipeline.swift:1687-1694);
+  * flux2b_denoise / flux2b_generate with device pointers return without synchronising the stream.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny(O, layers=(1, 1), guidance=False):
+    return O.DiTConfig(num_layers=layers[0], num_single_layers=layers[1], num_attention_heads=2, joint_attention_dim=256,
+                       guidance_embeds=guidance)
+
+
+def _inputs(O, cfg, S_img=64, S_txt=64, seed=42):
+    hidden = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(seed))
+    enc = torch.randn(1, S_txt, cfg.joint_attention_dim, generator=torch.Generator().manual_seed(seed + 1))
+    side = int(S_img ** 0.5)
+    return hidden, enc, torch.tensor([0.7]), O.image_position_ids(side * 16, side * 16), O.text_position_ids(S_txt)
+
+
+@pytest.mark.parametrize("name,sb", [("qint8", torch.bfloat16), ("int4", torch.bfloat16), ("qint8", torch.float32)])
+def test_affine_scales_in_checkpoint_dtype(flux2b, name, sb):
+    from oracle import flux2_oracle as O
+    from oracle import quant_oracle as Q
+    q = flux2b.QUANT[name]
+    bits = 8 if name == "qint8" else 4
+    cfg = _tiny(O)
+    W = O.random_dit_weights(cfg, seed=4, round_to=torch.float16)
+    ctx = flux2b.Context(dit=cfg, quant=q, options={"record_blocks": 1})
+    Wd = {}
+    for k, w in W.items():
+        if w.dim() != 2:
+            ctx.set_tensor(k, w); Wd[k] = w
+            continue
+        base = k[:-len(".weight")]
+        p0, s0, b0 = Q.quantize(q, w.half().numpy())
+        # a checkpoint whose float-category tensors are bf16 / f32 (PrequantizedCheckpoint.swift:41-59 accepts any float type)
+        s_t, b_t = torch.from_numpy(s0.astype(np.float32)).to(sb), torch.from_numpy(b0.astype(np.float32)).to(sb)
+        ctx.set_tensor(base + ".weight", p0); ctx.set_tensor(base + ".scales", s_t); ctx.set_tensor(base + ".biases", b_t)
+        # checker: q * scale + bias in fp32 with the stored scale values
+        per = 32 // bits
+        qv = ((p0[:, :, None] >> (np.arange(per, dtype=np.uint32) * bits)) & ((1 << bits) - 1)).reshape(p0.shape[0], -1).astype(np.float32)
+        sv = s_t.float().numpy().repeat(64, axis=1); bv = b_t.float().numpy().repeat(64, axis=1)
+        Wd[k] = torch.from_numpy(qv * sv + bv)
+    ctx.finalize()
+    hidden, enc, t, img_ids, txt_ids = _inputs(O, cfg)
+    out = ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), None, img_ids.numpy(), txt_ids.numpy())
+    ref = O.dit_forward(Wd, cfg, hidden, enc, t, None, img_ids, txt_ids)
+    e = rel_l2(out, ref)
+    print(f"{name} scales {sb}: output rel-L2 {e:.2e}")
+    assert e < 6e-3
+    # mismatched scale / bias types are refused, not reinterpreted
+    bad = flux2b.Context(dit=cfg, quant=q)
+    for k, w in W.items():
+        if w.dim() != 2:
+            bad.set_tensor(k, w)
+            continue
+        base = k[:-len(".weight")]
+        p0, s0, b0 = Q.quantize(q, w.half().numpy())
+        bad.set_tensor(base + ".weight", p0); bad.set_tensor(base + ".scales", torch.from_numpy(s0.astype(np.float32)).bfloat16())
+        bad.set_tensor(base + ".biases", b0)
+    with pytest.raises(flux2b.Flux2Error) as ei:
+        bad.finalize()
+    assert ei.value.case == "weightLoadingFailed"
+    ctx.close(); bad.close()
+
+
+def test_text_encoder_graph_survives_workspace_growth(flux2b):
+    from oracle import flux2_oracle as O
+    tcfg = O.TEConfig(vocab_size=256, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=2, num_kv_heads=1)
+    TW = O.random_te_weights(tcfg, seed=2)
+    te = flux2b.TextEncoder(tcfg)   # te_graph = 1 by default
+    te.load_weights(TW, dtype=torch.bfloat16)
+    te.finalize()
+    outs = {}
+    for rnd, S in enumerate((128, 512, 128, 256, 128)):
+        ids, mask = O.te_pad_tokens(list(range(3, 40)), S, 1, "right")
+        emb = te.forward_with_hidden_states(ids.numpy(), (1, 2), mask.numpy())
+        ref = O.te_hidden_states(TW, tcfg, ids, mask, (1, 2))
+        e = rel_l2(emb, ref)
+        print(f"round {rnd} S={S}: rel-L2 {e:.2e}")
+        assert e < 8e-3
+        if S in outs:
+            assert np.array_equal(outs[S], emb)   # the re-captured graph gives the same bits as the first capture
+        outs[S] = emb
+    te.close()
+
+
+def test_packed_layers_keep_scales_without_raw_weights(flux2b):
+    from oracle import flux2_oracle as O
+    from oracle import quant_oracle as Q
+    q = flux2b.QUANT["qint8"]
+    cfg = _tiny(O)
+    W = O.random_dit_weights(cfg, seed=5, round_to=torch.float16)
+    ctx = flux2b.Context(dit=cfg, quant=q, options={"keep_raw_weights": 0})
+    ctx.load_weights(W, dtype=torch.float16)
+    ctx.finalize()
+    key = "singleTransformerBlocks.0.attn.toOut"
+    w = W[key + ".weight"]
+    p0, s0, b0 = Q.quantize(q, w.half().numpy())
+    assert np.array_equal(ctx.get_tensor(key + ".scales").view(np.uint16), s0.view(np.uint16))
+    assert np.array_equal(ctx.get_tensor(key + ".biases").view(np.uint16), b0.view(np.uint16))
+    g = torch.Generator().manual_seed(6)
+    A, B = torch.randn(8, w.shape[1], generator=g) * 0.02, torch.randn(w.shape[0], 8, generator=g) * 0.02
+    ctx.merge_lora(key, A, B, 1.0)     # dequant -> add -> requant needs the scales / biases
+    deq = torch.from_numpy(Q.dequantize(q, p0, s0, b0, w.shape[1])).half()
+    p1, s1, b1 = Q.quantize(q, O.lora_merge(deq, A, B, 1.0, torch.float16).numpy())
+    assert np.array_equal(ctx.get_tensor(key + ".weight"), p1)
+    assert np.array_equal(ctx.get_tensor(key + ".scales").view(np.uint16), s1.view(np.uint16))
+    ctx.close()
+
+
+def test_merge_lora_loop_rebuilds_once_and_fails_cleanly(flux2b):
+    import time
+    from oracle import flux2_oracle as O
+    cfg = _tiny(O, layers=(2, 2))
+    W = O.random_dit_weights(cfg, seed=5, round_to=torch.bfloat16)
+    ctx = flux2b.Context(dit=cfg)
+    ctx.load_weights(W, dtype=torch.bfloat16)
+    ctx.finalize()
+    g = torch.Generator().manual_seed(6)
+    W2 = dict(W)
+    keys = [k[:-len(".weight")] for k, w in W.items() if w.dim() == 2 and (".attn." in k or ".ff" in k)]
+    l0 = ctx.launch_count()
+    for key in keys:   # the reference's merge is a loop over every targeted layer (WeightLoader.swift:736-856)
+        w = W[key + ".weight"]
+        A, B = torch.randn(4, w.shape[1], generator=g) * 0.02, torch.randn(w.shape[0], 4, generator=g) * 0.02
+        ctx.merge_lora(key, A, B, 0.5)
+        W2[key + ".weight"] = O.lora_merge(w, A, B, 0.5, torch.bfloat16).float()
+    hidden, enc, t, img_ids, txt_ids = _inputs(O, cfg)
+    out = ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), None, img_ids.numpy(), txt_ids.numpy())
+    assert rel_l2(out, O.dit_forward(W2, cfg, hidden, enc, t, None, img_ids, txt_ids)) < 4e-3
+    # quantized context without its scales: an error, not a null dereference on the device
+    q = flux2b.QUANT["qint8"]
+    c2 = flux2b.Context(dit=cfg, quant=q)
+    c2.load_weights(O.random_dit_weights(cfg, seed=5, round_to=torch.float16), dtype=torch.float16)
+    c2.finalize()
+    with pytest.raises(flux2b.Flux2Error):
+        c2.merge_lora("no.such.layer", torch.zeros(4, 256), torch.zeros(256, 4), 1.0)
+    ctx.close(); c2.close()
+
+
+def test_cfg_negative_prompt_of_its_own_length(flux2b):
+    from oracle import flux2_oracle as O
+    cfg = _tiny(O)
+    W = O.random_dit_weights(cfg, seed=3)
+    ctx = flux2b.Context(dit=cfg)
+    ctx.load_weights(W, dtype=torch.bfloat16)
+    ctx.finalize()
+    S_img, H = 64, 128
+    lat = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(1))
+    enc = torch.randn(1, 96, 256, generator=torch.Generator().manual_seed(2))
+    neg = torch.randn(1, 40, 256, generator=torch.Generator().manual_seed(3))   # shorter negative prompt
+    sched = flux2b.FlowMatchEulerScheduler(); sched.set_timesteps(2, S_img)
+    x = lat.numpy().copy()
+    ctx.denoise(x, enc.numpy(), sched.sigmas, H, H, enc_uncond=neg.numpy(), cfg_scale=3.0)
+    ref = O.denoise(W, cfg, lat, enc, sched.sigmas, H, H, enc_uncond=neg, cfg_scale=3.0)
+    e = rel_l2(x, ref)
+    print(f"CFG with S_txt 96 / S_txt_uncond 40: rel-L2 {e:.2e}")
+    assert e < 8e-3
+    ctx.close()
+
+
+def test_device_pointer_generate_does_not_synchronise(flux2b):
+    """include/flux2b.h: calls enqueue on the context stream and synchronise only when a destination is host memory."""
+    from oracle import flux2_oracle as O
+    cfg = _tiny(O, layers=(2, 2))
+    vcfg = O.vae_small_decoder()
+    ctx = flux2b.Context(dit=cfg, vae=vcfg)
+    ctx.load_weights(O.random_dit_weights(cfg, seed=0), dtype=torch.bfloat16)
+    ctx.load_weights(O.random_vae_weights(vcfg, seed=1))
+    ctx.finalize()
+    st = torch.cuda.Stream()
+    ctx.set_stream(st.cuda_stream)
+    H = 128
+    S_img = 64
+    lat = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(1)).cuda()
+    enc = torch.randn(1, 64, 256, generator=torch.Generator().manual_seed(2)).cuda()
+    rgb = torch.empty(H, H, 3, dtype=torch.uint8, device="cuda")
+    sched = flux2b.FlowMatchEulerScheduler(); sched.set_timesteps(2, S_img)
+    torch.cuda.synchronize()
+    x = lat.clone()
+    ctx.generate(x, enc, sched.sigmas, H, H, rgb_out=rgb)   # warm-up: workspaces, cached ids
+    torch.cuda.synchronize()
+    want_x, want_rgb = x.clone(), rgb.clone()
+    # a long-running kernel in front of the call on the same stream: if the call synchronised, it would block behind it
+    with torch.cuda.stream(st):
+        torch.cuda._sleep(int(2e9))   # ~1 s of device time
+        x2 = lat.clone()
+        ctx.generate(x2, enc, sched.sigmas, H, H, rgb_out=rgb)
+        returned_while_busy = not st.query()
+    torch.cuda.synchronize()
+    assert returned_while_busy, "flux2b_generate with device pointers blocked on the stream"
+    assert torch.equal(x2, want_x) and torch.equal(rgb, want_rgb)
+    ctx.close()

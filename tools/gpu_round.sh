@@ -40,6 +40,15 @@ for w in $WHAT; do
           > gpurun_out/bench_k9_nvfp4_native$nm.json 2> gpurun_out/bench_k9_$nm.err
         echo "bench k9 native=$nm rc=$?"; tail -c 2500 gpurun_out/bench_k9_nvfp4_native$nm.json; tail -n 3 gpurun_out/bench_k9_$nm.err
       done ;;
+    sanitize)
+      # compute-sanitizer over a small grouped forward + VAE decode (tools/sanitize_target.py): memcheck, racecheck, synccheck
+      for tool in memcheck racecheck synccheck; do
+        timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py > gpurun_out/sanitize_$tool.log 2>&1
+        echo "sanitize $tool rc=$?"; grep -E "SANITIZE_OK|ERROR SUMMARY|RACECHECK SUMMARY|hazard" gpurun_out/sanitize_$tool.log | head -5
+      done ;;
+    bench_nosp)
+      timeout 900 python bench.py --steps 5 --warmup 3 --no-sp-extra > gpurun_out/bench.json 2> gpurun_out/bench.err
+      echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err ;;
     full)
       # top kernels, full sections (few launches each)
       timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \

@@ -85,6 +85,9 @@ def traffic(src, dst):
         a[0] += 1; a[1] += v
     out = {c: a[1] / a[0] for c, a in cls.items()}
     out["_launches"] = {c: a[0] for c, a in cls.items()}
+    import os
+    sha_file = os.path.join(os.path.dirname(os.path.abspath(src)), "csrc_sha.txt")
+    out["csrc_sha"] = open(sha_file).read().strip() if os.path.exists(sha_file) else None   # kernel sources the pass ran on (bench.py csrc_sha)
     out["_source"] = "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one klein4b 1024x1024 image (bench.py --profile-one); mean bytes per launch"
     json.dump(out, open(dst, "w"), indent=1)
     print(json.dumps(out, indent=1)[:3000])
