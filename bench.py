@@ -269,7 +269,8 @@ def sp_measure(args, cfg, rank, local_rank, world, device, dist, res, refs, mode
     H = W = res
     S_img = (H // 16) * (W // 16)
     ctx = flux2b.Context(dit=cfg, device=local_rank, quant=flux2b.QUANT[args.quant],
-                         options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn, "gemm_cta_group": args.cta_group})
+                         options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn, "gemm_cta_group": args.cta_group,
+                                  "wq_inkernel": getattr(args, "wq_inkernel", 1)})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     n_lora = load_synthetic_dit(ctx, cfg, device, lora=lora)
     ctx.finalize()
@@ -402,7 +403,7 @@ def dtype_name(args) -> str:
         return "bf16"
     if args.native_mx:
         return f"{args.quant} (block-scaled tcgen05 MMA, weights and on-the-fly activations)"
-    return f"bf16 x dequant({args.quant}) (W-only)"
+    return f"bf16 x dequant({args.quant}) (W-only, {'dequantized inside the kernels' if getattr(args, 'wq_inkernel', 1) else 'dense 16-bit copies'})"
 
 
 def main():
@@ -418,6 +419,8 @@ def main():
     ap.add_argument("--native-mx", type=int, default=0,
                     help="1 = block linears on tcgen05 block-scaled MMA (mxfp8 / mxfp4 / nvfp4 weights consumed as packed, activations "
                          "quantised on the fly); 0 = W-only x · dequant(W)^T through the 16-bit GEMM (the reference's arithmetic)")
+    ap.add_argument("--wq-inkernel", type=int, default=1,
+                    help="W-only quantized layers: 1 = packed weights only, dequantized inside the GEMM / GEMV kernels; 0 = dense 16-bit copies")
     ap.add_argument("--mx-bn", type=int, default=0, help="N tile of the block-scaled GEMM (0 = auto / 128 / 256)")
     ap.add_argument("--cta-group", type=int, default=0, help="GEMM CTA group (0 = auto: CTA pairs / 1 / 2)")
     ap.add_argument("--sp", action="store_true",
@@ -462,14 +465,18 @@ def main():
     if args.sp:
         run_sp(args, cfg, rank, local_rank, world, device, dist)
         return
+    free0, _ = torch.cuda.mem_get_info()
     ctx = flux2b.Context(dit=cfg, vae=vcfg, device=local_rank, quant=flux2b.QUANT[args.quant],
                          options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn,
-                                  "gemm_cta_group": args.cta_group})
+                                  "gemm_cta_group": args.cta_group, "wq_inkernel": args.wq_inkernel})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     load_synthetic_dit(ctx, cfg, device)
     load_synthetic_vae(ctx, vcfg, device)
     ctx.finalize()
     torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    ctx_mem_gb = (free0 - free1) / 1e9   # resident weights of the context (DiT + VAE) after finalize
 
     S_img = (HEIGHT // 16) * (WIDTH // 16)
     sched = flux2b.FlowMatchEulerScheduler()
@@ -610,6 +617,7 @@ def main():
                    "images_per_rank": args.steps,
                    "kernel_timing": "roofline / kernel_classes come from a second pass over the same K steps with a CUDA-event pair around every launch"},
         "images_per_sec": n_img / (ms * 1e-3),
+        "mem_gb": ctx_mem_gb,
         "ms_per_step_with_kernel_events": ms_events / args.steps,
         "dit_only_steps_per_sec": n_img * NUM_STEPS / (ms_dit * 1e-3),
         "dit_tflops_per_gpu": (gemm_f + attn_f) * NUM_STEPS * args.steps / (ms_dit * 1e-3) / 1e12,

@@ -171,11 +171,11 @@ int flux2b_synchronize(flux2b_ctx* c) {
 int flux2b_set_option(flux2b_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "null argument");
   static const char* known[] = {"compute_f16", "fuse_qk_rope", "fuse_swiglu", "attn_variant", "gemm_cta_group",
-                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant", "attn_poly", "group_streams", "te_graph", "sp_disable", "vae_attn_chunk"};
+                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant", "attn_poly", "group_streams", "te_graph", "sp_disable", "vae_attn_chunk", "wq_inkernel"};
   bool ok = false;
   for (const char* k : known) ok = ok || !strcmp(k, name);
   if (!ok) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string("unknown option: ") + name);
-  if (c->finalized && (!strcmp(name, "compute_f16") || !strcmp(name, "fuse_swiglu") || !strcmp(name, "vae_f16") || !strcmp(name, "native_mx") || !strcmp(name, "mx_bn")))
+  if (c->finalized && (!strcmp(name, "compute_f16") || !strcmp(name, "fuse_swiglu") || !strcmp(name, "vae_f16") || !strcmp(name, "native_mx") || !strcmp(name, "mx_bn") || !strcmp(name, "wq_inkernel")))
     return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string(name) + " must be set before flux2b_finalize_weights");
   c->opt[name] = value;
   return 0;
@@ -438,6 +438,46 @@ int flux2b_op_gemm_mx(flux2b_ctx* c, int quant, const void* a16, const uint32_t*
   }
   return end_call(c, true);
 }
+// QuantizedLinear forward, W-only (x · dequant(W)^T): the packed codes are dequantized inside the GEMM kernel (in_kernel = 1) or
+// expanded to a dense 16-bit matrix first (in_kernel = 0, the cross-check); both give the same bits.
+int flux2b_op_linear_quantized(flux2b_ctx* c, int quant, const void* x16, const uint32_t* w_packed, const void* w_scales,
+                               const void* w_biases, int sb_dtype, int M, int N, int K, float* out, int in_kernel, int cta_group) {
+  F2B_TRY(check_ctx(c));
+  int bits, group, has_b, sdt;
+  if (!quant_params(quant, &bits, &group, &has_b, &sdt)) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "not a quantized mode");
+  if (M < 1 || N < 1 || K < 64 || K % 64) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "quantized linear: K must be a positive multiple of 64");
+  if (has_b && (!w_biases || (sb_dtype != FLUX2B_F16 && sb_dtype != FLUX2B_BF16_T)))
+    return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "affine modes need biases and 16-bit scales / biases (f16 or bf16)");
+  const size_t wrow = (size_t)K * bits / 8, G = (size_t)K / group, sb_bytes = G * (has_b ? 2 : 1);
+  const void *dx, *dw, *ds, *db;
+  F2B_TRY(dev_in(c, x16, (size_t)M * K * 2, &dx));
+  F2B_TRY(dev_in(c, w_packed, (size_t)N * wrow, &dw));
+  F2B_TRY(dev_in(c, w_scales, (size_t)N * sb_bytes, &ds));
+  F2B_TRY(dev_in(c, has_b ? w_biases : nullptr, (size_t)N * sb_bytes, &db));
+  void* dout; bool ho;
+  F2B_TRY(dev_out(c, out, (size_t)M * N * 4, &dout, &ho));
+  GemmProblem g;
+  g.A = dx; g.lda = K; g.M = M; g.N = N; g.K = K;
+  g.epi.mode = EPI_F32; g.epi.f16 = c->f16(); g.epi.out = dout; g.epi.ldo = N;
+  g.force_cta_group = cta_group;
+  DevBuf dense;
+  if (in_kernel) {
+    g.wq = quant; g.B = dw; g.ldb = (int64_t)wrow; g.wq_scales = ds; g.wq_biases = db; g.wq_sb_ld = (int)G;
+    g.wq_sb_bf16 = (has_b && sb_dtype == FLUX2B_BF16_T) ? 1 : 0;
+  } else {
+    F2B_CUDA(dense.alloc((size_t)N * K * 2));
+    F2B_CUDA(dequantize_matrix(quant, (const uint32_t*)dw, ds, db, N, K, dense.p, c->f16() ? FLUX2B_F16 : FLUX2B_BF16_T, c->stream,
+                               has_b ? sb_dtype : FLUX2B_F16));
+    g.B = dense.p; g.ldb = K; g.force_bn = 256;
+  }
+  {
+    ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * M * N * (double)K, 2.0 * M * K + (double)N * wrow + 4.0 * M * N);
+    F2B_CUDA(gemm_launch(g, c->stream));
+  }
+  F2B_TRY(finish_out(c, out, dout, (size_t)M * N * 4, ho));
+  return end_call(c, true);
+}
+
 int flux2b_op_gemm_mxfp8(flux2b_ctx* c, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N, int K,
                          float* out, uint8_t* a8_out, uint8_t* sfa_out) {
   return flux2b_op_gemm_mx(c, FLUX2B_MXFP8, a16, w_packed, w_scales, M, N, K, out, a8_out, sfa_out, 0, 0);

@@ -88,6 +88,12 @@ struct Lin {
   DevBuf wq, sfb;
   int mx = 0;  // 0 = dense 16-bit operand in `w`; 1 / 2 / 3 = mxfp8 / mxfp4 / nvfp4 operand in `wq` + `sfb`
   int bn = 0;  // block-scaled operands: GEMM N tile (128 | 256); SwiGLU producers are row-interleaved per tile of this size
+  // W-only quantized layers dequantized inside the kernels (option wq_inkernel, default 1): `wq` = MLX's packed codes
+  // [N, K * bits / 8] (rows fused / re-tiled like `w`), `ws` / `wb` = group scales / biases row-major [N, K / group] in the
+  // checkpoint's type. `w` is then not materialised: the packed form is the only resident copy of the layer.
+  DevBuf ws, wb;
+  int wmode = 0;       // 0 = off; 1..5 = flux2b_quant of the codes
+  int w_sb_bf16 = 0;   // affine scales / biases are bf16 (else f16)
 };
 struct DoubleBlockW {
   Lin qkv_img, qkv_txt, out_img, out_txt, ff_in_img, ff_out_img, ff_in_txt, ff_out_txt;

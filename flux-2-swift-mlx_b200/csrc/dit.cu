@@ -32,7 +32,18 @@ static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int
   epi.f16 = c->f16() ? 1 : 0;
   g.epi = epi;
   double bytes;
-  if (W.mx) {
+  if (W.wmode) {
+    // W-only: x · dequant(W)^T with the weight dequantized inside the kernel (packed codes are all that is read from HBM)
+    const int bits = (W.wmode == 1 || W.wmode == 3) ? 8 : 4, group = W.wmode <= 2 ? 64 : W.wmode == 5 ? 16 : 32;
+    const int esz = W.wmode <= 2 ? 2 : 1;
+    g.A = A; g.lda = lda;
+    g.wq = W.wmode; g.wq_sb_bf16 = W.w_sb_bf16; g.wq_sb_ld = W.K / group;
+    g.B = W.wq.as<uint8_t>() + k_off * bits / 8; g.ldb = (int64_t)W.K * bits / 8;
+    g.wq_scales = W.ws.as<uint8_t>() + (k_off / group) * esz;
+    g.wq_biases = W.wb.p ? W.wb.as<uint8_t>() + (k_off / group) * esz : nullptr;
+    g.force_cta_group = c->option("gemm_cta_group", 0);
+    bytes = 2.0 * ((double)M * g.K + (double)M * g.N) + (double)g.N * g.K * bits / 8 + (double)g.N * (g.K / group) * esz * (W.wb.p ? 2 : 1);
+  } else if (W.mx) {
     if (!qa || !qa->q) return fail(FLUX2B_ERR_GENERATION_FAILED, "internal: block-scaled weight without a quantised activation");
     const int bits = W.mx == 1 ? 8 : 4, group = W.mx == 3 ? 16 : 32;
     g.mx = W.mx; g.force_bn = W.bn;
@@ -221,6 +232,13 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
     F2B_CUDA(timestep_sinusoid(t, sinus, 1, 1000.0f, st));
   }
   auto gemv_p = [&](const float* x, const Lin& W, float* y, bool silu_in, bool accumulate) -> int {
+    if (W.wmode) {
+      const int bits = (W.wmode == 1 || W.wmode == 3) ? 8 : 4, group = W.wmode <= 2 ? 64 : W.wmode == 5 ? 16 : 32;
+      ProfScope ps(c, FLUX2B_PROF_GEMV, 2.0 * W.N * W.K, (double)W.N * W.K * bits / 8 + (double)W.N * (W.K / group) * (W.wmode <= 2 ? 4 : 1));
+      F2B_CUDA(gemv_q(x, W.K, W.wq.p, (int64_t)W.K * bits / 8, W.ws.p, W.wb.p, W.K / group, W.wmode, W.w_sb_bf16, y, W.N, 1, W.N, W.K,
+                      silu_in, accumulate, f16, st));
+      return 0;
+    }
     ProfScope ps(c, FLUX2B_PROF_GEMV, 2.0 * W.N * W.K, 2.0 * W.N * W.K);
     F2B_CUDA(gemv(x, W.K, W.w.p, W.K, y, W.N, 1, W.N, W.K, silu_in, accumulate, f16, st));
     return 0;
@@ -407,7 +425,13 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
   QView q_img, q_txt, q_all, q_mlp;
   // option group_streams (default 1): one launch per operation for both streams (16-bit operands, fused epilogues, single GPU)
   bool group = P == 1 && !mxk && fuse_qk && S_txt > 0 && S_txt % 256 == 0 && S_im_all > 0 && c->option("group_streams", 1) != 0;
-  for (int i = 0; group && i < cfg.num_layers; ++i) group = c->dbl[i].ff_tiled && !c->dbl[i].qkv_img.mx;
+  for (int i = 0; group && i < cfg.num_layers; ++i) {
+    const DoubleBlockW& b = c->dbl[i];
+    group = b.ff_tiled && !b.qkv_img.mx && b.qkv_img.wmode == b.qkv_txt.wmode && b.out_img.wmode == b.out_txt.wmode &&
+            b.ff_in_img.wmode == b.ff_in_txt.wmode && b.ff_out_img.wmode == b.ff_out_txt.wmode &&
+            b.qkv_img.w_sb_bf16 == b.qkv_txt.w_sb_bf16 && b.out_img.w_sb_bf16 == b.out_txt.w_sb_bf16 &&
+            b.ff_in_img.w_sb_bf16 == b.ff_in_txt.w_sb_bf16 && b.ff_out_img.w_sb_bf16 == b.ff_out_txt.w_sb_bf16;
+  }
   for (int i = 0; i < cfg.num_layers; ++i) {
     DoubleBlockW& b = c->dbl[i];
     uint16_t* XNi = XN + (size_t)S_txt * D;
@@ -425,11 +449,18 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
         GemmProblem g;
         g.M = S; g.N = Wimg.N; g.K = Wimg.K;
         g.A = A; g.lda = lda; g.B = Wimg.w.p; g.ldb = Wimg.K; g.B_lo = Wtxt.w.p; g.M_lo = S_txt;
+        double wbytes = 2.0 * 2.0 * (double)g.N * g.K;
+        if (Wimg.wmode) {
+          const int bits = (Wimg.wmode == 1 || Wimg.wmode == 3) ? 8 : 4, group = Wimg.wmode <= 2 ? 64 : Wimg.wmode == 5 ? 16 : 32;
+          g.wq = Wimg.wmode; g.wq_sb_bf16 = Wimg.w_sb_bf16; g.wq_sb_ld = Wimg.K / group;
+          g.B = Wimg.wq.p; g.B_lo = Wtxt.wq.p; g.ldb = (int64_t)Wimg.K * bits / 8;
+          g.wq_scales = Wimg.ws.p; g.wq_biases = Wimg.wb.p; g.wq_scales_lo = Wtxt.ws.p; g.wq_biases_lo = Wtxt.wb.p;
+          wbytes = 2.0 * ((double)g.N * g.K * bits / 8 + (double)g.N * (g.K / group) * (Wimg.wmode <= 2 ? 4 : 1));
+        }
         e.f16 = f16 ? 1 : 0; e.split_row = S_txt;
         g.epi = e;
         g.force_cta_group = c->option("gemm_cta_group", 0);
-        ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * S * (double)g.N * g.K,
-                     2.0 * ((double)S * g.K + 2.0 * (double)g.N * g.K + (double)S * g.N));
+        ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * S * (double)g.N * g.K, 2.0 * ((double)S * g.K + (double)S * g.N) + wbytes);
         F2B_CUDA(gemm_launch(g, st));
         return 0;
       };

@@ -331,6 +331,86 @@ cudaError_t gemv(const float* x, int64_t ldx, const void* W16, int64_t ldw, floa
   return cudaGetLastError();
 }
 
+// GEMV over a W-only quantized weight (MLX's packed codes + group scales / biases, modes 1..5 = flux2b_quant): the same loop as
+// gemv_kernel — lane = 8 consecutive k per iteration, fp32 FMA chain in the same order — with the eight weights produced in
+// registers by dequantize_kernel's arithmetic (quant.cu) and rounded once to the 16-bit operand type, i.e. exactly the numbers
+// the dense working copy would hold: the result is bit-identical to gemv over the dequantized matrix.
+template <int MAXB>
+__global__ void __launch_bounds__(256) gemv_q_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ codes,
+                                                     int64_t row_bytes, const uint8_t* __restrict__ scales,
+                                                     const uint8_t* __restrict__ biases, int64_t sb_ld, int mode, int sb_bf16,
+                                                     float* __restrict__ y, int64_t ldy, int B, int N, int K, bool silu_in,
+                                                     bool accumulate, bool f16) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const bool eight = mode == 1 || mode == 3;
+  const int group = mode <= 2 ? 64 : mode == 5 ? 16 : 32;
+  const uint8_t* cr = codes + (int64_t)warp * row_bytes;
+  float acc[MAXB];
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+  auto sb = [&](const uint8_t* p, int64_t i) {
+    const uint16_t h = __ldg(reinterpret_cast<const uint16_t*>(p) + i);
+    return sb_bf16 ? __uint_as_float((uint32_t)h << 16) : __half2float(__ushort_as_half(h));
+  };
+  for (int k = lane * 8; k < K; k += 256) {
+    uint32_t w0, w1 = 0;
+    if (eight) { const uint2 q = __ldg(reinterpret_cast<const uint2*>(cr + k)); w0 = q.x; w1 = q.y; }
+    else w0 = __ldg(reinterpret_cast<const uint32_t*>(cr + (k >> 1)));
+    const int64_t gi = (int64_t)warp * sb_ld + k / group;
+    float wf[8];
+    if (mode <= 2) {
+      const float s = sb(scales, gi), bi = sb(biases, gi);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t q = eight ? (((j < 4 ? w0 : w1) >> (8 * (j & 3))) & 0xffu) : ((w0 >> (4 * j)) & 0xfu);
+        wf[j] = __fadd_rn(__fmul_rn((float)q, s), bi);
+      }
+    } else {
+      const uint8_t sbyte = __ldg(scales + gi);
+      const float s = mode == 5 ? from_e4m3(sbyte) : from_e8m0(sbyte);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float ev = eight ? from_e4m3((uint8_t)(((j < 4 ? w0 : w1) >> (8 * (j & 3))) & 0xffu)) : from_e2m1((uint8_t)((w0 >> (4 * j)) & 0xfu));
+        wf[j] = __fmul_rn(ev, s);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wf[j] = f16 ? __half2float(__float2half_rn(wf[j])) : __bfloat162float(__float2bfloat16(wf[j]));
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+      if (b < B) {
+        const float4 x0 = *reinterpret_cast<const float4*>(x + b * ldx + k);
+        const float4 x1 = *reinterpret_cast<const float4*>(x + b * ldx + k + 4);
+        float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xi = silu_in ? silu_f(xv[i]) : xv[i];
+          acc[b] = fmaf(xi, wf[i], acc[b]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) {
+    if (b < B) {
+      const float r = warp_sum(acc[b]);
+      if (lane == 0) y[b * ldy + warp] = accumulate ? y[b * ldy + warp] + r : r;
+    }
+  }
+}
+cudaError_t gemv_q(const float* x, int64_t ldx, const void* codes, int64_t row_bytes, const void* scales, const void* biases, int64_t sb_ld,
+                   int mode, int sb_bf16, float* y, int64_t ldy, int B, int N, int K, bool silu_in, bool accumulate, bool f16, cudaStream_t s) {
+  if (B > 8 || K % 16 || row_bytes % 8 || ldx % 4 || mode < 1 || mode > 5 || !scales || (mode <= 2 && !biases)) return cudaErrorInvalidValue;
+  const int blocks = (N * 32 + 255) / 256;
+  const uint8_t *c8 = (const uint8_t*)codes, *s8 = (const uint8_t*)scales, *b8 = (const uint8_t*)biases;
+  if (B <= 1) gemv_q_kernel<1><<<blocks, 256, 0, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
+  else if (B <= 2) gemv_q_kernel<2><<<blocks, 256, 0, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
+  else gemv_q_kernel<8><<<blocks, 256, 0, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ sinusoid / rope table
 __global__ void sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int B, float pre_scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -34,6 +34,10 @@ cudaError_t copy_f32_to_any(const float* in, int64_t ldi, void* out, int64_t ldo
 // y[b, n] = sum_k act(x[b, k]) * W[n, k] ; W 16-bit [N, K] row-major; act = SiLU if silu_in. B <= 8.
 cudaError_t gemv(const float* x, int64_t ldx, const void* W16, int64_t ldw, float* y, int64_t ldy, int B, int N, int K,
                  bool silu_in, bool accumulate, bool f16, cudaStream_t s);
+// the same over a W-only quantized weight (packed codes [N, row_bytes], scales / biases [N, sb_ld]; mode = flux2b_quant 1..5):
+// bit-identical to gemv over the dequantized 16-bit matrix
+cudaError_t gemv_q(const float* x, int64_t ldx, const void* codes, int64_t row_bytes, const void* scales, const void* biases, int64_t sb_ld,
+                   int mode, int sb_bf16, float* y, int64_t ldy, int B, int N, int K, bool silu_in, bool accumulate, bool f16, cudaStream_t s);
 
 // Timesteps(256): out[b, 0:128] = cos(t*1000*f_i), out[b, 128:256] = sin(...), f_i = exp(-ln(1e4) i / 128)
 // (Flux2Embeddings.swift:27-44; the x1000 is Flux2Transformer.swift:145-146).

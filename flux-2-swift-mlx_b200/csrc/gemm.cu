@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <string>
+#include <type_traits>
 
 namespace f2b {
 
@@ -45,11 +46,20 @@ struct KParams {
   const uint8_t* sfb;
   int sfa_ld, sfb_ld;
   int split_units;  // two-problem launch: M units below this one read B through the second weight map (passed in the tmSFB slot)
+  // W-only quantized weights (WQ kernels): B arrives as MLX's packed bytes and is dequantized to the 16-bit operand by four
+  // extra warps on its way into the swizzled B stage. wq_mode = flux2b_quant (1 qint8, 2 int4, 3 mxfp8, 4 mxfp4, 5 nvfp4);
+  // scales / biases row-major [N, wq_sb_ld groups] in their checkpoint type (affine: f16 / bf16, wq_sb_bf16; mx: one byte)
+  int wq_mode, wq_sb_bf16, wq_sb_ld, wq_vec;   // wq_vec: 16 B loads of 8 (4 for nvfp4) k-blocks of scales are aligned
+  const uint8_t* wq_s;  const uint8_t* wq_b;   // main problem
+  const uint8_t* wq_s_lo; const uint8_t* wq_b_lo;  // rows below split_units (two-problem launch)
   int dbg;  // FLUX2B_GEMM_TIMELINE=1: cluster 0 prints where its producer / issuer / epilogue warps waited (debug aid)
 };
 
 // MXK: 0 = 16-bit operands, 1 = mxfp8 (E4M3, E8M0 scale / 32), 2 = mxfp4 (E2M1, E8M0 / 32), 3 = nvfp4 (E2M1, E4M3 / 16)
-template <int BN, int CG, int MXK = 0>
+// WQ kernels: a ring of packed-weight slots (TMA destination, 64 B-/32 B-swizzled rows of 64 / 32 bytes = 64 K elements) beside
+// the operand stages; 128 more threads (warps 6..9) turn slot -> 16-bit B stage
+static constexpr int WQ_PSTAGES = 4;
+template <int BN, int CG, int MXK = 0, int WQ = 0>
 struct Cfg {
   static constexpr int B_ROWS = BN / CG;
   static constexpr int A_BYTES = BM * BK * 2;      // 128 rows x 128 B: 64 bf16, 128 fp8 or 256 fp4 elements along K
@@ -61,7 +71,9 @@ struct Cfg {
   static constexpr int SFB_BYTES = (BN / 128) * 512 * SFPK;
   static constexpr int SF_BYTES = SFA_BYTES + SFB_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + SF_BYTES;
-  static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+  static constexpr int PSLOT_BYTES = WQ ? B_ROWS * 64 : 0;            // sized for 8-bit codes; 4-bit modes use half of a slot
+  static constexpr int PRING_BYTES = WQ_PSTAGES * PSLOT_BYTES;
+  static constexpr int STAGES_RAW = (196 * 1024 - PRING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // accumulator stages in TMEM: two, except the 256-wide block-scaled tile, whose scale factors need columns too
   static constexpr int ACC_STAGES = (MXK && BN == 256) ? 1 : 2;
@@ -70,7 +82,8 @@ struct Cfg {
   static constexpr int COLS_NEEDED = ACC_STAGES * BN + SF_COLS;
   static constexpr int TMEM_COLS = (COLS_NEEDED <= 32) ? 32 : (COLS_NEEDED <= 64) ? 64 : (COLS_NEEDED <= 128) ? 128 : (COLS_NEEDED <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PRING_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int THREADS = WQ ? 320 : 192;
 };
 
 // ------------------------------------------------------------------------------------------------ epilogue
@@ -364,24 +377,118 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ W-only dequant (WQ kernels)
+// One B row of one k-block: 64 packed codes from a slot row (TMA wrote the slot 64 B- / 32 B-swizzled, so the 16 B loads of a
+// quarter warp hit distinct banks) -> 64 16-bit operands in the 128 B-swizzled K-major B stage. The arithmetic is
+// dequantize_kernel's (quant.cu), operation for operation — q * scale + bias as separate fp32 multiply and add, block-scaled
+// element * scale as one fp32 multiply, one rounding to the operand type — so the tile holds exactly the bits the dense working
+// copy would hold and the GEMM result is bit-identical to the dense-copy path.
+__device__ __forceinline__ float wq_u8_to_float(uint32_t word, int j) {
+  // (float)byte_j without I2F (quarter rate): 0x4B000000 | q is the float 2^23 + q; the subtraction is exact
+  return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (uint32_t)j)) - 8388608.0f;
+}
+__device__ __forceinline__ float wq_sb_to_float(uint16_t h, int bf16) {
+  return bf16 ? __uint_as_float((uint32_t)h << 16) : __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ void wq_store_chunk(uint8_t* brow, int r, int oc, const float (&v)[8], int f16) {
+  *reinterpret_cast<uint4*>(brow + ((oc ^ (r & 7)) << 4)) =
+      make_uint4(pk2(v[0], v[1], f16), pk2(v[2], v[3], f16), pk2(v[4], v[5], f16), pk2(v[6], v[7], f16));
+}
+// MODE = flux2b_quant. `sc` / `bi`: this row's scales / biases for THIS k-block, already in registers:
+//   affine: sc = scale, bi = bias (fp32 values of the stored 16-bit numbers); mx: sc[0..1] (group 32) / nv: sc[0..3] (group 16)
+template <int MODE>
+__device__ __forceinline__ void wq_dequant_row(const uint8_t* slot, uint8_t* bstage, int r, const float (&sc)[4], float bi, int f16) {
+  uint8_t* brow = bstage + r * 128;
+  if constexpr (MODE == 1) {          // qint8: 64 bytes, slot rows of 64 B, 64 B swizzle: chunk c at c ^ ((r >> 1) & 3)
+    const uint8_t* src = slot + r * 64;
+    const int sw = (r >> 1) & 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 q = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __fadd_rn(__fmul_rn(wq_u8_to_float(w[2 * h + (j >> 2)], j & 3), sc[0]), bi);
+        wq_store_chunk(brow, r, 2 * c + h, v, f16);
+      }
+    }
+  } else if constexpr (MODE == 3) {   // mxfp8: E4M3 bytes, scale per 32 elements
+    const uint8_t* src = slot + r * 64;
+    const int sw = (r >> 1) & 3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 q = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      const float s = sc[c >> 1];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t word = w[2 * h + (j >> 1)];
+          const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((word >> (16 * (j & 1))) & 0xffffu), __NV_E4M3);
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hr));
+          v[2 * j] = __fmul_rn(f.x, s); v[2 * j + 1] = __fmul_rn(f.y, s);
+        }
+        wq_store_chunk(brow, r, 2 * c + h, v, f16);
+      }
+    }
+  } else {                            // 4-bit codes: 32 bytes, slot rows of 32 B, 32 B swizzle: chunk c at c ^ ((r >> 2) & 1)
+    const uint8_t* src = slot + r * 32;
+    const int sw = (r >> 2) & 1;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const uint4 q = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {   // one word = 8 codes = one 16 B operand chunk
+        float v[8];
+        if constexpr (MODE == 2) {    // int4 affine
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float qf = __uint_as_float(0x4B000000u | ((w[i] >> (4 * j)) & 0xFu)) - 8388608.0f;
+            v[j] = __fadd_rn(__fmul_rn(qf, sc[0]), bi);
+          }
+        } else {                      // mxfp4 (scale per 32 = per 4 words) / nvfp4 (scale per 16 = per 2 words)
+          const float s = MODE == 4 ? sc[c] : sc[2 * c + (i >> 1)];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __half2_raw hr = __nv_cvt_fp4x2_to_halfraw2((__nv_fp4x2_storage_t)((w[i] >> (8 * j)) & 0xffu), __NV_E2M1);
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hr));
+            v[2 * j] = __fmul_rn(f.x, s); v[2 * j + 1] = __fmul_rn(f.y, s);
+          }
+        }
+        wq_store_chunk(brow, r, 4 * c + i, v, f16);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN, int CG, bool CONV, int MXK = 0>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int CG, bool CONV, int MXK = 0, int WQ = 0>
+__global__ void __launch_bounds__(WQ ? 320 : 192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmSFA, const __grid_constant__ CUtensorMap tmSFB, const KParams p) {
-  using C = Cfg<BN, CG, MXK>;
+  using C = Cfg<BN, CG, MXK, WQ>;
   static_assert(!MXK || (!CONV && (BN == 128 || (BN == 256 && CG == 1))), "block-scaled tiles: BN 128 (1 or 2 CTAs) / 256 (1 CTA)");
+  static_assert(!WQ || (!CONV && !MXK && BN == 256), "W-only quantized weights: plain GEMM, 256-wide tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;
   uint8_t* smB = smem + C::STAGES * C::A_BYTES;
   uint8_t* smSF = smB + C::STAGES * C::B_BYTES;  // [STAGES][SFA SFPK x 512 | SFB (BN/128) x SFPK x 512]   (block-scaled only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
-  uint64_t* empty = bars + C::STAGES;       // [STAGES]  MMA -> TMA
+  uint8_t* smP = smem + C::STAGES * C::STAGE_BYTES;   // [WQ_PSTAGES][PSLOT_BYTES] packed-weight slots (WQ only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smP + C::PRING_BYTES);
+  uint64_t* full = bars;                    // [STAGES]  TMA (+ dequant warps) -> MMA
+  uint64_t* empty = bars + C::STAGES;       // [STAGES]  MMA -> TMA (+ dequant warps)
   uint64_t* tfull = bars + 2 * C::STAGES;   // [2]       MMA -> epilogue
   uint64_t* tempty = tfull + 2;             // [2]       epilogue -> MMA   (only ACC_STAGES of each are used)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* pfull = tempty + 2;             // [WQ_PSTAGES]  TMA -> dequant warps   (WQ only)
+  uint64_t* pempty = pfull + WQ_PSTAGES;    // [WQ_PSTAGES]  dequant warps -> TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + WQ_PSTAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -399,8 +506,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full[s], CG);  // one arrive.expect_tx per CTA of the pair
+      mbar_init(&full[s], WQ ? CG * 5 : CG);  // one arrive.expect_tx per CTA of the pair (+ one arrive per dequant warp)
       mbar_init(&empty[s], 1);  // one tcgen05.commit
+    }
+    if (WQ) {
+      for (int s = 0; s < WQ_PSTAGES; ++s) {
+        mbar_init(&pfull[s], 1);    // the producer's arrive.expect_tx (CTA-local)
+        mbar_init(&pempty[s], 4);   // one arrive per dequant warp
+      }
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);        // one tcgen05.commit
@@ -423,6 +536,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int pstage = 0, pk_tile = unit_id, pk_kb = 0;   // WQ: cursor of the packed-weight stream
+      uint32_t pphase = 0;
+      (void)pstage; (void)pphase; (void)pk_tile; (void)pk_kb;
       const bool dbg = p.dbg && unit_id == 0;
       long long w_empty = 0, t_begin = dbg ? clock64() : 0;
       for (int t = unit_id; t < total_tiles; t += num_units) {
@@ -431,6 +547,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m_blk = m_unit * CG + (int)cta_rank;
         const int nrow0 = n_blk * BN + (int)cta_rank * C::B_ROWS;
         const CUtensorMap* tmBsel = (MXK == 0 && !CONV && m_unit < p.split_units) ? &tmSFB : &tmB;
+        (void)tmBsel;
         int img = 0, y0 = 0, x0 = 0;
         if (CONV) {
           const int per_img = p.tiles_x * p.tiles_y;
@@ -439,6 +556,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           y0 = (r / p.tiles_x) * CONV_TH;
           x0 = (r % p.tiles_x) * CONV_TW;
         }
+        if constexpr (WQ != 0) {
+          // W-only quantized weights: this CTA's B rows arrive as packed codes in their own slot ring, as one continuous stream
+          // over (tile, k-block) that runs WQ_PSTAGES - 1 blocks ahead of the A loads — across tile boundaries too (the dequant
+          // warps need the codes the moment a B stage frees). A goes the usual way, and only its bytes are expected on `full`:
+          // the dequant warps arrive there once the 16-bit B tile is written.
+          const int pcol = (p.wq_mode == 1 || p.wq_mode == 3) ? 64 : 32;   // packed bytes per row per k-block
+          auto packed_next = [&]() {
+            if (pk_tile >= total_tiles) return;
+            const int pm_unit = pk_tile % p.num_m_units, pn_blk = pk_tile / p.num_m_units;
+            const CUtensorMap* tmP = (pm_unit < p.split_units) ? &tmSFB : &tmB;
+            mbar_wait(&pempty[pstage], pphase ^ 1, 5);
+            mbar_expect_tx(&pfull[pstage], (uint32_t)(C::B_ROWS * pcol));
+            tma_load_2d(smP + pstage * C::PSLOT_BYTES, tmP, &pfull[pstage], pk_kb * pcol, pn_blk * BN + (int)cta_rank * C::B_ROWS);
+            if (++pstage == WQ_PSTAGES) { pstage = 0; pphase ^= 1; }
+            if (++pk_kb == p.num_kb) { pk_kb = 0; pk_tile += num_units; }
+          };
+          if (t == unit_id)
+            for (int i = 0; i < WQ_PSTAGES - 1; ++i) packed_next();
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            packed_next();
+            mbar_wait(&empty[stage], phase ^ 1, 1);
+            void* a_dst = smA + stage * C::A_BYTES;
+            if (CG == 1) {
+              mbar_expect_tx(&full[stage], C::A_BYTES);
+              tma_load_2d(a_dst, &tmA, &full[stage], kb * BK, m_blk * BM);
+            } else {
+              const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+              mbar_expect_tx_cluster(lbar, C::A_BYTES);
+              tma_load_2d_cg2(a_dst, &tmA, lbar, kb * BK, m_blk * BM);
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        if constexpr (WQ == 0)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           long long t0 = dbg ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1, 1);
@@ -586,6 +737,103 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         printf("[gemm timeline] issuer: total %lld clk, waited on operands %lld clk, on accumulator drain %lld clk (%d k-blocks / tile); last MMA issued at %llu ns\n",
                clock64() - t_begin, w_full, w_tempty, p.num_kb, (unsigned long long)(globaltimer_ns() - t_entry));
     }
+  } else if (warp >= 6) {
+   if constexpr (WQ != 0) {
+    // ===================================================== dequant warps (6..9, WQ only): packed slot -> 16-bit B stage
+    // Thread = B row (two rows per thread for single-CTA tiles). Scales / biases of 8 k-blocks (4 for nvfp4) sit in registers,
+    // fetched with one 16 B load per tensor when the row's group array is 16 B aligned (K % 512 == 0), else one by one.
+    const int dt = threadIdx.x - 192;
+    auto run = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
+      constexpr int RPT = C::B_ROWS / 128;           // rows per thread
+      constexpr int GPK = MODE <= 2 ? 1 : MODE == 5 ? 4 : 2;   // scale groups per k-block
+      constexpr int KBV = MODE <= 2 ? 8 : 16 / GPK;            // k-blocks covered by one 16 B load
+      int stage = 0, pstage = 0;
+      uint32_t phase = 0, pphase = 0;
+      for (int t = unit_id; t < total_tiles; t += num_units) {
+        const int m_unit = t % p.num_m_units;
+        const int n_blk = t / p.num_m_units;
+        const bool lo = m_unit < p.split_units;
+        const uint8_t* sbase = lo ? p.wq_s_lo : p.wq_s;
+        const uint8_t* bbase = lo ? p.wq_b_lo : p.wq_b;
+        const int nrow0 = n_blk * BN + (int)cta_rank * C::B_ROWS;
+        uint4 sv[RPT], bv[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) { sv[i] = make_uint4(0, 0, 0, 0); bv[i] = make_uint4(0, 0, 0, 0); }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          if (p.wq_vec && (kb % KBV) == 0) {
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+              const int64_t grow = nrow0 + dt + 128 * i;
+              if (grow < p.N) {
+                const size_t off = ((size_t)grow * p.wq_sb_ld + (size_t)kb * GPK) * (MODE <= 2 ? 2 : 1);
+                sv[i] = __ldg(reinterpret_cast<const uint4*>(sbase + off));
+                if (MODE <= 2) bv[i] = __ldg(reinterpret_cast<const uint4*>(bbase + off));
+              }
+            }
+          }
+          mbar_wait(&pfull[pstage], pphase, 6);
+          mbar_wait(&empty[stage], phase ^ 1, 7);
+          const uint8_t* slot = smP + pstage * C::PSLOT_BYTES;
+          uint8_t* bst = smB + stage * C::B_BYTES;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            const int r = dt + 128 * i;
+            const int64_t grow = nrow0 + r;
+            float sc[4] = {0.f, 0.f, 0.f, 0.f};
+            float bi = 0.f;
+            if (grow < p.N) {
+              if (MODE <= 2) {
+                uint16_t sh, bh;
+                if (p.wq_vec) {
+                  const int j = kb % 8;
+                  const uint32_t sw = j < 2 ? sv[i].x : j < 4 ? sv[i].y : j < 6 ? sv[i].z : sv[i].w;
+                  const uint32_t bw = j < 2 ? bv[i].x : j < 4 ? bv[i].y : j < 6 ? bv[i].z : bv[i].w;
+                  sh = (uint16_t)(sw >> (16 * (j & 1))); bh = (uint16_t)(bw >> (16 * (j & 1)));
+                } else {
+                  const size_t off = (size_t)grow * p.wq_sb_ld + kb;
+                  sh = __ldg(reinterpret_cast<const uint16_t*>(sbase) + off); bh = __ldg(reinterpret_cast<const uint16_t*>(bbase) + off);
+                }
+                sc[0] = wq_sb_to_float(sh, p.wq_sb_bf16); bi = wq_sb_to_float(bh, p.wq_sb_bf16);
+              } else {
+                uint32_t word;   // this k-block's GPK scale bytes in the low bytes
+                if (p.wq_vec) {
+                  const int j = (kb % KBV) * GPK;   // byte index within the 16 B
+                  const uint32_t w4 = j < 4 ? sv[i].x : j < 8 ? sv[i].y : j < 12 ? sv[i].z : sv[i].w;
+                  word = w4 >> (8 * (j & 3));
+                } else {
+                  word = 0;
+                  for (int g = 0; g < GPK; ++g) word |= (uint32_t)__ldg(sbase + (size_t)grow * p.wq_sb_ld + (size_t)kb * GPK + g) << (8 * g);
+                }
+#pragma unroll
+                for (int g = 0; g < GPK; ++g) {
+                  const uint8_t sb = (uint8_t)(word >> (8 * g));
+                  sc[g] = MODE == 5 ? from_e4m3(sb) : from_e8m0(sb);
+                }
+              }
+            }
+            // rows past N: the TMA zero-filled the codes and the scales stay 0 -> zeros (never read back by a valid output column)
+            wq_dequant_row<MODE>(slot, bst, r, sc, bi, p.epi.f16);
+          }
+          fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 1) mbar_arrive(&full[stage]); else mbar_arrive_cluster(mapa_u32(smem_u32(&full[stage]), 0));
+            mbar_arrive(&pempty[pstage]);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++pstage == WQ_PSTAGES) { pstage = 0; pphase ^= 1; }
+        }
+      }
+    };
+    switch (p.wq_mode) {
+      case 1: run(std::integral_constant<int, 1>{}); break;
+      case 2: run(std::integral_constant<int, 2>{}); break;
+      case 3: run(std::integral_constant<int, 3>{}); break;
+      case 4: run(std::integral_constant<int, 4>{}); break;
+      default: run(std::integral_constant<int, 5>{}); break;
+    }
+   }
   } else {
     // ===================================================== epilogue warps (2..5): TMEM lane quarter = warp % 4
     const int quarter = warp & 3;
@@ -795,6 +1043,71 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmSFA, tmSFB, p);
 }
 
+// W-only quantized weights: 256-wide tiles, CTA pairs when there are at least two 128-row blocks
+template <int CG>
+static cudaError_t launch_wq(const GemmProblem& g, cudaStream_t stream) {
+  constexpr int BN = 256;
+  using C = Cfg<BN, CG, 0, 1>;
+  KParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.epi = g.epi;
+  p.num_kb = g.K / BK;
+  const int bits = (g.wq == 1 || g.wq == 3) ? 8 : 4;
+  const int group = g.wq <= 2 ? 64 : g.wq == 5 ? 16 : 32;
+  p.wq_mode = g.wq; p.wq_sb_bf16 = g.wq_sb_bf16; p.wq_sb_ld = g.wq_sb_ld ? g.wq_sb_ld : g.K / group;
+  p.wq_s = reinterpret_cast<const uint8_t*>(g.wq_scales); p.wq_b = reinterpret_cast<const uint8_t*>(g.wq_biases);
+  p.wq_s_lo = reinterpret_cast<const uint8_t*>(g.wq_scales_lo); p.wq_b_lo = reinterpret_cast<const uint8_t*>(g.wq_biases_lo);
+  {
+    // 16 B loads of a row's scales cover 8 k-blocks (4 for nvfp4): rows and the K-slice start must be 16 B aligned, and the
+    // k-block count a multiple of the span so that the last load of a row stays inside it
+    const int esz = g.wq <= 2 ? 2 : 1, span = g.wq <= 2 ? 8 : g.wq == 5 ? 4 : 8;
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    p.wq_vec = ((size_t)p.wq_sb_ld * esz) % 16 == 0 && p.num_kb % span == 0 && al(g.wq_scales) && (g.wq > 2 || al(g.wq_biases)) &&
+               (!g.B_lo || (al(g.wq_scales_lo) && (g.wq > 2 || al(g.wq_biases_lo))));
+  }
+  CUtensorMap tmA, tmB, tmBlo;
+  const int num_m_blks = (g.M + BM - 1) / BM;
+  uint64_t ad[2] = {(uint64_t)g.K, (uint64_t)g.M};
+  uint64_t as[1] = {(uint64_t)g.lda * 2};
+  uint32_t ab[2] = {BK, BM};
+  if (!make_tmap_bf16(&tmA, g.A, 2, ad, as, ab)) return cudaErrorInvalidValue;
+  // packed codes as bytes: one k-block of a row = 64 B (8-bit) or 32 B (4-bit); the slot is written 64 B- / 32 B-swizzled
+  uint64_t bd[2] = {(uint64_t)g.K * bits / 8, (uint64_t)g.N};
+  uint64_t bs[1] = {(uint64_t)g.ldb};
+  uint32_t bb[2] = {(uint32_t)(bits == 8 ? 64 : 32), (uint32_t)C::B_ROWS};
+  const CUtensorMapSwizzle swz = bits == 8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  if (!make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, g.B, 2, bd, bs, bb, swz)) return cudaErrorInvalidValue;
+  tmBlo = tmB;
+  if (g.B_lo) {
+    if (!make_tmap(&tmBlo, CU_TENSOR_MAP_DATA_TYPE_UINT8, g.B_lo, 2, bd, bs, bb, swz)) return cudaErrorInvalidValue;
+    p.split_units = g.M_lo / (BM * CG);
+  }
+  p.num_m_units = (num_m_blks + CG - 1) / CG;
+  p.num_n_blks = (g.N + BN - 1) / BN;
+  const int total = p.num_m_units * p.num_n_blks;
+  const int units = std::min(total, g_num_sms / CG);
+  auto kern = gemm_kernel<BN, CG, false, 0, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * CG);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CG; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA, tmBlo, p);
+}
+
 template <bool CONV>
 static cudaError_t dispatch(const GemmProblem& g, cudaStream_t s, int bn, int cg) {
 #define F2B_CASE(BN_)                                                     \
@@ -848,6 +1161,20 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
       case 13: return launch_cfg<256, 1, false, 3>(g, stream);
       default: return launch_cfg<128, 2, false, 3>(g, stream);
     }
+  }
+  if (g.wq) {
+    const int group = g.wq <= 2 ? 64 : g.wq == 5 ? 16 : 32;
+    if (g.wq < 1 || g.wq > 5 || conv || g.K % BK || g.lda % 8 || g.ldb % 16 || !g.wq_scales || (g.wq <= 2 && !g.wq_biases) ||
+        (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15) ||
+        (g.B_lo && (g.M_lo <= 0 || g.M_lo >= g.M || g.M_lo % (2 * BM) || (reinterpret_cast<uintptr_t>(g.B_lo) & 15) || !g.wq_scales_lo ||
+                    (g.wq <= 2 && !g.wq_biases_lo) || g.epi.split_row != g.M_lo)) ||
+        (g.epi.mode == EPI_SWIGLU && g.N % 256) || (g.wq_sb_ld && g.wq_sb_ld < g.K / group)) {
+      g_err = "W-only quantized GEMM: plain GEMM, K % 64 == 0, 16 B aligned packed rows, scales (+ biases for the affine modes)";
+      return cudaErrorInvalidValue;
+    }
+    const int m_blks = (g.M + BM - 1) / BM;
+    const bool pair = g.force_cta_group != 1 && m_blks >= 2;
+    return pair ? launch_wq<2>(g, stream) : launch_wq<1>(g, stream);
   }
   if (!conv && (g.lda % 8 || g.ldb % 8)) { g_err = "lda/ldb must be multiples of 8 elements (TMA 16 B stride)"; return cudaErrorInvalidValue; }
   if (g.B_lo && (conv || g.M_lo <= 0 || g.M_lo >= g.M || g.M_lo % (2 * BM) || (reinterpret_cast<uintptr_t>(g.B_lo) & 15) || g.epi.split_row != g.M_lo)) {

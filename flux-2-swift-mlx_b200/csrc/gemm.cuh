@@ -87,6 +87,18 @@ struct GemmProblem {
   int sfa_ld = 0, sfb_ld = 0;
   int force_cta_group = 0;  // 0 = auto, 1, 2
   int force_bn = 0;         // 0 = auto
+  // W-only quantized weights, dequantized inside the kernel on their way into the B stage (x · dequant(W)^T, the reference's
+  // arithmetic; QuantizedLinear forward, Flux2Pipeline.swift:567-578). wq = flux2b_quant 1..5; plain GEMM, K % 64 == 0.
+  // B (and B_lo) = MLX's packed codes [N, K * bits / 8] with ldb in BYTES; wq_scales / wq_biases (+ _lo) row-major
+  // [N, wq_sb_ld groups] in the checkpoint's type: affine f16 (or bf16: wq_sb_bf16), block-scaled one byte, no biases.
+  // A K-slice of a wider weight passes offset pointers and the full row's group count in wq_sb_ld.
+  int wq = 0;
+  const void* wq_scales = nullptr;
+  const void* wq_biases = nullptr;
+  const void* wq_scales_lo = nullptr;
+  const void* wq_biases_lo = nullptr;
+  int wq_sb_ld = 0;
+  int wq_sb_bf16 = 0;
 };
 
 // Returns cudaSuccess or the launch error. Never synchronises.

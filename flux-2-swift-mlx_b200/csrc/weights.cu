@@ -186,7 +186,13 @@ static int expect_shape(const std::string& base, int N, int K, int eN, int eK) {
   return 0;
 }
 
+static bool wq_eligible(flux2b_ctx* c, const std::string& base, int eK);
+static int wq_rows(flux2b_ctx* c, const std::string& base, int eN, int eK, int64_t src_row0, int64_t nrows, Lin* L, int N_total,
+                   int64_t dst_row0, bool tiled, int Hm);
+static void lin_dense_reset(Lin* L) { L->wq.release(); L->ws.release(); L->wb.release(); L->sfb.release(); L->wmode = 0; L->mx = 0; }
 static int build_lin(flux2b_ctx* c, const std::string& base, Lin* L, int eN, int eK) {
+  if (c->has_dit && wq_eligible(c, base, eK)) return wq_rows(c, base, eN, eK, 0, eN, L, eN, 0, false, 0);
+  lin_dense_reset(L);
   int N, K;
   F2B_TRY(dense16_from_key(c, base, &L->w, &N, &K));
   F2B_TRY(expect_shape(base, N, K, eN, eK));
@@ -234,12 +240,77 @@ static int mx_rows(flux2b_ctx* c, const std::string& base, int eN, int eK, int64
   if (!L->wq.p || L->N != N_total || L->K != eK || L->mx != kind || L->bn != bn) {
     F2B_CUDA(L->wq.alloc((size_t)N_total * eK * bits / 8));
     F2B_CUDA(L->sfb.alloc(mx_sf_bytes(kind, N_total, eK)));
-    L->w.release();
+    L->w.release(); L->ws.release(); L->wb.release(); L->wmode = 0;
     L->N = N_total; L->K = eK; L->mx = kind; L->bn = bn;
   }
   if (tiled && (nrows % bn || Hm % (bn / 2))) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "SwiGLU tile does not divide the MLP width: " + base);
   F2B_CUDA(mx_copy_rows(kind, w->buf.as<uint8_t>(), s->buf.as<uint8_t>(), src_row0, L->wq.as<uint8_t>(), L->sfb.as<uint8_t>(), dst_row0,
                         nrows, eK, tiled ? bn : 0, Hm, c->stream));
+  return 0;
+}
+
+// ---- W-only quantized working copies (dequantized inside the GEMM / GEMV kernels)
+// rows of `src` (row_bytes each) -> rows [dst_row0, ...) of `dst`, optionally through the SwiGLU 256-row tile interleave
+__global__ void copy_row_bytes_kernel(const uint8_t* __restrict__ src, int64_t src_row0, uint8_t* __restrict__ dst, int64_t dst_row0,
+                                      int64_t nrows, int64_t row_bytes, int unit, int tiled, int64_t Hm) {
+  const int64_t per_row = row_bytes / unit;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows * per_row) return;
+  const int64_t r = i / per_row, v = i % per_row;
+  int64_t sr = r;
+  if (tiled) {
+    const int64_t tile = r / 256, j = r % 256;
+    sr = (j < 128) ? tile * 128 + j : Hm + tile * 128 + (j - 128);
+  }
+  const uint8_t* s = src + (src_row0 + sr) * row_bytes + v * unit;
+  uint8_t* d = dst + (dst_row0 + r) * row_bytes + v * unit;
+  if (unit == 16) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+  else if (unit == 2) *reinterpret_cast<uint16_t*>(d) = *reinterpret_cast<const uint16_t*>(s);
+  else *d = *s;
+}
+static int copy_row_bytes(flux2b_ctx* c, const void* src, int64_t src_row0, void* dst, int64_t dst_row0, int64_t nrows, int64_t row_bytes,
+                          bool tiled, int64_t Hm) {
+  const int unit = (row_bytes % 16 == 0) ? 16 : (row_bytes % 2 == 0) ? 2 : 1;
+  const int64_t n = nrows * (row_bytes / unit);
+  if (n <= 0) return 0;
+  copy_row_bytes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint8_t*>(src), src_row0,
+                                                                           reinterpret_cast<uint8_t*>(dst), dst_row0, nrows, row_bytes, unit,
+                                                                           tiled ? 1 : 0, Hm);
+  F2B_CUDA(cudaGetLastError());
+  return 0;
+}
+// Can Linear `base` ([eN, eK]) run W-only inside the kernels? (packed, K a multiple of the 64-element k-block, 16-bit affine scales)
+static bool wq_eligible(flux2b_ctx* c, const std::string& base, int eK) {
+  if (c->quant == FLUX2B_BF16 || !c->option("wq_inkernel", 1) || eK % 64) return false;
+  Tensor* w = find(c, base + ".weight");
+  if (!w) return false;
+  if (w->dtype != FLUX2B_U32) return is_float_dtype(w->dtype);   // will be packed by ensure_packed with f16 scales
+  Tensor* s = find(c, base + ".scales");
+  return s && s->dtype != FLUX2B_F32;   // f32 scales (unusual) take the dense fallback
+}
+// rows [src_row0, src_row0 + nrows) of the packed Linear `base` (shape [eN, eK]) -> rows [dst_row0, ...) of L (N_total rows)
+static int wq_rows(flux2b_ctx* c, const std::string& base, int eN, int eK, int64_t src_row0, int64_t nrows, Lin* L, int N_total,
+                   int64_t dst_row0, bool tiled, int Hm) {
+  F2B_TRY(ensure_packed(c, base));
+  PackedMeta pm;
+  F2B_TRY(packed_meta(c, base, &pm));
+  F2B_TRY(expect_shape(base, (int)pm.rows, (int)pm.cols, eN, eK));
+  const int64_t row_bytes = (int64_t)eK * pm.bits / 8, G = eK / pm.group;
+  const int64_t sb_bytes = G * (pm.has_b ? 2 : 1);
+  const int sb_bf16 = (pm.has_b && pm.sb_dtype == FLUX2B_BF16_T) ? 1 : 0;
+  if (!L->wq.p || L->N != N_total || L->K != eK || L->wmode != c->quant) {
+    F2B_CUDA(L->wq.alloc((size_t)N_total * row_bytes));
+    F2B_CUDA(L->ws.alloc((size_t)N_total * sb_bytes));
+    if (pm.has_b) F2B_CUDA(L->wb.alloc((size_t)N_total * sb_bytes)); else L->wb.release();
+    L->w.release(); L->sfb.release();
+    L->N = N_total; L->K = eK; L->wmode = c->quant; L->mx = 0;
+  }
+  if (dst_row0 != 0 && L->w_sb_bf16 != sb_bf16) return fail(FLUX2B_ERR_WEIGHT_LOADING, "fused layers must share one scale type: " + base);
+  L->w_sb_bf16 = sb_bf16;
+  if (tiled && (nrows % 256 || Hm % 128)) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "SwiGLU tile does not divide the MLP width: " + base);
+  F2B_TRY(copy_row_bytes(c, pm.w->buf.p, src_row0, L->wq.p, dst_row0, nrows, row_bytes, tiled, Hm));
+  F2B_TRY(copy_row_bytes(c, pm.s->buf.p, src_row0, L->ws.p, dst_row0, nrows, sb_bytes, tiled, Hm));
+  if (pm.has_b) F2B_TRY(copy_row_bytes(c, pm.b->buf.p, src_row0, L->wb.p, dst_row0, nrows, sb_bytes, tiled, Hm));
   return 0;
 }
 
@@ -279,7 +350,14 @@ int finalize_dit(flux2b_ctx* c) {
     return build_lin(c, base, L, eN, eK);
   };
   auto stacked = [&](const std::vector<std::string>& bases, Lin* L, int eN_each, int eK) -> int {
-    if (!mx) return build_stacked(c, bases, L, eN_each, eK);
+    if (!mx) {
+      bool wq = true;
+      for (const auto& b : bases) wq = wq && wq_eligible(c, b, eK);
+      if (!wq) { lin_dense_reset(L); return build_stacked(c, bases, L, eN_each, eK); }
+      for (size_t i = 0; i < bases.size(); ++i)
+        F2B_TRY(wq_rows(c, bases[i], eN_each, eK, 0, eN_each, L, (int)bases.size() * eN_each, (int64_t)i * eN_each, false, 0));
+      return 0;
+    }
     for (size_t i = 0; i < bases.size(); ++i)
       F2B_TRY(mx_rows(c, bases[i], eN_each, eK, 0, eN_each, L, (int)bases.size() * eN_each, (int64_t)i * eN_each, false, 0));
     return 0;
@@ -290,6 +368,11 @@ int finalize_dit(flux2b_ctx* c) {
       *tiled = tile_ok;
       return mx_rows(c, base, eN, D, row0, 2 * (int64_t)Hm, L, 2 * Hm, 0, tile_ok, Hm);
     }
+    if (wq_eligible(c, base, D)) {
+      *tiled = tile_ok;
+      return wq_rows(c, base, eN, D, row0, 2 * (int64_t)Hm, L, 2 * Hm, 0, tile_ok, Hm);
+    }
+    lin_dense_reset(L);
     DevBuf tmp; int N, K;
     F2B_TRY(dense16_from_key(c, base, &tmp, &N, &K));
     F2B_TRY(expect_shape(base, N, K, eN, D));
@@ -322,7 +405,10 @@ int finalize_dit(flux2b_ctx* c) {
     // fused projection column order q | k | v | gate | up, widths D,D,D,Hm,Hm (Flux2ParallelAttention.swift:56,83-87)
     if (mx) {
       F2B_TRY(mx_rows(c, p + "attn.toQkvMlp", 3 * D + 2 * Hm, D, 0, 3 * (int64_t)D, &b.qkv, 3 * D, 0, false, 0));
+    } else if (wq_eligible(c, p + "attn.toQkvMlp", D)) {
+      F2B_TRY(wq_rows(c, p + "attn.toQkvMlp", 3 * D + 2 * Hm, D, 0, 3 * (int64_t)D, &b.qkv, 3 * D, 0, false, 0));
     } else {
+      lin_dense_reset(&b.qkv);
       DevBuf tmp; int N, K;
       F2B_TRY(dense16_from_key(c, p + "attn.toQkvMlp", &tmp, &N, &K));
       F2B_TRY(expect_shape(p + "attn.toQkvMlp", N, K, 3 * D + 2 * Hm, D));
@@ -338,13 +424,17 @@ int finalize_dit(flux2b_ctx* c) {
   }
   F2B_CUDA(cudaStreamSynchronize(c->stream));
   if (!c->option("keep_raw_weights", 1)) {
+    // Forward-only context: what the kernels consume are the working copies, so the handed-over Linear tensors go — the dense
+    // `.weight` matrices and, for quantized layers, `.weight` (uint32) together with its `.scales` / `.biases` (never one
+    // without the others: a packed weight whose scales are gone cannot be exported or LoRA-merged, and must say so cleanly).
+    // get_tensor / save_prequantized / merge_lora on such a context report the tensor as missing. With in-kernel dequantisation
+    // (wq_inkernel) or native_mx the packed working copy is then the ONLY resident copy of a quantized layer.
     for (auto it = c->tensors.begin(); it != c->tensors.end();) {
-      const bool dit_key = it->first.rfind("decoder.", 0) != 0 && it->first.rfind("encoder.", 0) != 0 &&
-                           it->first.rfind("postQuantConv", 0) != 0 && it->first.rfind("quantConv", 0) != 0 &&
-                           it->first.rfind("latentBatchNorm", 0) != 0;
-      // only dense `.weight` matrices: the f16 `.scales` / `.biases` of packed layers are [rows, groups] floats too and must stay
-      // (get_tensor, save_prequantized and merge_lora need them)
-      if (dit_key && is_float_dtype(it->second.dtype) && it->second.shape.size() == 2 && ends_with(it->first, ".weight")) it = c->tensors.erase(it);
+      const std::string& k = it->first;
+      const bool dit_key = k.rfind("decoder.", 0) != 0 && k.rfind("encoder.", 0) != 0 && k.rfind("postQuantConv", 0) != 0 &&
+                           k.rfind("quantConv", 0) != 0 && k.rfind("latentBatchNorm", 0) != 0;
+      const bool linear_part = it->second.shape.size() == 2 && (ends_with(k, ".weight") || ends_with(k, ".scales") || ends_with(k, ".biases"));
+      if (dit_key && linear_part) it = c->tensors.erase(it);
       else ++it;
     }
   }

@@ -91,7 +91,7 @@ EXPORTS = [
     "flux2b_text_position_ids", "flux2b_reference_position_ids", "flux2b_vae_decode", "flux2b_vae_decode_u8", "flux2b_vae_encode", "flux2b_encode_image_to_sequence", "flux2b_load_safetensors", "flux2b_save_prequantized",
     "flux2b_load_prequantized", "flux2b_prequantized_is_valid",
     "flux2b_denoise", "flux2b_generate", "flux2b_repaint_blend", "flux2b_sp_unique_id", "flux2b_sp_init", "flux2b_sp_layout",
-    "flux2b_prof_enable", "flux2b_prof_reset", "flux2b_prof_get", "flux2b_launch_count", "flux2b_op_gemm", "flux2b_op_gemm_mx", "flux2b_op_gemm_mxfp8",
+    "flux2b_prof_enable", "flux2b_prof_reset", "flux2b_prof_get", "flux2b_launch_count", "flux2b_op_gemm", "flux2b_op_gemm_mx", "flux2b_op_gemm_mxfp8", "flux2b_op_linear_quantized",
     "flux2b_op_attention", "flux2b_op_ln_modulate", "flux2b_op_qk_norm_rope", "flux2b_op_rope_table",
     "flux2b_op_timestep_embedding", "flux2b_op_conv2d", "flux2b_op_groupnorm_silu",
     "flux2b_te_create", "flux2b_te_hidden_states", "flux2b_op_attention_causal",
@@ -570,6 +570,19 @@ class Context:
         sfa = np.zeros((M, K // group), dtype=np.uint8) if return_quantized else None
         _ck(lib().flux2b_op_gemm_mx(self._h, q, _ptr(a16), _ptr(w_packed), _ptr(w_scales), M, N, K, _ptr(out), _ptr(aq), _ptr(sfa), bn, cta_group))
         return (out, aq, sfa) if return_quantized else out
+
+    def op_linear_quantized(self, quant, x16, w_packed, w_scales, w_biases=None, in_kernel=True, cta_group=0):
+        """QuantizedLinear forward, W-only (x · dequant(W)^T). x16 [M, K] 16-bit torch tensor; w_packed uint32 [N, K*bits/32],
+        w_scales / w_biases [N, K/group] as MLX holds them (f16 / bf16 for the affine modes, uint8 scales otherwise) -> f32 [M, N]."""
+        import torch
+        q = QUANT[quant] if isinstance(quant, str) else int(quant)
+        M, K = x16.shape
+        N = w_packed.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=x16.device)
+        sbd = _dtype_code(w_scales) if w_biases is not None else F16
+        _ck(lib().flux2b_op_linear_quantized(self._h, q, _ptr(x16), _ptr(w_packed), _ptr(w_scales), _ptr(w_biases), sbd, M, N, K,
+                                             _ptr(out), int(in_kernel), cta_group))
+        return out
 
     def op_gemm_mxfp8(self, a16, w_packed, w_scales, return_quantized=False):
         return self.op_gemm_mx(3, a16, w_packed, w_scales, return_quantized)

@@ -86,7 +86,15 @@ int flux2b_synchronize(flux2b_ctx* ctx);
  * "uint8_round" (0 = truncate like MLX asType(.uint8) [default], 1 = round to nearest),
  * "native_mx" (0 = W-only: x · dequant(W)^T through the 16-bit GEMM [default, matches the reference's arithmetic];
  *  1 = with quant = mxfp8 the block linears run on tcgen05 block-scaled MMA with on-the-fly mxfp8 activations: faster,
- *  but activations carry E4M3 precision — set before flux2b_finalize_weights) */
+ *  but activations carry E4M3 precision — set before flux2b_finalize_weights),
+ * "wq_inkernel" (1 [default] = W-only quantized layers keep ONLY their packed form (codes + group scales / biases, re-tiled for
+ *  the fused kernels) and are dequantized inside the GEMM / GEMV kernels on the way into the operand stage; 0 = a dense 16-bit
+ *  expansion per layer at finalize. Same output bits either way — set before flux2b_finalize_weights),
+ * "keep_raw_weights" (1 [default]; 0 = forward-only context: after finalize the handed-over Linear tensors — dense weights, and
+ *  packed weights together with their scales / biases — are released, so get_tensor / save_prequantized / merge_lora report them
+ *  missing; with wq_inkernel or native_mx the packed working copy is then the only resident copy of a quantized layer),
+ * "sp_disable" (1 = a sequence-parallel context runs the forward alone on its own GPU: the parity reference of the sharded forward),
+ * "group_streams", "attn_poly", "te_graph", "sp_mode", "sp_overlap", "mx_bn", "mx_fuse_quant", "vae_attn_chunk": see DESIGN.md */
 int flux2b_set_option(flux2b_ctx* ctx, const char* name, int value);
 
 /* ------------------------------------------------------------------ weights (Loading/WeightLoader.swift:567-623)
@@ -310,6 +318,14 @@ int flux2b_op_gemm_mx(flux2b_ctx* ctx, int quant, const void* a16, const uint32_
 /* = flux2b_op_gemm_mx(ctx, FLUX2B_MXFP8, ..., 0, 0) */
 int flux2b_op_gemm_mxfp8(flux2b_ctx* ctx, const void* a16, const uint32_t* w_packed, const uint8_t* w_scales, int M, int N, int K,
                          float* out, uint8_t* a8_out, uint8_t* sfa_out);
+/* QuantizedLinear forward as the reference computes it (W-only: x · dequant(W)^T; quantize(model:) Flux2Pipeline.swift:567-578,
+ * dequantized() WeightLoader.swift:795-815): x16 [M, K] 16-bit, w_packed / w_scales / w_biases exactly as MLX holds them for mode
+ * `quant` (biases NULL for the block-scaled modes; sb_dtype = FLUX2B_F16 or FLUX2B_BF16_T for the affine modes' scales / biases),
+ * out f32 [M, N]. K % 64 == 0. in_kernel = 1: the packed codes are dequantized inside the tcgen05 GEMM on their way into the
+ * operand stage (the product path: packed weights are the only copy read from HBM); 0: dense 16-bit expansion first (the
+ * cross-check). Both produce identical bits. */
+int flux2b_op_linear_quantized(flux2b_ctx* ctx, int quant, const void* x16, const uint32_t* w_packed, const void* w_scales,
+                               const void* w_biases, int sb_dtype, int M, int N, int K, float* out, int in_kernel, int cta_group);
 int flux2b_op_attention(flux2b_ctx* ctx, const void* qkv16 /* [B*S, 3*H*128] */, int B, int S, int H, void* out16 /* [B*S, H*128] */,
                         int variant);
 /* causal grouped-query attention with the text encoders' additive padding mask (createCausalMask, Qwen3Model.swift:196-231):

@@ -96,28 +96,46 @@ def test_text_encoder_graph_survives_workspace_growth(flux2b):
     te.close()
 
 
-def test_packed_layers_keep_scales_without_raw_weights(flux2b):
+def test_forward_only_context_is_consistent(flux2b):
+    """keep_raw_weights = 0: a packed weight never stays without its scales / biases (r01: the erase filter took the f16
+    `.scales` / `.biases` and left `.weight`, and merge_lora then ran dequantize on null buffers). Everything the forward does
+    not need is released together; export / merge calls fail cleanly; with keep_raw_weights = 1 they work."""
     from oracle import flux2_oracle as O
     from oracle import quant_oracle as Q
     q = flux2b.QUANT["qint8"]
     cfg = _tiny(O)
     W = O.random_dit_weights(cfg, seed=5, round_to=torch.float16)
-    ctx = flux2b.Context(dit=cfg, quant=q, options={"keep_raw_weights": 0})
-    ctx.load_weights(W, dtype=torch.float16)
-    ctx.finalize()
     key = "singleTransformerBlocks.0.attn.toOut"
     w = W[key + ".weight"]
-    p0, s0, b0 = Q.quantize(q, w.half().numpy())
-    assert np.array_equal(ctx.get_tensor(key + ".scales").view(np.uint16), s0.view(np.uint16))
-    assert np.array_equal(ctx.get_tensor(key + ".biases").view(np.uint16), b0.view(np.uint16))
     g = torch.Generator().manual_seed(6)
     A, B = torch.randn(8, w.shape[1], generator=g) * 0.02, torch.randn(w.shape[0], 8, generator=g) * 0.02
-    ctx.merge_lora(key, A, B, 1.0)     # dequant -> add -> requant needs the scales / biases
-    deq = torch.from_numpy(Q.dequantize(q, p0, s0, b0, w.shape[1])).half()
-    p1, s1, b1 = Q.quantize(q, O.lora_merge(deq, A, B, 1.0, torch.float16).numpy())
-    assert np.array_equal(ctx.get_tensor(key + ".weight"), p1)
-    assert np.array_equal(ctx.get_tensor(key + ".scales").view(np.uint16), s1.view(np.uint16))
-    ctx.close()
+    hidden, enc, t, img_ids, txt_ids = _inputs(O, cfg)
+    outs = {}
+    for keep in (0, 1):
+        ctx = flux2b.Context(dit=cfg, quant=q, options={"keep_raw_weights": keep})
+        ctx.load_weights(W, dtype=torch.float16)
+        ctx.finalize()
+        outs[keep] = ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), None, img_ids.numpy(), txt_ids.numpy())
+        if keep == 0:
+            for suffix in (".weight", ".scales", ".biases"):
+                with pytest.raises(flux2b.Flux2Error) as ei:
+                    ctx.get_tensor(key + suffix)
+                assert ei.value.case == "weightLoadingFailed"
+            with pytest.raises(flux2b.Flux2Error) as ei:
+                ctx.merge_lora(key, A, B, 1.0)
+            assert ei.value.case == "weightLoadingFailed"
+            # and the context still runs
+            assert np.array_equal(outs[0], ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), None, img_ids.numpy(), txt_ids.numpy()))
+        else:
+            p0, s0, b0 = Q.quantize(q, w.half().numpy())
+            assert np.array_equal(ctx.get_tensor(key + ".scales").view(np.uint16), s0.view(np.uint16))
+            ctx.merge_lora(key, A, B, 1.0)     # dequant -> add -> requant with the layer's own scales / biases
+            deq = torch.from_numpy(Q.dequantize(q, p0, s0, b0, w.shape[1])).half()
+            p1, s1, b1 = Q.quantize(q, O.lora_merge(deq, A, B, 1.0, torch.float16).numpy())
+            assert np.array_equal(ctx.get_tensor(key + ".weight"), p1)
+            assert np.array_equal(ctx.get_tensor(key + ".scales").view(np.uint16), s1.view(np.uint16))
+        ctx.close()
+    assert np.array_equal(outs[0], outs[1])
 
 
 def test_merge_lora_loop_rebuilds_once_and_fails_cleanly(flux2b):
@@ -203,3 +221,117 @@ def test_device_pointer_generate_does_not_synchronise(flux2b):
     assert returned_while_busy, "flux2b_generate with device pointers blocked on the stream"
     assert torch.equal(x2, want_x) and torch.equal(rgb, want_rgb)
     ctx.close()
+
+
+# ------------------------------------------------------------------ W-only quantized kernels (in-kernel dequantisation)
+QMODES = ["qint8", "int4", "mxfp8", "mxfp4", "nvfp4"]
+
+
+@pytest.mark.parametrize("name", QMODES)
+@pytest.mark.parametrize("M,N,K", [(300, 384, 256), (1024, 768, 1024), (130, 128, 64), (4608, 512, 3072)])
+def test_quantized_linear_in_kernel_matches_dense_bits(flux2b, name, M, N, K):
+    """QuantizedLinear forward: dequantisation inside the GEMM == dense expansion + GEMM, bit for bit, and both follow the
+    oracle's x · dequant(W)^T (ragged M, N below / not a multiple of the 256-wide tile, scalar and 16 B scale loads)"""
+    from oracle import quant_oracle as Q
+    q = flux2b.QUANT[name]
+    ctx = flux2b.Context()
+    g = torch.Generator().manual_seed(K + N)
+    w = ((torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5).half()
+    w[0, :64] = 0; w[1, :64] = 0.01; w[2, 0] = 3.0     # zero / constant / outlier groups
+    x = torch.randn(M, K, generator=g).bfloat16()
+    p, s, b = Q.quantize(q, w.numpy())
+    pt, st = torch.from_numpy(p.view(np.int32)).cuda(), torch.from_numpy(s.view(np.int16) if s.dtype == np.float16 else s).cuda()
+    if s.dtype == np.float16:
+        st = st.view(torch.float16)
+    bt = torch.from_numpy(b).cuda() if b is not None else None
+    y1 = ctx.op_linear_quantized(q, x.cuda(), pt, st, bt, in_kernel=True).cpu()
+    y0 = ctx.op_linear_quantized(q, x.cuda(), pt, st, bt, in_kernel=False).cpu()
+    assert torch.equal(y1, y0), f"{name}: max |delta| {(y1 - y0).abs().max()}"
+    wd = torch.from_numpy(Q.dequantize(q, p, s, b, K)).bfloat16().double()   # the operand the tensor core sees
+    ref = x.double() @ wd.T
+    e = rel_l2(y1, ref)
+    print(f"{name} {M}x{N}x{K}: rel-L2 vs fp64 {e:.2e}")
+    assert e < 1e-5
+    if M >= 256:
+        y2 = ctx.op_linear_quantized(q, x.cuda(), pt, st, bt, in_kernel=True, cta_group=1).cpu()
+        assert torch.equal(y2, y0)
+    ctx.close()
+
+
+def test_quantized_linear_bf16_scales(flux2b):
+    from oracle import quant_oracle as Q
+    q = flux2b.QUANT["qint8"]
+    ctx = flux2b.Context()
+    g = torch.Generator().manual_seed(3)
+    N, K, M = 512, 1024, 256
+    w = ((torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5).half()
+    x = torch.randn(M, K, generator=g).bfloat16()
+    p, s, b = Q.quantize(q, w.numpy())
+    sb, bb = torch.from_numpy(s.astype(np.float32)).bfloat16(), torch.from_numpy(b.astype(np.float32)).bfloat16()
+    pt = torch.from_numpy(p.view(np.int32)).cuda()
+    y1 = ctx.op_linear_quantized(q, x.cuda(), pt, sb.cuda(), bb.cuda(), in_kernel=True).cpu()
+    y0 = ctx.op_linear_quantized(q, x.cuda(), pt, sb.cuda(), bb.cuda(), in_kernel=False).cpu()
+    assert torch.equal(y1, y0)
+    qv = ((p[:, :, None] >> (np.arange(4, dtype=np.uint32) * 8)) & 0xff).reshape(N, -1).astype(np.float32)
+    wd = torch.from_numpy(qv * sb.float().numpy().repeat(64, 1) + bb.float().numpy().repeat(64, 1)).bfloat16().double()
+    assert rel_l2(y1, x.double() @ wd.T) < 1e-5
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", QMODES)
+def test_dit_forward_in_kernel_dequant_matches_dense_copy(flux2b, name):
+    """whole forward: wq_inkernel = 1 (packed weights only) == wq_inkernel = 0 (dense 16-bit copies), bit for bit — GEMMs with
+    every fused epilogue, the grouped two-problem launches, the M = 1 GEMVs"""
+    from oracle import flux2_oracle as O
+    q = flux2b.QUANT[name]
+    cfg = O.DiTConfig(num_layers=2, num_single_layers=2, num_attention_heads=2, joint_attention_dim=256, guidance_embeds=True)
+    W = O.random_dit_weights(cfg, seed=4, round_to=torch.float16)
+    hidden = torch.randn(1, 256, 128, generator=torch.Generator().manual_seed(1))
+    enc = torch.randn(1, 256, 256, generator=torch.Generator().manual_seed(2))
+    t, gd = torch.tensor([0.7]), torch.tensor([4.0])
+    img_ids, txt_ids = O.image_position_ids(256, 256), O.text_position_ids(256)
+    outs = []
+    for ink in (1, 0):
+        ctx = flux2b.Context(dit=cfg, quant=q, options={"wq_inkernel": ink, "record_blocks": 1})
+        ctx.load_weights(W, dtype=torch.float16)
+        ctx.finalize()
+        out = ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), gd.numpy(), img_ids.numpy(), txt_ids.numpy())
+        blocks = [ctx.block_output(i, 512, cfg.inner_dim) for i in range(4)]
+        outs.append((out, blocks))
+        ctx.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a, b)
+
+
+def test_klein4b_width_in_kernel_dequant(flux2b):
+    """Klein-4B width at S = 4608 with int4 weights: CTA-pair tiles over many waves, 16 B scale loads (K % 512 == 0); same bits
+    as the dense-copy path and within tolerance of the oracle on the dequantized weights"""
+    import os
+    from oracle import flux2_oracle as O
+    from oracle import quant_oracle as Q
+    torch.set_num_threads(os.cpu_count() or 1)
+    q = flux2b.QUANT["int4"]
+    cfg = O.DiTConfig(num_layers=1, num_single_layers=1, num_attention_heads=24, joint_attention_dim=7680, guidance_embeds=False)
+    W = O.random_dit_weights(cfg, seed=12, round_to=torch.float16)
+    hidden = torch.randn(1, 4096, 128, generator=torch.Generator().manual_seed(1))
+    enc = torch.randn(1, 512, 7680, generator=torch.Generator().manual_seed(2))
+    t = torch.tensor([0.7])
+    img_ids, txt_ids = O.image_position_ids(1024, 1024), O.text_position_ids(512)
+    outs = []
+    for ink in (1, 0):
+        ctx = flux2b.Context(dit=cfg, quant=q, options={"wq_inkernel": ink, "record_blocks": 1, "keep_raw_weights": 0})
+        ctx.load_weights(W, dtype=torch.float16)
+        ctx.finalize()
+        outs.append(ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), None, img_ids.numpy(), txt_ids.numpy()))
+        if ink:
+            blocks = [ctx.block_output(i, 4608, cfg.inner_dim) for i in range(2)]
+        ctx.close()
+    assert np.array_equal(outs[0], outs[1])
+    Wd = {k: (torch.from_numpy(Q.dequantize(q, *Q.quantize(q, w.half().numpy()), w.shape[1])) if w.dim() == 2 else w) for k, w in W.items()}
+    rec = []
+    with torch.no_grad():
+        ref = O.dit_forward(Wd, cfg, hidden, enc, t, None, img_ids, txt_ids, record=rec)
+    errs = [rel_l2(b, r) for b, r in zip(blocks, rec)]
+    print(f"klein4b width int4 W-only in-kernel: per-block rel-L2 {['%.2e' % e for e in errs]}, output {rel_l2(outs[0], ref):.2e}")
+    assert max(errs) < 3e-3 and rel_l2(outs[0], ref) < 6e-3

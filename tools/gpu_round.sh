@@ -49,6 +49,23 @@ for w in $WHAT; do
     bench_nosp)
       timeout 900 python bench.py --steps 5 --warmup 3 --no-sp-extra > gpurun_out/bench.json 2> gpurun_out/bench.err
       echo "bench rc=$?"; tail -c 3000 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err ;;
+    bench_wq)
+      # W-only quantized Klein 9B (BASELINE.json configs[2] weights, reference arithmetic): in-kernel dequantisation vs dense copies
+      for q in int4 qint8 nvfp4; do for ink in 1 0; do
+        timeout 600 python bench.py --model klein9b --quant $q --wq-inkernel $ink --steps 3 --warmup 3 --no-cpu-baseline --no-sp-extra \
+          > gpurun_out/bench_k9_${q}_ink$ink.json 2> gpurun_out/bench_k9_${q}_ink$ink.err
+        echo "bench k9 $q inkernel=$ink rc=$?"; python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/bench_k9_${q}_ink$ink.json").read().strip().splitlines()[-1])
+    print({k: d[k] for k in ("value", "ms_per_step")}, d["kernel_classes"]["gemm"], d.get("mem_gb"))
+except Exception as e:
+    print("no result:", e); print(open("gpurun_out/bench_k9_${q}_ink$ink.err").read()[-1500:])
+PY
+      done; done ;;
+    tests_wq)
+      timeout 900 python -m pytest tests -m gpu -q -x -k "quantized or in_kernel or forward_only or lora or prequantized or affine" > gpurun_out/pytest_wq.log 2>&1
+      echo "pytest wq rc=$?"; tail -n 25 gpurun_out/pytest_wq.log ;;
     full)
       # top kernels, full sections (few launches each)
       timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \
