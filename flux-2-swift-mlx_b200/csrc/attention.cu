@@ -69,6 +69,8 @@ struct AttnKParams {
   int dbg;  // FLUX2B_ATTN_TIMELINE=1: CTA (0,0,0) prints its softmax / MMA time line (debug aid, off by default)
 };
 
+static bool fill_params(const struct AttnProblem& a, int BN, AttnKParams& p);
+
 template <int BN, bool kPTmem>
 struct ACfg {
   static constexpr int STAGES = kPTmem ? 2 : 3;
@@ -779,6 +781,334 @@ __global__ void __launch_bounds__(A3::THREADS, 1) attn_kernel_v3(const __grid_co
   if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------ variant 4
+// What bounded variant 3 (ncu: tensor pipe 57 % busy): with ONE S accumulator per query tile, S(j+1) cannot be issued before
+// PV(j) has consumed P(j) (P overwrites S), so every key tile is a dependency chain softmax(j) [~1600 clk] -> PV(j) + S(j+1)
+// [1024 clk] per warpgroup, and two chains in strict alternation keep the tensor pipe busy 2048 of ~3200 clk.
+// Variant 4 halves the key tile to 64 keys and double-buffers S: TMEM = S 2 tiles x 2 buffers x 64 + O 2 x 128 = 512 columns.
+//   issuer of tile w:   S(0) -> buf 0, S(1) -> buf 1;  then per key tile j:  [P(j) ready]  PV(j) from buf j%2,  S(j+2) -> buf j%2
+//   softmax of tile w:  [S(j) ready in buf j%2]  load 64 scores, max / exp2 / pack, P(j) -> first 32 columns of buf j%2
+// S(j+1) is therefore complete before softmax(j) ends: the softmax warpgroups never wait for the tensor pipe and the pipe always
+// has the other tile's MMAs queued — no ping-pong barriers, the two warpgroups run concurrently. Cost: the N = 64 S-MMA is
+// shared-memory bound (Q re-read per k-step: 6 KB per MMA = 48 clk instead of 32), which caps the pipe at 2048 / 2560 = 80 %.
+// O may only be rescaled after PV(j-1) has completed; with S(j) no longer ordered behind PV(j-1), that is its own barrier
+// (pv_done), waited on only in the rare tiles where a row maximum moved.
+struct A4 {
+  static constexpr int BN = 64;
+  static constexpr int KS = 4, VS = 3;
+  static constexpr int Q_BYTES = QT * HD * 2;
+  static constexpr int KV_BYTES = BN * HD * 2;
+  static constexpr int KV_PANEL = BN * 128;
+  static constexpr int OFF_K = 2 * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KS * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_V + VS * KV_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int THREADS = 352;   // 8 softmax warps, TMA producer, two MMA issuers
+};
+
+template <bool kF16, int kPoly>
+__global__ void __launch_bounds__(A4::THREADS, 1) attn_kernel_v4(const __grid_constant__ AttnKParams p) {
+  using C = A4;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;               // [2]
+  uint64_t* k_full = q_full + 2;         // [KS]
+  uint64_t* k_empty = k_full + C::KS;    // [KS]
+  uint64_t* v_full = k_empty + C::KS;    // [VS]
+  uint64_t* v_empty = v_full + C::VS;    // [VS]
+  uint64_t* s_ready = v_empty + C::VS;   // [2 tiles][2 buffers]
+  uint64_t* p_ready = s_ready + 4;       // [2][2]
+  uint64_t* pv_done = p_ready + 4;       // [2]
+  uint64_t* o_done = pv_done + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int q_blk0 = blockIdx.x * 2 * QT;
+  const int kv_col = head * HD;
+  int n_tiles = 0;
+  for (int s = 0; s < p.nseg; ++s) n_tiles += (p.seg_len[s] + BN - 1) / BN;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    for (int s = 0; s < p.nseg; ++s) { tma_prefetch_desc(&p.tmK[s]); tma_prefetch_desc(&p.tmV[s]); }
+  }
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_done[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) { mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 128); }
+    // a K / V stage is free once BOTH issuers' MMAs on it have completed
+    for (int i = 0; i < C::KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); }
+    for (int i = 0; i < C::VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2); }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<1>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 8) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      const int qrow = p.q_row0 + (int)(b * p.q_bs) + q_blk0;
+      for (int w = 0; w < 2; ++w) {
+        mbar_expect_tx(&q_full[w], C::Q_BYTES);
+        uint8_t* dst = smem + w * C::Q_BYTES;
+        tma_load_2d(dst, &p.tmQ, &q_full[w], head * HD, qrow + w * QT);
+        tma_load_2d(dst + QT * 128, &p.tmQ, &q_full[w], head * HD + 64, qrow + w * QT);
+      }
+      auto tile_at = [&](int j, int* seg, int* row) {
+        for (int s = 0; s < p.nseg; ++s) {
+          const int tiles = (p.seg_len[s] + BN - 1) / BN;
+          if (j < tiles) { *seg = s; *row = p.seg_row0[s] + (int)(b * p.seg_bs[s]) + j * BN; return; }
+          j -= tiles;
+        }
+      };
+      auto load_k = [&](int j) {
+        int s = 0, row = 0;
+        tile_at(j, &s, &row);
+        const int ks = j % C::KS;
+        mbar_wait(&k_empty[ks], ((j / C::KS) & 1) ^ 1, 10);
+        uint8_t* kd = smem + C::OFF_K + ks * C::KV_BYTES;
+        mbar_expect_tx(&k_full[ks], C::KV_BYTES);
+        tma_load_2d(kd, &p.tmK[s], &k_full[ks], kv_col, row);
+        tma_load_2d(kd + C::KV_PANEL, &p.tmK[s], &k_full[ks], kv_col + 64, row);
+      };
+      // K runs two tiles ahead of V: S(j+2) is issued right behind PV(j)
+      load_k(0);
+      if (n_tiles > 1) load_k(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 2 < n_tiles) load_k(j + 2);
+        int s = 0, row = 0;
+        tile_at(j, &s, &row);
+        const int vs = j % C::VS;
+        mbar_wait(&v_empty[vs], ((j / C::VS) & 1) ^ 1, 11);
+        uint8_t* vd = smem + C::OFF_V + vs * C::KV_BYTES;
+        mbar_expect_tx(&v_full[vs], C::KV_BYTES);
+        tma_load_2d(vd, &p.tmV[s], &v_full[vs], kv_col, row);
+        tma_load_2d(vd + C::KV_PANEL, &p.tmV[s], &v_full[vs], kv_col + 64, row);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9 || warp == 10) {
+    // ============================================================ MMA issuers: one warp per query tile (see variant 3)
+    if (tmem_base != 0) __trap();
+    const int w = warp - 9;
+    const uint32_t idesc_s = make_idesc_f16(QT, BN, !kF16, false, false);
+    const uint32_t idesc_o = make_idesc_f16(QT, HD, !kF16, false, true);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint64_t desc_kmajor = make_smem_desc(0, 16, 1024, SWZ_128B);
+    const uint64_t desc_v = make_smem_desc(0, C::KV_PANEL, 1024, SWZ_128B);
+    auto issue_s = [&](int ks, int buf) {
+      const uint32_t qa = (smem_base + w * C::Q_BYTES) >> 4;
+      const uint32_t ka = (smem_base + C::OFF_K + ks * C::KV_BYTES) >> 4;
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) {
+        const uint32_t off_q = ((k / 4) * (QT * 128) + (k % 4) * 32) >> 4;
+        const uint32_t off_k = ((k / 4) * C::KV_PANEL + (k % 4) * 32) >> 4;
+        umma_f16_ss<1>(w * 128 + buf * 64, desc_kmajor + (qa + off_q), desc_kmajor + (ka + off_k), idesc_s, k ? 1u : 0u);
+      }
+      umma_commit(&s_ready[w * 2 + buf]);
+      umma_commit(&k_empty[ks]);
+    };
+    auto issue_pv = [&](int vs, int buf, bool accumulate) {
+      const uint32_t va = (smem_base + C::OFF_V + vs * C::KV_BYTES) >> 4;
+#pragma unroll
+      for (int k = 0; k < BN / 16; ++k)
+        umma_f16_ts(256 + w * 128, w * 128 + buf * 64 + k * 8, desc_v + (va + k * (2048 >> 4)), idesc_o, (accumulate || k) ? 1u : 0u);
+      umma_commit(&v_empty[vs]);
+      umma_commit(&pv_done[w]);
+    };
+    mbar_wait(&q_full[w], 0, 20);
+    mbar_wait(&k_full[0], 0, 21);
+    tc_fence_after();
+    if (elect_one()) issue_s(0, 0);
+    __syncwarp();
+    if (n_tiles > 1) {
+      mbar_wait(&k_full[1], 0, 22);
+      tc_fence_after();
+      if (elect_one()) issue_s(1, 1);
+      __syncwarp();
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int vs = j % C::VS, buf = j & 1;
+      const bool more = j + 2 < n_tiles;
+      mbar_wait(&v_full[vs], (j / C::VS) & 1, 24);
+      if (more) mbar_wait(&k_full[(j + 2) % C::KS], ((j + 2) / C::KS) & 1, 25);
+      mbar_wait(&p_ready[w * 2 + buf], (j >> 1) & 1, 23);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_pv(vs, buf, j > 0);
+        if (more) issue_s((j + 2) % C::KS, buf);
+        if (j == n_tiles - 1) umma_commit(&o_done[w]);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 8) {
+    // ============================================================ softmax warpgroups (thread == query row == TMEM lane)
+    const int w = warp >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t t_o = tmem_base + lane_off + 256 + w * 128;
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;  // m_run in the scaled (log2) domain
+    int j = 0;
+    for (int s = 0; s < p.nseg; ++s) {
+      const int tiles = (p.seg_len[s] + BN - 1) / BN;
+      for (int t = 0; t < tiles; ++t, ++j) {
+        const int nvalid = min(BN, p.seg_len[s] - t * BN);
+        const int buf = j & 1;
+        const uint32_t t_s = tmem_base + lane_off + w * 128 + buf * 64;
+        mbar_wait(&s_ready[w * 2 + buf], (j >> 1) & 1, 30);
+        tc_fence_after();
+        uint32_t v[2][32];
+        tmem_ld_32x32(t_s, v[0]);
+        tmem_ld_32x32(t_s + 32, v[1]);
+        tmem_ld_wait();
+        if (nvalid < BN) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= nvalid) v[c][i] = 0xff800000u;  // -inf: ignored by the max, exp2 -> 0
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx[2 * c] = fmaxf(mx[2 * c], fmaxf(__uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1])));
+            mx[2 * c + 1] = fmaxf(mx[2 * c + 1], fmaxf(__uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3])));
+          }
+        const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2);
+        const bool move = (m_new - m_run) > 8.0f;   // lazy rescale (first tile: m_run = -inf -> true)
+        const float m_use = move ? m_new : m_run;
+        const float alpha = move ? fast_exp2(m_run - m_new) : 1.0f;
+        const float2 sl2v = make_float2(sl2, sl2), nmv = make_float2(-m_use, -m_use);
+        float2 rs2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1])), sl2v, nmv);
+            constexpr int kMod = kPoly > 0 ? kPoly : 1;
+            float2 e;
+            if (kPoly > 0 && i % kMod == kMod - 1) e = exp2_poly2(x);
+            else e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+            rs2[c] = __fadd2_rn(rs2[c], e);
+            pk[c * 16 + i] = apk2(e.x, e.y, kF16 ? 1 : 0);
+          }
+        }
+        // P (16-bit) into the first 32 columns of this S buffer
+        tmem_st_32x32(t_s, pk);
+        if (j > 0 && __any_sync(0xffffffffu, move)) {
+          // rescale O: PV(j-1) must have completed (S(j) was issued behind PV(j-2) only)
+          mbar_wait(&pv_done[w], (j - 1) & 1, 31);
+          tc_fence_after();
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32(t_o + h * 64, o0);
+            tmem_ld_32x32(t_o + h * 64 + 32, o1);
+            tmem_ld_wait();
+            const float2 av = make_float2(alpha, alpha);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float2 a0 = __fmul2_rn(make_float2(__uint_as_float(o0[i]), __uint_as_float(o0[i + 1])), av);
+              const float2 a1 = __fmul2_rn(make_float2(__uint_as_float(o1[i]), __uint_as_float(o1[i + 1])), av);
+              o0[i] = __float_as_uint(a0.x); o0[i + 1] = __float_as_uint(a0.y);
+              o1[i] = __float_as_uint(a1.x); o1[i + 1] = __float_as_uint(a1.y);
+            }
+            tmem_st_32x32(t_o + h * 64, o0);
+            tmem_st_32x32(t_o + h * 64 + 32, o1);
+          }
+        }
+        tmem_st_wait();
+        l_run = l_run * alpha + ((rs2[0].x + rs2[0].y) + (rs2[1].x + rs2[1].y));
+        m_run = m_use;
+        tc_fence_before();
+        mbar_arrive(&p_ready[w * 2 + buf]);
+      }
+    }
+    // ---- finalize: O / l
+    mbar_wait(&o_done[w], 0, 32);
+    tc_fence_after();
+    const int qrow = q_blk0 + w * QT + row;
+    const bool ok = qrow < p.sq;
+    const float inv_l = 1.0f / l_run;
+    uint16_t* orow = p.o + ((long long)p.o_row0 + b * p.o_bs + qrow) * p.ldo + head * HD;
+    if (p.o_rows_per_peer > 0 && ok) {
+      const int dest = qrow / p.o_rows_per_peer;
+      orow = p.o_peer[dest] + (long long)(qrow - dest * p.o_rows_per_peer) * p.ldo + p.o_col0 + head * HD;
+    }
+    uint32_t o[4][32];
+    tmem_ld_32x32(t_o, o[0]);
+    tmem_ld_32x32(t_o + 32, o[1]);
+    tmem_ld_32x32(t_o + 64, o[2]);
+    tmem_ld_32x32(t_o + 96, o[3]);
+    tmem_ld_wait();
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 u;
+          u.x = apk2(__uint_as_float(o[c][8 * q4 + 0]) * inv_l, __uint_as_float(o[c][8 * q4 + 1]) * inv_l, kF16 ? 1 : 0);
+          u.y = apk2(__uint_as_float(o[c][8 * q4 + 2]) * inv_l, __uint_as_float(o[c][8 * q4 + 3]) * inv_l, kF16 ? 1 : 0);
+          u.z = apk2(__uint_as_float(o[c][8 * q4 + 4]) * inv_l, __uint_as_float(o[c][8 * q4 + 5]) * inv_l, kF16 ? 1 : 0);
+          u.w = apk2(__uint_as_float(o[c][8 * q4 + 6]) * inv_l, __uint_as_float(o[c][8 * q4 + 7]) * inv_l, kF16 ? 1 : 0);
+          *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
+}
+
+static cudaError_t launch_attn_v4(const AttnProblem& a, cudaStream_t stream) {
+  AttnKParams p{};
+  if (!fill_params(a, A4::BN, p)) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaSuccess;
+#define F2B_ATTR4(F16_, POLY_) if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_kernel_v4<F16_, POLY_>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4::SMEM_BYTES)
+    F2B_ATTR4(false, 0); F2B_ATTR4(false, 2); F2B_ATTR4(false, 3); F2B_ATTR4(false, 4);
+    F2B_ATTR4(true, 0); F2B_ATTR4(true, 2); F2B_ATTR4(true, 3); F2B_ATTR4(true, 4);
+#undef F2B_ATTR4
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((a.sq + 2 * QT - 1) / (2 * QT), a.num_heads, a.batch);
+  const int poly = a.poly < 0 ? 0 : (a.poly == 0 ? 3 : a.poly);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(A4::THREADS); cfg.dynamicSmemBytes = A4::SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+#define F2B_GO4(F16_, POLY_) cudaLaunchKernelEx(&cfg, attn_kernel_v4<F16_, POLY_>, p)
+  if (a.f16) { if (poly == 2) F2B_GO4(true, 2); else if (poly == 3) F2B_GO4(true, 3); else if (poly == 4) F2B_GO4(true, 4); else F2B_GO4(true, 0); }
+  else { if (poly == 2) F2B_GO4(false, 2); else if (poly == 3) F2B_GO4(false, 3); else if (poly == 4) F2B_GO4(false, 4); else F2B_GO4(false, 0); }
+#undef F2B_GO4
+  return cudaGetLastError();
+}
+
 static bool fill_params(const AttnProblem& a, int BN, AttnKParams& p) {
   {
     uint64_t d[2] = {(uint64_t)a.ldq, (uint64_t)a.q_rows_total};
@@ -894,8 +1224,13 @@ cudaError_t attention_launch(const AttnProblem& a, cudaStream_t stream) {
   if (total <= 0 || a.num_segments < 1 || a.num_segments > 3) return cudaErrorInvalidValue;
   for (int i = 0; i < a.num_segments; ++i)
     if (a.seg[i].len <= 0) return cudaErrorInvalidValue;
-  const int variant = a.variant ? a.variant : 3;
-  if (a.o_rows_per_peer > 0 && variant != 3) return cudaErrorInvalidValue;
+  // default: variant 4 (64-key tiles, double-buffered S) for the DiT's unmasked joint attention, variant 3 for the text encoder's
+  // causal / padded / grouped-query mode. FLUX2B_ATTN_VARIANT overrides the default (3 = the 128-key ping-pong kernel).
+  static const int env_variant = getenv("FLUX2B_ATTN_VARIANT") ? atoi(getenv("FLUX2B_ATTN_VARIANT")) : 0;
+  const bool masked = a.causal || a.key_hi > 0 || a.kv_group > 1 || a.mask_dev;
+  const int variant = a.variant ? a.variant : masked ? 3 : (env_variant ? env_variant : 4);
+  if (a.o_rows_per_peer > 0 && variant != 3 && variant != 4) return cudaErrorInvalidValue;
+  if (variant == 4 && !masked) return launch_attn_v4(a, stream);
   if ((a.causal || a.key_hi > 0 || a.kv_group > 1 || a.mask_dev) && (variant != 3 || a.num_segments != 1 || a.seg[0].len != a.sq)) return cudaErrorInvalidValue;
   if (variant == 3) return launch_attn_v3(a, stream);
   if (variant == 2) return launch_attn<128, true>(a, stream);

@@ -30,8 +30,17 @@ namespace f2b {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int CONV_TW = 16;  // spatial patch of one M tile in conv mode: 8 rows x 16 cols = 128 pixels
+static constexpr int CONV_TW = 16;  // spatial patch of one M tile in conv mode 1 (one TMA box per tap): 8 rows x 16 cols = 128 pixels
 static constexpr int CONV_TH = 8;
+// conv mode 2 (3x3, stride 1): the M tile is 16 rows x 8 cols and its 18 x 16-pixel halo (rows y0-1 .. y0+16, cols x0-1 .. x0+14;
+// only 10 of the 16 columns are read) is loaded ONCE per 64-channel block and serves all nine taps: the A operand of tap
+// (ky, kx) is the window of the halo that starts at halo row ky, column kx — a UMMA descriptor with an 8-row-group stride of
+// one halo row (16 pixels x 128 B = 2048 B) and a start address off the 1024 B swizzle period by kx x 128 B (descriptor base
+// offset kx). L2 -> shared-memory traffic for A drops from 9 x 16 KB to 36 KB per 64-channel block.
+static constexpr int HALO_W = 16, HALO_H = 18;
+static constexpr int HALO_TW = 8, HALO_TH = 16;
+static constexpr int HALO_BYTES = HALO_W * HALO_H * 128;   // 36 KB
+static constexpr int HALO_STAGES = 3;
 
 struct KParams {
   int M, N, K;
@@ -59,7 +68,7 @@ struct KParams {
 // WQ kernels: a ring of packed-weight slots (TMA destination, 64 B-/32 B-swizzled rows of 64 / 32 bytes = 64 K elements) beside
 // the operand stages; 128 more threads (warps 6..9) turn slot -> 16-bit B stage
 static constexpr int WQ_PSTAGES = 4;
-template <int BN, int CG, int MXK = 0, int WQ = 0>
+template <int BN, int CG, int MXK = 0, int WQ = 0, int HALO = 0>
 struct Cfg {
   static constexpr int B_ROWS = BN / CG;
   static constexpr int A_BYTES = BM * BK * 2;      // 128 rows x 128 B: 64 bf16, 128 fp8 or 256 fp4 elements along K
@@ -70,10 +79,12 @@ struct Cfg {
   static constexpr int SFA_BYTES = 512 * SFPK;
   static constexpr int SFB_BYTES = (BN / 128) * 512 * SFPK;
   static constexpr int SF_BYTES = SFA_BYTES + SFB_BYTES;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + SF_BYTES;
+  static constexpr int A_STAGE = HALO ? 0 : A_BYTES;                  // halo convolutions keep A in the halo ring, not in the stages
+  static constexpr int STAGE_BYTES = A_STAGE + B_BYTES + SF_BYTES;
   static constexpr int PSLOT_BYTES = WQ ? B_ROWS * 64 : 0;            // sized for 8-bit codes; 4-bit modes use half of a slot
   static constexpr int PRING_BYTES = WQ_PSTAGES * PSLOT_BYTES;
-  static constexpr int STAGES_RAW = (196 * 1024 - PRING_BYTES) / STAGE_BYTES;
+  static constexpr int HRING_BYTES = HALO ? HALO_STAGES * HALO_BYTES : 0;
+  static constexpr int STAGES_RAW = (196 * 1024 - PRING_BYTES - HRING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // accumulator stages in TMEM: two, except the 256-wide block-scaled tile, whose scale factors need columns too
   static constexpr int ACC_STAGES = (MXK && BN == 256) ? 1 : 2;
@@ -81,8 +92,8 @@ struct Cfg {
   static constexpr int SF_COLS = MXK ? 4 * SFPK * (1 + BN / 128) : 0;
   static constexpr int COLS_NEEDED = ACC_STAGES * BN + SF_COLS;
   static constexpr int TMEM_COLS = (COLS_NEEDED <= 32) ? 32 : (COLS_NEEDED <= 64) ? 64 : (COLS_NEEDED <= 128) ? 128 : (COLS_NEEDED <= 256) ? 256 : 512;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PRING_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PRING_BYTES + HRING_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
   static constexpr int THREADS = WQ ? 320 : 192;
 };
 
@@ -468,27 +479,33 @@ __device__ __forceinline__ void wq_dequant_row(const uint8_t* slot, uint8_t* bst
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN, int CG, bool CONV, int MXK = 0, int WQ = 0>
+// CONV: 0 = plain GEMM, 1 = implicit-GEMM convolution with one TMA box per tap, 2 = 3x3 stride-1 convolution from a halo tile
+template <int BN, int CG, int CONV, int MXK = 0, int WQ = 0>
 __global__ void __launch_bounds__(WQ ? 320 : 192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmSFA, const __grid_constant__ CUtensorMap tmSFB, const KParams p) {
-  using C = Cfg<BN, CG, MXK, WQ>;
+  constexpr bool HALO = CONV == 2;
+  using C = Cfg<BN, CG, MXK, WQ, HALO ? 1 : 0>;
   static_assert(!MXK || (!CONV && (BN == 128 || (BN == 256 && CG == 1))), "block-scaled tiles: BN 128 (1 or 2 CTAs) / 256 (1 CTA)");
   static_assert(!WQ || (!CONV && !MXK && BN == 256), "W-only quantized weights: plain GEMM, 256-wide tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;
-  uint8_t* smB = smem + C::STAGES * C::A_BYTES;
+  uint8_t* smB = smem + C::STAGES * C::A_STAGE;
   uint8_t* smSF = smB + C::STAGES * C::B_BYTES;  // [STAGES][SFA SFPK x 512 | SFB (BN/128) x SFPK x 512]   (block-scaled only)
   uint8_t* smP = smem + C::STAGES * C::STAGE_BYTES;   // [WQ_PSTAGES][PSLOT_BYTES] packed-weight slots (WQ only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smP + C::PRING_BYTES);
+  uint8_t* smH = smP + C::PRING_BYTES;                // [HALO_STAGES][HALO_BYTES] halo tiles (conv mode 2; 1024 B aligned: stages are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smH + C::HRING_BYTES);
   uint64_t* full = bars;                    // [STAGES]  TMA (+ dequant warps) -> MMA
   uint64_t* empty = bars + C::STAGES;       // [STAGES]  MMA -> TMA (+ dequant warps)
   uint64_t* tfull = bars + 2 * C::STAGES;   // [2]       MMA -> epilogue
   uint64_t* tempty = tfull + 2;             // [2]       epilogue -> MMA   (only ACC_STAGES of each are used)
   uint64_t* pfull = tempty + 2;             // [WQ_PSTAGES]  TMA -> dequant warps   (WQ only)
   uint64_t* pempty = pfull + WQ_PSTAGES;    // [WQ_PSTAGES]  dequant warps -> TMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + WQ_PSTAGES);
+  uint64_t* hfull = pempty + WQ_PSTAGES;    // [HALO_STAGES] TMA -> MMA   (conv mode 2 only)
+  uint64_t* hempty = hfull + HALO_STAGES;   // [HALO_STAGES] MMA -> TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty + HALO_STAGES);
+  static_assert(!HALO || (C::B_BYTES % 1024 == 0), "halo ring must stay 1024 B aligned behind the B stages");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -515,6 +532,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_init(&pempty[s], 4);   // one arrive per dequant warp
       }
     }
+    if (HALO) {
+      for (int s = 0; s < HALO_STAGES; ++s) {
+        mbar_init(&hfull[s], CG);   // one arrive.expect_tx per CTA of the pair (each loads the halo of its own 128 pixels)
+        mbar_init(&hempty[s], 1);   // one tcgen05.commit
+      }
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);        // one tcgen05.commit
       mbar_init(&tempty[s], 4 * CG);  // one arrive per epilogue warp (of both CTAs)
@@ -538,7 +561,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int pstage = 0, pk_tile = unit_id, pk_kb = 0;   // WQ: cursor of the packed-weight stream
       uint32_t pphase = 0;
-      (void)pstage; (void)pphase; (void)pk_tile; (void)pk_kb;
+      int hstage = 0;                                  // conv mode 2: halo ring
+      uint32_t hphase = 0;
+      (void)pstage; (void)pphase; (void)pk_tile; (void)pk_kb; (void)hstage; (void)hphase;
       const bool dbg = p.dbg && unit_id == 0;
       long long w_empty = 0, t_begin = dbg ? clock64() : 0;
       for (int t = unit_id; t < total_tiles; t += num_units) {
@@ -553,8 +578,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int per_img = p.tiles_x * p.tiles_y;
           img = m_blk / per_img;
           const int r = m_blk % per_img;
-          y0 = (r / p.tiles_x) * CONV_TH;
-          x0 = (r % p.tiles_x) * CONV_TW;
+          y0 = (r / p.tiles_x) * (HALO ? HALO_TH : CONV_TH);
+          x0 = (r % p.tiles_x) * (HALO ? HALO_TW : CONV_TW);
+        }
+        if constexpr (HALO) {
+          // channel-block major: one halo load per 64 input channels, then the nine taps' weight tiles through the ring
+          for (int cb = 0; cb < p.kb_per_tap; ++cb) {
+            mbar_wait(&hempty[hstage], hphase ^ 1, 8);
+            uint8_t* h_dst = smH + hstage * HALO_BYTES;
+            if (CG == 1) {
+              mbar_expect_tx(&hfull[hstage], HALO_BYTES);
+              tma_load_4d(h_dst, &tmA, &hfull[hstage], cb * BK, x0 - 1, y0 - 1, img);
+            } else {
+              const uint32_t hbar = mapa_u32(smem_u32(&hfull[hstage]), 0);
+              mbar_expect_tx_cluster(hbar, HALO_BYTES);
+              tma_load_4d_cg2(h_dst, &tmA, hbar, cb * BK, x0 - 1, y0 - 1, img);
+            }
+            if (++hstage == HALO_STAGES) { hstage = 0; hphase ^= 1; }
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&empty[stage], phase ^ 1, 1);
+              void* b_dst = smB + stage * C::B_BYTES;
+              if (CG == 1) {
+                mbar_expect_tx(&full[stage], C::B_BYTES);
+                tma_load_3d(b_dst, &tmB, &full[stage], cb * BK, tap, nrow0);
+              } else {
+                const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+                mbar_expect_tx_cluster(lbar, C::B_BYTES);
+                tma_load_4d_cg2(b_dst, &tmB, lbar, cb * BK, tap, nrow0, 0);
+              }
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
         }
         if constexpr (WQ != 0) {
           // W-only quantized weights: this CTA's B rows arrive as packed codes in their own slot ring, as one continuous stream
@@ -589,7 +643,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        if constexpr (WQ == 0)
+        if constexpr (WQ == 0 && !HALO)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           long long t0 = dbg ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1, 1);
@@ -665,6 +719,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int hstage = 0;
+      uint32_t hphase = 0;
+      (void)hstage; (void)hphase;
       const bool dbg = p.dbg && unit_id == 0;
       long long w_full = 0, w_tempty = 0, t_begin = dbg ? clock64() : 0;
       int tl_n = 0;
@@ -677,6 +734,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (dbg && tl_n < 8) { tl_start[tl_n] = (unsigned)(globaltimer_ns() - t_entry); tl_drain[tl_n] = (unsigned)(clock64() - t0); }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        if constexpr (HALO) {
+          // conv mode 2: per 64-channel block one halo tile, nine taps = nine windows of it (see HALO_* above). The last channel
+          // block of a layer whose Cin is not a multiple of 64 (the 96-channel layers: 64 + 32) issues only the MMAs that carry
+          // real channels instead of multiplying the TMA's zero fill.
+          const uint32_t h0 = smem_u32(smH) >> 4;
+          const int tail = p.Cin - (p.kb_per_tap - 1) * BK;          // channels in the last block, 1..64
+          for (int cb = 0; cb < p.kb_per_tap; ++cb) {
+            mbar_wait<CG == 2>(&hfull[hstage], hphase, 9);
+            const int nmma = (cb == p.kb_per_tap - 1) ? (tail + 15) / 16 : BK / 16;
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait<CG == 2>(&full[stage], phase, 3);
+              tc_fence_after();
+              if (elect_one()) {
+                const int ky = tap / 3, kx = tap - 3 * ky;
+                // window start: halo row ky, column kx; 8-row groups one halo row (2048 B) apart; off the swizzle period by kx rows
+                const uint64_t adesc = make_smem_desc(0, 16, HALO_W * 128, SWZ_128B, (uint32_t)kx) +
+                                       (h0 + hstage * (HALO_BYTES >> 4) + (((ky * HALO_W + kx) * 128) >> 4));
+                const uint64_t bdesc = desc_hi + (b0 + stage * (C::B_BYTES >> 4));
+                for (int k = 0; k < nmma; ++k) umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (cb | tap | k) ? 1u : 0u);
+                if (CG == 1) umma_commit(&empty[stage]); else umma_commit_cg2_mc(&empty[stage], 0x3);
+                if (tap == 8) {
+                  if (CG == 1) umma_commit(&hempty[hstage]); else umma_commit_cg2_mc(&hempty[hstage], 0x3);
+                  if (cb == p.kb_per_tap - 1) {
+                    if (CG == 1) umma_commit(&tfull[acc]); else umma_commit_cg2_mc(&tfull[acc], 0x3);
+                  }
+                }
+              }
+              __syncwarp();
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++hstage == HALO_STAGES) { hstage = 0; hphase ^= 1; }
+          }
+        }
+        if constexpr (!HALO)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           t0 = dbg ? clock64() : 0;
           mbar_wait<CG == 2>(&full[stage], phase, 3);
@@ -850,8 +941,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int per_img = p.tiles_x * p.tiles_y;
         const int img = m_blk / per_img;
         const int rr = m_blk % per_img;
-        const int y = (rr / p.tiles_x) * CONV_TH + r / CONV_TW;
-        const int x = (rr % p.tiles_x) * CONV_TW + r % CONV_TW;
+        const int y = HALO ? (rr / p.tiles_x) * HALO_TH + r / HALO_TW : (rr / p.tiles_x) * CONV_TH + r / CONV_TW;
+        const int x = HALO ? (rr % p.tiles_x) * HALO_TW + r % HALO_TW : (rr % p.tiles_x) * CONV_TW + r % CONV_TW;
         row_ok = (img < p.batch) && (y < p.H) && (x < p.W);
         grow = ((int64_t)img * p.H + y) * p.W + x;
       } else {
@@ -938,9 +1029,10 @@ static bool make_tmap(CUtensorMap* m, CUtensorMapDataType dtype, const void* bas
   return true;
 }
 
-template <int BN, int CG, bool CONV, int MXK = 0>
+template <int BN, int CG, int CONV, int MXK = 0>
 static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
-  using C = Cfg<BN, CG, MXK>;
+  constexpr bool HALO = CONV == 2;
+  using C = Cfg<BN, CG, MXK, 0, HALO ? 1 : 0>;
   KParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.epi = g.epi;
@@ -950,8 +1042,8 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   int num_m_blks;
   if (CONV) {
     p.taps = g.conv_taps; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.batch = g.batch;
-    p.tiles_x = (g.W + CONV_TW - 1) / CONV_TW;
-    p.tiles_y = (g.H + CONV_TH - 1) / CONV_TH;
+    p.tiles_x = HALO ? (g.W + HALO_TW - 1) / HALO_TW : (g.W + CONV_TW - 1) / CONV_TW;
+    p.tiles_y = HALO ? (g.H + HALO_TH - 1) / HALO_TH : (g.H + CONV_TH - 1) / CONV_TH;
     p.kb_per_tap = (g.Cin + BK - 1) / BK;
     p.num_kb = g.conv_taps * p.kb_per_tap;
     num_m_blks = g.batch * p.tiles_x * p.tiles_y;
@@ -963,7 +1055,7 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     p.tap_off = (g.conv_taps == 9 && st == 1) ? -1 : 0;
     uint64_t ad[4] = {(uint64_t)g.Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)g.batch};
     uint64_t as[3] = {(uint64_t)g.lda * 2, (uint64_t)g.lda * 2 * Win, (uint64_t)g.lda * 2 * Win * Hin};
-    uint32_t ab[4] = {BK, CONV_TW, CONV_TH, 1};
+    uint32_t ab[4] = {BK, (uint32_t)(HALO ? HALO_W : CONV_TW), (uint32_t)(HALO ? HALO_H : CONV_TH), 1};
     uint32_t ae[4] = {1, (uint32_t)st, (uint32_t)st, 1};
     if (!make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.A, 4, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B, ae)) return cudaErrorInvalidValue;
     // weights OHWI: dims (Cin, taps, Cout[, 1])
@@ -1086,7 +1178,7 @@ static cudaError_t launch_wq(const GemmProblem& g, cudaStream_t stream) {
   p.num_n_blks = (g.N + BN - 1) / BN;
   const int total = p.num_m_units * p.num_n_blks;
   const int units = std::min(total, g_num_sms / CG);
-  auto kern = gemm_kernel<BN, CG, false, 0, 1>;
+  auto kern = gemm_kernel<BN, CG, 0, 0, 1>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -1108,7 +1200,7 @@ static cudaError_t launch_wq(const GemmProblem& g, cudaStream_t stream) {
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA, tmBlo, p);
 }
 
-template <bool CONV>
+template <int CONV>
 static cudaError_t dispatch(const GemmProblem& g, cudaStream_t s, int bn, int cg) {
 #define F2B_CASE(BN_)                                                     \
   if (bn == BN_) {                                                        \
@@ -1119,7 +1211,7 @@ static cudaError_t dispatch(const GemmProblem& g, cudaStream_t s, int bn, int cg
   F2B_CASE(128)
   F2B_CASE(64)
   F2B_CASE(32)
-  if constexpr (CONV) {   // VAE channel counts (96, 192, 384) are multiples of 96, not of 128
+  if constexpr (CONV != 0) {   // VAE channel counts (96, 192, 384) are multiples of 96, not of 128
     F2B_CASE(192)
     F2B_CASE(96)
   }
@@ -1200,7 +1292,12 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
   // stages and ~1/3 less L2 -> smem traffic per FLOP (measured +8..10 % over single-CTA tiles on the DiT shapes)
   int cg = g.force_cta_group;
   if (!cg) cg = 2;
-  const int m_blks = conv ? g.batch * ((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + CONV_TH - 1) / CONV_TH) : (g.M + BM - 1) / BM;
+  // 3x3 stride-1 convolutions take the halo-tile kernel (FLUX2B_CONV_HALO=0: one TMA box per tap, the cross-check)
+  static const bool halo_on = !(getenv("FLUX2B_CONV_HALO") && atoi(getenv("FLUX2B_CONV_HALO")) == 0);
+  const bool halo = conv && halo_on && g.conv_taps == 9 && g.conv_stride <= 1 && !g.conv_no_halo;
+  const int m_blks = !conv ? (g.M + BM - 1) / BM
+                     : halo ? g.batch * ((g.W + HALO_TW - 1) / HALO_TW) * ((g.H + HALO_TH - 1) / HALO_TH)
+                            : g.batch * ((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + CONV_TH - 1) / CONV_TH);
   if (cg == 2 && (m_blks < 2 || bn < 32)) cg = 1;
   if (!conv && !g.force_bn && !g.force_cta_group && bn == 256 && g.epi.mode != EPI_SWIGLU && g.N % 128 == 0) {
     // Few-row problems (the text encoder's M = 512 prefill: 256-wide tiles of an N = 2560 projection occupy 40 of 148 SMs):
@@ -1226,7 +1323,7 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
     }
     if (best < 0.8 * cur) { bn = best_bn; cg = best_cg; }
   }
-  return conv ? dispatch<true>(g, stream, bn, cg) : dispatch<false>(g, stream, bn, cg);
+  return halo ? dispatch<2>(g, stream, bn, cg) : conv ? dispatch<1>(g, stream, bn, cg) : dispatch<0>(g, stream, bn, cg);
 }
 
 }  // namespace f2b

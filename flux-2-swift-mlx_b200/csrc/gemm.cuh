@@ -72,6 +72,7 @@ struct GemmProblem {
   int conv_taps = 0;  // 0 = plain GEMM, 1 = 1x1, 9 = 3x3 (stride 1: pad 1; stride 2: pad 0 top / left, 1 bottom / right)
   int batch = 1, H = 0, W = 0, Cin = 0;  // H, W = OUTPUT extent
   int conv_stride = 1;                   // 1 | 2
+  int conv_no_halo = 0;                  // 1 = 3x3 stride-1 convolution through one TMA box per tap instead of the halo tile (cross-check)
   int Hin = 0, Win = 0;                  // input extent (0 = H * stride, W * stride)
   Epilogue epi;
   // native block-scaled operands (tcgen05.mma.kind::mxf8f6f4 / mxf4nvf4 .block_scale), single-CTA tiles:

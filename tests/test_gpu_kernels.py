@@ -96,14 +96,19 @@ def _attn_ref(qkv, B, S, H):
     return torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * S, D)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
-@pytest.mark.parametrize("B,S,H", [(1, 256, 2), (2, 328, 2), (1, 77, 1), (1, 768, 3), (1, 4608, 4)])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("B,S,H", [(1, 256, 2), (2, 328, 2), (1, 77, 1), (1, 768, 3), (1, 4608, 4), (1, 64, 1), (1, 130, 2), (2, 1000, 1)])
 def test_attention(ctx, B, S, H, variant):
     qkv = torch.randn(B * S, 3 * H * 128, generator=torch.Generator().manual_seed(S + H)).to(torch.bfloat16).cuda()
     out = ctx.op_attention(qkv, B, S, H, variant=variant)
     ctx.synchronize()
-    # P is rounded to bf16 before the PV product and the result once more: ~2 roundings
-    assert rel_l2(out, _attn_ref(qkv, B, S, H)) < 4e-3
+    ref = _attn_ref(qkv, B, S, H)
+    e = rel_l2(out, ref)
+    # the kernel's own arithmetic against fp32 SDPA rounded once to the bf16 output type: what is left is the bf16 rounding of P
+    e_round = rel_l2(out, ref.to(torch.bfloat16).float())
+    print(f"attention v{variant} B={B} S={S} H={H}: rel-L2 {e:.2e} (vs bf16-rounded reference {e_round:.2e})")
+    # P is rounded to bf16 before the PV product and the result once more: two roundings of 2^-9 relative each
+    assert e < 4e-3
 
 
 def test_attention_f16_and_large_logits(ctx_f16):
@@ -112,7 +117,7 @@ def test_attention_f16_and_large_logits(ctx_f16):
     qkv = torch.randn(B * S, 3 * H * 128, generator=torch.Generator().manual_seed(9))
     qkv[:, :2 * H * 128] *= 4.0
     qkv = qkv.to(torch.float16).cuda()
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         out = ctx_f16.op_attention(qkv, B, S, H, variant=variant)
         ctx_f16.synchronize()
         assert rel_l2(out, _attn_ref(qkv, B, S, H)) < 2e-3
@@ -122,6 +127,10 @@ def test_attention_f16_and_large_logits(ctx_f16):
     (1, 32, 32, 64, 64, 3, 1, False), (1, 40, 24, 96, 96, 3, 1, True), (2, 16, 16, 32, 32, 1, 1, False),
     (1, 32, 32, 96, 3, 3, 1, False), (1, 32, 32, 64, 64, 3, 2, False), (1, 9, 21, 32, 384, 3, 1, False),
     (2, 24, 24, 384, 192, 1, 2, False), (1, 128, 128, 192, 192, 3, 2, True),
+    # halo-tile kernel (3x3, stride 1): 16 x 8-pixel tiles with ragged borders, Cin below / not a multiple of the 64-channel block
+    # (tail MMAs), CTA pairs with an odd tile count, batch > 1, the small decoder's widths
+    (1, 17, 9, 32, 96, 3, 0, False), (2, 33, 23, 96, 192, 3, 2, True), (1, 64, 64, 384, 384, 3, 2, False),
+    (1, 48, 40, 192, 96, 3, 0, True), (3, 16, 8, 64, 64, 3, 2, False), (1, 100, 60, 96, 3, 3, 0, False),
 ])
 def test_conv2d(ctx_f16, B, H, W, Cin, Cout, k, cg, res):
     g = torch.Generator().manual_seed(H * W + Cin)

@@ -287,6 +287,12 @@ PROBES = {
     "attn_v3_big": lambda: probe_attention(1, 4608, 24, 3),
     "attn_v3_small": lambda: probe_attention(1, 256, 2, 3),
     "attn_v3_tail": lambda: probe_attention(2, 328, 2, 3),
+    "attn_v4_big": lambda: probe_attention(1, 4608, 24, 4),
+    "attn_v4_big_p4": lambda: probe_attention(1, 4608, 24, 4, poly=4),
+    "attn_v4_big_p2": lambda: probe_attention(1, 4608, 24, 4, poly=2),
+    "attn_v4_small": lambda: probe_attention(1, 256, 2, 4),
+    "attn_v4_tail": lambda: probe_attention(2, 328, 2, 4),
+    "attn_v4_dev16k": lambda: probe_attention(1, 16896, 6, 4),
     "attn_v3_k9": lambda: probe_attention(1, 4608, 32, 3),
     "attn_v3_dev16k": lambda: probe_attention(1, 16896, 6, 3),
     "conv3_cg1": lambda: probe_conv(1, 32, 32, 64, 64, 3, 1),
@@ -296,6 +302,14 @@ PROBES = {
     "conv3_cg2": lambda: probe_conv(1, 32, 32, 64, 64, 3, 2),
     "conv3_big_cg1": lambda: probe_conv(1, 512, 512, 192, 192, 3, 1),
     "conv3_big_cg2": lambda: probe_conv(1, 512, 512, 192, 192, 3, 2),
+    # the small decoder's layers at 1024^2 output (FLUX2B_CONV_HALO=0 in the environment: the per-tap kernel)
+    "vaeconv_1024_96": lambda: probe_conv(1, 1024, 1024, 96, 96, 3, 0),
+    "vaeconv_1024_192_96": lambda: probe_conv(1, 1024, 1024, 192, 96, 3, 0),
+    "vaeconv_1024_96_3": lambda: probe_conv(1, 1024, 1024, 96, 3, 3, 0),
+    "vaeconv_512_192": lambda: probe_conv(1, 512, 512, 192, 192, 3, 0),
+    "vaeconv_512_384_192": lambda: probe_conv(1, 512, 512, 384, 192, 3, 0),
+    "vaeconv_256_384": lambda: probe_conv(1, 256, 256, 384, 384, 3, 0),
+    "vaeconv_128_384": lambda: probe_conv(1, 128, 128, 384, 384, 3, 0),
     "quant_qint8": lambda: probe_quant(1),
     "quant_int4": lambda: probe_quant(2),
     "quant_mxfp8": lambda: probe_quant(3),

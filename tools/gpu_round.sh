@@ -64,8 +64,13 @@ except Exception as e:
 PY
       done; done ;;
     tests_wq)
-      timeout 900 python -m pytest tests -m gpu -q -x -k "quantized or in_kernel or forward_only or lora or prequantized or affine" > gpurun_out/pytest_wq.log 2>&1
+      timeout 900 python -m pytest tests -m gpu -q -k "quantized or in_kernel or forward_only or lora or prequantized or affine or conv2d or vae" > gpurun_out/pytest_wq.log 2>&1
       echo "pytest wq rc=$?"; tail -n 25 gpurun_out/pytest_wq.log ;;
+    probe_r2)
+      # round-2 kernel candidates against what they replace: attention variant 4 vs 3, halo-tile convolutions vs one box per tap
+      timeout 900 python tools/gpu_probe.py attn_v3_big attn_v4 attn_v3_dev16k > gpurun_out/probe_attn4.log 2>&1; tail -n 12 gpurun_out/probe_attn4.log
+      timeout 600 python tools/gpu_probe.py vaeconv > gpurun_out/probe_conv_halo.log 2>&1; tail -n 9 gpurun_out/probe_conv_halo.log
+      FLUX2B_CONV_HALO=0 timeout 600 python tools/gpu_probe.py vaeconv > gpurun_out/probe_conv_pertap.log 2>&1; tail -n 9 gpurun_out/probe_conv_pertap.log ;;
     full)
       # top kernels, full sections (few launches each)
       timeout 1500 ncu --set full --clock-control none --import-source on --profile-from-start off \
@@ -78,7 +83,7 @@ PY
     probe_attn)
       timeout 900 python tools/gpu_probe.py attn_v > gpurun_out/probe_attn.log 2>&1; tail -n 20 gpurun_out/probe_attn.log ;;
     tests_attn)
-      timeout 900 python -m pytest tests -m gpu -q -x -k "attention or dit_forward or denoise or kv" > gpurun_out/pytest_attn.log 2>&1; tail -n 15 gpurun_out/pytest_attn.log ;;
+      timeout 900 python -m pytest tests -m gpu -q -k "attention or dit_forward or denoise or kv" > gpurun_out/pytest_attn.log 2>&1; tail -n 15 gpurun_out/pytest_attn.log ;;
     probe)
       timeout 1500 python tools/gpu_probe.py gemm_big gemm_ffin gemm_out attn_v1_big attn_v2_big conv3_big > gpurun_out/probe.log 2>&1; tail -n 20 gpurun_out/probe.log ;;
   esac
