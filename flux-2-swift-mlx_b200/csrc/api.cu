@@ -149,6 +149,7 @@ void flux2b_destroy(flux2b_ctx* c) {
   cudaStreamSynchronize(c->stream);
   sp_destroy(c);
   te_destroy_graphs(c);
+  destroy_graphs(c);
   for (auto& pk : c->prof)
     for (auto& e : pk.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -161,6 +162,7 @@ int flux2b_set_stream(flux2b_ctx* c, void* s) {
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   c->stream = reinterpret_cast<cudaStream_t>(s);
   c->own_stream = false;
+  ++c->opt_gen;
   return 0;
 }
 int flux2b_synchronize(flux2b_ctx* c) {
@@ -171,13 +173,14 @@ int flux2b_synchronize(flux2b_ctx* c) {
 int flux2b_set_option(flux2b_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "null argument");
   static const char* known[] = {"compute_f16", "fuse_qk_rope", "fuse_swiglu", "attn_variant", "gemm_cta_group",
-                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant", "attn_poly", "group_streams", "te_graph", "sp_disable", "vae_attn_chunk", "wq_inkernel"};
+                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant", "attn_poly", "group_streams", "te_graph", "sp_disable", "vae_attn_chunk", "wq_inkernel", "dit_graph"};
   bool ok = false;
   for (const char* k : known) ok = ok || !strcmp(k, name);
   if (!ok) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string("unknown option: ") + name);
   if (c->finalized && (!strcmp(name, "compute_f16") || !strcmp(name, "fuse_swiglu") || !strcmp(name, "vae_f16") || !strcmp(name, "native_mx") || !strcmp(name, "mx_bn") || !strcmp(name, "wq_inkernel")))
     return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string(name) + " must be set before flux2b_finalize_weights");
   c->opt[name] = value;
+  ++c->opt_gen;   // captured launch sequences may depend on any option
   return 0;
 }
 

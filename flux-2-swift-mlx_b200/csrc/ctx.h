@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -44,6 +45,9 @@ inline size_t dtype_size(int dt) {
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  // bumped whenever any buffer of the process is (re)allocated or freed: a captured CUDA graph holds raw device addresses, so
+  // a graph is valid only for the epoch it was captured in (steady-state calls allocate nothing, the epoch then stands still)
+  static inline uint64_t g_epoch = 0;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -53,9 +57,10 @@ struct DevBuf {
     return *this;
   }
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void release() { if (p) { cudaFree(p); ++g_epoch; } p = nullptr; bytes = 0; }
   cudaError_t alloc(size_t n) {
     release();
+    ++g_epoch;
     if (n == 0) n = 16;
     cudaError_t e = cudaMalloc(&p, n);
     if (e == cudaSuccess) bytes = n; else p = nullptr;
@@ -191,6 +196,15 @@ struct DenoiseCache {
   std::vector<float> sigmas;   // [sigmas ..., guidance]
 };
 
+// A captured launch sequence (the denoise loop of one shape / schedule, the VAE decode of one resolution): replayed with one
+// cudaGraphLaunch instead of ~740 kernel launches per image, each of which re-encodes 2 - 4 tensor maps on the host.
+struct CachedGraph {
+  std::string key;          // every scalar / pointer the sequence depends on
+  void* exec = nullptr;     // cudaGraphExec_t; nullptr = this key could not be captured (plain launches are used)
+  int64_t launches = 0;     // kernels per replay (for flux2b_launch_count)
+  uint64_t epoch = 0, opt_gen = 0;
+};
+
 struct ProfKind {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
   size_t used = 0;
@@ -265,6 +279,8 @@ struct flux2b_ctx {
   }
 
   f2b::DenoiseCache dn_cache;
+  std::vector<f2b::CachedGraph> graphs;   // option dit_graph (default 1)
+  uint64_t opt_gen = 0;                   // bumped by set_option / set_stream / sp_init: cached graphs of older generations are dropped
 
   // ---- sequence parallelism
   f2b::SpState sp;
@@ -321,6 +337,12 @@ int finalize_te(flux2b_ctx* c);
 int te_forward_device(flux2b_ctx* c, int S, const int32_t* ids, int key_lo, int key_hi, const int* layers, int n_layers,
                       float* out_f32, int64_t ldo, const int* mask_dev = nullptr);
 void te_destroy_graphs(flux2b_ctx* c);
+
+// Run `body` (pure device work enqueued on c->stream, no allocation after its first execution) through the graph cache: the
+// first call for a key executes it directly and then captures it; later calls replay the graph. Falls back to plain launches
+// when graphs are off, the profiler is on, or capture fails.
+int run_graphed(flux2b_ctx* c, const std::string& key, const std::function<int()>& body);
+void destroy_graphs(flux2b_ctx* c);
 
 // forward passes
 struct DitIO {

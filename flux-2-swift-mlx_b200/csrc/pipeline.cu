@@ -10,6 +10,65 @@ namespace f2b {
 int vector_f32_from_key(flux2b_ctx* c, const std::string& key, DevBuf* out, int64_t expect, bool required, float fill);
 }
 
+namespace f2b {
+
+void destroy_graphs(flux2b_ctx* c) {
+  for (CachedGraph& g : c->graphs)
+    if (g.exec) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(g.exec));
+  c->graphs.clear();
+}
+
+int run_graphed(flux2b_ctx* c, const std::string& key, const std::function<int()>& body) {
+  if (!c->option("dit_graph", 1) || c->prof_on) return body();
+  // graphs of an older allocation epoch hold stale addresses; graphs of an older option generation a different launch sequence
+  for (size_t i = 0; i < c->graphs.size();) {
+    if (c->graphs[i].epoch != DevBuf::g_epoch || c->graphs[i].opt_gen != c->opt_gen) {
+      if (c->graphs[i].exec) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(c->graphs[i].exec));
+      c->graphs.erase(c->graphs.begin() + (long)i);
+    } else ++i;
+  }
+  for (CachedGraph& g : c->graphs)
+    if (g.key == key) {
+      if (!g.exec) return body();
+      F2B_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(g.exec), c->stream));
+      c->launches += g.launches;
+      return 0;
+    }
+  // first call for this key: the real execution doubles as the warm-up that grows every workspace
+  const uint64_t epoch0 = DevBuf::g_epoch;
+  const int64_t l0 = c->launches;
+  F2B_TRY(body());
+  if (DevBuf::g_epoch != epoch0) return 0;   // buffers moved during this call: capture on the next one
+  if (c->graphs.size() >= 16) destroy_graphs(c);
+  CachedGraph g;
+  g.key = key; g.launches = c->launches - l0; g.epoch = DevBuf::g_epoch; g.opt_gen = c->opt_gen;
+  int64_t prof_launches[FLUX2B_PROF_KINDS]; double prof_flops[FLUX2B_PROF_KINDS], prof_bytes[FLUX2B_PROF_KINDS];
+  for (int i = 0; i < FLUX2B_PROF_KINDS; ++i) { prof_launches[i] = c->prof[i].launches; prof_flops[i] = c->prof[i].flops; prof_bytes[i] = c->prof[i].bytes; }
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  if (ok) {
+    const int rc = body();
+    ok = cudaStreamEndCapture(c->stream, &graph) == cudaSuccess && rc == 0 && graph != nullptr;
+  }
+  // the capture enqueued nothing: undo its bookkeeping
+  c->launches = l0 + g.launches;
+  for (int i = 0; i < FLUX2B_PROF_KINDS; ++i) { c->prof[i].launches = prof_launches[i]; c->prof[i].flops = prof_flops[i]; c->prof[i].bytes = prof_bytes[i]; }
+  if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok || DevBuf::g_epoch != g.epoch) {   // not capturable (or it allocated): remember, so that later calls do not retry
+    cudaGetLastError();
+    if (exec) cudaGraphExecDestroy(exec);
+    exec = nullptr;
+    g.epoch = DevBuf::g_epoch;
+  }
+  g.exec = exec;
+  c->graphs.push_back(std::move(g));
+  return 0;
+}
+
+}  // namespace f2b
+
 extern "C" {
 
 // ------------------------------------------------------------------ scheduler (host; FlowMatchEulerScheduler.swift)
@@ -340,6 +399,23 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
   const int steps = n_sig - 1;
   const bool kv = p->kv_cache != 0 && S_ref > 0;
   if (kv && p->enc_uncond) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "the KV-cached loop has no classical-CFG branch (as the reference)");
+  // Without a hook the whole loop is one fixed launch sequence over context-owned buffers: it is captured once per (shape,
+  // schedule) as a CUDA graph and replayed (option dit_graph, default 1; not under sequence parallelism — NCCL calls and the
+  // peer-mapping handshake stay outside graphs). The text embeddings are then read from a context-owned copy, so the graph does
+  // not depend on the caller's pointers.
+  const bool graphed = !p->hook && c->sp.world == 1 && c->option("dit_graph", 1) && !c->prof_on;
+  if (graphed) {
+    Buf enc_c{c->scratch_buf("dn.enc", enc_bytes)}, encu_c{p->enc_uncond ? c->scratch_buf("dn.enc_u", encu_bytes) : nullptr};
+    if (!enc_c.p || (p->enc_uncond && !encu_c.p)) { cudaGetLastError(); return fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "denoise state allocation failed"); }
+    F2B_CUDA(cudaMemcpyAsync(enc_c.p, enc_d, enc_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    if (p->enc_uncond) F2B_CUDA(cudaMemcpyAsync(encu_c.p, encu_d, encu_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    enc_d = enc_c.p; encu_d = encu_c.p;
+    if (guid_d && guid_d != tbuf.as<float>() + n_sig) {   // a device-resident guidance scalar: into the schedule buffer's tail
+      F2B_CUDA(cudaMemcpyAsync(tbuf.as<float>() + n_sig, guid_d, 4, cudaMemcpyDeviceToDevice, c->stream));
+      guid_d = tbuf.as<float>() + n_sig;
+    }
+  }
+  auto loop_body = [&]() -> int {
   for (int i = 0; i < steps; ++i) {
     const float sigma = p->sigmas[i], sigma_next = p->sigmas[i + 1];
     F2B_CUDA(cudaMemcpyAsync(hid.p, x.p, n_lat * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -381,6 +457,18 @@ int flux2b_denoise(flux2b_ctx* c, const flux2b_denoise_params* p, float* latents
       F2B_CUDA(cudaStreamSynchronize(c->stream));
     }
   }
+  return 0;
+  };
+  if (graphed) {
+    std::string key = "denoise";
+    auto add = [&](const void* v, size_t n) { key.append(reinterpret_cast<const char*>(v), n); };
+    const int scalars[] = {p->height, p->width, p->S_txt, S_txt_u, S_ref, (int)kv, p->enc_uncond ? 1 : 0, guid_d ? 1 : 0, p->enc_dtype, n_sig};
+    const void* ptrs[] = {x.p, hid.p, pred.p, pred_u.p, ids_img.p, ids_txt.p, ids_txt_u.p, tbuf.p, enc_d, encu_d};
+    add(scalars, sizeof(scalars)); add(ptrs, sizeof(ptrs)); add(&p->cfg_scale, 4); add(p->sigmas, (size_t)n_sig * 4);
+    F2B_TRY(run_graphed(c, key, loop_body));
+  } else {
+    F2B_TRY(loop_body());
+  }
   F2B_CUDA(cudaMemcpyAsync(latents, x.p, n_lat * 4, lat_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
   // host latents: the copy must have landed when the call returns; device pointers: stream-ordered, no synchronisation
   return end_call(c, lat_host);
@@ -402,18 +490,30 @@ int flux2b_generate(flux2b_ctx* c, const flux2b_denoise_params* p, float* latent
   F2B_CUDA(cudaMemcpyAsync(latents, xdev.p, n_lat * 4, lat_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, c->stream));
   // unpack -> BN denorm (eps 1e-4) -> unpatchify -> NHWC 16-bit, one fused gather (Flux2Pipeline.swift:2059-2079)
   const bool vf16 = c->option("vae_f16", 1) != 0;
-  {
-    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 6.0 * n_lat);
-    F2B_CUDA(seq_to_vae_input(xdev.as<float>(), c->vw.bn_mean.as<float>(), c->vw.bn_var.as<float>(), 1e-4f, z.p, 1, h, w, vf16, c->stream));
-  }
-  void* img16; int ld;
-  F2B_TRY(vae_decode_device(c, 1, 2 * h, 2 * w, z.p, &img16, &ld));
   const int64_t npix = (int64_t)p->height * p->width;
   void* dout; bool ho;
   F2B_TRY(dev_out(c, rgb, (size_t)npix * 3, &dout, &ho));
+  // latents -> uint8 image: ~200 launches over context-owned buffers, captured per resolution like the denoise loop
+  auto decode_body = [&]() -> int {
+    {
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 6.0 * n_lat);
+      F2B_CUDA(seq_to_vae_input(xdev.as<float>(), c->vw.bn_mean.as<float>(), c->vw.bn_var.as<float>(), 1e-4f, z.p, 1, h, w, vf16, c->stream));
+    }
+    void* img16; int ld;
+    F2B_TRY(vae_decode_device(c, 1, 2 * h, 2 * w, z.p, &img16, &ld));
+    {
+      ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 9.0 * npix);
+      F2B_CUDA(postprocess_u8(img16, ld, (uint8_t*)dout, npix, vf16, c->stream));
+    }
+    return 0;
+  };
   {
-    ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, 9.0 * npix);
-    F2B_CUDA(postprocess_u8(img16, ld, (uint8_t*)dout, npix, vf16, c->stream));
+    std::string key = "decode";
+    const int scalars[] = {p->height, p->width, (int)vf16};
+    const void* ptrs[] = {xdev.p, z.p, dout};
+    key.append(reinterpret_cast<const char*>(scalars), sizeof(scalars));
+    key.append(reinterpret_cast<const char*>(ptrs), sizeof(ptrs));
+    F2B_TRY(run_graphed(c, key, decode_body));
   }
   F2B_TRY(finish_out(c, rgb, dout, (size_t)npix * 3, ho));
   return end_call(c, lat_host || ho);   // all-device call: stream-ordered, returns without synchronising

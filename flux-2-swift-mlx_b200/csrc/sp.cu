@@ -259,6 +259,7 @@ int flux2b_sp_init(flux2b_ctx* c, const void* id128, int rank, int world) {
   c->sp.world = world;
   c->sp.rank = rank;
   c->sp.mode = c->option("sp_mode", 0);
+  ++c->opt_gen;
   return 0;
 }
 

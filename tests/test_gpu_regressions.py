@@ -335,3 +335,51 @@ def test_klein4b_width_in_kernel_dequant(flux2b):
     errs = [rel_l2(b, r) for b, r in zip(blocks, rec)]
     print(f"klein4b width int4 W-only in-kernel: per-block rel-L2 {['%.2e' % e for e in errs]}, output {rel_l2(outs[0], ref):.2e}")
     assert max(errs) < 3e-3 and rel_l2(outs[0], ref) < 6e-3
+
+
+# ------------------------------------------------------------------ CUDA-graphed denoise loop / decode
+@pytest.mark.parametrize("flavor", ["t2i", "cfg", "i2i", "kv"])
+def test_graph_replay_equals_plain_launches(flux2b, flavor):
+    """option dit_graph: the first call for a (shape, schedule) runs plain launches and captures them, later calls replay the
+    graph — same bits as the plain sequence (dit_graph = 0), for every loop flavour, and a changed schedule is not served a stale graph"""
+    from oracle import flux2_oracle as O
+    cfg = _tiny(O, layers=(2, 2))
+    vcfg = O.vae_small_decoder()
+    W, VW = O.random_dit_weights(cfg, seed=0), O.random_vae_weights(vcfg, seed=1)
+    H, S_img = 128, 64
+    lat = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(1))
+    enc = torch.randn(1, 64, 256, generator=torch.Generator().manual_seed(2))
+    neg = torch.randn(1, 32, 256, generator=torch.Generator().manual_seed(3))
+    ref_lat = torch.randn(1, 64, 128, generator=torch.Generator().manual_seed(4))
+    ref_ids = O.reference_position_ids([8], [8])
+    sched = flux2b.FlowMatchEulerScheduler(); sched.set_timesteps(3, S_img)
+    kw = {"t2i": {}, "cfg": dict(enc_uncond=neg.numpy(), cfg_scale=3.0),
+          "i2i": dict(ref_latents=ref_lat.numpy(), ref_ids=ref_ids.numpy()),
+          "kv": dict(ref_latents=ref_lat.numpy(), ref_ids=ref_ids.numpy(), kv_cache=True)}[flavor]
+    results = {}
+    for graph in (1, 0):
+        ctx = flux2b.Context(dit=cfg, vae=vcfg, options={"dit_graph": graph})
+        ctx.load_weights(W, dtype=torch.bfloat16); ctx.load_weights(VW); ctx.finalize()
+        outs = []
+        for rep in range(3):   # with graphs: plain + capture, replay, replay
+            x = lat.numpy().copy()
+            if flavor == "kv":
+                ctx.denoise(x, enc.numpy(), sched.sigmas, H, H, **kw)
+                rgb = None
+            else:
+                rgb = ctx.generate(x, enc.numpy(), sched.sigmas, H, H, **kw)
+            outs.append((x, rgb))
+        # a different schedule of the same length must not hit the cached graph (Euler's step sizes are baked into it)
+        x2 = lat.numpy().copy()
+        sig2 = [s * 0.9 for s in sched.sigmas]
+        ctx.denoise(x2, enc.numpy(), sig2, H, H, **{k: v for k, v in kw.items()})
+        results[graph] = (outs, x2)
+        ctx.close()
+    for graph in (1, 0):
+        outs, _ = results[graph]
+        for x, rgb in outs[1:]:
+            assert np.array_equal(x, outs[0][0])
+            assert rgb is None or np.array_equal(rgb, outs[0][1])
+    assert np.array_equal(results[1][0][0][0], results[0][0][0][0])
+    assert np.array_equal(results[1][1], results[0][1])
+    assert not np.array_equal(results[1][1], results[1][0][0][0])
