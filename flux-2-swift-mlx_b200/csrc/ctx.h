@@ -112,6 +112,7 @@ struct SingleBlockW {
 };
 struct ConvW {
   DevBuf w;     // 16-bit OHWI [Cout, taps, Cin]
+  DevBuf w_up;  // Upsample2D convolutions only: the pre-summed [Cout, 16, Cin] phase kernels of the folded upsample (gemm.cuh: conv_up2)
   DevBuf bias;  // fp32 [Cout]
   int cin = 0, cout = 0, taps = 0;
 };

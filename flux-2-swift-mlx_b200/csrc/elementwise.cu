@@ -411,6 +411,32 @@ cudaError_t gemv_q(const float* x, int64_t ldx, const void* codes, int64_t row_b
   return cudaGetLastError();
 }
 
+// Pre-summed weights of the folded Upsample2D (gemm.cuh: conv_up2): w OHWI [Cout, 3, 3, Cin] 16-bit -> [Cout, 16, Cin] with
+// tap index (py * 2 + px) * 4 + ty * 2 + tx = sum of w[ky, kx] over ky in R(py, ty), kx in R(px, tx),
+// R(0,0) = {0}, R(0,1) = {1,2}, R(1,0) = {0,1}, R(1,1) = {2}: after nearest-2x upsampling, those 3x3 taps land on the same source
+// pixel. Summed in fp32, rounded once to the operand type.
+__global__ void fold_upsample_weights_kernel(const uint16_t* __restrict__ w, uint16_t* __restrict__ out, int64_t Cout, int Cin, bool f16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 16 * Cin) return;
+  const int c = (int)(i % Cin);
+  const int tap = (int)((i / Cin) % 16);
+  const int64_t o = i / ((int64_t)16 * Cin);
+  const int py = tap >> 3, px = (tap >> 2) & 1, ty = (tap >> 1) & 1, tx = tap & 1;
+  const int ky0 = (py == 0) ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = (py == 0) ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+  const int kx0 = (px == 0) ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = (px == 0) ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+  float acc = 0.f;
+  for (int ky = ky0; ky <= ky1; ++ky)
+    for (int kx = kx0; kx <= kx1; ++kx) acc += load16(w, ((o * 3 + ky) * 3 + kx) * Cin + c, f16);
+  store16(out, i, acc, f16);
+}
+cudaError_t fold_upsample_weights(const void* w_ohwi16, void* out16, int64_t Cout, int Cin, bool f16, cudaStream_t s) {
+  const int64_t n = Cout * 16 * Cin;
+  if (n <= 0) return cudaSuccess;
+  fold_upsample_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint16_t*>(w_ohwi16),
+                                                                          reinterpret_cast<uint16_t*>(out16), Cout, Cin, f16);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ sinusoid / rope table
 __global__ void sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int B, float pre_scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

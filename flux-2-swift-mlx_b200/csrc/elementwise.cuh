@@ -90,6 +90,8 @@ cudaError_t seq_to_vae_input(const float* seq, const float* mean, const float* v
 size_t groupnorm_ws_bytes(int B, int G);
 cudaError_t groupnorm_silu(const void* x16, void* y16, const float* gamma, const float* beta, double* stats_ws, int B,
                            int64_t HW, int C, int G, float eps, bool silu, bool f16, cudaStream_t s);
+// OHWI [Cout, 3, 3, Cin] -> [Cout, 16, Cin]: the four 2x2 phase kernels of nearest-2x upsample + conv3x3 (gemm.cuh: conv_up2)
+cudaError_t fold_upsample_weights(const void* w_ohwi16, void* out16, int64_t Cout, int Cin, bool f16, cudaStream_t s);
 cudaError_t upsample_nearest2x(const void* x16, void* y16, int B, int H, int W, int C, cudaStream_t s);
 // softmax over the last dim of fp32 scores -> 16-bit probabilities (VAE mid attention, ResnetBlock.swift:302-304)
 cudaError_t softmax_rows(const float* x, int64_t ldx, void* y16, int64_t ldy, int rows, int cols, float scale, bool f16,

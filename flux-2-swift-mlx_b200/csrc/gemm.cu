@@ -48,6 +48,7 @@ struct KParams {
   // conv
   int taps, H, W, Cin, batch, tiles_x, tiles_y, kb_per_tap;  // H, W: OUTPUT extent
   int stride, tap_off;  // input coordinate of tap (ky, kx) for output (y, x): (y * stride + ky + tap_off, x * stride + kx + tap_off)
+  int up2;              // conv mode 2 only: nearest-2x upsample folded into the 3x3 convolution (four 2x2 phase kernels, see gemm.cuh)
   Epilogue epi;
   // block-scaled kinds: scale factors of A [ceil(M/128)][sfa_ld][512 B], of B [N/128][sfb_ld][512 B]; one 512 B block =
   // 128 rows x 4 scale bytes in the tcgen05 layout (quant.cuh); *_ld = blocks per 128-row block (the full K extent)
@@ -514,7 +515,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const bool leader = (cta_rank == 0);
   const int unit_id = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
   const int num_units = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
-  const int total_tiles = p.num_m_units * p.num_n_blks;
+  const int total_tiles = p.num_m_units * p.num_n_blks * ((HALO && p.up2) ? 4 : 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -567,8 +568,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool dbg = p.dbg && unit_id == 0;
       long long w_empty = 0, t_begin = dbg ? clock64() : 0;
       for (int t = unit_id; t < total_tiles; t += num_units) {
-        const int m_unit = t % p.num_m_units;
-        const int n_blk = t / p.num_m_units;
+        // (folded upsample: the four output phases of an M tile are four consecutive tiles of the schedule)
+        const int tq = (HALO && p.up2) ? t >> 2 : t;
+        const int phase_idx = (HALO && p.up2) ? (t & 3) : 0;
+        const int m_unit = tq % p.num_m_units;
+        const int n_blk = tq / p.num_m_units;
         const int m_blk = m_unit * CG + (int)cta_rank;
         const int nrow0 = n_blk * BN + (int)cta_rank * C::B_ROWS;
         const CUtensorMap* tmBsel = (MXK == 0 && !CONV && m_unit < p.split_units) ? &tmSFB : &tmB;
@@ -595,16 +599,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_4d_cg2(h_dst, &tmA, hbar, cb * BK, x0 - 1, y0 - 1, img);
             }
             if (++hstage == HALO_STAGES) { hstage = 0; hphase ^= 1; }
-            for (int tap = 0; tap < 9; ++tap) {
+            const int ntaps = p.up2 ? 4 : 9, tap0 = p.up2 ? phase_idx * 4 : 0;
+            for (int tap = 0; tap < ntaps; ++tap) {
               mbar_wait(&empty[stage], phase ^ 1, 1);
               void* b_dst = smB + stage * C::B_BYTES;
               if (CG == 1) {
                 mbar_expect_tx(&full[stage], C::B_BYTES);
-                tma_load_3d(b_dst, &tmB, &full[stage], cb * BK, tap, nrow0);
+                tma_load_3d(b_dst, &tmB, &full[stage], cb * BK, tap0 + tap, nrow0);
               } else {
                 const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
                 mbar_expect_tx_cluster(lbar, C::B_BYTES);
-                tma_load_4d_cg2(b_dst, &tmB, lbar, cb * BK, tap, nrow0, 0);
+                tma_load_4d_cg2(b_dst, &tmB, lbar, cb * BK, tap0 + tap, nrow0, 0);
               }
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -740,21 +745,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // real channels instead of multiplying the TMA's zero fill.
           const uint32_t h0 = smem_u32(smH) >> 4;
           const int tail = p.Cin - (p.kb_per_tap - 1) * BK;          // channels in the last block, 1..64
+          // folded upsample: phase (py, px) of the output reads the 2x2 source window that starts at halo (py, px)
+          const int ntaps = p.up2 ? 4 : 9, py = p.up2 ? ((t & 3) >> 1) : 0, px = p.up2 ? (t & 1) : 0;
           for (int cb = 0; cb < p.kb_per_tap; ++cb) {
             mbar_wait<CG == 2>(&hfull[hstage], hphase, 9);
             const int nmma = (cb == p.kb_per_tap - 1) ? (tail + 15) / 16 : BK / 16;
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < ntaps; ++tap) {
               mbar_wait<CG == 2>(&full[stage], phase, 3);
               tc_fence_after();
               if (elect_one()) {
-                const int ky = tap / 3, kx = tap - 3 * ky;
+                const int ky = p.up2 ? py + (tap >> 1) : tap / 3, kx = p.up2 ? px + (tap & 1) : tap - 3 * (tap / 3);
                 // window start: halo row ky, column kx; 8-row groups one halo row (2048 B) apart; off the swizzle period by kx rows
                 const uint64_t adesc = make_smem_desc(0, 16, HALO_W * 128, SWZ_128B, (uint32_t)kx) +
                                        (h0 + hstage * (HALO_BYTES >> 4) + (((ky * HALO_W + kx) * 128) >> 4));
                 const uint64_t bdesc = desc_hi + (b0 + stage * (C::B_BYTES >> 4));
                 for (int k = 0; k < nmma; ++k) umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (cb | tap | k) ? 1u : 0u);
                 if (CG == 1) umma_commit(&empty[stage]); else umma_commit_cg2_mc(&empty[stage], 0x3);
-                if (tap == 8) {
+                if (tap == ntaps - 1) {
                   if (CG == 1) umma_commit(&hempty[hstage]); else umma_commit_cg2_mc(&hempty[hstage], 0x3);
                   if (cb == p.kb_per_tap - 1) {
                     if (CG == 1) umma_commit(&tfull[acc]); else umma_commit_cg2_mc(&tfull[acc], 0x3);
@@ -931,8 +938,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = unit_id; t < total_tiles; t += num_units) {
-      const int m_unit = t % p.num_m_units;
-      const int n_blk = t / p.num_m_units;
+      const int tq = (HALO && p.up2) ? t >> 2 : t;
+      const int m_unit = tq % p.num_m_units;
+      const int n_blk = tq / p.num_m_units;
       const int m_blk = m_unit * CG + (int)cta_rank;
       const int r = quarter * 32 + lane;
       bool row_ok;
@@ -945,6 +953,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int x = HALO ? (rr % p.tiles_x) * HALO_TW + r % HALO_TW : (rr % p.tiles_x) * CONV_TW + r % CONV_TW;
         row_ok = (img < p.batch) && (y < p.H) && (x < p.W);
         grow = ((int64_t)img * p.H + y) * p.W + x;
+        if (HALO && p.up2)   // source pixel (y, x) -> output pixel (2y + py, 2x + px) of the 2H x 2W image
+          grow = ((int64_t)img * 2 * p.H + 2 * y + ((t & 3) >> 1)) * (2 * p.W) + 2 * x + (t & 1);
       } else {
         grow = (int64_t)m_blk * BM + r;
         row_ok = grow < p.M;
@@ -1042,6 +1052,7 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   int num_m_blks;
   if (CONV) {
     p.taps = g.conv_taps; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.batch = g.batch;
+    p.up2 = (HALO && g.conv_up2) ? 1 : 0;
     p.tiles_x = HALO ? (g.W + HALO_TW - 1) / HALO_TW : (g.W + CONV_TW - 1) / CONV_TW;
     p.tiles_y = HALO ? (g.H + HALO_TH - 1) / HALO_TH : (g.H + CONV_TH - 1) / CONV_TH;
     p.kb_per_tap = (g.Cin + BK - 1) / BK;
@@ -1059,8 +1070,9 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     uint32_t ae[4] = {1, (uint32_t)st, (uint32_t)st, 1};
     if (!make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, g.A, 4, ad, as, ab, CU_TENSOR_MAP_SWIZZLE_128B, ae)) return cudaErrorInvalidValue;
     // weights OHWI: dims (Cin, taps, Cout[, 1])
-    uint64_t bd[4] = {(uint64_t)g.Cin, (uint64_t)g.conv_taps, (uint64_t)g.N, 1};
-    uint64_t bs[3] = {(uint64_t)g.Cin * 2, (uint64_t)g.Cin * 2 * g.conv_taps, (uint64_t)g.Cin * 2 * g.conv_taps * g.N};
+    const int wtaps = (HALO && g.conv_up2) ? 16 : g.conv_taps;   // folded upsample: 4 phases x 4 pre-summed taps
+    uint64_t bd[4] = {(uint64_t)g.Cin, (uint64_t)wtaps, (uint64_t)g.N, 1};
+    uint64_t bs[3] = {(uint64_t)g.Cin * 2, (uint64_t)g.Cin * 2 * wtaps, (uint64_t)g.Cin * 2 * wtaps * g.N};
     uint32_t bb[4] = {BK, 1, (uint32_t)C::B_ROWS, 1};
     if (!make_tmap_bf16(&tmB, g.B, CG == 2 ? 4 : 3, bd, bs, bb)) return cudaErrorInvalidValue;
   } else if (MXK) {
@@ -1106,7 +1118,7 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   }
   p.num_m_units = (num_m_blks + CG - 1) / CG;
   p.num_n_blks = (g.N + BN - 1) / BN;
-  const int total = p.num_m_units * p.num_n_blks;
+  const int total = p.num_m_units * p.num_n_blks * (p.up2 ? 4 : 1);
   const int max_units = g_num_sms / CG;
   const int units = std::min(total, max_units);
 
@@ -1294,7 +1306,8 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
   if (!cg) cg = 2;
   // 3x3 stride-1 convolutions take the halo-tile kernel (FLUX2B_CONV_HALO=0: one TMA box per tap, the cross-check)
   static const bool halo_on = !(getenv("FLUX2B_CONV_HALO") && atoi(getenv("FLUX2B_CONV_HALO")) == 0);
-  const bool halo = conv && halo_on && g.conv_taps == 9 && g.conv_stride <= 1 && !g.conv_no_halo;
+  const bool halo = conv && (g.conv_up2 || (halo_on && g.conv_taps == 9 && g.conv_stride <= 1 && !g.conv_no_halo));
+  if (g.conv_up2 && (g.conv_taps != 9 || g.conv_stride > 1)) { g_err = "folded upsample: 3x3 stride-1 convolution only"; return cudaErrorInvalidValue; }
   const int m_blks = !conv ? (g.M + BM - 1) / BM
                      : halo ? g.batch * ((g.W + HALO_TW - 1) / HALO_TW) * ((g.H + HALO_TH - 1) / HALO_TH)
                             : g.batch * ((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + CONV_TH - 1) / CONV_TH);

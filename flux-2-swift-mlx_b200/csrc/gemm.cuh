@@ -73,6 +73,12 @@ struct GemmProblem {
   int batch = 1, H = 0, W = 0, Cin = 0;  // H, W = OUTPUT extent
   int conv_stride = 1;                   // 1 | 2
   int conv_no_halo = 0;                  // 1 = 3x3 stride-1 convolution through one TMA box per tap instead of the halo tile (cross-check)
+  // Upsample2D (nearest 2x, then conv3x3 pad 1; VAE/ResnetBlock.swift:240-252) as ONE kernel over the low-resolution input:
+  // output pixel (2y + py, 2x + px) only ever sees the 2x2 source window {y + py - 1, y + py} x {x + px - 1, x + px}, with the
+  // 3x3 taps that fall on the same source pixel summed. H, W = SOURCE extent, the output is [batch, 2H, 2W, N]; B holds the
+  // pre-summed weights [N, 16, Cin] = [phase py * 2 + px][tap ty * 2 + tx] (fold_upsample_weights). 4/9 of the FLOPs of the
+  // convolution over the upsampled tensor, and the 4x intermediate is never written.
+  int conv_up2 = 0;
   int Hin = 0, Win = 0;                  // input extent (0 = H * stride, W * stride)
   Epilogue epi;
   // native block-scaled operands (tcgen05.mma.kind::mxf8f6f4 / mxf4nvf4 .block_scale), single-CTA tiles:

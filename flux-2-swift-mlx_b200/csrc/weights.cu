@@ -668,6 +668,11 @@ int finalize_vae(flux2b_ctx* c) {
       if (!rc && i < 3) {
         rc = build_conv(c, "decoder.upBlocks." + std::to_string(i) + ".1.conv", &v.upconv[i], co, co, 3);
         v.has_upconv[i] = true;
+        if (!rc) {
+          // Upsample2D = nearest 2x + this convolution (ResnetBlock.swift:240-252): its four 2x2 phase kernels, summed once here
+          if (v.upconv[i].w_up.alloc((size_t)co * 16 * co * 2) != cudaSuccess) { cudaGetLastError(); rc = fail(FLUX2B_ERR_INSUFFICIENT_MEMORY, "upsample weights"); }
+          else if (fold_upsample_weights(v.upconv[i].w.p, v.upconv[i].w_up.p, co, co, vae_f16 != 0, c->stream) != cudaSuccess) rc = fail(FLUX2B_ERR_CUDA, "fold_upsample_weights");
+        }
       }
     }
     if (rc) break;

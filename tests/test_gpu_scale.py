@@ -140,3 +140,25 @@ def test_vae_mid_attention_chunked(flux2b):
         ref = O.vae_decode(VW, vcfg, z)
     assert rel_l2(outs[0], ref) < 5e-3
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("small,h,w", [(True, 16, 16), (False, 8, 12), (True, 9, 20)])
+def test_vae_folded_upsample(flux2b, small, h, w):
+    """Upsample2D folded into its convolution (four 2x2 phase kernels over the low-resolution tensor, ResnetBlock.swift:240-252)
+    against the oracle's nearest-2x + conv3x3, and against the unfused device path (upsample kernel + 3x3 convolution)"""
+    from oracle import flux2_oracle as O
+    vcfg = O.vae_small_decoder() if small else O.VAEConfig()
+    VW = O.random_vae_weights(vcfg, seed=1)
+    z = torch.randn(2, 32, h, w, generator=torch.Generator().manual_seed(5))
+    outs = {}
+    for fold in (1, 0):
+        ctx = flux2b.Context(vae=vcfg, options={"vae_fold_upsample": fold})
+        ctx.load_weights(VW)
+        ctx.finalize()
+        outs[fold] = ctx.vae_decode(z.numpy())
+        ctx.close()
+    with torch.no_grad():
+        ref = O.vae_decode(VW, vcfg, z)
+    e1, e0, e10 = rel_l2(outs[1], ref), rel_l2(outs[0], ref), rel_l2(outs[1], outs[0])
+    print(f"vae {h}x{w} small={small}: folded vs oracle {e1:.2e}, unfused vs oracle {e0:.2e}, folded vs unfused {e10:.2e}")
+    assert e1 < 5e-3 and e0 < 5e-3 and e10 < 3e-3
