@@ -35,8 +35,10 @@ static constexpr int CONV_TH = 8;
 // conv mode 2 (3x3, stride 1): the M tile is 16 rows x 8 cols and its 18 x 16-pixel halo (rows y0-1 .. y0+16, cols x0-1 .. x0+14;
 // only 10 of the 16 columns are read) is loaded ONCE per 64-channel block and serves all nine taps: the A operand of tap
 // (ky, kx) is the window of the halo that starts at halo row ky, column kx — a UMMA descriptor with an 8-row-group stride of
-// one halo row (16 pixels x 128 B = 2048 B) and a start address off the 1024 B swizzle period by kx x 128 B (descriptor base
-// offset kx). L2 -> shared-memory traffic for A drops from 9 x 16 KB to 36 KB per 64-channel block.
+// one halo row (16 pixels x 128 B = 2048 B) and a start address off the 1024 B swizzle period by kx x 128 B. The descriptor's
+// base-offset field stays 0: the tensor core applies the 128 B swizzle to absolute shared-memory address bits (as TMA does when
+// it writes the tile), so a window that starts part-way into the pattern needs no correction (measured: base offset kx or 8 - kx
+// gives wrong taps for kx != 0, 0 is exact — profiles/r02_halo_base_offset.md). L2 -> shared-memory traffic for A drops from 9 x 16 KB to 36 KB per 64-channel block.
 static constexpr int HALO_W = 16, HALO_H = 18;
 static constexpr int HALO_TW = 8, HALO_TH = 16;
 static constexpr int HALO_BYTES = HALO_W * HALO_H * 128;   // 36 KB
@@ -69,6 +71,7 @@ struct KParams {
 // WQ kernels: a ring of packed-weight slots (TMA destination, 64 B-/32 B-swizzled rows of 64 / 32 bytes = 64 K elements) beside
 // the operand stages; 128 more threads (warps 6..9) turn slot -> 16-bit B stage
 static constexpr int WQ_PSTAGES = 4;
+static constexpr int WQ_DQ_WARPS = 8;   // two per scheduler: one warp per scheduler cannot hide its own dependent-issue latency (measured 2x)
 template <int BN, int CG, int MXK = 0, int WQ = 0, int HALO = 0>
 struct Cfg {
   static constexpr int B_ROWS = BN / CG;
@@ -95,7 +98,7 @@ struct Cfg {
   static constexpr int TMEM_COLS = (COLS_NEEDED <= 32) ? 32 : (COLS_NEEDED <= 64) ? 64 : (COLS_NEEDED <= 128) ? 128 : (COLS_NEEDED <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PRING_BYTES + HRING_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
-  static constexpr int THREADS = WQ ? 320 : 192;
+  static constexpr int THREADS = WQ ? 192 + 32 * WQ_DQ_WARPS : 192;
 };
 
 // ------------------------------------------------------------------------------------------------ epilogue
@@ -409,41 +412,36 @@ __device__ __forceinline__ void wq_store_chunk(uint8_t* brow, int r, int oc, con
 }
 // MODE = flux2b_quant. `sc` / `bi`: this row's scales / biases for THIS k-block, already in registers:
 //   affine: sc = scale, bi = bias (fp32 values of the stored 16-bit numbers); mx: sc[0..1] (group 32) / nv: sc[0..3] (group 16)
-template <int MODE>
-__device__ __forceinline__ void wq_dequant_row(const uint8_t* slot, uint8_t* bstage, int r, const float (&sc)[4], float bi, int f16) {
+// PARTS = threads per row (1: the whole row; 2: `part` selects the first / second 32 elements).
+// Affine modes: q * scale is exact in fp32 (q <= 8 bits, scale <= 11 bits), so one FFMA gives the same bits as
+// dequantize_kernel's separate multiply and add; codes become floats through PRMT into the mantissa of 2^23 (no I2F).
+template <int MODE, int PARTS>
+__device__ __forceinline__ void wq_dequant_row(const uint8_t* slot, uint8_t* bstage, int r, int part, const float (&sc)[4], float bi, int f16) {
   uint8_t* brow = bstage + r * 128;
-  if constexpr (MODE == 1) {          // qint8: 64 bytes, slot rows of 64 B, 64 B swizzle: chunk c at c ^ ((r >> 1) & 3)
+  if constexpr (MODE == 1 || MODE == 3) {   // 8-bit codes: 64 bytes, slot rows of 64 B, 64 B swizzle: chunk c at c ^ ((r >> 1) & 3)
     const uint8_t* src = slot + r * 64;
     const int sw = (r >> 1) & 3;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int ci = 0; ci < 4 / PARTS; ++ci) {
+      const int c = PARTS == 1 ? ci : 2 * part + ci;
       const uint4 q = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      float s = sc[0];
+      if constexpr (MODE == 3) s = PARTS == 1 ? sc[ci >> 1] : (part ? sc[1] : sc[0]);   // E8M0 scale per 32 elements
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         float v[8];
+        if constexpr (MODE == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __fadd_rn(__fmul_rn(wq_u8_to_float(w[2 * h + (j >> 2)], j & 3), sc[0]), bi);
-        wq_store_chunk(brow, r, 2 * c + h, v, f16);
-      }
-    }
-  } else if constexpr (MODE == 3) {   // mxfp8: E4M3 bytes, scale per 32 elements
-    const uint8_t* src = slot + r * 64;
-    const int sw = (r >> 1) & 3;
+          for (int j = 0; j < 8; ++j) v[j] = __fmaf_rn(wq_u8_to_float(w[2 * h + (j >> 2)], j & 3), s, bi);
+        } else {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint4 q = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-      const float s = sc[c >> 1];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t word = w[2 * h + (j >> 1)];
-          const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((word >> (16 * (j & 1))) & 0xffffu), __NV_E4M3);
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hr));
-          v[2 * j] = __fmul_rn(f.x, s); v[2 * j + 1] = __fmul_rn(f.y, s);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t word = w[2 * h + (j >> 1)];
+            const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((word >> (16 * (j & 1))) & 0xffffu), __NV_E4M3);
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hr));
+            v[2 * j] = __fmul_rn(f.x, s); v[2 * j + 1] = __fmul_rn(f.y, s);
+          }
         }
         wq_store_chunk(brow, r, 2 * c + h, v, f16);
       }
@@ -452,20 +450,24 @@ __device__ __forceinline__ void wq_dequant_row(const uint8_t* slot, uint8_t* bst
     const uint8_t* src = slot + r * 32;
     const int sw = (r >> 2) & 1;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int ci = 0; ci < 2 / PARTS; ++ci) {
+      const int c = PARTS == 1 ? ci : part;
       const uint4 q = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {   // one word = 8 codes = one 16 B operand chunk
         float v[8];
-        if constexpr (MODE == 2) {    // int4 affine
+        if constexpr (MODE == 2) {    // int4 affine: element 2b = low nibble of byte b, 2b + 1 = its high nibble
+          const uint32_t lo = w[i] & 0x0F0F0F0Fu, hi = (w[i] >> 4) & 0x0F0F0F0Fu;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float qf = __uint_as_float(0x4B000000u | ((w[i] >> (4 * j)) & 0xFu)) - 8388608.0f;
-            v[j] = __fadd_rn(__fmul_rn(qf, sc[0]), bi);
+          for (int b = 0; b < 4; ++b) {
+            v[2 * b] = __fmaf_rn(wq_u8_to_float(lo, b), sc[0], bi);
+            v[2 * b + 1] = __fmaf_rn(wq_u8_to_float(hi, b), sc[0], bi);
           }
         } else {                      // mxfp4 (scale per 32 = per 4 words) / nvfp4 (scale per 16 = per 2 words)
-          const float s = MODE == 4 ? sc[c] : sc[2 * c + (i >> 1)];
+          float s;
+          if constexpr (MODE == 4) s = PARTS == 1 ? sc[ci] : (part ? sc[1] : sc[0]);
+          else s = PARTS == 1 ? sc[2 * ci + (i >> 1)] : (part ? sc[2 + (i >> 1)] : sc[i >> 1]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const __half2_raw hr = __nv_cvt_fp4x2_to_halfraw2((__nv_fp4x2_storage_t)((w[i] >> (8 * j)) & 0xffu), __NV_E2M1);
@@ -482,7 +484,7 @@ __device__ __forceinline__ void wq_dequant_row(const uint8_t* slot, uint8_t* bst
 // ------------------------------------------------------------------------------------------------ kernel
 // CONV: 0 = plain GEMM, 1 = implicit-GEMM convolution with one TMA box per tap, 2 = 3x3 stride-1 convolution from a halo tile
 template <int BN, int CG, int CONV, int MXK = 0, int WQ = 0>
-__global__ void __launch_bounds__(WQ ? 320 : 192, 1)
+__global__ void __launch_bounds__(WQ ? 192 + 32 * WQ_DQ_WARPS : 192, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmSFA, const __grid_constant__ CUtensorMap tmSFB, const KParams p) {
   constexpr bool HALO = CONV == 2;
@@ -524,13 +526,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full[s], WQ ? CG * 5 : CG);  // one arrive.expect_tx per CTA of the pair (+ one arrive per dequant warp)
+      mbar_init(&full[s], WQ ? CG * (1 + WQ_DQ_WARPS) : CG);  // one arrive.expect_tx per CTA of the pair (+ one arrive per dequant warp)
       mbar_init(&empty[s], 1);  // one tcgen05.commit
     }
     if (WQ) {
       for (int s = 0; s < WQ_PSTAGES; ++s) {
         mbar_init(&pfull[s], 1);    // the producer's arrive.expect_tx (CTA-local)
-        mbar_init(&pempty[s], 4);   // one arrive per dequant warp
+        mbar_init(&pempty[s], WQ_DQ_WARPS);   // one arrive per dequant warp
       }
     }
     if (HALO) {
@@ -755,8 +757,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tc_fence_after();
               if (elect_one()) {
                 const int ky = p.up2 ? py + (tap >> 1) : tap / 3, kx = p.up2 ? px + (tap & 1) : tap - 3 * (tap / 3);
-                // window start: halo row ky, column kx; 8-row groups one halo row (2048 B) apart; off the swizzle period by kx rows
-                const uint64_t adesc = make_smem_desc(0, 16, HALO_W * 128, SWZ_128B, (uint32_t)kx) +
+                // window start: halo row ky, column kx; 8-row groups one halo row (2048 B) apart
+                const uint64_t adesc = make_smem_desc(0, 16, HALO_W * 128, SWZ_128B) +
                                        (h0 + hstage * (HALO_BYTES >> 4) + (((ky * HALO_W + kx) * 128) >> 4));
                 const uint64_t bdesc = desc_hi + (b0 + stage * (C::B_BYTES >> 4));
                 for (int k = 0; k < nmma; ++k) umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (cb | tap | k) ? 1u : 0u);
@@ -837,13 +839,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 6) {
    if constexpr (WQ != 0) {
-    // ===================================================== dequant warps (6..9, WQ only): packed slot -> 16-bit B stage
-    // Thread = B row (two rows per thread for single-CTA tiles). Scales / biases of 8 k-blocks (4 for nvfp4) sit in registers,
-    // fetched with one 16 B load per tensor when the row's group array is 16 B aligned (K % 512 == 0), else one by one.
-    const int dt = threadIdx.x - 192;
+    // ===================================================== dequant warps (6..13, WQ only): packed slot -> 16-bit B stage
+    // CTA pairs (128 B rows per CTA): two threads per row, 32 elements each; single-CTA tiles (256 rows): thread = row.
+    // Scales / biases of 8 k-blocks (4 for nvfp4) sit in registers, fetched with one 16 B load per tensor when the row's
+    // group array is 16 B aligned (K % 512 == 0), else one by one.
+    constexpr int PARTS = (32 * WQ_DQ_WARPS) / C::B_ROWS;   // threads per row
+    static_assert(PARTS == 1 || PARTS == 2, "dequant warps: one or two threads per B row");
+    const int dt = (threadIdx.x - 192) % C::B_ROWS;
+    const int part = (threadIdx.x - 192) / C::B_ROWS;       // warp-uniform
     auto run = [&](auto mode_tag) {
       constexpr int MODE = decltype(mode_tag)::value;
-      constexpr int RPT = C::B_ROWS / 128;           // rows per thread
+      constexpr int RPT = 1;                         // rows per thread
       constexpr int GPK = MODE <= 2 ? 1 : MODE == 5 ? 4 : 2;   // scale groups per k-block
       constexpr int KBV = MODE <= 2 ? 8 : 16 / GPK;            // k-blocks covered by one 16 B load
       int stage = 0, pstage = 0;
@@ -911,7 +917,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
             // rows past N: the TMA zero-filled the codes and the scales stay 0 -> zeros (never read back by a valid output column)
-            wq_dequant_row<MODE>(slot, bst, r, sc, bi, p.epi.f16);
+            wq_dequant_row<MODE, PARTS>(slot, bst, r, part, sc, bi, p.epi.f16);
           }
           fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
           __syncwarp();

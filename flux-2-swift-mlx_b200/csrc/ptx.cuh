@@ -255,8 +255,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"):
 //  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle (2 = 128B, 4 = 64B, 6 = 32B)
 enum : uint32_t { SWZ_NONE = 0, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };
-//  [49,52) matrix base offset: (start address >> 7) & 7 when the start address is not aligned to the swizzle pattern's repeat
-//  (1024 B for 128 B swizzle) — a window that begins part-way into a swizzled buffer
+//  [49,52) matrix base offset: left 0 everywhere. On sm_100a the swizzle is applied to absolute shared-memory address bits, so a
+//  start address that is not aligned to the pattern's repeat (gemm.cu's halo windows) needs no correction; a non-zero value there
+//  was measured to give wrong data (profiles/r02_halo_base_offset.md).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t swizzle, uint32_t base_offset = 0) {
   uint64_t d = (uint64_t)(base_offset & 7) << 49;
