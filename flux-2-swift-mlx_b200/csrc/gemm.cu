@@ -42,7 +42,8 @@ static constexpr int CONV_TH = 8;
 static constexpr int HALO_W = 16, HALO_H = 18;
 static constexpr int HALO_TW = 8, HALO_TH = 16;
 static constexpr int HALO_BYTES = HALO_W * HALO_H * 128;   // 36 KB
-static constexpr int HALO_STAGES = 3;
+static constexpr int HALO_STAGES = 2;
+static constexpr int CONV_BIAS_MAX = 512;   // convolution bias vectors up to this many channels are staged in shared memory
 
 struct KParams {
   int M, N, K;
@@ -76,7 +77,13 @@ template <int BN, int CG, int MXK = 0, int WQ = 0, int HALO = 0>
 struct Cfg {
   static constexpr int B_ROWS = BN / CG;
   static constexpr int A_BYTES = BM * BK * 2;      // 128 rows x 128 B: 64 bf16, 128 fp8 or 256 fp4 elements along K
-  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  // halo convolutions: one B stage carries the weight tiles of a GROUP of taps (one kernel row: 3 taps; folded upsample: 2), so
+  // that one barrier round trip of the issuer covers 3 x 4 MMAs. With one tap per stage the issuer's ~160 instructions per
+  // stage (waits, descriptor arithmetic, commit) cost ~560 clk against 96 - 192 clk of MMA work for the 96-wide VAE tiles
+  // (ncu source page, profiles/r02_conv_halo.md). Single-CTA tiles wider than 128 keep one tap per stage (shared memory).
+  static constexpr int TG = HALO ? (B_ROWS <= 128 ? 3 : 1) : 1;
+  static constexpr int B_TAP_BYTES = B_ROWS * BK * 2;
+  static constexpr int B_BYTES = TG * B_TAP_BYTES;
   static constexpr int KB_ELEMS = MXK == 0 ? BK : MXK == 1 ? 128 : 256;   // K elements per pipeline stage
   // 512 B scale-factor blocks (128 rows x 4 scale bytes) per 128 operand rows per stage
   static constexpr int SFPK = MXK == 0 ? 0 : MXK == 1 ? 1 : MXK == 2 ? 2 : 4;
@@ -88,7 +95,8 @@ struct Cfg {
   static constexpr int PSLOT_BYTES = WQ ? B_ROWS * 64 : 0;            // sized for 8-bit codes; 4-bit modes use half of a slot
   static constexpr int PRING_BYTES = WQ_PSTAGES * PSLOT_BYTES;
   static constexpr int HRING_BYTES = HALO ? HALO_STAGES * HALO_BYTES : 0;
-  static constexpr int STAGES_RAW = (196 * 1024 - PRING_BYTES - HRING_BYTES) / STAGE_BYTES;
+  static constexpr int BUDGET = HALO ? 220 * 1024 : 196 * 1024;
+  static constexpr int STAGES_RAW = (BUDGET - PRING_BYTES - HRING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // accumulator stages in TMEM: two, except the 256-wide block-scaled tile, whose scale factors need columns too
   static constexpr int ACC_STAGES = (MXK && BN == 256) ? 1 : 2;
@@ -97,7 +105,9 @@ struct Cfg {
   static constexpr int COLS_NEEDED = ACC_STAGES * BN + SF_COLS;
   static constexpr int TMEM_COLS = (COLS_NEEDED <= 32) ? 32 : (COLS_NEEDED <= 64) ? 64 : (COLS_NEEDED <= 128) ? 128 : (COLS_NEEDED <= 256) ? 256 : 512;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PRING_BYTES + HRING_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int BIAS_BYTES = CONV_BIAS_MAX * 4;   // convolutions: the bias vector, staged once per CTA
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + PRING_BYTES + HRING_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // +1024 for manual alignment
+  static_assert(STAGES >= 2, "operand ring needs two stages");
   static constexpr int THREADS = WQ ? 192 + 32 * WQ_DQ_WARPS : 192;
 };
 
@@ -171,7 +181,7 @@ __device__ __forceinline__ void store_quantised32(const Epilogue& e, const uint3
 
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_acc, int quarter, int lane, bool row_ok,
-                                              int64_t grow, int n0) {
+                                              int64_t grow, int n0, uint32_t sbias = 0) {
   const Epilogue& e = p.epi;
   const uint32_t tq = tmem_acc + ((uint32_t)(quarter * 32) << 16);
   uint32_t v[32];
@@ -325,7 +335,14 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
     float a[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
-    if (e.bias) {
+    if (sbias) {   // convolutions: bias staged in shared memory, zero beyond N
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint4 b4 = lds128(sbias + (uint32_t)(col + 4 * j) * 4);
+        a[4 * j] += __uint_as_float(b4.x); a[4 * j + 1] += __uint_as_float(b4.y);
+        a[4 * j + 2] += __uint_as_float(b4.z); a[4 * j + 3] += __uint_as_float(b4.w);
+      }
+    } else if (e.bias) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (full || col + j < p.N) a[j] += __ldg(e.bias + col + j);
@@ -406,9 +423,8 @@ __device__ __forceinline__ float wq_u8_to_float(uint32_t word, int j) {
 __device__ __forceinline__ float wq_sb_to_float(uint16_t h, int bf16) {
   return bf16 ? __uint_as_float((uint32_t)h << 16) : __half2float(__ushort_as_half(h));
 }
-__device__ __forceinline__ void wq_store_chunk(uint8_t* brow, int r, int oc, const float (&v)[8], int f16) {
-  *reinterpret_cast<uint4*>(brow + ((oc ^ (r & 7)) << 4)) =
-      make_uint4(pk2(v[0], v[1], f16), pk2(v[2], v[3], f16), pk2(v[4], v[5], f16), pk2(v[6], v[7], f16));
+__device__ __forceinline__ void wq_store_chunk(uint32_t brow, int r, int oc, const float (&v)[8], int f16) {
+  sts128(brow + ((oc ^ (r & 7)) << 4), make_uint4(pk2(v[0], v[1], f16), pk2(v[2], v[3], f16), pk2(v[4], v[5], f16), pk2(v[6], v[7], f16)));
 }
 // MODE = flux2b_quant. `sc` / `bi`: this row's scales / biases for THIS k-block, already in registers:
 //   affine: sc = scale, bi = bias (fp32 values of the stored 16-bit numbers); mx: sc[0..1] (group 32) / nv: sc[0..3] (group 16)
@@ -416,15 +432,15 @@ __device__ __forceinline__ void wq_store_chunk(uint8_t* brow, int r, int oc, con
 // Affine modes: q * scale is exact in fp32 (q <= 8 bits, scale <= 11 bits), so one FFMA gives the same bits as
 // dequantize_kernel's separate multiply and add; codes become floats through PRMT into the mantissa of 2^23 (no I2F).
 template <int MODE, int PARTS>
-__device__ __forceinline__ void wq_dequant_row(const uint8_t* slot, uint8_t* bstage, int r, int part, const float (&sc)[4], float bi, int f16) {
-  uint8_t* brow = bstage + r * 128;
+__device__ __forceinline__ void wq_dequant_row(uint32_t slot, uint32_t bstage, int r, int part, const float (&sc)[4], float bi, int f16) {
+  const uint32_t brow = bstage + r * 128;
   if constexpr (MODE == 1 || MODE == 3) {   // 8-bit codes: 64 bytes, slot rows of 64 B, 64 B swizzle: chunk c at c ^ ((r >> 1) & 3)
-    const uint8_t* src = slot + r * 64;
+    const uint32_t src = slot + r * 64;
     const int sw = (r >> 1) & 3;
 #pragma unroll
     for (int ci = 0; ci < 4 / PARTS; ++ci) {
       const int c = PARTS == 1 ? ci : 2 * part + ci;
-      const uint4 q = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+      const uint4 q = lds128(src + ((c ^ sw) << 4));
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
       float s = sc[0];
       if constexpr (MODE == 3) s = PARTS == 1 ? sc[ci >> 1] : (part ? sc[1] : sc[0]);   // E8M0 scale per 32 elements
@@ -447,12 +463,12 @@ __device__ __forceinline__ void wq_dequant_row(const uint8_t* slot, uint8_t* bst
       }
     }
   } else {                            // 4-bit codes: 32 bytes, slot rows of 32 B, 32 B swizzle: chunk c at c ^ ((r >> 2) & 1)
-    const uint8_t* src = slot + r * 32;
+    const uint32_t src = slot + r * 32;
     const int sw = (r >> 2) & 1;
 #pragma unroll
     for (int ci = 0; ci < 2 / PARTS; ++ci) {
       const int c = PARTS == 1 ? ci : part;
-      const uint4 q = *reinterpret_cast<const uint4*>(src + ((c ^ sw) << 4));
+      const uint4 q = lds128(src + ((c ^ sw) << 4));
       const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {   // one word = 8 codes = one 16 B operand chunk
@@ -508,7 +524,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* hfull = pempty + WQ_PSTAGES;    // [HALO_STAGES] TMA -> MMA   (conv mode 2 only)
   uint64_t* hempty = hfull + HALO_STAGES;   // [HALO_STAGES] MMA -> TMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty + HALO_STAGES);
-  static_assert(!HALO || (C::B_BYTES % 1024 == 0), "halo ring must stay 1024 B aligned behind the B stages");
+  static_assert(!HALO || (C::B_TAP_BYTES % 1024 == 0), "tap tiles and the halo ring behind them must stay 1024 B aligned");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -546,6 +562,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tempty[s], 4 * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
+  }
+  // convolutions: bias -> shared memory (a weight: safe to read before the dependency wait). The epilogue's per-chunk global
+  // loads of it were an exposed L2 round trip per 32 columns (the 200+ KB of dynamic shared memory leaves almost no L1).
+  const bool bias_staged = CONV && p.epi.bias && p.N <= CONV_BIAS_MAX;
+  const uint32_t sbias = bias_staged ? smem_u32(reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES) : 0u;
+  if (bias_staged) {
+    float* sb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES);
+    for (int i = threadIdx.x; i < CONV_BIAS_MAX; i += blockDim.x) sb[i] = i < p.N ? __ldg(p.epi.bias + i) : 0.f;
   }
   if (warp == 1) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
@@ -601,17 +625,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_4d_cg2(h_dst, &tmA, hbar, cb * BK, x0 - 1, y0 - 1, img);
             }
             if (++hstage == HALO_STAGES) { hstage = 0; hphase ^= 1; }
-            const int ntaps = p.up2 ? 4 : 9, tap0 = p.up2 ? phase_idx * 4 : 0;
-            for (int tap = 0; tap < ntaps; ++tap) {
+            // weight tiles: one stage per tap group (one kernel row; folded upsample: one row of the 2 x 2 phase kernel)
+            const int tg = p.up2 ? (C::TG == 3 ? 2 : 1) : C::TG;
+            const int ngroups = (p.up2 ? 4 : 9) / tg, tap0 = p.up2 ? phase_idx * 4 : 0;
+            for (int grp = 0; grp < ngroups; ++grp) {
               mbar_wait(&empty[stage], phase ^ 1, 1);
-              void* b_dst = smB + stage * C::B_BYTES;
+              uint8_t* b_dst = smB + stage * C::B_BYTES;
               if (CG == 1) {
-                mbar_expect_tx(&full[stage], C::B_BYTES);
-                tma_load_3d(b_dst, &tmB, &full[stage], cb * BK, tap0 + tap, nrow0);
+                mbar_expect_tx(&full[stage], (uint32_t)(tg * C::B_TAP_BYTES));
+                for (int j = 0; j < tg; ++j)
+                  tma_load_3d(b_dst + j * C::B_TAP_BYTES, &tmB, &full[stage], cb * BK, tap0 + grp * tg + j, nrow0);
               } else {
                 const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
-                mbar_expect_tx_cluster(lbar, C::B_BYTES);
-                tma_load_4d_cg2(b_dst, &tmB, lbar, cb * BK, tap0 + tap, nrow0, 0);
+                mbar_expect_tx_cluster(lbar, (uint32_t)(tg * C::B_TAP_BYTES));
+                for (int j = 0; j < tg; ++j)
+                  tma_load_4d_cg2(b_dst + j * C::B_TAP_BYTES, &tmB, lbar, cb * BK, tap0 + grp * tg + j, nrow0, 0);
               }
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -721,6 +749,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t idesc = make_idesc_f16(BM * CG, BN, p.epi.f16 == 0, false, false);
       const uint64_t desc_hi = make_smem_desc(0, 16, 1024, SWZ_128B);
       const uint64_t desc_sf = make_smem_desc(0, 0, 128, SWZ_NONE);  // 32 x 16 B block: 8-row atoms 128 B apart
+      const uint64_t desc_halo = make_smem_desc(0, 16, HALO_W * 128, SWZ_128B);   // halo windows: 8-row groups one halo row apart
+      (void)desc_halo;
       const uint32_t a0 = smem_u32(smA) >> 4, b0 = smem_u32(smB) >> 4, sf0 = smem_u32(smSF) >> 4;
       int stage = 0;
       uint32_t phase = 0;
@@ -748,22 +778,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t h0 = smem_u32(smH) >> 4;
           const int tail = p.Cin - (p.kb_per_tap - 1) * BK;          // channels in the last block, 1..64
           // folded upsample: phase (py, px) of the output reads the 2x2 source window that starts at halo (py, px)
-          const int ntaps = p.up2 ? 4 : 9, py = p.up2 ? ((t & 3) >> 1) : 0, px = p.up2 ? (t & 1) : 0;
+          const int py = p.up2 ? ((t & 3) >> 1) : 0, px = p.up2 ? (t & 1) : 0;
+          const int tg = p.up2 ? (C::TG == 3 ? 2 : 1) : C::TG;
+          const int ngroups = (p.up2 ? 4 : 9) / tg;
           for (int cb = 0; cb < p.kb_per_tap; ++cb) {
+            t0 = dbg ? clock64() : 0;
             mbar_wait<CG == 2>(&hfull[hstage], hphase, 9);
+            if (dbg) w_full += clock64() - t0;
             const int nmma = (cb == p.kb_per_tap - 1) ? (tail + 15) / 16 : BK / 16;
-            for (int tap = 0; tap < ntaps; ++tap) {
+            const uint32_t hbase = h0 + hstage * (HALO_BYTES >> 4);
+            for (int grp = 0; grp < ngroups; ++grp) {
+              t0 = dbg ? clock64() : 0;
               mbar_wait<CG == 2>(&full[stage], phase, 3);
+              if (dbg) w_full += clock64() - t0;
               tc_fence_after();
               if (elect_one()) {
-                const int ky = p.up2 ? py + (tap >> 1) : tap / 3, kx = p.up2 ? px + (tap & 1) : tap - 3 * (tap / 3);
-                // window start: halo row ky, column kx; 8-row groups one halo row (2048 B) apart
-                const uint64_t adesc = make_smem_desc(0, 16, HALO_W * 128, SWZ_128B) +
-                                       (h0 + hstage * (HALO_BYTES >> 4) + (((ky * HALO_W + kx) * 128) >> 4));
-                const uint64_t bdesc = desc_hi + (b0 + stage * (C::B_BYTES >> 4));
-                for (int k = 0; k < nmma; ++k) umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (cb | tap | k) ? 1u : 0u);
+                const uint64_t bdesc0 = desc_hi + (b0 + stage * (C::B_BYTES >> 4));
+#pragma unroll
+                for (int j = 0; j < C::TG; ++j) {
+                  if (j < tg) {
+                    const int tap = grp * tg + j;
+                    int ky, kx;
+                    if (p.up2) { ky = py + (tap >> 1); kx = px + (tap & 1); } else { ky = tap / 3; kx = tap - 3 * ky; }
+                    // window start: halo row ky, column kx; 8-row groups one halo row (2048 B) apart
+                    const uint64_t adesc = desc_halo + (hbase + (((ky * HALO_W + kx) * 128) >> 4));
+                    const uint64_t bdesc = bdesc0 + j * (C::B_TAP_BYTES >> 4);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                      if (k < nmma) umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (cb | tap | k) ? 1u : 0u);
+                  }
+                }
                 if (CG == 1) umma_commit(&empty[stage]); else umma_commit_cg2_mc(&empty[stage], 0x3);
-                if (tap == ntaps - 1) {
+                if (grp == ngroups - 1) {
                   if (CG == 1) umma_commit(&hempty[hstage]); else umma_commit_cg2_mc(&hempty[hstage], 0x3);
                   if (cb == p.kb_per_tap - 1) {
                     if (CG == 1) umma_commit(&tfull[acc]); else umma_commit_cg2_mc(&tfull[acc], 0x3);
@@ -878,8 +924,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           mbar_wait(&pfull[pstage], pphase, 6);
           mbar_wait(&empty[stage], phase ^ 1, 7);
-          const uint8_t* slot = smP + pstage * C::PSLOT_BYTES;
-          uint8_t* bst = smB + stage * C::B_BYTES;
+          const uint32_t slot = smem_u32(smP) + pstage * C::PSLOT_BYTES;
+          const uint32_t bst = smem_u32(smB) + stage * C::B_BYTES;
 #pragma unroll
           for (int i = 0; i < RPT; ++i) {
             const int r = dt + 128 * i;
@@ -968,7 +1014,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait<CG == 2>(&tfull[acc], acc_phase, 4);
       tc_fence_after();
       const uint64_t t_e0 = p.dbg ? globaltimer_ns() : 0;
-      epilogue_tile<BN>(p, tmem_base + acc * BN, quarter, lane, row_ok, grow, n_blk * BN);
+      epilogue_tile<BN>(p, tmem_base + acc * BN, quarter, lane, row_ok, grow, n_blk * BN, sbias);
       tc_fence_before();
       __syncwarp();
       const uint64_t t_e1 = p.dbg ? globaltimer_ns() : 0;

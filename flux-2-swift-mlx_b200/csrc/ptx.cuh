@@ -251,6 +251,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// explicit shared-space 16 B accesses (a pointer derived from the dynamic shared-memory base otherwise compiles to generic
+// LD.E / ST.E with 64-bit addresses)
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"):
 //  [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) swizzle (2 = 128B, 4 = 64B, 6 = 32B)

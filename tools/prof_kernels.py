@@ -30,6 +30,21 @@ def main():
                 ctx.op_gemm(a, w2, epilogue=3, cta_group=1)
             elif name == "gemm_ff_cg2":
                 ctx.op_gemm(a, w2, epilogue=3, cta_group=2)
+            elif name.startswith("wq_"):
+                # W-only quantized GEMM with in-kernel dequantisation (random codes: timing only), Klein-9B width
+                q = name[3:]
+                Kq = Nq = 4096
+                bits = 8 if q in ("qint8", "mxfp8") else 4
+                group = 64 if q in ("qint8", "int4") else 16 if q == "nvfp4" else 32
+                xq = torch.randn(M, Kq, generator=g).to(torch.bfloat16).cuda()
+                wp = torch.randint(0, 2 ** 31 - 1, (Nq, Kq * bits // 32), generator=g, dtype=torch.int32).cuda()
+                if q in ("qint8", "int4"):
+                    sc = torch.full((Nq, Kq // group), 0.01, dtype=torch.float16).cuda()
+                    bi = torch.full((Nq, Kq // group), -0.08, dtype=torch.float16).cuda()
+                else:
+                    sc = torch.full((Nq, Kq // group), 120 if q != "nvfp4" else 0x38, dtype=torch.uint8).cuda()
+                    bi = None
+                ctx.op_linear_quantized(q, xq, wp, sc, bi, in_kernel=True)
             elif name.startswith("attn"):
                 ctx.op_attention(qkv, 1, S, H, variant=int(name[4:]))
         ctx.synchronize()
