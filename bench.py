@@ -270,7 +270,7 @@ def sp_measure(args, cfg, rank, local_rank, world, device, dist, res, refs, mode
     S_img = (H // 16) * (W // 16)
     ctx = flux2b.Context(dit=cfg, device=local_rank, quant=flux2b.QUANT[args.quant],
                          options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn, "gemm_cta_group": args.cta_group,
-                                  "wq_inkernel": getattr(args, "wq_inkernel", 1)})
+                                  "wq_inkernel": getattr(args, "wq_inkernel", 2)})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     n_lora = load_synthetic_dit(ctx, cfg, device, lora=lora)
     ctx.finalize()
@@ -403,7 +403,7 @@ def dtype_name(args) -> str:
         return "bf16"
     if args.native_mx:
         return f"{args.quant} (block-scaled tcgen05 MMA, weights and on-the-fly activations)"
-    return f"bf16 x dequant({args.quant}) (W-only, {'dequantized inside the kernels' if getattr(args, 'wq_inkernel', 1) else 'dense 16-bit copies'})"
+    return f"bf16 x dequant({args.quant}) (W-only, {('dense 16-bit copies', 'packed weights only, dequantized inside the kernels', 'packed weights only, dequantized per launch into a 16-bit stage')[getattr(args, 'wq_inkernel', 2)]})"
 
 
 def main():
@@ -419,8 +419,9 @@ def main():
     ap.add_argument("--native-mx", type=int, default=0,
                     help="1 = block linears on tcgen05 block-scaled MMA (mxfp8 / mxfp4 / nvfp4 weights consumed as packed, activations "
                          "quantised on the fly); 0 = W-only x · dequant(W)^T through the 16-bit GEMM (the reference's arithmetic)")
-    ap.add_argument("--wq-inkernel", type=int, default=1,
-                    help="W-only quantized layers: 1 = packed weights only, dequantized inside the GEMM / GEMV kernels; 0 = dense 16-bit copies")
+    ap.add_argument("--wq-inkernel", type=int, default=2,
+                    help="W-only quantized layers: 2 = packed weights only, many-row GEMMs dequantize the layer into a 16-bit stage per launch; "
+                         "1 = packed weights only, always dequantized inside the GEMM / GEMV kernels; 0 = dense 16-bit copies")
     ap.add_argument("--mx-bn", type=int, default=0, help="N tile of the block-scaled GEMM (0 = auto / 128 / 256)")
     ap.add_argument("--cta-group", type=int, default=0, help="GEMM CTA group (0 = auto: CTA pairs / 1 / 2)")
     ap.add_argument("--sp", action="store_true",

@@ -249,6 +249,10 @@ struct flux2b_ctx {
 
   // ---- workspaces (grown on demand)
   f2b::DevBuf ws_x, ws_xn, ws_qkv, ws_cat, ws_cos, ws_sin, ws_ids, ws_small, ws_hid16, ws_enc16, ws_out;
+  // W-only quantized layers, staged variant (option wq_inkernel = 2): 16-bit scratch the layer in flight is dequantized into
+  // (one per weight set of a two-stream launch), sized once for the largest quantized Linear of the model
+  f2b::DevBuf wq_stage[2];
+  size_t wq_stage_max = 0;
   // on-the-fly block-scaled activations (native path): quantised XN and CAT, and their scale factors per row range
   // (0 = text rows of XN, 1 = image rows / whole sequence of XN, 2 and 3 likewise for CAT)
   f2b::DevBuf ws_aq_xn, ws_aq_cat, ws_sfa[4];

@@ -23,6 +23,26 @@ struct QView {
   int sf_ld = 0;                // blocks per 128-row block
 };
 
+// W-only quantized GEMMs with many rows dequantize the layer once into a context-owned 16-bit stage and run the plain kernel
+// (gemm.cuh: wq_stage); few-row GEMMs (HBM-bound on the weights) dequantize inside the kernel. Option wq_inkernel: 1 = always
+// inside the kernel, 2 (default) = staged above WQ_STAGE_MIN_ROWS rows.
+static constexpr int WQ_STAGE_MIN_ROWS = 1024;
+static int wq_stage_buffers(flux2b_ctx* c, int M, const Lin& W, bool two, void** s0, void** s1) {
+  *s0 = *s1 = nullptr;
+  if (!W.wmode || c->option("wq_inkernel", 2) != 2 || M <= WQ_STAGE_MIN_ROWS) return 0;
+  if (!c->wq_stage_max) {
+    auto upd = [&](const Lin& L) { if (L.wmode) c->wq_stage_max = std::max(c->wq_stage_max, (size_t)L.N * L.K * 2); };
+    for (const DoubleBlockW& b : c->dbl) { upd(b.qkv_img); upd(b.qkv_txt); upd(b.out_img); upd(b.out_txt); upd(b.ff_in_img); upd(b.ff_out_img); upd(b.ff_in_txt); upd(b.ff_out_txt); }
+    for (const SingleBlockW& b : c->sgl) { upd(b.qkv); upd(b.mlp); upd(b.out); }
+    upd(c->x_embed); upd(c->ctx_embed); upd(c->proj_out);
+  }
+  const size_t need = std::max(c->wq_stage_max, (size_t)W.N * W.K * 2);
+  F2B_CUDA(c->wq_stage[0].ensure(need));
+  *s0 = c->wq_stage[0].p;
+  if (two) { F2B_CUDA(c->wq_stage[1].ensure(need)); *s1 = c->wq_stage[1].p; }
+  return 0;
+}
+
 // C = A · W^T (+ epilogue). k_off / K_override select a K-slice of W (the single-stream out projection split under SP).
 // Weights in block-scaled form (W.mx) need the activation's QView; the 16-bit A pointer is then unused.
 static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int M, Epilogue epi, const QView* qa = nullptr,
@@ -42,7 +62,9 @@ static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int
     g.wq_scales = W.ws.as<uint8_t>() + (k_off / group) * esz;
     g.wq_biases = W.wb.p ? W.wb.as<uint8_t>() + (k_off / group) * esz : nullptr;
     g.force_cta_group = c->option("gemm_cta_group", 0);
+    F2B_TRY(wq_stage_buffers(c, M, W, false, &g.wq_stage, &g.wq_stage_lo));
     bytes = 2.0 * ((double)M * g.K + (double)M * g.N) + (double)g.N * g.K * bits / 8 + (double)g.N * (g.K / group) * esz * (W.wb.p ? 2 : 1);
+    if (g.wq_stage) bytes += 2.0 * 2.0 * (double)g.N * g.K;   // the 16-bit stage is written once and read once
   } else if (W.mx) {
     if (!qa || !qa->q) return fail(FLUX2B_ERR_GENERATION_FAILED, "internal: block-scaled weight without a quantised activation");
     const int bits = W.mx == 1 ? 8 : 4, group = W.mx == 3 ? 16 : 32;
@@ -456,6 +478,8 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
           g.B = Wimg.wq.p; g.B_lo = Wtxt.wq.p; g.ldb = (int64_t)Wimg.K * bits / 8;
           g.wq_scales = Wimg.ws.p; g.wq_biases = Wimg.wb.p; g.wq_scales_lo = Wtxt.ws.p; g.wq_biases_lo = Wtxt.wb.p;
           wbytes = 2.0 * ((double)g.N * g.K * bits / 8 + (double)g.N * (g.K / group) * (Wimg.wmode <= 2 ? 4 : 1));
+          F2B_TRY(wq_stage_buffers(c, S, Wimg, true, &g.wq_stage, &g.wq_stage_lo));
+          if (g.wq_stage) wbytes += 2.0 * 2.0 * 2.0 * (double)g.N * g.K;
         }
         e.f16 = f16 ? 1 : 0; e.split_row = S_txt;
         g.epi = e;

@@ -497,6 +497,65 @@ __device__ __forceinline__ void wq_dequant_row(uint32_t slot, uint32_t bstage, i
   }
 }
 
+// ------------------------------------------------------------------------------------------------ W-only staging kernel
+// Packed codes [N, K * bits / 8] (row stride ldb bytes) -> 16-bit [N, K] operand. One thread per 8 elements (one 16 B store; a
+// warp reads 128 / 256 contiguous bytes of codes and writes 512 contiguous bytes), eight elements never straddle a scale group.
+// Arithmetic = wq_dequant_row's = dequantize_kernel's.
+template <int MODE>
+__global__ void __launch_bounds__(256) wq_stage_kernel(const uint8_t* __restrict__ packed, int64_t ldb, const uint8_t* __restrict__ scales,
+                                                       const uint8_t* __restrict__ biases, int sb_ld, int sb_bf16, int N, int K,
+                                                       uint16_t* __restrict__ out, int f16) {
+  const int cpr = K >> 3;                                     // 8-element chunks per row
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * cpr) return;
+  const int row = (int)(idx / cpr), c = (int)(idx - (int64_t)row * cpr);
+  const int k0 = c << 3;
+  float v[8];
+  if constexpr (MODE == 1 || MODE == 3) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(packed + (int64_t)row * ldb) + c);
+    if constexpr (MODE == 1) {
+      const int64_t gi = (int64_t)row * sb_ld + (k0 >> 6);
+      const float s = wq_sb_to_float(__ldg(reinterpret_cast<const uint16_t*>(scales) + gi), sb_bf16);
+      const float b = wq_sb_to_float(__ldg(reinterpret_cast<const uint16_t*>(biases) + gi), sb_bf16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __fmaf_rn(wq_u8_to_float(j < 4 ? q.x : q.y, j & 3), s, b);
+    } else {
+      const float s = from_e8m0(__ldg(scales + (int64_t)row * sb_ld + (k0 >> 5)));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t word = j < 2 ? q.x : q.y;
+        const __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((word >> (16 * (j & 1))) & 0xffffu), __NV_E4M3);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hr));
+        v[2 * j] = __fmul_rn(f.x, s); v[2 * j + 1] = __fmul_rn(f.y, s);
+      }
+    }
+  } else {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(packed + (int64_t)row * ldb) + c);
+    if constexpr (MODE == 2) {
+      const int64_t gi = (int64_t)row * sb_ld + (k0 >> 6);
+      const float s = wq_sb_to_float(__ldg(reinterpret_cast<const uint16_t*>(scales) + gi), sb_bf16);
+      const float b = wq_sb_to_float(__ldg(reinterpret_cast<const uint16_t*>(biases) + gi), sb_bf16);
+      const uint32_t lo = w & 0x0F0F0F0Fu, hi = (w >> 4) & 0x0F0F0F0Fu;
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        v[2 * bb] = __fmaf_rn(wq_u8_to_float(lo, bb), s, b);
+        v[2 * bb + 1] = __fmaf_rn(wq_u8_to_float(hi, bb), s, b);
+      }
+    } else {
+      const uint8_t sb = __ldg(scales + (int64_t)row * sb_ld + (MODE == 4 ? (k0 >> 5) : (k0 >> 4)));
+      const float s = MODE == 4 ? from_e8m0(sb) : from_e4m3(sb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2_raw hr = __nv_cvt_fp4x2_to_halfraw2((__nv_fp4x2_storage_t)((w >> (8 * j)) & 0xffu), __NV_E2M1);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hr));
+        v[2 * j] = __fmul_rn(f.x, s); v[2 * j + 1] = __fmul_rn(f.y, s);
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(out + (int64_t)row * K + k0) =
+      make_uint4(pk2(v[0], v[1], f16), pk2(v[2], v[3], f16), pk2(v[4], v[5], f16), pk2(v[6], v[7], f16));
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 // CONV: 0 = plain GEMM, 1 = implicit-GEMM convolution with one TMA box per tap, 2 = 3x3 stride-1 convolution from a halo tile
 template <int BN, int CG, int CONV, int MXK = 0, int WQ = 0>
@@ -1327,6 +1386,37 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
         (g.epi.mode == EPI_SWIGLU && g.N % 256) || (g.wq_sb_ld && g.wq_sb_ld < g.K / group)) {
       g_err = "W-only quantized GEMM: plain GEMM, K % 64 == 0, 16 B aligned packed rows, scales (+ biases for the affine modes)";
       return cudaErrorInvalidValue;
+    }
+    if (g.wq_stage) {
+      // staged: dequantize the layer once into the caller's 16-bit scratch, then the plain 16-bit kernel
+      if ((g.B_lo && !g.wq_stage_lo) || (reinterpret_cast<uintptr_t>(g.wq_stage) & 15) || (reinterpret_cast<uintptr_t>(g.wq_stage_lo) & 15)) {
+        g_err = "W-only staged GEMM: 16 B aligned stage buffers (one per weight set)";
+        return cudaErrorInvalidValue;
+      }
+      const int64_t nthreads = (int64_t)g.N * (g.K / 8);
+      const unsigned blocks = (unsigned)((nthreads + 255) / 256);
+      const int sb_ld = g.wq_sb_ld ? g.wq_sb_ld : g.K / group;
+      for (int which = 0; which < (g.B_lo ? 2 : 1); ++which) {
+        const uint8_t* pk = reinterpret_cast<const uint8_t*>(which ? g.B_lo : g.B);
+        const uint8_t* sc = reinterpret_cast<const uint8_t*>(which ? g.wq_scales_lo : g.wq_scales);
+        const uint8_t* bi = reinterpret_cast<const uint8_t*>(which ? g.wq_biases_lo : g.wq_biases);
+        uint16_t* out = reinterpret_cast<uint16_t*>(which ? g.wq_stage_lo : g.wq_stage);
+        switch (g.wq) {
+          case 1: wq_stage_kernel<1><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
+          case 2: wq_stage_kernel<2><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
+          case 3: wq_stage_kernel<3><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
+          case 4: wq_stage_kernel<4><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
+          default: wq_stage_kernel<5><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+      }
+      GemmProblem h = g;
+      h.wq = 0; h.wq_stage = nullptr; h.wq_stage_lo = nullptr;
+      h.wq_scales = h.wq_biases = h.wq_scales_lo = h.wq_biases_lo = nullptr;
+      h.B = g.wq_stage; h.ldb = g.K;
+      if (g.B_lo) h.B_lo = g.wq_stage_lo;
+      return gemm_launch(h, stream);
     }
     const int m_blks = (g.M + BM - 1) / BM;
     const bool pair = g.force_cta_group != 1 && m_blks >= 2;

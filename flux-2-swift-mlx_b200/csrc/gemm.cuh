@@ -106,6 +106,12 @@ struct GemmProblem {
   const void* wq_biases_lo = nullptr;
   int wq_sb_ld = 0;
   int wq_sb_bf16 = 0;
+  // Staged variant: when wq_stage is set the layer is first dequantized by a streaming kernel into this 16-bit [N, K] scratch
+  // (wq_stage_lo for B_lo; each N * K * 2 bytes, caller-owned, fixed address) and the plain 16-bit kernel reads it — same operand
+  // bits as the in-kernel path. For many-row GEMMs (M in the thousands) the dequantisation inside the kernel is repeated for
+  // every 256-row M tile and costs more issue slots than the tensor core leaves idle; staging does it once per launch.
+  void* wq_stage = nullptr;
+  void* wq_stage_lo = nullptr;
 };
 
 // Returns cudaSuccess or the launch error. Never synchronises.

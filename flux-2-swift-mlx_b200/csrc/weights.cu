@@ -281,7 +281,7 @@ static int copy_row_bytes(flux2b_ctx* c, const void* src, int64_t src_row0, void
 }
 // Can Linear `base` ([eN, eK]) run W-only inside the kernels? (packed, K a multiple of the 64-element k-block, 16-bit affine scales)
 static bool wq_eligible(flux2b_ctx* c, const std::string& base, int eK) {
-  if (c->quant == FLUX2B_BF16 || !c->option("wq_inkernel", 1) || eK % 64) return false;
+  if (c->quant == FLUX2B_BF16 || !c->option("wq_inkernel", 2) || eK % 64) return false;
   Tensor* w = find(c, base + ".weight");
   if (!w) return false;
   if (w->dtype != FLUX2B_U32) return is_float_dtype(w->dtype);   // will be packed by ensure_packed with f16 scales
@@ -319,6 +319,7 @@ int finalize_dit(flux2b_ctx* c) {
   const int D = g.num_attention_heads * g.attention_head_dim;
   const int Hm = (int)((float)D * g.mlp_ratio);  // Int(Float(dim) * mlpRatio), Flux2TransformerBlock.swift:53
   c->D = D; c->H = g.num_attention_heads; c->Hm = Hm;
+  c->wq_stage_max = 0;
   if (g.attention_head_dim != 128) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "attention_head_dim must be 128");
   if (g.axes_dims_rope[0] + g.axes_dims_rope[1] + g.axes_dims_rope[2] + g.axes_dims_rope[3] != 128)
     return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "axes_dims_rope must sum to 128");

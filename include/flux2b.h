@@ -87,9 +87,11 @@ int flux2b_synchronize(flux2b_ctx* ctx);
  * "native_mx" (0 = W-only: x · dequant(W)^T through the 16-bit GEMM [default, matches the reference's arithmetic];
  *  1 = with quant = mxfp8 the block linears run on tcgen05 block-scaled MMA with on-the-fly mxfp8 activations: faster,
  *  but activations carry E4M3 precision — set before flux2b_finalize_weights),
- * "wq_inkernel" (1 [default] = W-only quantized layers keep ONLY their packed form (codes + group scales / biases, re-tiled for
- *  the fused kernels) and are dequantized inside the GEMM / GEMV kernels on the way into the operand stage; 0 = a dense 16-bit
- *  expansion per layer at finalize. Same output bits either way — set before flux2b_finalize_weights),
+ * "wq_inkernel" (W-only quantized layers. 1 or 2 = they keep ONLY their packed form (codes + group scales / biases, re-tiled for
+ *  the fused kernels): 1 = always dequantized inside the GEMM / GEMV kernels on the way into the operand stage; 2 [default] =
+ *  the same for GEMMs of up to 1024 rows and the GEMVs, while many-row GEMMs dequantize the layer in flight once into a
+ *  context-owned 16-bit stage (sized for the largest layer) and run the plain kernel on it. 0 = a dense 16-bit expansion of every
+ *  layer at finalize. Same output bits in all three — set before flux2b_finalize_weights),
  * "keep_raw_weights" (1 [default]; 0 = forward-only context: after finalize the handed-over Linear tensors — dense weights, and
  *  packed weights together with their scales / biases — are released, so get_tensor / save_prequantized / merge_lora report them
  *  missing; with wq_inkernel or native_mx the packed working copy is then the only resident copy of a quantized layer),

@@ -304,6 +304,34 @@ def test_dit_forward_in_kernel_dequant_matches_dense_copy(flux2b, name):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("name", QMODES)
+def test_dit_forward_staged_dequant_matches_dense_copy(flux2b, name):
+    """wq_inkernel = 2 (default: packed weights only; GEMMs above 1024 rows dequantize the layer into the context's 16-bit stage
+    right before the plain kernel, the grouped two-stream launches with one stage per weight set) == dense copies, bit for bit"""
+    from oracle import flux2_oracle as O
+    q = flux2b.QUANT[name]
+    cfg = O.DiTConfig(num_layers=2, num_single_layers=2, num_attention_heads=2, joint_attention_dim=256, guidance_embeds=True)
+    W = O.random_dit_weights(cfg, seed=5, round_to=torch.float16)
+    S_img, S_txt = 1024, 256   # image stream and the joint sequence above the staging threshold, text stream below it
+    hidden = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(1))
+    enc = torch.randn(1, S_txt, 256, generator=torch.Generator().manual_seed(2))
+    t, gd = torch.tensor([0.7]), torch.tensor([4.0])
+    img_ids, txt_ids = O.image_position_ids(512, 512), O.text_position_ids(S_txt)
+    outs = []
+    for ink, group in ((2, 1), (2, 0), (0, 1)):
+        ctx = flux2b.Context(dit=cfg, quant=q, options={"wq_inkernel": ink, "record_blocks": 1, "group_streams": group})
+        ctx.load_weights(W, dtype=torch.float16)
+        ctx.finalize()
+        out = ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), gd.numpy(), img_ids.numpy(), txt_ids.numpy())
+        blocks = [ctx.block_output(i, S_img + S_txt, cfg.inner_dim) for i in range(4)]
+        outs.append((out, blocks))
+        ctx.close()
+    for o in outs[:2]:
+        assert np.array_equal(o[0], outs[2][0])
+        for a, b in zip(o[1], outs[2][1]):
+            assert np.array_equal(a, b)
+
+
 def test_klein4b_width_in_kernel_dequant(flux2b):
     """Klein-4B width at S = 4608 with int4 weights: CTA-pair tiles over many waves, 16 B scale loads (K % 512 == 0); same bits
     as the dense-copy path and within tolerance of the oracle on the dequantized weights"""
@@ -319,15 +347,16 @@ def test_klein4b_width_in_kernel_dequant(flux2b):
     t = torch.tensor([0.7])
     img_ids, txt_ids = O.image_position_ids(1024, 1024), O.text_position_ids(512)
     outs = []
-    for ink in (1, 0):
+    for ink in (1, 2, 0):
         ctx = flux2b.Context(dit=cfg, quant=q, options={"wq_inkernel": ink, "record_blocks": 1, "keep_raw_weights": 0})
         ctx.load_weights(W, dtype=torch.float16)
         ctx.finalize()
         outs.append(ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), None, img_ids.numpy(), txt_ids.numpy()))
-        if ink:
+        if ink == 1:
             blocks = [ctx.block_output(i, 4608, cfg.inner_dim) for i in range(2)]
         ctx.close()
-    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[2])
+    assert np.array_equal(outs[1], outs[2])
     Wd = {k: (torch.from_numpy(Q.dequantize(q, *Q.quantize(q, w.half().numpy()), w.shape[1])) if w.dim() == 2 else w) for k, w in W.items()}
     rec = []
     with torch.no_grad():
