@@ -32,17 +32,22 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int CONV_TW = 16;  // spatial patch of one M tile in conv mode 1 (one TMA box per tap): 8 rows x 16 cols = 128 pixels
 static constexpr int CONV_TH = 8;
-// conv mode 2 (3x3, stride 1): the M tile is 16 rows x 8 cols and its 18 x 16-pixel halo (rows y0-1 .. y0+16, cols x0-1 .. x0+14;
-// only 10 of the 16 columns are read) is loaded ONCE per 64-channel block and serves all nine taps: the A operand of tap
-// (ky, kx) is the window of the halo that starts at halo row ky, column kx — a UMMA descriptor with an 8-row-group stride of
-// one halo row (16 pixels x 128 B = 2048 B) and a start address off the 1024 B swizzle period by kx x 128 B. The descriptor's
-// base-offset field stays 0: the tensor core applies the 128 B swizzle to absolute shared-memory address bits (as TMA does when
-// it writes the tile), so a window that starts part-way into the pattern needs no correction (measured: base offset kx or 8 - kx
-// gives wrong taps for kx != 0, 0 is exact — profiles/r02_halo_base_offset.md). L2 -> shared-memory traffic for A drops from 9 x 16 KB to 36 KB per 64-channel block.
-static constexpr int HALO_W = 16, HALO_H = 18;
+// conv mode 2 (3x3, stride 1): the M tile is 16 rows x 8 cols and its 18 x 10-pixel halo (rows y0-1 .. y0+16, cols x0-1 .. x0+8)
+// is loaded ONCE per 64-channel block and serves all nine taps: the A operand of tap (ky, kx) is the window of the halo that
+// starts at halo row ky, column kx — a UMMA descriptor with an 8-row-group stride of one halo row (10 pixels x 128 B = 1280 B)
+// and a start address off the 1024 B swizzle period. The descriptor's base-offset field stays 0: the tensor core applies the
+// 128 B swizzle to absolute shared-memory address bits (as TMA does when it writes the tile), so neither a window that starts
+// part-way into the pattern nor a group stride that is not a multiple of it needs a correction (measured: base offset kx or
+// 8 - kx gives wrong taps for kx != 0, 0 is exact — profiles/r02_halo_base_offset.md). L2 -> shared-memory traffic for A drops
+// from 9 x 16 KB to 22.5 KB per 64-channel block.
+#ifndef F2B_HALO_W
+#define F2B_HALO_W 10
+#endif
+static constexpr int HALO_W = F2B_HALO_W, HALO_H = 18;   // 10 = exactly the columns the nine windows touch (16: 8-row groups 2048 B apart)
 static constexpr int HALO_TW = 8, HALO_TH = 16;
-static constexpr int HALO_BYTES = HALO_W * HALO_H * 128;   // 36 KB
-static constexpr int HALO_STAGES = 2;
+static constexpr int HALO_BYTES = HALO_W * HALO_H * 128;   // 22.5 KB of TMA payload per stage
+static constexpr int HALO_STRIDE = (HALO_BYTES + 1023) / 1024 * 1024;   // stages start on the 1024 B swizzle repeat
+static constexpr int HALO_STAGES = 3;
 static constexpr int CONV_BIAS_MAX = 512;   // convolution bias vectors up to this many channels are staged in shared memory
 
 struct KParams {
@@ -94,7 +99,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE + B_BYTES + SF_BYTES;
   static constexpr int PSLOT_BYTES = WQ ? B_ROWS * 64 : 0;            // sized for 8-bit codes; 4-bit modes use half of a slot
   static constexpr int PRING_BYTES = WQ_PSTAGES * PSLOT_BYTES;
-  static constexpr int HRING_BYTES = HALO ? HALO_STAGES * HALO_BYTES : 0;
+  static constexpr int HRING_BYTES = HALO ? HALO_STAGES * HALO_STRIDE : 0;
   static constexpr int BUDGET = HALO ? 220 * 1024 : 196 * 1024;
   static constexpr int STAGES_RAW = (BUDGET - PRING_BYTES - HRING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -325,20 +330,30 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
     return;
   }
 
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  // Software-pipelined over 32-column chunks: the TMEM load of chunk c + 1 (and, for convolutions, its bias from shared memory) is
+  // in flight while chunk c is converted and stored. One chunk at a time exposed a TMEM round trip (~500 clk beside a running
+  // MMA, which has priority on TMEM) plus a shared-memory round trip per chunk: 1.9 k clk per chunk on the 96-wide VAE tiles,
+  // where the epilogue, not the tensor pipe, set the tile period (ncu source page, profiles/r02_conv_halo.md).
+  constexpr int NC = BN / 32;
+  uint32_t vb[32];
+  uint4 bq[2][8];
+  auto prefetch_bias = [&](int c, uint4 (&b)[8]) {
+    if (sbias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = lds128(sbias + (uint32_t)(n0 + c * 32 + 4 * j) * 4);
+    }
+  };
+  auto process = [&](int c, const uint32_t (&vv)[32], const uint4 (&b)[8]) {
     const int col = n0 + c * 32;
-    tmem_ld_32x32(tq + c * 32, v);
-    tmem_ld_wait();
-    if (!row_ok || col >= p.N) continue;
-    const bool full = (col + 32 <= p.N);
+    if (!row_ok || col >= p.N) return;
     float a[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]);
+    for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(vv[j]);
+    const bool full = (col + 32 <= p.N);
     if (sbias) {   // convolutions: bias staged in shared memory, zero beyond N
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint4 b4 = lds128(sbias + (uint32_t)(col + 4 * j) * 4);
+        const uint4 b4 = b[j];
         a[4 * j] += __uint_as_float(b4.x); a[4 * j + 1] += __uint_as_float(b4.y);
         a[4 * j + 2] += __uint_as_float(b4.z); a[4 * j + 3] += __uint_as_float(b4.w);
       }
@@ -405,6 +420,19 @@ __device__ __forceinline__ void epilogue_tile(const KParams& p, uint32_t tmem_ac
       } else {
         for (int j = 0; j < 32 && col + j < p.N; ++j) reinterpret_cast<uint16_t*>(out)[j] = (uint16_t)(pk2(a[j], 0.f, e.f16) & 0xffff);
       }
+    }
+  };
+  tmem_ld_32x32(tq, v);
+  prefetch_bias(0, bq[0]);
+#pragma unroll 1
+  for (int c = 0; c < NC; c += 2) {
+    tmem_ld_wait();
+    if (c + 1 < NC) { tmem_ld_32x32(tq + (c + 1) * 32, vb); prefetch_bias(c + 1, bq[1]); }
+    process(c, v, bq[0]);
+    if (c + 1 < NC) {
+      tmem_ld_wait();
+      if (c + 2 < NC) { tmem_ld_32x32(tq + (c + 2) * 32, v); prefetch_bias(c + 2, bq[0]); }
+      process(c + 1, vb, bq[1]);
     }
   }
 }
@@ -674,7 +702,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // channel-block major: one halo load per 64 input channels, then the nine taps' weight tiles through the ring
           for (int cb = 0; cb < p.kb_per_tap; ++cb) {
             mbar_wait(&hempty[hstage], hphase ^ 1, 8);
-            uint8_t* h_dst = smH + hstage * HALO_BYTES;
+            uint8_t* h_dst = smH + hstage * HALO_STRIDE;
             if (CG == 1) {
               mbar_expect_tx(&hfull[hstage], HALO_BYTES);
               tma_load_4d(h_dst, &tmA, &hfull[hstage], cb * BK, x0 - 1, y0 - 1, img);
@@ -845,7 +873,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait<CG == 2>(&hfull[hstage], hphase, 9);
             if (dbg) w_full += clock64() - t0;
             const int nmma = (cb == p.kb_per_tap - 1) ? (tail + 15) / 16 : BK / 16;
-            const uint32_t hbase = h0 + hstage * (HALO_BYTES >> 4);
+            const uint32_t hbase = h0 + hstage * (HALO_STRIDE >> 4);
             for (int grp = 0; grp < ngroups; ++grp) {
               t0 = dbg ? clock64() : 0;
               mbar_wait<CG == 2>(&full[stage], phase, 3);

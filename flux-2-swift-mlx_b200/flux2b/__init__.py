@@ -22,7 +22,8 @@ from typing import Callable, Dict, List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libflux2b.so")
+# FLUX2B_LIB: A/B aid — load another build of the same library (kernel variants measured on the same GPU box)
+LIB_PATH = os.environ.get("FLUX2B_LIB") or os.path.join(os.path.dirname(_HERE), "libflux2b.so")
 
 F32, F16, BF16, U32, U8, I32 = 0, 1, 2, 3, 4, 5
 QUANT = {"bf16": 0, "qint8": 1, "int4": 2, "mxfp8": 3, "mxfp4": 4, "nvfp4": 5}

@@ -290,6 +290,7 @@ PROBES = {
     "attn_v4_big": lambda: probe_attention(1, 4608, 24, 4),
     "attn_v4_big_p4": lambda: probe_attention(1, 4608, 24, 4, poly=4),
     "attn_v4_big_p2": lambda: probe_attention(1, 4608, 24, 4, poly=2),
+    "attn_v4_big_p0": lambda: probe_attention(1, 4608, 24, 4, poly=-1),
     "attn_v4_small": lambda: probe_attention(1, 256, 2, 4),
     "attn_v4_tail": lambda: probe_attention(2, 328, 2, 4),
     "attn_v4_dev16k": lambda: probe_attention(1, 16896, 6, 4),
