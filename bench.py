@@ -345,7 +345,10 @@ def sp_measure(args, cfg, rank, local_rank, world, device, dist, res, refs, mode
             if single is None:
                 single = step().float().cpu()
             ctx.set_option("sp_disable", 0)
-            parity = float((x_sp.double() - single.double()).norm() / single.double().norm())
+            # relative to the UPDATE of the step (x - x0 = dt * velocity), not to the latents: one Euler step moves x by a few
+            # percent, so a difference measured against |x| would be diluted by that factor
+            x0 = lat.float().cpu().double()
+            parity = float((x_sp.double() - single.double()).norm() / (single.double() - x0).norm())
         barrier()
         ms_step = ms / steps
         gp = prof["gemm"]

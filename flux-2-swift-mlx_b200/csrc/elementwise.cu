@@ -278,10 +278,23 @@ cudaError_t ln_modulate(const float* x, int64_t ldx, void* out16, int64_t ldo, i
 }
 
 // ------------------------------------------------------------------ GEMV (M = batch <= 8): weight-bandwidth bound
-template <int MAXB>
+// STAGED: the CTA first puts the (SiLU'd) input vector(s) into shared memory. Unstaged, every warp (= output row) re-evaluated
+// SiLU on all K inputs — 2 MUFU operations per element per row made the modulation GEMVs MUFU-bound (1.75 TB/s of weights)
+// instead of HBM-bound. Same values, same FMA order: bit-identical results.
+__device__ __forceinline__ void gemv_stage_x(float* gx, const float* __restrict__ x, int64_t ldx, int B, int K, bool silu_in) {
+  for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
+    const int b = i / K, k = i - b * K;
+    const float v = x[b * ldx + k];
+    gx[i] = silu_in ? silu_f(v) : v;
+  }
+  __syncthreads();
+}
+template <int MAXB, bool STAGED>
 __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, int64_t ldx, const void* __restrict__ W,
                                                    int64_t ldw, float* __restrict__ y, int64_t ldy, int B, int N, int K,
                                                    bool silu_in, bool accumulate, bool f16) {
+  extern __shared__ float gx[];
+  if (STAGED) { gemv_stage_x(gx, x, ldx, B, K, silu_in); x = gx; ldx = K; silu_in = false; }
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= N) return;
@@ -289,6 +302,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
   float acc[MAXB];
 #pragma unroll
   for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+#pragma unroll 4
   for (int k = lane * 8; k < K; k += 256) {
     const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wr + k));
     float wf[8];
@@ -325,9 +339,14 @@ cudaError_t gemv(const float* x, int64_t ldx, const void* W16, int64_t ldw, floa
                  bool silu_in, bool accumulate, bool f16, cudaStream_t s) {
   if (B > 8 || K % 8 || ldw % 8 || ldx % 4) return cudaErrorInvalidValue;
   const int blocks = (N * 32 + 255) / 256;
-  if (B <= 1) gemv_kernel<1><<<blocks, 256, 0, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
-  else if (B <= 2) gemv_kernel<2><<<blocks, 256, 0, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
-  else gemv_kernel<8><<<blocks, 256, 0, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
+  const size_t sm = (size_t)B * K * 4;
+  if (sm <= 48 * 1024) {
+    if (B <= 1) gemv_kernel<1, true><<<blocks, 256, sm, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
+    else if (B <= 2) gemv_kernel<2, true><<<blocks, 256, sm, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
+    else gemv_kernel<8, true><<<blocks, 256, sm, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
+  } else if (B <= 1) gemv_kernel<1, false><<<blocks, 256, 0, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
+  else if (B <= 2) gemv_kernel<2, false><<<blocks, 256, 0, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
+  else gemv_kernel<8, false><<<blocks, 256, 0, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
   return cudaGetLastError();
 }
 
@@ -335,12 +354,14 @@ cudaError_t gemv(const float* x, int64_t ldx, const void* W16, int64_t ldw, floa
 // gemv_kernel — lane = 8 consecutive k per iteration, fp32 FMA chain in the same order — with the eight weights produced in
 // registers by dequantize_kernel's arithmetic (quant.cu) and rounded once to the 16-bit operand type, i.e. exactly the numbers
 // the dense working copy would hold: the result is bit-identical to gemv over the dequantized matrix.
-template <int MAXB>
+template <int MAXB, bool STAGED>
 __global__ void __launch_bounds__(256) gemv_q_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ codes,
                                                      int64_t row_bytes, const uint8_t* __restrict__ scales,
                                                      const uint8_t* __restrict__ biases, int64_t sb_ld, int mode, int sb_bf16,
                                                      float* __restrict__ y, int64_t ldy, int B, int N, int K, bool silu_in,
                                                      bool accumulate, bool f16) {
+  extern __shared__ float gx[];
+  if (STAGED) { gemv_stage_x(gx, x, ldx, B, K, silu_in); x = gx; ldx = K; silu_in = false; }
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= N) return;
@@ -405,9 +426,14 @@ cudaError_t gemv_q(const float* x, int64_t ldx, const void* codes, int64_t row_b
   if (B > 8 || K % 16 || row_bytes % 8 || ldx % 4 || mode < 1 || mode > 5 || !scales || (mode <= 2 && !biases)) return cudaErrorInvalidValue;
   const int blocks = (N * 32 + 255) / 256;
   const uint8_t *c8 = (const uint8_t*)codes, *s8 = (const uint8_t*)scales, *b8 = (const uint8_t*)biases;
-  if (B <= 1) gemv_q_kernel<1><<<blocks, 256, 0, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
-  else if (B <= 2) gemv_q_kernel<2><<<blocks, 256, 0, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
-  else gemv_q_kernel<8><<<blocks, 256, 0, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
+  const size_t sm = (size_t)B * K * 4;
+  if (sm <= 48 * 1024) {
+    if (B <= 1) gemv_q_kernel<1, true><<<blocks, 256, sm, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
+    else if (B <= 2) gemv_q_kernel<2, true><<<blocks, 256, sm, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
+    else gemv_q_kernel<8, true><<<blocks, 256, sm, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
+  } else if (B <= 1) gemv_q_kernel<1, false><<<blocks, 256, 0, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
+  else if (B <= 2) gemv_q_kernel<2, false><<<blocks, 256, 0, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
+  else gemv_q_kernel<8, false><<<blocks, 256, 0, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
   return cudaGetLastError();
 }
 

@@ -56,6 +56,7 @@ struct KParams {
   // conv
   int taps, H, W, Cin, batch, tiles_x, tiles_y, kb_per_tap;  // H, W: OUTPUT extent
   int stride, tap_off;  // input coordinate of tap (ky, kx) for output (y, x): (y * stride + ky + tap_off, x * stride + kx + tap_off)
+  int wres;             // conv mode 2: the layer's weights for this CTA's N rows fit the operand ring and stay resident in shared memory (loaded once)
   int up2;              // conv mode 2 only: nearest-2x upsample folded into the 3x3 convolution (four 2x2 phase kernels, see gemm.cuh)
   Epilogue epi;
   // block-scaled kinds: scale factors of A [ceil(M/128)][sfa_ld][512 B], of B [N/128][sfb_ld][512 B]; one 512 B block =
@@ -629,7 +630,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full[s], WQ ? CG * (1 + WQ_DQ_WARPS) : CG);  // one arrive.expect_tx per CTA of the pair (+ one arrive per dequant warp)
+      // one arrive.expect_tx per CTA of the pair (+ one arrive per dequant warp; resident conv weights: one per channel block)
+      mbar_init(&full[s], WQ ? CG * (1 + WQ_DQ_WARPS) : (HALO && p.wres && s == 0) ? CG * p.kb_per_tap : CG);
       mbar_init(&empty[s], 1);  // one tcgen05.commit
     }
     if (WQ) {
@@ -712,6 +714,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_4d_cg2(h_dst, &tmA, hbar, cb * BK, x0 - 1, y0 - 1, img);
             }
             if (++hstage == HALO_STAGES) { hstage = 0; hphase ^= 1; }
+            if (p.wres) {
+              // resident weights: all (channel block, tap) tiles of this CTA's N rows go into the ring area once, behind the first
+              // halo; every later tile only loads halos (the 96-wide 1024^2 layers re-fetched 108 KB of weights per 256 pixels)
+              if (t == unit_id) {
+                const uint32_t bytes = (uint32_t)(9 * C::B_TAP_BYTES);
+                if (CG == 1) {
+                  mbar_expect_tx(&full[0], bytes);
+                  for (int tap = 0; tap < 9; ++tap)
+                    tma_load_3d(smB + (cb * 9 + tap) * C::B_TAP_BYTES, &tmB, &full[0], cb * BK, tap, nrow0);
+                } else {
+                  const uint32_t lbar = mapa_u32(smem_u32(&full[0]), 0);
+                  mbar_expect_tx_cluster(lbar, bytes);
+                  for (int tap = 0; tap < 9; ++tap)
+                    tma_load_4d_cg2(smB + (cb * 9 + tap) * C::B_TAP_BYTES, &tmB, lbar, cb * BK, tap, nrow0, 0);
+                }
+              }
+              continue;
+            }
             // weight tiles: one stage per tap group (one kernel row; folded upsample: one row of the 2 x 2 phase kernel)
             const int tg = p.up2 ? (C::TG == 3 ? 2 : 1) : C::TG;
             const int ngroups = (p.up2 ? 4 : 9) / tg, tap0 = p.up2 ? phase_idx * 4 : 0;
@@ -876,11 +896,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t hbase = h0 + hstage * (HALO_STRIDE >> 4);
             for (int grp = 0; grp < ngroups; ++grp) {
               t0 = dbg ? clock64() : 0;
-              mbar_wait<CG == 2>(&full[stage], phase, 3);
+              if (!p.wres) mbar_wait<CG == 2>(&full[stage], phase, 3);
+              else if (t == unit_id && cb == 0 && grp == 0) mbar_wait<CG == 2>(&full[0], 0, 3);   // resident weights have landed
               if (dbg) w_full += clock64() - t0;
               tc_fence_after();
               if (elect_one()) {
-                const uint64_t bdesc0 = desc_hi + (b0 + stage * (C::B_BYTES >> 4));
+                const uint64_t bdesc0 = desc_hi + (p.wres ? b0 + (cb * 9 + grp * tg) * (C::B_TAP_BYTES >> 4) : b0 + stage * (C::B_BYTES >> 4));
 #pragma unroll
                 for (int j = 0; j < C::TG; ++j) {
                   if (j < tg) {
@@ -895,7 +916,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                       if (k < nmma) umma_f16_ss<CG>(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (cb | tap | k) ? 1u : 0u);
                   }
                 }
-                if (CG == 1) umma_commit(&empty[stage]); else umma_commit_cg2_mc(&empty[stage], 0x3);
+                if (!p.wres) { if (CG == 1) umma_commit(&empty[stage]); else umma_commit_cg2_mc(&empty[stage], 0x3); }
                 if (grp == ngroups - 1) {
                   if (CG == 1) umma_commit(&hempty[hstage]); else umma_commit_cg2_mc(&hempty[hstage], 0x3);
                   if (cb == p.kb_per_tap - 1) {
@@ -1192,6 +1213,8 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   if (CONV) {
     p.taps = g.conv_taps; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.batch = g.batch;
     p.up2 = (HALO && g.conv_up2) ? 1 : 0;
+    static const bool wres_on = !(getenv("FLUX2B_CONV_WRES") && atoi(getenv("FLUX2B_CONV_WRES")) == 0);
+    p.wres = (HALO && wres_on && !p.up2 && g.N <= BN && 9 * ((g.Cin + BK - 1) / BK) * C::B_TAP_BYTES <= C::STAGES * C::B_BYTES) ? 1 : 0;
     p.tiles_x = HALO ? (g.W + HALO_TW - 1) / HALO_TW : (g.W + CONV_TW - 1) / CONV_TW;
     p.tiles_y = HALO ? (g.H + HALO_TH - 1) / HALO_TH : (g.H + CONV_TH - 1) / CONV_TH;
     p.kb_per_tap = (g.Cin + BK - 1) / BK;

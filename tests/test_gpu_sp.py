@@ -25,5 +25,10 @@ def test_sequence_parallel_matches_single_gpu(world, mode):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(29540 + world + 10 * mode),
                         os.path.join(ROOT, "tools", "sp_check.py")], capture_output=True, text=True, timeout=600, env=env)
-    lines = [json.loads(l[len("SP_CHECK "):]) for l in r.stdout.splitlines() if l.startswith("SP_CHECK ")]
+    # ranks share one stdout pipe: two records can land on one line, so records are decoded wherever the marker appears
+    dec, lines, pos = json.JSONDecoder(), [], 0
+    while (pos := r.stdout.find("SP_CHECK ", pos)) >= 0:
+        obj, end = dec.raw_decode(r.stdout, pos + len("SP_CHECK "))
+        lines.append(obj)
+        pos = end
     assert r.returncode == 0 and len(lines) == world and all(l["ok"] for l in lines), (r.stdout[-2000:], r.stderr[-2000:])

@@ -40,8 +40,25 @@ def main():
     sched.set_timesteps(1, S_img)
     rgb = ctx.generate(lat, enc, sched.sigmas, H, W)
     assert np.isfinite(lat).all() and rgb.shape == (H, W, 3)
-    print("SANITIZE_OK launches", ctx.launch_count())
+    n1 = ctx.launch_count()
     ctx.close()
+    # W-only int4 weights dequantized inside the GEMM kernels: generic-proxy stores of the dequant warps into the B stage, read
+    # by the tensor core's async proxy (fence.proxy.async + mbarrier hand-off), and the staged variant's streaming kernel
+    n2 = 0
+    for ink in (1, 2):
+        qctx = flux2b.Context(dit=cfg, quant=flux2b.QUANT["int4"], options={"wq_inkernel": ink})
+        g2 = torch.Generator().manual_seed(1)
+        for k, shp in configs.dit_weight_manifest(cfg).items():
+            qctx.set_tensor(k, ((torch.rand(shp, generator=g2) * 2 - 1) / shp[1] ** 0.5).half())
+        qctx.finalize()
+        S_img2 = 1024 if ink == 2 else 256
+        lat2 = torch.randn(1, S_img2, 128, generator=g2).numpy()
+        sched.set_timesteps(1, S_img2)
+        qctx.denoise(lat2, enc, sched.sigmas, 16 * int(S_img2 ** 0.5), 16 * int(S_img2 ** 0.5))
+        assert np.isfinite(lat2).all()
+        n2 += qctx.launch_count()
+        qctx.close()
+    print("SANITIZE_OK launches", n1, n2)
 
 
 if __name__ == "__main__":
