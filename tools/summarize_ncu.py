@@ -79,7 +79,7 @@ def traffic(src, dst):
         per[(row[ii], name)] += v
     cls = collections.OrderedDict()
     for (_, name), v in per.items():
-        c = ("conv" if re.search(r"gemm_kernel<\d+, \d+, 1", name) else "gemm" if name.startswith("gemm_kernel") else
+        c = ("conv" if re.search(r"gemm_kernel<\d+, \d+, [12]", name) else "gemm" if name.startswith("gemm_kernel") else
              "attn" if name.startswith("attn_kernel") else name)
         a = cls.setdefault(c, [0, 0.0])
         a[0] += 1; a[1] += v
