@@ -43,7 +43,7 @@ for w in $WHAT; do
     sanitize)
       # compute-sanitizer over a small grouped forward + VAE decode (tools/sanitize_target.py): memcheck, racecheck, synccheck
       for tool in memcheck racecheck synccheck; do
-        timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_target.py > gpurun_out/sanitize_$tool.log 2>&1
+        timeout 900 compute-sanitizer --tool $tool --print-limit 400 python tools/sanitize_target.py > gpurun_out/sanitize_$tool.log 2>&1
         echo "sanitize $tool rc=$?"; grep -E "SANITIZE_OK|ERROR SUMMARY|RACECHECK SUMMARY|hazard" gpurun_out/sanitize_$tool.log | head -5
       done ;;
     bench_nosp)
