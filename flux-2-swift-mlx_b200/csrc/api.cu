@@ -615,7 +615,7 @@ int flux2b_op_groupnorm_silu(flux2b_ctx* c, const void* x16, void* y16, const fl
   F2B_TRY(dev_in(c, beta, (size_t)C * 4, &db));
   void* dout; bool ho;
   F2B_TRY(dev_out(c, y16, bytes, &dout, &ho));
-  F2B_CUDA(c->gn_stats.ensure(groupnorm_ws_bytes(B, G)));
+  F2B_CUDA(ensure_zeroed(c->gn_stats, groupnorm_ws_bytes(B, G), c->stream));
   {
     ProfScope ps(c, FLUX2B_PROF_ELEMWISE, 0, (double)bytes * 3);
     F2B_CUDA(groupnorm_silu(dx, dout, (const float*)dg, (const float*)db, c->gn_stats.as<double>(), B, HW, C, G, eps, silu != 0, c->f16(), c->stream));

@@ -70,6 +70,14 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// ensure() for buffers whose contents must start as zeros (GroupNorm's arrival counters): zero-filled whenever (re)allocated
+inline cudaError_t ensure_zeroed(DevBuf& b, size_t n, cudaStream_t s) {
+  void* before = b.p;
+  cudaError_t e = b.ensure(n);
+  if (e == cudaSuccess && b.p != before) e = cudaMemsetAsync(b.p, 0, b.bytes, s);
+  return e;
+}
+
 // non-owning view of a context-owned scratch buffer
 struct Buf {
   void* p = nullptr;

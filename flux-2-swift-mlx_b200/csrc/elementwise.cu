@@ -749,10 +749,12 @@ cudaError_t seq_to_vae_input(const float* seq, const float* mean, const float* v
 //  pass 1 (gn_stats_kernel): grid (chunks, B), blockDim = a multiple of C/8. Thread t owns channel slot t % (C/8)
 //    (8 consecutive channels = one 16 B vector) for a strided set of pixels and keeps 8 (sum, sumsq) pairs in registers;
 //    the CTA folds threads of equal slot, then channels of equal group, in index order and writes one partial per group.
-//  pass 1b (gn_finalize_kernel): sums the per-CTA partials in index order (fp64) -> mean / rstd per (batch, group).
+//  pass 1b (tail of gn_stats_kernel, run by the last-arriving CTA of a batch item): sums the per-CTA partials in index order
+//  (fp64) -> mean / rstd per (batch, group).
 //  pass 2 (gn_apply_kernel): normalise, affine, optional SiLU.
-__global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ x, float* __restrict__ partial, int64_t HW,
-                                                       int C, int G, bool f16) {
+__global__ void __launch_bounds__(512) gn_stats_kernel(const void* __restrict__ x, float* __restrict__ partial, int64_t HW,
+                                                       int C, int G, bool f16, double* __restrict__ stats,
+                                                       unsigned int* __restrict__ counter, double count, float eps) {
   extern __shared__ float gsm[];  // [blockDim][16] thread accumulators, then [2*C] channel sums
   const int b = blockIdx.y;
   const int vpp = C / 8;
@@ -814,40 +816,45 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const void* __restrict__ 
     dst[threadIdx.x] = gs;
     dst[G + threadIdx.x] = gq;
   }
-}
-// grid (B), block 1024 = `lanes` sub-lanes per statistic (2G statistics, G <= 128), statistic index fastest so that a warp reads
-// consecutive floats: sub-lane l sums partials l, l + lanes, ... in index order (eight loads in flight, folded in order), then
-// thread g folds the sub-lanes of (sum_g, sumsq_g) in index order
-__global__ void __launch_bounds__(1024) gn_finalize_kernel(const float* __restrict__ partial, double* __restrict__ stats,
-                                                           int chunks, int G, double count, float eps) {
-  __shared__ double sm[1024];
-  const int b = blockIdx.x;
+  // ---- finalize in the LAST-ARRIVING CTA of this batch item (was a launch of its own: 9 us of a 66 us norm). The fold order is
+  // fixed by partial index, not by arrival: sub-lane l of statistic j sums partials l, l + lanes, ... in index order (fp64), then
+  // thread g folds the sub-lanes in index order, so the result does not depend on which CTA happens to be last.
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counter[b], 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double* sm = reinterpret_cast<double*>(gsm);   // blockDim x 16 floats = blockDim x 8 doubles >= lanes x 2G
+  const int chunks = gridDim.x;
   const int nstat = 2 * G;
-  const int lanes = 1024 / nstat;
-  const int j = threadIdx.x % nstat, l = threadIdx.x / nstat;  // statistic j in [0, 2G), sub-lane l
-  double a = 0.0;
+  const int lanes = blockDim.x / nstat;          // >= 1: the launcher keeps blockDim >= 2G
+  const int j = threadIdx.x % nstat, l = threadIdx.x / nstat;
   if (l < lanes) {
+    double a = 0.0;
     const float* src = partial + (int64_t)b * chunks * nstat + j;
     int c = l;
     for (; c + 7 * lanes < chunks; c += 8 * lanes) {
       float t[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) t[k] = src[(int64_t)(c + k * lanes) * nstat];
+      for (int k = 0; k < 8; ++k) t[k] = __ldcg(src + (int64_t)(c + k * lanes) * nstat);
 #pragma unroll
       for (int k = 0; k < 8; ++k) a += (double)t[k];
     }
-    for (; c < chunks; c += lanes) a += (double)src[(int64_t)c * nstat];
+    for (; c < chunks; c += lanes) a += (double)__ldcg(src + (int64_t)c * nstat);
     sm[l * nstat + j] = a;
   }
   __syncthreads();
   if (threadIdx.x < G) {
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < lanes; ++k) { s += sm[k * nstat + threadIdx.x]; q += sm[k * nstat + G + threadIdx.x]; }
-    const double m = s / count;
-    const double var = q / count - m * m;
+    double sg = 0.0, qg = 0.0;
+    for (int k = 0; k < lanes; ++k) { sg += sm[k * nstat + threadIdx.x]; qg += sm[k * nstat + G + threadIdx.x]; }
+    const double m = sg / count;
+    const double var = qg / count - m * m;
     stats[((int64_t)b * G + threadIdx.x) * 2] = m;
     stats[((int64_t)b * G + threadIdx.x) * 2 + 1] = (double)rsqrtf(fmaxf((float)var, 0.f) + eps);
   }
+  if (threadIdx.x == 0) counter[b] = 0;   // ready for the next launch
 }
 __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ x, void* __restrict__ y,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -900,22 +907,27 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const void* __restrict__ 
   }
   for (; k >= 0; --k) apply(__ldg(reinterpret_cast<const uint4*>(xb + (i0 + k * stride) * 8)), i0 + k * stride);
 }
+static constexpr int GN_MAX_CHUNKS = 148 * 2;
 size_t groupnorm_ws_bytes(int B, int G) {
-  // [B, G] x (mean, rstd) doubles followed by the per-CTA partials [B, <= 592 chunks, 2G] floats
-  return sizeof(double) * 2 * G * B + sizeof(float) * 2 * G * B * (148 * 4);
+  // [B, G] x (mean, rstd) doubles, the per-CTA partials [B, <= 296 chunks, 2G] floats, and one arrival counter per batch item
+  // (zero when idle: the buffer must be zero-filled once after allocation, ensure_zeroed in ctx.h)
+  return sizeof(double) * 2 * G * B + sizeof(float) * 2 * G * B * GN_MAX_CHUNKS + sizeof(unsigned int) * B;
 }
 cudaError_t groupnorm_silu(const void* x16, void* y16, const float* gamma, const float* beta, double* stats_ws, int B,
                            int64_t HW, int C, int G, float eps, bool silu, bool f16, cudaStream_t s) {
   const int vpp = C / 8;
   if (C % 8 || C % G || vpp > 256 || G < 1 || G > 128) return cudaErrorInvalidValue;
-  const int threads = (256 / vpp) * vpp;  // largest multiple of the channel-slot count <= 256
-  if (C > 2 * threads) return cudaErrorInvalidValue;  // the CTA fold gives every thread at most two channels
+  // statistics pass: up to 512 threads (a multiple of the channel-slot count) and at most two CTAs per SM, so that the fold in the
+  // last-arriving CTA is over <= 296 partials with >= 8 sub-lanes per statistic (~1 us instead of a 9 us launch)
+  const int threads_s = (512 / vpp) * vpp;
+  const int threads = (256 / vpp) * vpp;  // apply pass: largest multiple of the channel-slot count <= 256
+  if (C > 2 * threads || threads_s < 2 * G) return cudaErrorInvalidValue;  // the CTA fold gives every thread at most two channels
   const int64_t nvec = HW * vpp;
   float* partial = reinterpret_cast<float*>(stats_ws + (size_t)2 * G * B);
-  const int chunks = (int)std::min<int64_t>((nvec + threads - 1) / threads, 148 * 4);
-  const size_t smem = std::max((size_t)threads * 16, (size_t)2 * C) * sizeof(float);
-  gn_stats_kernel<<<dim3(chunks, B), threads, smem, s>>>(x16, partial, HW, C, G, f16);
-  gn_finalize_kernel<<<B, 1024, 0, s>>>(partial, stats_ws, chunks, G, (double)HW * (C / G), eps);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partial + (size_t)2 * G * B * GN_MAX_CHUNKS);
+  const int chunks = (int)std::min<int64_t>((nvec + threads_s - 1) / threads_s, GN_MAX_CHUNKS);
+  const size_t smem = std::max((size_t)threads_s * 16, (size_t)2 * C) * sizeof(float);
+  gn_stats_kernel<<<dim3(chunks, B), threads_s, smem, s>>>(x16, partial, HW, C, G, f16, stats_ws, counter, (double)HW * (C / G), eps);
   const int chunks2 = (int)std::min<int64_t>((nvec + threads - 1) / threads, 148 * 8);
   gn_apply_kernel<<<dim3(chunks2, B), threads, 0, s>>>(x16, y16, gamma, beta, stats_ws, HW, C, G, silu, f16);
   return cudaGetLastError();

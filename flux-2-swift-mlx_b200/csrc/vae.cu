@@ -35,8 +35,8 @@ static int conv(flux2b_ctx* c, bool f16, const ConvW& w, const void* x, void* y,
 }
 static int gn(flux2b_ctx* c, bool f16, const NormW& n, const void* x, void* y, int B, int64_t HW, bool silu) {
   const int G = c->vae.norm_num_groups;
-  F2B_CUDA(c->gn_stats.ensure(groupnorm_ws_bytes(B, G)));
-  ProfScope ps(c, FLUX2B_PROF_GROUPNORM, 0, (double)B * HW * n.C * 6, 3);   // statistics, finalize, apply
+  F2B_CUDA(ensure_zeroed(c->gn_stats, groupnorm_ws_bytes(B, G), c->stream));
+  ProfScope ps(c, FLUX2B_PROF_GROUPNORM, 0, (double)B * HW * n.C * 6, 2);   // statistics (+ finalize in its last CTA), apply
   F2B_CUDA(groupnorm_silu(x, y, n.gamma.as<float>(), n.beta.as<float>(), c->gn_stats.as<double>(), B, HW, n.C, G,
                           c->vae.norm_eps, silu, f16, c->stream));
   return 0;
