@@ -295,9 +295,10 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
                                                    bool silu_in, bool accumulate, bool f16) {
   extern __shared__ float gx[];
   if (STAGED) { gemv_stage_x(gx, x, ldx, B, K, silu_in); x = gx; ldx = K; silu_in = false; }
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= N) return;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // grid-stride over output rows: a CTA stages the input once and then streams many weight rows (one row per warp at a time)
+  for (int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < N; warp += nwarps) {
   const uint16_t* wr = reinterpret_cast<const uint16_t*>(W) + (int64_t)warp * ldw;
   float acc[MAXB];
 #pragma unroll
@@ -334,12 +335,14 @@ __global__ void __launch_bounds__(256) gemv_kernel(const float* __restrict__ x, 
       if (lane == 0) y[b * ldy + warp] = accumulate ? y[b * ldy + warp] + r : r;
     }
   }
+  }
 }
 cudaError_t gemv(const float* x, int64_t ldx, const void* W16, int64_t ldw, float* y, int64_t ldy, int B, int N, int K,
                  bool silu_in, bool accumulate, bool f16, cudaStream_t s) {
   if (B > 8 || K % 8 || ldw % 8 || ldx % 4) return cudaErrorInvalidValue;
-  const int blocks = (N * 32 + 255) / 256;
   const size_t sm = (size_t)B * K * 4;
+  // staged: 4 CTAs per SM keep ~64 KB of weight loads in flight per SM; each CTA amortises its input staging over N / (8 * blocks) rows
+  const int blocks = sm <= 48 * 1024 ? std::min((N * 32 + 255) / 256, 148 * 4) : (N * 32 + 255) / 256;
   if (sm <= 48 * 1024) {
     if (B <= 1) gemv_kernel<1, true><<<blocks, 256, sm, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
     else if (B <= 2) gemv_kernel<2, true><<<blocks, 256, sm, s>>>(x, ldx, W16, ldw, y, ldy, B, N, K, silu_in, accumulate, f16);
@@ -362,11 +365,11 @@ __global__ void __launch_bounds__(256) gemv_q_kernel(const float* __restrict__ x
                                                      bool accumulate, bool f16) {
   extern __shared__ float gx[];
   if (STAGED) { gemv_stage_x(gx, x, ldx, B, K, silu_in); x = gx; ldx = K; silu_in = false; }
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= N) return;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const bool eight = mode == 1 || mode == 3;
   const int group = mode <= 2 ? 64 : mode == 5 ? 16 : 32;
+  for (int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; warp < N; warp += nwarps) {
   const uint8_t* cr = codes + (int64_t)warp * row_bytes;
   float acc[MAXB];
 #pragma unroll
@@ -420,13 +423,14 @@ __global__ void __launch_bounds__(256) gemv_q_kernel(const float* __restrict__ x
       if (lane == 0) y[b * ldy + warp] = accumulate ? y[b * ldy + warp] + r : r;
     }
   }
+  }
 }
 cudaError_t gemv_q(const float* x, int64_t ldx, const void* codes, int64_t row_bytes, const void* scales, const void* biases, int64_t sb_ld,
                    int mode, int sb_bf16, float* y, int64_t ldy, int B, int N, int K, bool silu_in, bool accumulate, bool f16, cudaStream_t s) {
   if (B > 8 || K % 16 || row_bytes % 8 || ldx % 4 || mode < 1 || mode > 5 || !scales || (mode <= 2 && !biases)) return cudaErrorInvalidValue;
-  const int blocks = (N * 32 + 255) / 256;
   const uint8_t *c8 = (const uint8_t*)codes, *s8 = (const uint8_t*)scales, *b8 = (const uint8_t*)biases;
   const size_t sm = (size_t)B * K * 4;
+  const int blocks = sm <= 48 * 1024 ? std::min((N * 32 + 255) / 256, 148 * 4) : (N * 32 + 255) / 256;
   if (sm <= 48 * 1024) {
     if (B <= 1) gemv_q_kernel<1, true><<<blocks, 256, sm, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
     else if (B <= 2) gemv_q_kernel<2, true><<<blocks, 256, sm, s>>>(x, ldx, c8, row_bytes, s8, b8, sb_ld, mode, sb_bf16, y, ldy, B, N, K, silu_in, accumulate, f16);
