@@ -425,6 +425,7 @@ def main():
     ap.add_argument("--wq-inkernel", type=int, default=2,
                     help="W-only quantized layers: 2 = packed weights only, many-row GEMMs dequantize the layer into a 16-bit stage per launch; "
                          "1 = packed weights only, always dequantized inside the GEMM / GEMV kernels; 0 = dense 16-bit copies")
+    ap.add_argument("--wq-stage-mb", type=int, default=0, help="staged W-only path: MB of 16-bit weights per N chunk (0 = library default)")
     ap.add_argument("--mx-bn", type=int, default=0, help="N tile of the block-scaled GEMM (0 = auto / 128 / 256)")
     ap.add_argument("--cta-group", type=int, default=0, help="GEMM CTA group (0 = auto: CTA pairs / 1 / 2)")
     ap.add_argument("--sp", action="store_true",
@@ -472,7 +473,7 @@ def main():
     free0, _ = torch.cuda.mem_get_info()
     ctx = flux2b.Context(dit=cfg, vae=vcfg, device=local_rank, quant=flux2b.QUANT[args.quant],
                          options={"keep_raw_weights": 0, "native_mx": args.native_mx, "mx_bn": args.mx_bn,
-                                  "gemm_cta_group": args.cta_group, "wq_inkernel": args.wq_inkernel})
+                                  "gemm_cta_group": args.cta_group, "wq_inkernel": args.wq_inkernel, "wq_stage_kb": args.wq_stage_mb * 1024})
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     load_synthetic_dit(ctx, cfg, device)
     load_synthetic_vae(ctx, vcfg, device)

@@ -173,7 +173,7 @@ int flux2b_synchronize(flux2b_ctx* c) {
 int flux2b_set_option(flux2b_ctx* c, const char* name, int value) {
   if (!c || !name) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, "null argument");
   static const char* known[] = {"compute_f16", "fuse_qk_rope", "fuse_swiglu", "attn_variant", "gemm_cta_group",
-                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant", "attn_poly", "group_streams", "te_graph", "sp_disable", "vae_attn_chunk", "wq_inkernel", "dit_graph", "vae_fold_upsample"};
+                                "keep_raw_weights", "vae_f16", "uint8_round", "record_blocks", "vae_conv_cta_group", "sp_mode", "sp_overlap", "native_mx", "mx_bn", "mx_fuse_quant", "attn_poly", "group_streams", "te_graph", "sp_disable", "vae_attn_chunk", "wq_inkernel", "dit_graph", "vae_fold_upsample", "wq_stage_kb"};
   bool ok = false;
   for (const char* k : known) ok = ok || !strcmp(k, name);
   if (!ok) return fail(FLUX2B_ERR_INVALID_CONFIGURATION, std::string("unknown option: ") + name);

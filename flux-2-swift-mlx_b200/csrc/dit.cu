@@ -63,6 +63,7 @@ static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int
     g.wq_biases = W.wb.p ? W.wb.as<uint8_t>() + (k_off / group) * esz : nullptr;
     g.force_cta_group = c->option("gemm_cta_group", 0);
     F2B_TRY(wq_stage_buffers(c, M, W, false, &g.wq_stage, &g.wq_stage_lo));
+    g.wq_stage_kb = c->option("wq_stage_kb", 0);
     bytes = 2.0 * ((double)M * g.K + (double)M * g.N) + (double)g.N * g.K * bits / 8 + (double)g.N * (g.K / group) * esz * (W.wb.p ? 2 : 1);
     if (g.wq_stage) bytes += 2.0 * 2.0 * (double)g.N * g.K;   // the 16-bit stage is written once and read once
   } else if (W.mx) {
@@ -81,7 +82,7 @@ static int run_gemm(flux2b_ctx* c, const void* A, int64_t lda, const Lin& W, int
     bytes = 2.0 * ((double)M * g.K + (double)g.N * g.K + (double)M * g.N);
   }
   const double flops = 2.0 * M * (double)g.N * g.K;
-  ProfScope ps(c, FLUX2B_PROF_GEMM, flops, bytes);
+  ProfScope ps(c, FLUX2B_PROF_GEMM, flops, bytes, gemm_launch_count(g));
   F2B_CUDA(gemm_launch(g, c->stream));
   return 0;
 }
@@ -479,12 +480,13 @@ static int forward_one(flux2b_ctx* c, int S_img, int S_txt, const float* hidden,
           g.wq_scales = Wimg.ws.p; g.wq_biases = Wimg.wb.p; g.wq_scales_lo = Wtxt.ws.p; g.wq_biases_lo = Wtxt.wb.p;
           wbytes = 2.0 * ((double)g.N * g.K * bits / 8 + (double)g.N * (g.K / group) * (Wimg.wmode <= 2 ? 4 : 1));
           F2B_TRY(wq_stage_buffers(c, S, Wimg, true, &g.wq_stage, &g.wq_stage_lo));
+          g.wq_stage_kb = c->option("wq_stage_kb", 0);
           if (g.wq_stage) wbytes += 2.0 * 2.0 * 2.0 * (double)g.N * g.K;
         }
         e.f16 = f16 ? 1 : 0; e.split_row = S_txt;
         g.epi = e;
         g.force_cta_group = c->option("gemm_cta_group", 0);
-        ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * S * (double)g.N * g.K, 2.0 * ((double)S * g.K + (double)S * g.N) + wbytes);
+        ProfScope ps(c, FLUX2B_PROF_GEMM, 2.0 * S * (double)g.N * g.K, 2.0 * ((double)S * g.K + (double)S * g.N) + wbytes, gemm_launch_count(g));
         F2B_CUDA(gemm_launch(g, st));
         return 0;
       };

@@ -71,6 +71,7 @@ struct KParams {
   int wq_mode, wq_sb_bf16, wq_sb_ld, wq_vec;   // wq_vec: 16 B loads of 8 (4 for nvfp4) k-blocks of scales are aligned
   const uint8_t* wq_s;  const uint8_t* wq_b;   // main problem
   const uint8_t* wq_s_lo; const uint8_t* wq_b_lo;  // rows below split_units (two-problem launch)
+  int n_off;  // absolute output column of this launch's first B row (staged W-only chunks), 0 otherwise
   int dbg;  // FLUX2B_GEMM_TIMELINE=1: cluster 0 prints where its producer / issuer / epilogue warps waited (debug aid)
 };
 
@@ -1122,7 +1123,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait<CG == 2>(&tfull[acc], acc_phase, 4);
       tc_fence_after();
       const uint64_t t_e0 = p.dbg ? globaltimer_ns() : 0;
-      epilogue_tile<BN>(p, tmem_base + acc * BN, quarter, lane, row_ok, grow, n_blk * BN, sbias);
+      epilogue_tile<BN>(p, tmem_base + acc * BN, quarter, lane, row_ok, grow, p.n_off + n_blk * BN, sbias);
       tc_fence_before();
       __syncwarp();
       const uint64_t t_e1 = p.dbg ? globaltimer_ns() : 0;
@@ -1269,17 +1270,18 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
     uint64_t as[1] = {(uint64_t)g.lda * 2};
     uint32_t ab[2] = {BK, BM};
     if (!make_tmap_bf16(&tmA, g.A, 2, ad, as, ab)) return cudaErrorInvalidValue;
-    uint64_t bd[2] = {(uint64_t)g.K, (uint64_t)g.N};
+    uint64_t bd[2] = {(uint64_t)g.K, (uint64_t)(g.N - g.n_off)};
     uint64_t bs[1] = {(uint64_t)g.ldb * 2};
     uint32_t bb[2] = {BK, (uint32_t)C::B_ROWS};
     if (!make_tmap_bf16(&tmB, g.B, 2, bd, bs, bb)) return cudaErrorInvalidValue;
+    p.n_off = g.n_off;
     if (g.B_lo) {
       if (!make_tmap_bf16(&tmSFB, g.B_lo, 2, bd, bs, bb)) return cudaErrorInvalidValue;
       p.split_units = g.M_lo / (BM * CG);
     }
   }
   p.num_m_units = (num_m_blks + CG - 1) / CG;
-  p.num_n_blks = (g.N + BN - 1) / BN;
+  p.num_n_blks = (g.N - g.n_off + BN - 1) / BN;
   const int total = p.num_m_units * p.num_n_blks * (p.up2 ? 4 : 1);
   const int max_units = g_num_sms / CG;
   const int units = std::min(total, max_units);
@@ -1394,6 +1396,21 @@ static cudaError_t dispatch(const GemmProblem& g, cudaStream_t s, int bn, int cg
   return cudaErrorInvalidValue;
 }
 
+// staged W-only GEMM: rows per N chunk. Default: the whole layer in one chunk. Chunks small enough to keep the stage L2-resident
+// (option wq_stage_kb) were measured slower on Klein 9B int4 @1024^2 — 13.6 steps/s at 64 / 128 MB, 13.9 at 256 MB, 14.0 - 14.2 unchunked:
+// the extra launches and the wave quantisation of the narrower GEMMs cost more than the saved HBM round trip of the stage.
+static int wq_stage_chunk_rows(const GemmProblem& g) {
+  if (g.wq_stage_kb <= 0) return std::max(256, (g.N + 255) / 256 * 256);
+  const int64_t chunk_bytes = (int64_t)g.wq_stage_kb << 10;
+  const int nchunks = (int)std::max<int64_t>(1, ((int64_t)g.N * g.K * 2 + chunk_bytes - 1) / chunk_bytes);
+  return std::max(256, ((g.N + nchunks - 1) / nchunks + 255) / 256 * 256);
+}
+int gemm_launch_count(const GemmProblem& g) {
+  if (!g.wq || !g.wq_stage) return 1;
+  const int cn = wq_stage_chunk_rows(g);
+  return ((g.N + cn - 1) / cn) * (1 + (g.B_lo ? 2 : 1));
+}
+
 cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
   if (!gemm_init()) {
     g_err = "gemm_init failed (driver entry point or device query)";
@@ -1444,30 +1461,41 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
         g_err = "W-only staged GEMM: 16 B aligned stage buffers (one per weight set)";
         return cudaErrorInvalidValue;
       }
-      const int64_t nthreads = (int64_t)g.N * (g.K / 8);
-      const unsigned blocks = (unsigned)((nthreads + 255) / 256);
+      // One chunk = the whole layer by default; with option wq_stage_kb the layer runs in N chunks that are dequantized into the SAME
+      // stage (which then stays L2-resident) and multiplied by the plain kernel with a column window (n_off).
+      const int esz_ = g.wq <= 2 ? 2 : 1;
       const int sb_ld = g.wq_sb_ld ? g.wq_sb_ld : g.K / group;
-      for (int which = 0; which < (g.B_lo ? 2 : 1); ++which) {
-        const uint8_t* pk = reinterpret_cast<const uint8_t*>(which ? g.B_lo : g.B);
-        const uint8_t* sc = reinterpret_cast<const uint8_t*>(which ? g.wq_scales_lo : g.wq_scales);
-        const uint8_t* bi = reinterpret_cast<const uint8_t*>(which ? g.wq_biases_lo : g.wq_biases);
-        uint16_t* out = reinterpret_cast<uint16_t*>(which ? g.wq_stage_lo : g.wq_stage);
-        switch (g.wq) {
-          case 1: wq_stage_kernel<1><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
-          case 2: wq_stage_kernel<2><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
-          case 3: wq_stage_kernel<3><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
-          case 4: wq_stage_kernel<4><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
-          default: wq_stage_kernel<5><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, g.N, g.K, out, g.epi.f16); break;
+      const int cn_max = wq_stage_chunk_rows(g);
+      for (int n0 = 0; n0 < g.N; n0 += cn_max) {
+        const int cn = std::min(cn_max, g.N - n0);
+        const int64_t nthreads = (int64_t)cn * (g.K / 8);
+        const unsigned blocks = (unsigned)((nthreads + 255) / 256);
+        for (int which = 0; which < (g.B_lo ? 2 : 1); ++which) {
+          const uint8_t* pk = reinterpret_cast<const uint8_t*>(which ? g.B_lo : g.B) + (int64_t)n0 * g.ldb;
+          const uint8_t* sc = reinterpret_cast<const uint8_t*>(which ? g.wq_scales_lo : g.wq_scales) + (int64_t)n0 * sb_ld * esz_;
+          const uint8_t* bi0 = reinterpret_cast<const uint8_t*>(which ? g.wq_biases_lo : g.wq_biases);
+          const uint8_t* bi = bi0 ? bi0 + (int64_t)n0 * sb_ld * esz_ : nullptr;
+          uint16_t* out = reinterpret_cast<uint16_t*>(which ? g.wq_stage_lo : g.wq_stage);
+          switch (g.wq) {
+            case 1: wq_stage_kernel<1><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, cn, g.K, out, g.epi.f16); break;
+            case 2: wq_stage_kernel<2><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, cn, g.K, out, g.epi.f16); break;
+            case 3: wq_stage_kernel<3><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, cn, g.K, out, g.epi.f16); break;
+            case 4: wq_stage_kernel<4><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, cn, g.K, out, g.epi.f16); break;
+            default: wq_stage_kernel<5><<<blocks, 256, 0, stream>>>(pk, g.ldb, sc, bi, sb_ld, g.wq_sb_bf16, cn, g.K, out, g.epi.f16); break;
+          }
+          cudaError_t e = cudaGetLastError();
+          if (e != cudaSuccess) return e;
         }
-        cudaError_t e = cudaGetLastError();
+        GemmProblem h = g;
+        h.wq = 0; h.wq_stage = nullptr; h.wq_stage_lo = nullptr;
+        h.wq_scales = h.wq_biases = h.wq_scales_lo = h.wq_biases_lo = nullptr;
+        h.B = g.wq_stage; h.ldb = g.K;
+        if (g.B_lo) h.B_lo = g.wq_stage_lo;
+        h.n_off = n0; h.N = n0 + cn;
+        cudaError_t e = gemm_launch(h, stream);
         if (e != cudaSuccess) return e;
       }
-      GemmProblem h = g;
-      h.wq = 0; h.wq_stage = nullptr; h.wq_stage_lo = nullptr;
-      h.wq_scales = h.wq_biases = h.wq_scales_lo = h.wq_biases_lo = nullptr;
-      h.B = g.wq_stage; h.ldb = g.K;
-      if (g.B_lo) h.B_lo = g.wq_stage_lo;
-      return gemm_launch(h, stream);
+      return cudaSuccess;
     }
     const int m_blks = (g.M + BM - 1) / BM;
     const bool pair = g.force_cta_group != 1 && m_blks >= 2;
@@ -1481,7 +1509,9 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
   if (conv && (g.Cin % 8 || g.lda % 8)) { g_err = "conv Cin / pixel stride must be multiples of 8"; return cudaErrorInvalidValue; }
   if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) { g_err = "A/B must be 16 B aligned"; return cudaErrorInvalidValue; }
   int bn = g.force_bn;
-  if (!bn) bn = g.N > 128 ? 256 : g.N > 64 ? 128 : g.N > 32 ? 64 : 32;
+  const int Nw = g.N - g.n_off;   // columns this launch computes
+  if (g.n_off && (conv || g.n_off < 0 || g.n_off >= g.N)) { g_err = "n_off: plain GEMM only, 0 <= n_off < N"; return cudaErrorInvalidValue; }
+  if (!bn) bn = Nw > 128 ? 256 : Nw > 64 ? 128 : Nw > 32 ? 64 : 32;
   if (conv && !g.force_bn) {
     // N tile with the least padding (ties -> the wider tile): Cout = 384 -> 2 x 192 (256-wide tiles would compute 512 columns),
     // 192 -> 192, 96 -> 96. The small decoder's 96 / 192 / 384-channel layers lose a quarter of the tensor pipe otherwise.
@@ -1505,13 +1535,13 @@ cudaError_t gemm_launch(const GemmProblem& g, cudaStream_t stream) {
                      : halo ? g.batch * ((g.W + HALO_TW - 1) / HALO_TW) * ((g.H + HALO_TH - 1) / HALO_TH)
                             : g.batch * ((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + CONV_TH - 1) / CONV_TH);
   if (cg == 2 && (m_blks < 2 || bn < 32)) cg = 1;
-  if (!conv && !g.force_bn && !g.force_cta_group && bn == 256 && g.epi.mode != EPI_SWIGLU && g.N % 128 == 0) {
+  if (!conv && !g.force_bn && !g.force_cta_group && bn == 256 && g.epi.mode != EPI_SWIGLU && Nw % 128 == 0) {
     // Few-row problems (the text encoder's M = 512 prefill: 256-wide tiles of an N = 2560 projection occupy 40 of 148 SMs):
     // pick the narrower tile when a simple wave model says it is clearly faster. Per k-step of 16 a CTA needs
     // max(MMA clocks = bn / 2, shared-memory operand reads = (128 + bn / cg) / 4) clocks; a wave costs ~3000 clocks of
     // pipeline fill + epilogue on top. The DiT shapes (M = 4608, many waves) keep the measured-best 256 x 256 pair tile.
     auto est = [&](int bn_, int cg_) {
-      const long units = (long)((g.M + BM * cg_ - 1) / (BM * cg_)) * ((g.N + bn_ - 1) / bn_);
+      const long units = (long)((g.M + BM * cg_ - 1) / (BM * cg_)) * ((Nw + bn_ - 1) / bn_);
       const long slots = g_num_sms / cg_;
       const double per = (g.K / 16.0) * std::max(bn_ / 2.0, (128.0 + bn_ / cg_) / 4.0) + 3000.0;
       return (double)((units + slots - 1) / slots) * per;

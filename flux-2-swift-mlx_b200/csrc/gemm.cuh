@@ -112,10 +112,16 @@ struct GemmProblem {
   // every 256-row M tile and costs more issue slots than the tensor core leaves idle; staging does it once per launch.
   void* wq_stage = nullptr;
   void* wq_stage_lo = nullptr;
+  int wq_stage_kb = 0;   // staged path: KB of 16-bit weights per N chunk (0 = the whole layer at once, the measured-fastest setting)
+  // Column window of a wider problem (plain 16-bit GEMM only; used by the staged W-only path, which runs a layer in N chunks whose
+  // stage stays L2-resident): B holds rows [n_off, N) of the weight, the epilogue addresses outputs / bias / gate by absolute column.
+  int n_off = 0;
 };
 
 // Returns cudaSuccess or the launch error. Never synchronises.
 cudaError_t gemm_launch(const GemmProblem& p, cudaStream_t stream);
+// kernels gemm_launch issues for this problem (1, except the staged W-only path: per N chunk one staging kernel per weight set + the GEMM)
+int gemm_launch_count(const GemmProblem& p);
 // One-time driver entry point lookup; returns false if cuTensorMapEncodeTiled cannot be resolved.
 bool gemm_init();
 const char* gemm_last_error();

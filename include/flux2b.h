@@ -96,7 +96,8 @@ int flux2b_synchronize(flux2b_ctx* ctx);
  *  packed weights together with their scales / biases — are released, so get_tensor / save_prequantized / merge_lora report them
  *  missing; with wq_inkernel or native_mx the packed working copy is then the only resident copy of a quantized layer),
  * "sp_disable" (1 = a sequence-parallel context runs the forward alone on its own GPU: the parity reference of the sharded forward),
- * "group_streams", "attn_poly", "te_graph", "sp_mode", "sp_overlap", "mx_bn", "mx_fuse_quant", "vae_attn_chunk": see DESIGN.md */
+ * "group_streams", "attn_poly", "te_graph", "dit_graph", "sp_mode", "sp_overlap", "mx_bn", "mx_fuse_quant", "vae_attn_chunk",
+ * "vae_fold_upsample", "wq_stage_kb": see DESIGN.md / INTEGRATION.md */
 int flux2b_set_option(flux2b_ctx* ctx, const char* name, int value);
 
 /* ------------------------------------------------------------------ weights (Loading/WeightLoader.swift:567-623)

@@ -318,17 +318,19 @@ def test_dit_forward_staged_dequant_matches_dense_copy(flux2b, name):
     t, gd = torch.tensor([0.7]), torch.tensor([4.0])
     img_ids, txt_ids = O.image_position_ids(512, 512), O.text_position_ids(S_txt)
     outs = []
-    for ink, group in ((2, 1), (2, 0), (0, 1)):
-        ctx = flux2b.Context(dit=cfg, quant=q, options={"wq_inkernel": ink, "record_blocks": 1, "group_streams": group})
+    # wq_stage_kb = 128: every layer runs in several 256-row N chunks through one L2-resident stage (column windows of the
+    # QKV + RoPE, SwiGLU and gate + residual epilogues, two weight sets per chunk in the grouped launches); 0 = one chunk (default)
+    for ink, group, kb in ((2, 1, 128), (2, 0, 128), (2, 1, 0), (0, 1, 0)):
+        ctx = flux2b.Context(dit=cfg, quant=q, options={"wq_inkernel": ink, "record_blocks": 1, "group_streams": group, "wq_stage_kb": kb})
         ctx.load_weights(W, dtype=torch.float16)
         ctx.finalize()
         out = ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), gd.numpy(), img_ids.numpy(), txt_ids.numpy())
         blocks = [ctx.block_output(i, S_img + S_txt, cfg.inner_dim) for i in range(4)]
         outs.append((out, blocks))
         ctx.close()
-    for o in outs[:2]:
-        assert np.array_equal(o[0], outs[2][0])
-        for a, b in zip(o[1], outs[2][1]):
+    for o in outs[:3]:
+        assert np.array_equal(o[0], outs[3][0])
+        for a, b in zip(o[1], outs[3][1]):
             assert np.array_equal(a, b)
 
 
