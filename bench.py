@@ -368,6 +368,62 @@ def sp_measure(args, cfg, rank, local_rank, world, device, dist, res, refs, mode
     return out
 
 
+def k9_measure(args, rank, local_rank, world, device, dist, steps=2):
+    """BASELINE.json configs[2] in the same bench line (key `configs2`): Klein 9B with nvfp4 weights at 1024x1024, 4 Euler steps + VAE decode
+    per image, image-parallel over all ranks — W-only (the reference's arithmetic: x . dequant(W)^T, packed weights only) and native
+    block-scaled tcgen05 MMA (activations quantised on the fly), side by side with what each mode's parity is."""
+    import torch
+    import flux2b
+    from flux2b import configs
+    cfg, vcfg = configs.klein_9b(), configs.vae_small_decoder()
+    S_img = (HEIGHT // 16) * (WIDTH // 16)
+    sched = flux2b.FlowMatchEulerScheduler()
+    sched.set_timesteps(NUM_STEPS, S_img)
+    lat = torch.randn(1, S_img, 128, generator=torch.Generator().manual_seed(42 + rank)).to(device)
+    enc = torch.randn(1, S_TXT, cfg.joint_attention_dim, generator=torch.Generator().manual_seed(43)).to(torch.bfloat16).to(device)
+    rgb = torch.empty(HEIGHT, WIDTH, 3, dtype=torch.uint8, device=device)
+    out = {"workload": f"klein9b nvfp4 t2i {HEIGHT}x{WIDTH} ({S_img} img + {S_TXT} txt tokens), {NUM_STEPS} Euler steps + small-decoder VAE decode per image; "
+                       f"random-init weights; image-parallel over {world} rank(s)", "steps": steps, "n_gpus": world, "modes": {}}
+    notes = {"w_only": "x . dequant(W)^T, the reference's arithmetic (per-block rel-L2 <= 2e-3 vs the oracle on the dequantized weights); packed weights are the only resident copy",
+             "native_block_scaled": "tcgen05 block-scaled MMA on MLX's packed nvfp4 bytes, activations quantised on the fly to nvfp4: ~5.9e-2 rel-L2 from the reference arithmetic by construction (its own parity protocol: exact vs the emulation)"}
+    for name, native in (("w_only", 0), ("native_block_scaled", 1)):
+        free0, _ = torch.cuda.mem_get_info()
+        ctx = flux2b.Context(dit=cfg, vae=vcfg, device=local_rank, quant=flux2b.QUANT["nvfp4"], options={"keep_raw_weights": 0, "native_mx": native})
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        load_synthetic_dit(ctx, cfg, device)
+        load_synthetic_vae(ctx, vcfg, device)
+        ctx.finalize()
+        torch.cuda.empty_cache(); torch.cuda.synchronize()
+        free1, _ = torch.cuda.mem_get_info()
+
+        def one():
+            x = lat.clone()
+            ctx.generate(x, enc, sched.sigmas, HEIGHT, WIDTH, rgb_out=rgb)
+        for _ in range(3):
+            one()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        out["modes"][name] = {"value": steps * world * NUM_STEPS / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                              "images_per_sec": steps * world / (ms * 1e-3), "mem_gb": (free0 - free1) / 1e9,
+                              "gpu_launches": int(ctx.launch_count()), "parity": notes[name]}
+        ctx.close()
+        del ctx
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_sp(args, cfg, rank, local_rank, world, device, dist):
     """--sp: the sequence-parallel measurement as the bench line itself (BASELINE.json configs[3] / [4])."""
     sampler = ClockSampler(local_rank)
@@ -436,7 +492,7 @@ def main():
     ap.add_argument("--refs", type=int, default=0, help="number of reference images (image-to-image conditioning tokens); without --sp also times the KV-cached loop")
     ap.add_argument("--lora", action="store_true", help="--sp mode: merge a rank-16 LoRA into every attention / FF linear at load time")
     ap.add_argument("--no-sp-extra", dest="sp_extra", action="store_false",
-                    help="skip the extra Ulysses measurement (key `sp`) that follows the image-parallel headline")
+                    help="skip the extra measurements that follow the image-parallel headline (keys `sp`: Ulysses Dev 2048^2, `configs2`: Klein 9B nvfp4)")
     ap.add_argument("--sp-model", default="dev", choices=["dev", "klein9b", "klein4b"])
     ap.add_argument("--sp-res", type=int, default=2048)
     ap.add_argument("--sp-steps", type=int, default=10)
@@ -584,7 +640,7 @@ def main():
     # Ulysses sequence parallelism in front of the driver (north_star's second split, BASELINE.json configs[3]): after the
     # image-parallel headline every run — N = 1 included, so that strong-scaling efficiency has its denominator — times one
     # Dev 32B bf16 denoising step at 2048^2 over all ranks of the job, both transports, with parity against the single-GPU step.
-    sp = None
+    sp = cfg2 = None
     if args.sp_extra and args.model == "klein4b" and args.quant == "bf16":
         ctx.close()
         del ctx
@@ -596,6 +652,10 @@ def main():
                             args.sp_steps, model_name=args.sp_model)
         except Exception as e:   # the headline must survive a failure of the extra measurement
             sp = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            cfg2 = k9_measure(args, rank, local_rank, world, device, dist)
+        except Exception as e:
+            cfg2 = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if dist is not None:
@@ -646,6 +706,8 @@ def main():
         out["i2i"] = i2i
     if sp is not None:
         out["sp"] = sp
+    if cfg2 is not None:
+        out["configs2"] = cfg2
     if world == 1 and not args.no_cpu_baseline:
         c = cpu_sample(os.cpu_count() or 1)
         out["cpu_baseline"] = {"value": 1.0 / c["step_s"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
