@@ -807,8 +807,9 @@ def lora_merge(weight: Tensor, A: Tensor, B: Tensor, scale: float, dtype: torch.
 
 
 # ----------------------------------------------------------------------------------------------- text encoder
-# Cites below are relative to /root/reference/Sources/FluxTextEncoders. PARITY STATUS: unpinned (the reference holds no numeric
-# vectors for its text encoders; RMSNorm / RoPE / SDPA arithmetic lives in mlx-swift). What the reference does fix — layer
+# Cites below are relative to /root/reference/Sources/FluxTextEncoders. PARITY STATUS: the reference holds no numeric vectors for its
+# text encoders and RMSNorm / RoPE / SDPA arithmetic lives in mlx-swift (unpinned); the STRUCTURE restated here is pinned against
+# Hugging Face transformers' Qwen3Model / MistralModel — the modules the Swift files are ports of — in tests/test_te_hf_pin_cpu.py. What the reference does fix — layer
 # indexing, padding side, mask values, pair layout of the rotation, GQA head mapping — is restated here and self-tested in
 # tests/test_oracle_pins.py.
 @dataclass
