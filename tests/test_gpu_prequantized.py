@@ -31,6 +31,23 @@ def test_export_and_reload_bit_identical(flux2b, tmp_path, name, native):
     ctx.save_prequantized(p, "tiny-model", "w.safetensors:1:2")
     assert flux2b.prequantized_is_valid(p, name, "tiny-model", "w.safetensors:1:2")
     assert not os.path.exists(os.path.join(os.path.dirname(p), ".tmp-transformer.safetensors"))
+    # writer pinned against the format's reference implementation: the official safetensors library opens the file, sees the
+    # metadata of PrequantizedCheckpoint.swift:177-185 and the same bytes get_tensor returns
+    try:
+        from safetensors import safe_open
+    except ImportError:
+        safe_open = None
+    if safe_open is not None:
+        with safe_open(p, framework="np") as f:
+            md = f.metadata()
+            assert md["format"] == "flux2-mlx-prequantized-v1" and md["quantization"] == name and md["source"] == "tiny-model"
+            assert md["source_fingerprint"] == "w.safetensors:1:2" and md["component"] == "transformer"
+            keys = set(f.keys())
+            k0 = next(k for k, w in W.items() if w.dim() == 2)
+            base0 = k0[:-len(".weight")]
+            assert {base0 + ".weight", base0 + ".scales"} <= keys
+            a = f.get_tensor(base0 + ".weight")
+            assert a.dtype == np.uint32 and np.array_equal(a, ctx.get_tensor(base0 + ".weight"))
 
     ctx2 = flux2b.Context(dit=cfg, quant=q, options={"record_blocks": 1, "native_mx": native})
     assert ctx2.load_prequantized(p, "tiny-model", "w.safetensors:1:2")

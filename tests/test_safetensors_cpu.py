@@ -74,3 +74,17 @@ def test_truncated_or_padded_payload_is_rejected(tmp_path):
     assert not flux2b.prequantized_is_valid(p, "nvfp4")
     open(p, "wb").write(struct.pack("<Q", 8) + b"{notjson")
     assert not flux2b.prequantized_is_valid(p, "nvfp4")
+
+
+def test_file_written_by_the_official_safetensors_library_is_read(tmp_path):
+    """reader pinned against the reference implementation of the format: a file produced by `safetensors.numpy.save_file`
+    (its own key order, header padding and alignment) passes the metadata / payload gate, and a metadata edit fails it"""
+    st = pytest.importorskip("safetensors.numpy")
+    import flux2b
+    T = {"xEmbedder.weight": np.arange(64, dtype=np.uint32).reshape(4, 16), "xEmbedder.scales": np.full((4, 8), 0x38, np.uint8),
+         "transformerBlocks.0.attn.normQ.weight": np.ones(128, np.float16), "singleTransformerBlocks.3.attn.normK.weight": np.ones(128, np.float32)}
+    p = str(tmp_path / "transformer.safetensors")
+    st.save_file(T, p, metadata=meta())
+    assert flux2b.prequantized_is_valid(p, "nvfp4", "FLUX.2-klein-4B", "a.safetensors:10:1700000000"), flux2b.last_error()
+    st.save_file(T, p, metadata=meta(bits="8"))
+    assert not flux2b.prequantized_is_valid(p, "nvfp4")
