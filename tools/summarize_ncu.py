@@ -42,6 +42,18 @@ def launches(src, dst):
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {a[0]} | {a[1] / 1e3:.3f} | {100 * a[1] / tot:.1f}% | {a[1] / a[0]:.1f} |\n")
     print(open(dst).read())
+    # the same durations per bench kernel class (bench.py reports them beside its event-pair timings while the kernel sources match)
+    import json, os
+    cls = collections.OrderedDict()
+    for k, a in agg.items():
+        c = ("conv" if re.search(r"gemm_kernel<\d+, \d+, [12]", k) else "gemm" if k.startswith("gemm_kernel") or k.startswith("wq_stage_kernel") else
+             "attn" if k.startswith("attn_kernel") else "gemv" if k.startswith("gemv") else "groupnorm" if k.startswith("gn_") else "elem")
+        e = cls.setdefault(c, {"launches": 0, "ms": 0.0})
+        e["launches"] += a[0]; e["ms"] += a[1] / 1e3
+    sha_file = os.path.join(os.path.dirname(os.path.abspath(src)), "csrc_sha.txt")
+    out = {"classes": cls, "csrc_sha": open(sha_file).read().strip() if os.path.exists(sha_file) else None,
+           "_source": "ncu --metrics gpu__time_duration.sum --clock-control none over every launch of one klein4b 1024x1024 image (cold-cache, serialised)"}
+    json.dump(out, open(os.path.splitext(dst)[0] + ".json", "w"), indent=1)
 
 
 def full(src, dst):
