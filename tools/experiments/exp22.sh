@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpurun --gpus N -- 'bash tools/exp22.sh N'
+# usage: gpurun --gpus N -- 'bash tools/experiments/exp22.sh N'
 N=$1
 mkdir -p gpurun_out
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err

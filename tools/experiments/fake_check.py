@@ -2,7 +2,7 @@
 """Timing-experiment sanity check (FLUX2B_GEMM_FAKE_HALF_B): are the activations of the faked forward still finite and of the usual
 magnitude? (If they degenerate to NaN / Inf / zeros the power draw of the faked run says nothing about the real one.)"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "flux-2-swift-mlx_b200")); sys.path.insert(0, ROOT)
 import numpy as np, torch, flux2b
 from flux2b import configs
