@@ -28,7 +28,14 @@ def rel_l2(a, b):
     import torch
     a = torch.as_tensor(a).detach().cpu().double().flatten()
     b = torch.as_tensor(b).detach().cpu().double().flatten()
-    return float((a - b).norm() / (b.norm() + 1e-30))
+    e = float((a - b).norm() / (b.norm() + 1e-30))
+    # F2B_PARITY_LOG=<file>: every measured relative error with the test that asked for it (tools/parity_margins.py turns the log
+    # into profiles/r02_parity_margins.md: measured error vs the bound written in the test)
+    log = os.environ.get("F2B_PARITY_LOG")
+    if log:
+        with open(log, "a") as f:
+            f.write(f"{os.environ.get('PYTEST_CURRENT_TEST', '?').split(' ')[0]}\t{e:.6e}\n")
+    return e
 
 
 @pytest.fixture(scope="session")

@@ -108,7 +108,7 @@ def test_attention(ctx, B, S, H, variant):
     e_round = rel_l2(out, ref.to(torch.bfloat16).float())
     print(f"attention v{variant} B={B} S={S} H={H}: rel-L2 {e:.2e} (vs bf16-rounded reference {e_round:.2e})")
     # P is rounded to bf16 before the PV product and the result once more: two roundings of 2^-9 relative each
-    assert e < 4e-3
+    assert e < 3.2e-3   # measured 2.3 - 2.6e-3 (profiles/r02_parity_margins.md)
 
 
 def test_attention_f16_and_large_logits(ctx_f16):

@@ -22,7 +22,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 pytestmark = pytest.mark.gpu
 
 TOL_BLOCK = 2e-3      # per-block residual stream, rel-L2 (north_star)
-TOL_OUT = 4e-3        # model output [S_img, 128]: one more bf16 GEMM operand rounding after the last block
+TOL_OUT = 3e-3        # model output [S_img, 128]: one more bf16 GEMM operand rounding after the last block (measured 2.3 - 2.4e-3)
 TOL_QUANT_BLOCK = 3e-3  # W-only quantized path: dequantized weights are rounded once more to the 16-bit operand type
 
 
@@ -280,7 +280,7 @@ def test_lora_merge_dense_bit_exact(flux2b):
         out = ctx.dit_forward(hidden.numpy(), enc.numpy(), t.numpy(), None, img_ids.numpy(), txt_ids.numpy())
         W2 = dict(W); W2[key + ".weight"] = want.float()
         # (activations are bf16 in both cases: only the stored weight dtype differs)
-        assert rel_l2(out, O.dit_forward(W2, cfg, hidden, enc, t, None, img_ids, txt_ids)) < TOL_OUT
+        assert rel_l2(out, O.dit_forward(W2, cfg, hidden, enc, t, None, img_ids, txt_ids)) < 4e-3   # merged weights: measured 3.25e-3 (the LoRA delta enlarges the output the rounding acts on)
         ctx.close()
 
 
@@ -330,7 +330,7 @@ def test_denoise_loop_variants(flux2b):
     x = lat.numpy().copy()
     ctx.denoise(x, enc.numpy(), sched.sigmas, HW, HW, enc_uncond=enc_u.numpy(), cfg_scale=3.0)
     want = O.denoise(W, cfg, lat, enc, sched.sigmas, HW, HW, enc_uncond=enc_u, cfg_scale=3.0)
-    assert cosine(x, want) >= 0.999 and rel_l2(x, want) < 2 * TOL_OUT
+    assert cosine(x, want) >= 0.999 and rel_l2(x, want) < 1.5 * TOL_OUT
     # (3) I2I with reference tokens [output | refs] (:1696-1767)
     ref_lat = torch.randn(1, 36, 128, generator=torch.Generator().manual_seed(45))
     ref_ids = O.reference_position_ids([6], [6])
@@ -408,7 +408,7 @@ def test_vae_decode_vs_oracle(flux2b, small, h, w):
     assert out.shape == (1, 3, 8 * h, 8 * w)
     e = rel_l2(out, ref)
     print(f"vae small={small} {h}x{w}: rel-L2 {e:.2e}")
-    assert e < 5e-3  # f16 activations through ~30 convolutions and 30 GroupNorms
+    assert e < 3.5e-3  # f16 activations through ~30 convolutions and 30 GroupNorms (measured <= 2.7e-3)
     u8 = ctx.vae_decode_u8(z.numpy())
     want = O.postprocess_vae_output(ref).numpy()
     d = np.abs(u8[0].astype(np.int32) - want.astype(np.int32))
@@ -424,11 +424,11 @@ def test_vae_golden_and_batch(flux2b, golden):
     ctx.load_weights(VW)
     ctx.finalize()
     out = ctx.vae_decode(golden["vae_z"])
-    assert rel_l2(out, golden["vae_out"]) < 5e-3
+    assert rel_l2(out, golden["vae_out"]) < 3.5e-3
     z2 = np.concatenate([golden["vae_z"], golden["vae_z"][:, :, ::-1].copy()])
     out2 = ctx.vae_decode(z2)
     assert np.array_equal(out2[0], out[0])
-    assert rel_l2(out2[1], O.vae_decode(VW, vcfg, torch.from_numpy(z2[1:2]))[0]) < 5e-3
+    assert rel_l2(out2[1], O.vae_decode(VW, vcfg, torch.from_numpy(z2[1:2]))[0]) < 3.5e-3
     with pytest.raises(flux2b.Flux2Error) as e:
         flux2b.Context(vae=vcfg).vae_decode(golden["vae_z"])
     assert e.value.case == "modelNotLoaded"

@@ -185,7 +185,7 @@ def test_cfg_negative_prompt_of_its_own_length(flux2b):
     ref = O.denoise(W, cfg, lat, enc, sched.sigmas, H, H, enc_uncond=neg, cfg_scale=3.0)
     e = rel_l2(x, ref)
     print(f"CFG with S_txt 96 / S_txt_uncond 40: rel-L2 {e:.2e}")
-    assert e < 8e-3
+    assert e < 4e-3   # measured 2.6e-3
     ctx.close()
 
 

@@ -86,7 +86,7 @@ def test_vae_decode_1024_vs_oracle(flux2b):
     e = rel_l2(out, ref)
     print(f"vae decode 1024x1024: rel-L2 {e:.2e}, cosine {_cos(out, ref):.6f} (oracle {time.time() - t0:.1f} s)")
     assert out.shape == (1, 3, 1024, 1024)
-    assert e < 5e-3 and _cos(out, ref) >= 0.999   # f16 activations through ~30 convolutions and 30 GroupNorms
+    assert e < 3.5e-3 and _cos(out, ref) >= 0.999   # f16 activations through ~30 convolutions and 30 GroupNorms (measured 2.3e-3)
     u8 = ctx.vae_decode_u8(z.numpy())
     want = O.postprocess_vae_output(ref).numpy()
     d = np.abs(u8[0].astype(np.int32) - want.astype(np.int32))
@@ -138,7 +138,7 @@ def test_vae_mid_attention_chunked(flux2b):
         ctx.close()
     with torch.no_grad():
         ref = O.vae_decode(VW, vcfg, z)
-    assert rel_l2(outs[0], ref) < 5e-3
+    assert rel_l2(outs[0], ref) < 3.5e-3
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
@@ -161,4 +161,4 @@ def test_vae_folded_upsample(flux2b, small, h, w):
         ref = O.vae_decode(VW, vcfg, z)
     e1, e0, e10 = rel_l2(outs[1], ref), rel_l2(outs[0], ref), rel_l2(outs[1], outs[0])
     print(f"vae {h}x{w} small={small}: folded vs oracle {e1:.2e}, unfused vs oracle {e0:.2e}, folded vs unfused {e10:.2e}")
-    assert e1 < 5e-3 and e0 < 5e-3 and e10 < 3e-3
+    assert e1 < 3.5e-3 and e0 < 3.5e-3 and e10 < 3e-3

@@ -7,7 +7,7 @@ residual stream in fp32 and rounds to 16 bits only where a tensor-core operand i
 numerator, attention output, SwiGLU product); the oracle is fp32 throughout. A decoder layer adds a branch several times larger
 than the residual it is added to, so with bf16 operands those six roundings show up at ~5e-3 rel-L2 per extracted hidden state
 (measured 3.9e-3 ... 5.5e-3; the reference's all-bf16 arithmetic is further from fp32 than that). Asserted:
-  * bf16 operands (default): rel-L2 <= TOL_BF16 = 8e-3 vs the fp32 oracle, and the device must be CLOSER to the oracle evaluated
+  * bf16 operands (default): rel-L2 <= TOL_BF16 = 7.5e-3 vs the fp32 oracle, and the device must be CLOSER to the oracle evaluated
     with `operand_dtype=bfloat16` (rounding at the device's storage points) than to the fp32 one — the error is operand rounding,
     not arithmetic. (The two cannot agree tightly: the flash kernel rounds P relative to a lazily updated running maximum, so
     its rounding decisions differ from any closed-form softmax and decorrelate everything downstream.)
@@ -23,7 +23,7 @@ from conftest import rel_l2
 pytestmark = pytest.mark.gpu
 
 TOL_ATTN = 4e-3
-TOL_BF16 = 8e-3
+TOL_BF16 = 7.5e-3
 TOL_F16 = 1.2e-3
 
 
