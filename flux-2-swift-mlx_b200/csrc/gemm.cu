@@ -72,6 +72,7 @@ struct KParams {
   const uint8_t* wq_s;  const uint8_t* wq_b;   // main problem
   const uint8_t* wq_s_lo; const uint8_t* wq_b_lo;  // rows below split_units (two-problem launch)
   int n_off;  // absolute output column of this launch's first B row (staged W-only chunks), 0 otherwise
+  int n_fast; // tile order: 0 = consecutive tiles walk M (share a weight tile), 1 = consecutive tiles walk N (share an activation tile) — see launch_cfg
   int dbg;  // FLUX2B_GEMM_TIMELINE=1: cluster 0 prints where its producer / issuer / epilogue warps waited (debug aid)
 };
 
@@ -687,8 +688,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // (folded upsample: the four output phases of an M tile are four consecutive tiles of the schedule)
         const int tq = (HALO && p.up2) ? t >> 2 : t;
         const int phase_idx = (HALO && p.up2) ? (t & 3) : 0;
-        const int m_unit = tq % p.num_m_units;
-        const int n_blk = tq / p.num_m_units;
+        const int m_unit = p.n_fast ? tq / p.num_n_blks : tq % p.num_m_units;
+        const int n_blk = p.n_fast ? tq % p.num_n_blks : tq / p.num_m_units;
         const int m_blk = m_unit * CG + (int)cta_rank;
         const int nrow0 = n_blk * BN + (int)cta_rank * C::B_ROWS;
         const CUtensorMap* tmBsel = (MXK == 0 && !CONV && m_unit < p.split_units) ? &tmSFB : &tmB;
@@ -761,7 +762,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int pcol = (p.wq_mode == 1 || p.wq_mode == 3) ? 64 : 32;   // packed bytes per row per k-block
           auto packed_next = [&]() {
             if (pk_tile >= total_tiles) return;
-            const int pm_unit = pk_tile % p.num_m_units, pn_blk = pk_tile / p.num_m_units;
+            const int pm_unit = p.n_fast ? pk_tile / p.num_n_blks : pk_tile % p.num_m_units, pn_blk = p.n_fast ? pk_tile % p.num_n_blks : pk_tile / p.num_m_units;
             const CUtensorMap* tmP = (pm_unit < p.split_units) ? &tmSFB : &tmB;
             mbar_wait(&pempty[pstage], pphase ^ 1, 5);
             mbar_expect_tx(&pfull[pstage], (uint32_t)(C::B_ROWS * pcol));
@@ -1010,8 +1011,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0, pstage = 0;
       uint32_t phase = 0, pphase = 0;
       for (int t = unit_id; t < total_tiles; t += num_units) {
-        const int m_unit = t % p.num_m_units;
-        const int n_blk = t / p.num_m_units;
+        const int m_unit = p.n_fast ? t / p.num_n_blks : t % p.num_m_units;
+        const int n_blk = p.n_fast ? t % p.num_n_blks : t / p.num_m_units;
         const bool lo = m_unit < p.split_units;
         const uint8_t* sbase = lo ? p.wq_s_lo : p.wq_s;
         const uint8_t* bbase = lo ? p.wq_b_lo : p.wq_b;
@@ -1100,8 +1101,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     for (int t = unit_id; t < total_tiles; t += num_units) {
       const int tq = (HALO && p.up2) ? t >> 2 : t;
-      const int m_unit = tq % p.num_m_units;
-      const int n_blk = tq / p.num_m_units;
+      const int m_unit = p.n_fast ? tq / p.num_n_blks : tq % p.num_m_units;
+      const int n_blk = p.n_fast ? tq % p.num_n_blks : tq / p.num_m_units;
       const int m_blk = m_unit * CG + (int)cta_rank;
       const int r = quarter * 32 + lane;
       bool row_ok;
@@ -1285,6 +1286,20 @@ static cudaError_t launch_cfg(const GemmProblem& g, cudaStream_t stream) {
   const int total = p.num_m_units * p.num_n_blks * (p.up2 ? 4 : 1);
   const int max_units = g_num_sms / CG;
   const int units = std::min(total, max_units);
+  if (!CONV) {
+    // Tile order. The `units` tiles in flight at a time touch either ALL M units x a few N blocks (M fastest) or all N blocks x a
+    // few M units (N fastest); the operand that is swept completely per wave has to stay in the 126 MB L2 from one wave to the next.
+    // M fastest keeps A resident (fine while A = M x K fits beside a few weight tiles); for the K = 12288 out projections A is
+    // 113 MB and was re-fetched from HBM by every wave (ncu: 484 MB read for 245 MB of operands) — there N fastest keeps the
+    // 75 MB of weights resident and streams A once.
+    static const int order = getenv("FLUX2B_GEMM_ORDER") ? atoi(getenv("FLUX2B_GEMM_ORDER")) : -1;   // -1 auto, 0 M fastest, 1 N fastest
+    const double a_bytes = (double)g.M * g.K * (MXK ? 1 : 2), b_bytes = (double)(g.N - g.n_off) * g.K * (MXK ? 1 : 2) * (g.B_lo ? 2 : 1);
+    const double waves_n = std::max(1.0, (double)units / p.num_m_units), waves_m = std::max(1.0, (double)units / p.num_n_blks);
+    const double ws_mfast = a_bytes + b_bytes * std::min(1.0, waves_n / p.num_n_blks);   // all of A + the N blocks of one wave
+    const double ws_nfast = b_bytes + a_bytes * std::min(1.0, waves_m / p.num_m_units);  // all of B + the M units of one wave
+    const double l2 = 100e6;
+    p.n_fast = order >= 0 ? order : (ws_mfast > l2 && ws_nfast < ws_mfast) ? 1 : 0;
+  }
 
   auto kern = gemm_kernel<BN, CG, CONV, MXK>;
   static bool attr_set = false;  // per template instantiation
